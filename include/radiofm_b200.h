@@ -1,0 +1,145 @@
+/* radiofm_b200.h -- C ABI of the B200-native IQ -> audio (+RDS) chain.
+ *
+ * Drop-in boundary for the DSP path of AlwinEsch/pvr.rtl.radiofm.  The reference
+ * has no FFI seam: its DSP is a set of C++ classes linked into the add-on.  The replacement keeps
+ * those class signatures in host C++ (pvr.rtl.radiofm_b200/host/<same-named>.h) as one-line forwards
+ * onto the entry points below; each entry point cites the reference interface it replaces
+ * (paths relative to the reference's src/).  Plain pointers and sizes only.
+ *
+ * Conventions
+ *   - IQ in : interleaved I,Q.  u8 offset-binary (RTL-SDR, 127.5 == 0) or float32 complex.
+ *   - audio : interleaved float32 L,R at sample_rate_pcm.
+ *   - Batched: a decoder handle owns n_streams independent streams that are always processed with
+ *     the same block length (row-major [stream][sample]).  n_streams == 1 reproduces one cFmDecoder.
+ *   - Every function returns RFM_OK (0) or a negative rfm_status; CUDA failures are RFM_ERR_CUDA and
+ *     rfm_last_error() gives the text.  There is NO CPU fallback: without a usable sm_100 device the
+ *     create calls fail.
+ *   - "_device" variants take device pointers and a cudaStream_t (as void*) and only enqueue work.
+ */
+#ifndef RADIOFM_B200_H
+#define RADIOFM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RFM_API __attribute__((visibility("default")))
+
+typedef enum rfm_status
+{
+  RFM_OK = 0,
+  RFM_ERR_INVALID = -1,     /* bad argument */
+  RFM_ERR_CUDA = -2,        /* CUDA runtime error, see rfm_last_error() */
+  RFM_ERR_UNSUPPORTED = -3, /* block shape the batched path does not implement */
+  RFM_ERR_NO_DEVICE = -4,   /* no sm_100 device / extension unusable */
+  RFM_ERR_OVERFLOW = -5     /* caller buffer too small */
+} rfm_status;
+
+RFM_API const char* rfm_last_error(void);
+RFM_API const char* rfm_version(void);
+/* number of kernels this library has launched in this process (bench.py "gpu_launches") */
+RFM_API uint64_t rfm_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * cFmDecoder (FmDecode.h:99-165, FmDecode.cpp:237-539), batched
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rfm_decoder rfm_decoder;
+
+typedef struct rfm_config
+{
+  double sample_rate_if;   /* cFmDecoder ctor arg, FmDecode.h:110-116 */
+  double tuning_offset;
+  double sample_rate_pcm;
+  double bandwidth_pcm;    /* DEFAULT_BANDWIDTH_PCM 15000 */
+  uint32_t downsample;     /* >= 1 */
+  int32_t us_deemphasis;   /* USver: 75 us instead of 50 us */
+  uint32_t n_streams;      /* >= 1 */
+  uint32_t max_block_len;  /* largest n per call; the reference's limit is 65536 (FmDecode.cpp:277) */
+  int32_t device;          /* CUDA device ordinal, -1 = current */
+  uint32_t n_groups;       /* internal stream groups pipelined on separate CUDA streams, 0 = auto */
+} rfm_config;
+
+RFM_API void rfm_config_default(rfm_config* cfg);
+
+/* new cFmDecoder(proc, sample_rate_if, tuning_offset, sample_rate_pcm, bandwidth_pcm, downsample, USver)
+ * -- RadioReceiver.cpp:296-300 */
+RFM_API int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out);
+/* delete m_FMDecoder -- RadioReceiver.cpp:371-374 */
+RFM_API void rfm_decoder_destroy(rfm_decoder* d);
+/* cFmDecoder::Reset -- FmDecode.cpp:326-338 (clears meters, demod PLL and the RDS receiver only) */
+RFM_API int rfm_decoder_reset(rfm_decoder* d);
+
+/* Upper bound of audio floats per stream for a block of n samples (caller allocates; the reference's
+ * caller allocates 2*n, RadioReceiver.cpp:519-520). */
+RFM_API uint32_t rfm_decoder_max_audio_floats(const rfm_decoder* d, uint32_t n);
+
+/* cRtlSdrSource::ReadAsyncCB conversion (RTL_SDR_Source.cpp:196-213) fused with
+ * cFmDecoder::ProcessStream (FmDecode.cpp:417-502).  Host buffers:
+ *   iq    [n_streams][n][2] u8
+ *   audio [n_streams][audio_stride] float, audio_stride >= *n_audio_floats
+ * *n_audio_floats = floats written per stream (2 x frames; identical for all streams). */
+RFM_API int rfm_decoder_process_u8(rfm_decoder* d, const uint8_t* iq, uint32_t n, float* audio,
+                                   size_t audio_stride, uint32_t* n_audio_floats);
+/* unsigned ProcessStream(const ComplexType* samples_in, unsigned samples, float* audio)
+ * -- FmDecode.h:135; iq is [n_streams][n] complex float. */
+RFM_API int rfm_decoder_process_cf32(rfm_decoder* d, const float* iq, uint32_t n, float* audio,
+                                     size_t audio_stride, uint32_t* n_audio_floats);
+
+/* Same with device-resident buffers; work is enqueued on `cuda_stream` (cudaStream_t) and the call
+ * returns without synchronising.  iq_stride is in samples per stream row. */
+RFM_API int rfm_decoder_process_u8_device(rfm_decoder* d, const uint8_t* d_iq, size_t iq_stride, uint32_t n,
+                                          float* d_audio, size_t audio_stride, uint32_t* n_audio_floats,
+                                          void* cuda_stream);
+RFM_API int rfm_decoder_process_cf32_device(rfm_decoder* d, const float* d_iq, size_t iq_stride, uint32_t n,
+                                            float* d_audio, size_t audio_stride, uint32_t* n_audio_floats,
+                                            void* cuda_stream);
+
+/* RDS output of cRDSRxSignalProcessor (RDSProcess.cpp:168 ProcessNewRdsBit sequence, :312,355
+ * DecodeRDS(uint16_t[4]) groups).  Bits are the differentially decoded data bits in arrival order.
+ * Both calls synchronise with the device, run the integer block-sync / FEC state machine
+ * (RDSProcess.cpp:272-431) on the host for new bits, and drain what they return. */
+RFM_API int rfm_decoder_rds_take_groups(rfm_decoder* d, uint32_t stream, uint16_t* groups /* [max][4] */,
+                                        uint32_t max_groups, uint32_t* n_groups);
+RFM_API int rfm_decoder_rds_take_bits(rfm_decoder* d, uint32_t stream, uint8_t* bits, uint32_t max_bits,
+                                      uint32_t* n_bits);
+
+typedef struct rfm_stream_status
+{
+  int32_t stereo_detected;  /* cFmDecoder::StereoDetected, FmDecode.h:140 */
+  float interface_level;    /* GetInterfaceLevel, FmDecode.h:155 */
+  float baseband_level;     /* GetBasebandLevel, FmDecode.h:160 */
+  float baseband_mean;      /* m_BasebandMean */
+  float pilot_level;        /* GetPilotLevel, FmDecode.h:165 */
+  float tuning_offset;      /* GetTuningOffset, FmDecode.h:146-150 */
+} rfm_stream_status;
+RFM_API int rfm_decoder_get_status(rfm_decoder* d, uint32_t stream, rfm_stream_status* out);
+
+/* Derived constants / tables for known-answer tests against the reference constructors.
+ * Same index list as oracle/ref_harness.cpp:ref_fm_constants / ref_fm_table. */
+RFM_API int rfm_decoder_constants(const rfm_decoder* d, double* out, uint32_t max);
+RFM_API int rfm_decoder_table(const rfm_decoder* d, int which, float* out, uint32_t max_floats, uint32_t* n);
+
+/* Debug taps of the last block, copied to host (rows of n_streams).  name: demod_in baseband rawstereo
+ * mono_rs stereo_rs lp rds_dec rds_lp rds_pll rds_mf.  Returns floats per stream in *n_floats. */
+RFM_API int rfm_decoder_tap(rfm_decoder* d, const char* name, uint32_t stream, float* out, uint32_t max_floats,
+                            uint32_t* n_floats);
+
+/* ------------------------------------------------------------------------------------------------
+ * RDS block synchronisation / FEC on explicit bits (host integer code, RDSProcess.cpp:272-431)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rfm_rdssync rfm_rdssync;
+RFM_API int rfm_rdssync_create(rfm_rdssync** out);
+RFM_API void rfm_rdssync_destroy(rfm_rdssync* s);
+RFM_API void rfm_rdssync_reset(rfm_rdssync* s);
+RFM_API int rfm_rdssync_push_bits(rfm_rdssync* s, const uint8_t* bits, uint32_t n);
+RFM_API int rfm_rdssync_take_groups(rfm_rdssync* s, uint16_t* groups, uint32_t max_groups, uint32_t* n_groups);
+/* cRDSRxSignalProcessor::CheckBlock, RDSProcess.cpp:377-431 */
+RFM_API uint32_t rfm_rds_check_block(uint32_t word26, uint32_t offset_syndrome, int use_fec, uint32_t* corrected);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RADIOFM_B200_H */

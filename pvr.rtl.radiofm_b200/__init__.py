@@ -1,0 +1,261 @@
+"""radiofm_b200 -- Python binding (ctypes) of the C ABI in include/radiofm_b200.h.
+
+The product is the shared library ``libradiofm_b200.so`` (hand-written sm_100a CUDA kernels + C++
+host); this module only loads it and wraps the calls for tests/ and bench.py.  There is no Python or
+CPU implementation of the chain behind it: if the library or a B200 is missing, creation fails loudly.
+
+The directory is called ``pvr.rtl.radiofm_b200`` (not importable by dotted name); load it with
+``importlib`` under the module name ``radiofm_b200`` -- see ``load_package()`` in tests/conftest.py or
+__graft_entry__.py.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libradiofm_b200.so")
+
+RFM_OK = 0
+_u8p = C.POINTER(C.c_uint8)
+_u16p = C.POINTER(C.c_uint16)
+_u32p = C.POINTER(C.c_uint32)
+_f32p = C.POINTER(C.c_float)
+_f64p = C.POINTER(C.c_double)
+
+
+class RfmConfig(C.Structure):
+    _fields_ = [("sample_rate_if", C.c_double), ("tuning_offset", C.c_double), ("sample_rate_pcm", C.c_double),
+                ("bandwidth_pcm", C.c_double), ("downsample", C.c_uint32), ("us_deemphasis", C.c_int32),
+                ("n_streams", C.c_uint32), ("max_block_len", C.c_uint32), ("device", C.c_int32),
+                ("n_groups", C.c_uint32)]
+
+
+class RfmStreamStatus(C.Structure):
+    _fields_ = [("stereo_detected", C.c_int32), ("interface_level", C.c_float), ("baseband_level", C.c_float),
+                ("baseband_mean", C.c_float), ("pilot_level", C.c_float), ("tuning_offset", C.c_float)]
+
+
+EXPORTED_SYMBOLS = (
+    "rfm_last_error", "rfm_version", "rfm_launch_count", "rfm_config_default", "rfm_decoder_create",
+    "rfm_decoder_destroy", "rfm_decoder_reset", "rfm_decoder_max_audio_floats", "rfm_decoder_process_u8",
+    "rfm_decoder_process_cf32", "rfm_decoder_process_u8_device", "rfm_decoder_process_cf32_device",
+    "rfm_decoder_rds_take_groups", "rfm_decoder_rds_take_bits", "rfm_decoder_get_status",
+    "rfm_decoder_constants", "rfm_decoder_table", "rfm_decoder_tap", "rfm_rdssync_create",
+    "rfm_rdssync_destroy", "rfm_rdssync_reset", "rfm_rdssync_push_bits", "rfm_rdssync_take_groups",
+    "rfm_rds_check_block",
+)
+
+
+class RadioFmError(RuntimeError):
+    pass
+
+
+def build(verbose: bool = False) -> str:
+    """Compile every CUDA source for sm_100a into the in-tree libradiofm_b200.so (nvcc cross-compiles)."""
+    out = subprocess.run(["sh", os.path.join(_HERE, "csrc", "build.sh")], capture_output=True, text=True)
+    if out.returncode != 0:
+        raise RadioFmError("build failed:\n" + out.stdout + out.stderr)
+    if verbose:
+        print(out.stdout)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RadioFmError(f"{LIB_PATH} is missing: run __graft_entry__.build() (no CPU fallback exists)")
+        L = C.CDLL(LIB_PATH)
+        L.rfm_last_error.restype = C.c_char_p
+        L.rfm_version.restype = C.c_char_p
+        L.rfm_launch_count.restype = C.c_uint64
+        L.rfm_config_default.argtypes = [C.POINTER(RfmConfig)]
+        L.rfm_decoder_create.argtypes = [C.POINTER(RfmConfig), C.POINTER(C.c_void_p)]
+        L.rfm_decoder_destroy.argtypes = [C.c_void_p]
+        L.rfm_decoder_reset.argtypes = [C.c_void_p]
+        L.rfm_decoder_max_audio_floats.restype = C.c_uint32
+        L.rfm_decoder_max_audio_floats.argtypes = [C.c_void_p, C.c_uint32]
+        L.rfm_decoder_process_u8.argtypes = [C.c_void_p, _u8p, C.c_uint32, _f32p, C.c_size_t, _u32p]
+        L.rfm_decoder_process_cf32.argtypes = [C.c_void_p, _f32p, C.c_uint32, _f32p, C.c_size_t, _u32p]
+        L.rfm_decoder_process_u8_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p,
+                                                    C.c_size_t, _u32p, C.c_void_p]
+        L.rfm_decoder_process_cf32_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p,
+                                                      C.c_size_t, _u32p, C.c_void_p]
+        L.rfm_decoder_rds_take_groups.argtypes = [C.c_void_p, C.c_uint32, _u16p, C.c_uint32, _u32p]
+        L.rfm_decoder_rds_take_bits.argtypes = [C.c_void_p, C.c_uint32, _u8p, C.c_uint32, _u32p]
+        L.rfm_decoder_get_status.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(RfmStreamStatus)]
+        L.rfm_decoder_constants.argtypes = [C.c_void_p, _f64p, C.c_uint32]
+        L.rfm_decoder_table.argtypes = [C.c_void_p, C.c_int, _f32p, C.c_uint32, _u32p]
+        L.rfm_decoder_tap.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, _f32p, C.c_uint32, _u32p]
+        L.rfm_rdssync_create.argtypes = [C.POINTER(C.c_void_p)]
+        L.rfm_rdssync_destroy.argtypes = [C.c_void_p]
+        L.rfm_rdssync_reset.argtypes = [C.c_void_p]
+        L.rfm_rdssync_push_bits.argtypes = [C.c_void_p, _u8p, C.c_uint32]
+        L.rfm_rdssync_take_groups.argtypes = [C.c_void_p, _u16p, C.c_uint32, _u32p]
+        L.rfm_rds_check_block.restype = C.c_uint32
+        L.rfm_rds_check_block.argtypes = [C.c_uint32, C.c_uint32, C.c_int, _u32p]
+        _lib = L
+    return _lib
+
+
+def _check(rc: int):
+    if rc != RFM_OK:
+        raise RadioFmError(f"radiofm_b200 error {rc}: {lib().rfm_last_error().decode()}")
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+def launch_count() -> int:
+    return int(lib().rfm_launch_count())
+
+
+_COMPLEX_TAPS = {"demod_in", "rds_dec", "rds_lp"}
+
+
+class FmDecoderBatch:
+    """n_streams x cFmDecoder (FmDecode.h:99-165) on one B200."""
+
+    def __init__(self, fs_if: float, tuning_offset: float, fs_pcm: float = 48000.0, bw_pcm: float = 15000.0,
+                 downsample: int = 1, usver: bool = False, n_streams: int = 1, max_block_len: int = 65536,
+                 device: int = -1, n_groups: int = 0):
+        cfg = RfmConfig()
+        lib().rfm_config_default(C.byref(cfg))
+        cfg.sample_rate_if, cfg.tuning_offset, cfg.sample_rate_pcm, cfg.bandwidth_pcm = fs_if, tuning_offset, fs_pcm, bw_pcm
+        cfg.downsample, cfg.us_deemphasis, cfg.n_streams = downsample, int(usver), n_streams
+        cfg.max_block_len, cfg.device, cfg.n_groups = max_block_len, device, n_groups
+        self.n_streams = n_streams
+        self._h = C.c_void_p()
+        _check(lib().rfm_decoder_create(C.byref(cfg), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().rfm_decoder_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reset(self):
+        _check(lib().rfm_decoder_reset(self._h))
+
+    def max_audio_floats(self, n: int) -> int:
+        return int(lib().rfm_decoder_max_audio_floats(self._h, n))
+
+    # ---- host buffers (numpy) ----
+    def process_u8(self, iq_u8: np.ndarray) -> np.ndarray:
+        """iq_u8 [S, n, 2] uint8 -> audio [S, floats] float32 (interleaved L,R)."""
+        iq_u8 = np.ascontiguousarray(iq_u8, dtype=np.uint8).reshape(self.n_streams, -1, 2)
+        n = iq_u8.shape[1]
+        stride = max(self.max_audio_floats(n), 2)
+        audio = np.empty((self.n_streams, stride), dtype=np.float32)
+        k = C.c_uint32(0)
+        _check(lib().rfm_decoder_process_u8(self._h, _p(iq_u8, _u8p), n, _p(audio, _f32p), stride, C.byref(k)))
+        return audio[:, :k.value].copy()
+
+    def process_cf32(self, iq: np.ndarray) -> np.ndarray:
+        iq = np.ascontiguousarray(iq, dtype=np.float32).reshape(self.n_streams, -1, 2)
+        n = iq.shape[1]
+        stride = max(self.max_audio_floats(n), 2)
+        audio = np.empty((self.n_streams, stride), dtype=np.float32)
+        k = C.c_uint32(0)
+        _check(lib().rfm_decoder_process_cf32(self._h, _p(iq, _f32p), n, _p(audio, _f32p), stride, C.byref(k)))
+        return audio[:, :k.value].copy()
+
+    # ---- device buffers (raw pointers, e.g. torch tensors' data_ptr()) ----
+    def process_u8_device(self, d_iq_ptr: int, iq_stride: int, n: int, d_audio_ptr: int, audio_stride: int,
+                          cuda_stream: int = 0) -> int:
+        k = C.c_uint32(0)
+        _check(lib().rfm_decoder_process_u8_device(self._h, C.c_void_p(d_iq_ptr), iq_stride, n,
+                                                   C.c_void_p(d_audio_ptr), audio_stride, C.byref(k),
+                                                   C.c_void_p(cuda_stream)))
+        return int(k.value)
+
+    def process_cf32_device(self, d_iq_ptr: int, iq_stride: int, n: int, d_audio_ptr: int, audio_stride: int,
+                            cuda_stream: int = 0) -> int:
+        k = C.c_uint32(0)
+        _check(lib().rfm_decoder_process_cf32_device(self._h, C.c_void_p(d_iq_ptr), iq_stride, n,
+                                                     C.c_void_p(d_audio_ptr), audio_stride, C.byref(k),
+                                                     C.c_void_p(cuda_stream)))
+        return int(k.value)
+
+    # ---- RDS / telemetry ----
+    def take_groups(self, stream: int = 0, max_groups: int = 4096) -> np.ndarray:
+        out = np.zeros((max_groups, 4), dtype=np.uint16)
+        k = C.c_uint32(0)
+        _check(lib().rfm_decoder_rds_take_groups(self._h, stream, _p(out, _u16p), max_groups, C.byref(k)))
+        return out[:k.value].copy()
+
+    def take_bits(self, stream: int = 0, max_bits: int = 1 << 20) -> np.ndarray:
+        out = np.zeros(max_bits, dtype=np.uint8)
+        k = C.c_uint32(0)
+        _check(lib().rfm_decoder_rds_take_bits(self._h, stream, _p(out, _u8p), max_bits, C.byref(k)))
+        return out[:k.value].copy()
+
+    def status(self, stream: int = 0) -> dict:
+        s = RfmStreamStatus()
+        _check(lib().rfm_decoder_get_status(self._h, stream, C.byref(s)))
+        return {"stereo": bool(s.stereo_detected), "if_level": np.float32(s.interface_level),
+                "bb_level": np.float32(s.baseband_level), "bb_mean": np.float32(s.baseband_mean),
+                "pilot_level": np.float32(s.pilot_level), "tuning_offset": np.float32(s.tuning_offset)}
+
+    def constants(self) -> np.ndarray:
+        s = np.zeros(64, dtype=np.float64)
+        rc = lib().rfm_decoder_constants(self._h, _p(s, _f64p), 64)
+        if rc < 0:
+            _check(rc)
+        return s
+
+    def table(self, which: int) -> np.ndarray:
+        out = np.zeros(4096, dtype=np.float32)
+        k = C.c_uint32(0)
+        _check(lib().rfm_decoder_table(self._h, which, _p(out, _f32p), out.size, C.byref(k)))
+        return out[:k.value].copy()
+
+    def tap(self, name: str, stream: int = 0) -> np.ndarray:
+        out = np.zeros(1 << 18, dtype=np.float32)
+        k = C.c_uint32(0)
+        _check(lib().rfm_decoder_tap(self._h, name.encode(), stream, _p(out, _f32p), out.size, C.byref(k)))
+        a = out[:k.value].copy()
+        return a.reshape(-1, 2) if name in _COMPLEX_TAPS else a
+
+
+class RdsBlockSync:
+    """Host-side RDS block sync / FEC (RDSProcess.cpp:272-431)."""
+
+    def __init__(self):
+        self._h = C.c_void_p()
+        _check(lib().rfm_rdssync_create(C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().rfm_rdssync_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reset(self):
+        lib().rfm_rdssync_reset(self._h)
+
+    def push_bits(self, bits: np.ndarray):
+        bits = np.ascontiguousarray(bits, dtype=np.uint8)
+        _check(lib().rfm_rdssync_push_bits(self._h, _p(bits, _u8p), bits.size))
+
+    def take_groups(self, max_groups: int = 4096) -> np.ndarray:
+        out = np.zeros((max_groups, 4), dtype=np.uint16)
+        k = C.c_uint32(0)
+        _check(lib().rfm_rdssync_take_groups(self._h, _p(out, _u16p), max_groups, C.byref(k)))
+        return out[:k.value].copy()
+
+
+def rds_check_block(word26: int, offset_syndrome: int, use_fec: bool):
+    c = C.c_uint32(0)
+    syn = lib().rfm_rds_check_block(word26, offset_syndrome, int(use_fec), C.byref(c))
+    return int(syn), int(c.value)

@@ -1,0 +1,947 @@
+// rfm_api.cu -- C ABI (include/radiofm_b200.h) over the sm_100a kernels: decoder handle, HBM buffers,
+// per-block launch schedule, stream-group pipelining, RDS bit drain.
+//
+// Execution model.  One decoder = n_streams independent IQ streams processed in lock step.  The
+// streams are split into G groups; each group owns a full set of V buffers and a CUDA stream, and runs
+// the per-block kernel chain
+//     front -> bb_lanes -> { resample -> lp29 -> audio_tail } , { halfband* -> rds lp -> rds pll ->
+//     matched filter -> slicer } -> tails
+// The chains of different groups overlap on the device, so the latency-bound one-lane-per-stream
+// kernels (PLLs: nonlinear recurrences that cannot be parallelised in time) of one group hide behind
+// the throughput-bound FIR kernels of the others.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/radiofm_b200.h"
+#include "rfm_kernels.cuh"
+#include "rfm_plan.h"
+#include "rfm_rdssync.h"
+
+using namespace rfm;
+
+namespace
+{
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+
+int Fail(int code, const std::string& msg)
+{
+  g_err = msg;
+  return code;
+}
+
+#define RFM_CUDA(expr)                                                                                   \
+  do                                                                                                     \
+  {                                                                                                      \
+    cudaError_t e_ = (expr);                                                                             \
+    if (e_ != cudaSuccess)                                                                               \
+      return Fail(RFM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));                    \
+  } while (0)
+
+unsigned AlignUp(unsigned v, unsigned a) { return (v + a - 1) / a * a; }
+
+template <typename T>
+struct DevBuf
+{
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t Alloc(size_t count)
+  {
+    n = count;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+    if (e == cudaSuccess)
+      e = cudaMemset(p, 0, std::max<size_t>(count, 1) * sizeof(T));
+    return e;
+  }
+  void Free()
+  {
+    if (p)
+      cudaFree(p);
+    p = nullptr;
+  }
+};
+
+struct Group
+{
+  unsigned s0 = 0, S = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+  DevBuf<cf32> tail, z;
+  DevBuf<float> bbV, rawV;
+  DevBuf<cf32> hbV[kMaxDecStages]; // input V buffer of stage k (k >= 1); stage 0 reads bbV x oscV
+  DevBuf<cf32> rlpV, rlp_out;
+  DevBuf<float> mfV, mf_out;
+  DevBuf<uint8_t> bits;
+  DevBuf<unsigned> bit_count;
+  DevBuf<float> lpS, lpM, fS, fM;
+  DevBuf<float> state;
+  DevBuf<uint8_t> in_stage;  // host-API staging of the input block
+  DevBuf<float> audio_stage; // host-API staging of the audio block
+};
+} // namespace
+
+struct rfm_decoder
+{
+  rfm_config cfg;
+  DecoderPlan plan;
+  int device = 0;
+  unsigned S = 0, maxn = 0;
+  unsigned nb_max = 0, na_max = 0, nr_max = 0;
+  unsigned z_stride = 0, a_stride = 0, lp_stride = 0, rlp_stride = 0, mf_stride = 0, nr_stride = 0;
+  unsigned hb_stride[kMaxDecStages] = {0};
+  unsigned osc_hist = 0, bits_cap = 0, audio_cap = 0;
+  // plan tables on the device
+  DevBuf<float> d_lut, d_tuner, d_in_coeff, d_a_coeff, d_lp_coef, d_rlp_coef, d_mf_coef;
+  DevBuf<float> d_hb[kMaxDecStages];
+  DevBuf<cf32> oscV;
+  DevBuf<float> osc1;
+  std::vector<Group> groups;
+  cudaStream_t main_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_osc = nullptr, ev_join = nullptr;
+  // lock-step state (identical for every stream)
+  unsigned tuner_idx = 0, in_pos = 0;
+  float a_pos = 0.0f;
+  unsigned lp_g = 0, rlp_g = 0, mf_g = 0;
+  unsigned pending_bits_bound = 0; // worst-case undrained bits per stream
+  // geometry of the last block (for taps)
+  unsigned last_n = 0, last_nb = 0, last_na = 0, last_nr = 0;
+  unsigned last_hb_n[kMaxDecStages + 1] = {0};
+  // host RDS state
+  std::vector<RdsBlockSync> sync;
+  std::vector<std::vector<uint8_t>> host_bits;
+  std::vector<uint8_t> h_bits;
+  std::vector<unsigned> h_counts;
+};
+
+namespace
+{
+
+void FreeDecoder(rfm_decoder* d)
+{
+  if (!d)
+    return;
+  cudaSetDevice(d->device);
+  for (auto& g : d->groups)
+  {
+    if (g.stream)
+      cudaStreamSynchronize(g.stream);
+    g.tail.Free(); g.z.Free(); g.bbV.Free(); g.rawV.Free();
+    for (auto& b : g.hbV) b.Free();
+    g.rlpV.Free(); g.rlp_out.Free(); g.mfV.Free(); g.mf_out.Free(); g.bits.Free(); g.bit_count.Free();
+    g.lpS.Free(); g.lpM.Free(); g.fS.Free(); g.fM.Free(); g.state.Free(); g.in_stage.Free(); g.audio_stage.Free();
+    if (g.done)
+      cudaEventDestroy(g.done);
+    if (g.stream)
+      cudaStreamDestroy(g.stream);
+  }
+  d->d_lut.Free(); d->d_tuner.Free(); d->d_in_coeff.Free(); d->d_a_coeff.Free(); d->d_lp_coef.Free();
+  d->d_rlp_coef.Free(); d->d_mf_coef.Free();
+  for (auto& b : d->d_hb) b.Free();
+  d->oscV.Free(); d->osc1.Free();
+  for (cudaEvent_t e : {d->ev_fork, d->ev_osc, d->ev_join})
+    if (e)
+      cudaEventDestroy(e);
+  if (d->main_stream)
+    cudaStreamDestroy(d->main_stream);
+  delete d;
+}
+
+cudaError_t Upload(DevBuf<float>& b, const float* src, size_t n)
+{
+  cudaError_t e = b.Alloc(n);
+  if (e == cudaSuccess && n)
+    e = cudaMemcpy(b.p, src, n * sizeof(float), cudaMemcpyHostToDevice);
+  return e;
+}
+
+unsigned StageHist(const HalfBandStage& s) { return s.len == 3 ? 2u : (unsigned)s.len - 1; }
+
+// cFmDecoder::Reset on the device state of one group (FmDecode.cpp:326-338 + RDSProcess.cpp:90-118)
+cudaError_t ResetGroupState(rfm_decoder* d, Group& g, bool initial)
+{
+  const unsigned S = g.S;
+  std::vector<float> st(g.state.n);
+  cudaError_t e = cudaMemcpy(st.data(), g.state.p, st.size() * sizeof(float), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess)
+    return e;
+  auto zero = [&](int f) { std::fill(st.begin() + (size_t)f * S, st.begin() + (size_t)(f + 1) * S, 0.0f); };
+  zero(SF_STEREO); zero(SF_IF_LEVEL); zero(SF_BB_MEAN); zero(SF_BB_LEVEL); zero(SF_DEMOD_DC);
+  zero(SF_DEMOD_INCR); zero(SF_DEMOD_PHASE);
+  zero(SF_RPLL_PHASE); zero(SF_RPLL_FREQ); zero(SF_RSYNC_W1); zero(SF_RSYNC_W2); zero(SF_RS_LASTSYNC);
+  zero(SF_RS_LASTSLOPE); zero(SF_RS_LASTDATA); zero(SF_RS_LASTBIT);
+  if (initial)
+  {
+    // cPilotPhaseLock ctor, FmDecode.cpp:131-139
+    std::fill(st.begin() + (size_t)SF_PILOT_FREQ * S, st.begin() + (size_t)(SF_PILOT_FREQ + 1) * S, d->plan.pilot.freq0);
+  }
+  e = cudaMemcpy(g.state.p, st.data(), st.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess)
+    return e;
+  // InitLPFilter / InitConstFir clear the delay lines (FirFilter.cpp:138-144,313-319)
+  e = cudaMemset(g.rlpV.p, 0, g.rlpV.n * sizeof(cf32));
+  if (e != cudaSuccess)
+    return e;
+  return cudaMemset(g.mfV.p, 0, g.mfV.n * sizeof(float));
+}
+
+// Bring undrained slicer bits to the host and run the block-sync state machines on them.
+int DrainBits(rfm_decoder* d)
+{
+  if (d->pending_bits_bound == 0)
+    return RFM_OK;
+  for (auto& g : d->groups)
+  {
+    RFM_CUDA(cudaStreamSynchronize(g.stream));
+    d->h_counts.resize(g.S);
+    RFM_CUDA(cudaMemcpy(d->h_counts.data(), g.bit_count.p, g.S * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    unsigned mx = 0;
+    for (unsigned c : d->h_counts)
+      mx = std::max(mx, c);
+    if (mx > d->bits_cap)
+      return Fail(RFM_ERR_OVERFLOW, "RDS bit buffer overflow (internal drain bound violated)");
+    if (mx == 0)
+      continue;
+    d->h_bits.resize((size_t)g.S * mx);
+    RFM_CUDA(cudaMemcpy2D(d->h_bits.data(), mx, g.bits.p, d->bits_cap, mx, g.S, cudaMemcpyDeviceToHost));
+    for (unsigned s = 0; s < g.S; ++s)
+    {
+      const uint8_t* b = d->h_bits.data() + (size_t)s * mx;
+      auto& hb = d->host_bits[g.s0 + s];
+      auto& sy = d->sync[g.s0 + s];
+      for (unsigned i = 0; i < d->h_counts[s]; ++i)
+      {
+        hb.push_back(b[i]);
+        sy.PushBit(b[i]);
+      }
+    }
+    RFM_CUDA(cudaMemset(g.bit_count.p, 0, g.S * sizeof(unsigned)));
+  }
+  d->pending_bits_bound = 0;
+  return RFM_OK;
+}
+
+struct BlockGeom
+{
+  unsigned n, nb, na, nr;
+  unsigned hb_n[kMaxDecStages + 1]; // samples entering stage k; hb_n[nstages] == nr
+  float a_pos_next;
+  unsigned in_pos_next;
+};
+
+int PlanBlock(const rfm_decoder* d, unsigned n, BlockGeom* g)
+{
+  const DecoderPlan& p = d->plan;
+  g->n = n;
+  const unsigned ds = p.downsample;
+  // integer decimator, DownConvert.cpp:105-132
+  unsigned pos = d->in_pos;
+  g->nb = (pos < n) ? (n - pos + ds - 1) / ds : 0;
+  g->in_pos_next = pos + g->nb * ds - n;
+  g->na = FractionalOutputs(d->a_pos, p.a_pstep, g->nb, &g->a_pos_next);
+  unsigned m = g->nb;
+  for (size_t k = 0; k < p.rds_stages.size(); ++k)
+  {
+    g->hb_n[k] = m;
+    const unsigned L = (unsigned)p.rds_stages[k].len;
+    if (m % 2 != 0 || m < std::max(L, 2u))
+      return Fail(RFM_ERR_UNSUPPORTED,
+                  "block length leaves an odd or too short (< FIR length) sample count in the RDS half-band "
+                  "chain; the reference mis-handles this case too (DownConvert.cpp:519-524): choose n so that "
+                  "n/downsample is a multiple of 2^stages");
+    m /= 2;
+  }
+  g->hb_n[p.rds_stages.size()] = m;
+  g->nr = m;
+  return RFM_OK;
+}
+
+// Enqueue the whole per-block chain of one group on its stream.
+void EnqueueGroup(rfm_decoder* d, Group& g, const void* d_in, size_t in_stride, bool u8, const BlockGeom& bg,
+                  float* d_audio, size_t audio_stride)
+{
+  const DecoderPlan& p = d->plan;
+  cudaStream_t st = g.stream;
+  const unsigned S = g.S;
+  const unsigned a_hist = p.a_order;
+  const unsigned lp_taps = (unsigned)p.lp_coef.size(), rlp_taps = (unsigned)p.rlp_coef.size();
+  const unsigned mf_taps = (unsigned)p.mf_coef.size();
+  const unsigned nst = (unsigned)p.rds_stages.size();
+
+  FrontParams fp;
+  fp.in = d_in; fp.in_stride = in_stride; fp.n = bg.n; fp.S = S; fp.order = p.in_order; fp.ds = p.downsample;
+  fp.p0 = d->in_pos; fp.nout = bg.nb; fp.idx0 = d->tuner_idx; fp.lut = d->d_lut.p; fp.tuner = d->d_tuner.p;
+  fp.coeff = d->d_in_coeff.p; fp.tail = g.tail.p; fp.z = g.z.p; fp.z_stride = d->z_stride;
+  launch_front(fp, u8, st);
+
+  LanesParams lp;
+  lp.front = fp; lp.z = g.z.p; lp.z_stride = d->z_stride; lp.nb = bg.nb; lp.S = S; lp.state = g.state.p;
+  lp.demod = {p.demod_gain, p.nco_lo, p.nco_hi, p.pll_alpha, p.pll_beta};
+  lp.pilot = {p.pilot.minfreq, p.pilot.maxfreq, p.pilot.b0, p.pilot.a1, p.pilot.a2, p.pilot.lb0, p.pilot.lb1,
+              p.pilot.minsignal, p.pilot.lock_delay};
+  lp.bbV = g.bbV.p; lp.rawV = g.rawV.p; lp.a_stride = d->a_stride; lp.a_hist = a_hist;
+  launch_bb_lanes(lp, u8, st);
+  launch_front_tail(fp, u8, st); // after the lanes kernel: its IF meter reads the same input block
+  g_launches += 3;
+
+  // ---- audio branch
+  ResampleParams rp;
+  rp.bbV = g.bbV.p; rp.rawV = g.rawV.p; rp.a_stride = d->a_stride; rp.order = p.a_order; rp.nb = bg.nb; rp.S = S;
+  rp.na = bg.na; rp.pos_frac = d->a_pos; rp.pstep = p.a_pstep; rp.coeff = d->d_a_coeff.p; rp.lpS = g.lpS.p;
+  rp.lpM = g.lpM.p; rp.lp_stride = d->lp_stride; rp.lp_hist = lp_taps - 1;
+  launch_resample(rp, st);
+
+  RotFirParams f29;
+  f29.inA = g.lpS.p; f29.inB = g.lpM.p; f29.in_stride = d->lp_stride; f29.outA = g.fS.p; f29.outB = g.fM.p;
+  f29.out_stride = d->na_max; f29.out_off = 0; f29.n = bg.na; f29.S = S; f29.taps = lp_taps; f29.g0 = d->lp_g;
+  f29.coef = d->d_lp_coef.p; f29.cplx = 0;
+  launch_rotfir(f29, st);
+
+  AudioTailParams at;
+  at.inS = g.fS.p; at.inM = g.fM.p; at.in_stride = d->na_max; at.na = bg.na; at.S = S; at.state = g.state.p;
+  at.de_alpha = p.de_alpha; at.notch = {p.notch.A1, p.notch.A2, p.notch.B0, p.notch.B1, p.notch.B2};
+  at.audio = d_audio; at.audio_stride = audio_stride;
+  launch_audio_tail(at, st);
+  g_launches += 3;
+
+  // ---- RDS branch
+  for (unsigned k = 0; k < nst; ++k)
+  {
+    const HalfBandStage& hs = p.rds_stages[k];
+    HalfBandParams hp;
+    memset(&hp, 0, sizeof(hp));
+    hp.mix = (k == 0);
+    hp.in = (k == 0) ? nullptr : g.hbV[k].p;
+    hp.in_stride = d->hb_stride[k];
+    hp.bbV = g.bbV.p; hp.a_stride = d->a_stride; hp.a_hist = a_hist;
+    hp.oscV = d->oscV.p; hp.osc_hist = d->osc_hist;
+    hp.kind = hs.len == 3 ? 2 : (hs.fixed11 ? 1 : 0);
+    hp.len = (unsigned)hs.len; hp.n_in = bg.hb_n[k]; hp.S = S; hp.h = d->d_hb[k].p;
+    if (k + 1 < nst)
+    {
+      hp.out = g.hbV[k + 1].p; hp.out_stride = d->hb_stride[k + 1]; hp.out_off = StageHist(p.rds_stages[k + 1]);
+    }
+    else
+    {
+      hp.out = g.rlpV.p; hp.out_stride = d->rlp_stride; hp.out_off = rlp_taps - 1;
+    }
+    launch_halfband(hp, st);
+    ++g_launches;
+  }
+  RotFirParams frl;
+  frl.inA = reinterpret_cast<const float*>(g.rlpV.p); frl.inB = nullptr; frl.in_stride = d->rlp_stride;
+  frl.outA = reinterpret_cast<float*>(g.rlp_out.p); frl.outB = nullptr; frl.out_stride = d->nr_stride;
+  frl.out_off = 0; frl.n = bg.nr; frl.S = S; frl.taps = rlp_taps; frl.g0 = d->rlp_g; frl.coef = d->d_rlp_coef.p;
+  frl.cplx = 1;
+  launch_rotfir(frl, st);
+
+  RdsPllParams pp;
+  pp.in = g.rlp_out.p; pp.in_stride = d->nr_stride; pp.nr = bg.nr; pp.S = S; pp.state = g.state.p;
+  pp.lo = p.rpll_lo; pp.hi = p.rpll_hi; pp.alpha = p.rpll_alpha; pp.beta = p.rpll_beta;
+  pp.out = g.mfV.p; pp.out_stride = d->mf_stride; pp.out_off = mf_taps - 1;
+  launch_rds_pll(pp, st);
+
+  RotFirParams fmf;
+  fmf.inA = g.mfV.p; fmf.inB = nullptr; fmf.in_stride = d->mf_stride; fmf.outA = g.mf_out.p; fmf.outB = nullptr;
+  fmf.out_stride = d->nr_stride; fmf.out_off = 0; fmf.n = bg.nr; fmf.S = S; fmf.taps = mf_taps; fmf.g0 = d->mf_g;
+  fmf.coef = d->d_mf_coef.p; fmf.cplx = 0;
+  launch_rotfir(fmf, st);
+
+  RdsSliceParams sp;
+  sp.in = g.mf_out.p; sp.in_stride = d->nr_stride; sp.nr = bg.nr; sp.S = S; sp.state = g.state.p;
+  sp.sync = {p.rsync.A1, p.rsync.A2, p.rsync.B0, p.rsync.B1, p.rsync.B2};
+  sp.bits = g.bits.p; sp.bits_cap = d->bits_cap; sp.bit_count = g.bit_count.p;
+  launch_rds_slice(sp, st);
+  g_launches += 4;
+
+  // ---- history carry of every V buffer of this group
+  TailParams tp;
+  tp.count = 0;
+  auto add = [&](void* base, size_t stride_elems, unsigned hist, unsigned n, unsigned elem) {
+    if (hist == 0)
+      return;
+    tp.d[tp.count++] = {base, stride_elems * elem, hist, n, elem, S};
+  };
+  add(g.bbV.p, d->a_stride, a_hist, bg.nb, 4);
+  add(g.rawV.p, d->a_stride, a_hist, bg.nb, 4);
+  add(g.lpS.p, d->lp_stride, lp_taps - 1, bg.na, 4);
+  add(g.lpM.p, d->lp_stride, lp_taps - 1, bg.na, 4);
+  for (unsigned k = 1; k < nst; ++k)
+    add(g.hbV[k].p, d->hb_stride[k], StageHist(p.rds_stages[k]), bg.hb_n[k], 8);
+  add(g.rlpV.p, d->rlp_stride, rlp_taps - 1, bg.nr, 8);
+  add(g.mfV.p, d->mf_stride, mf_taps - 1, bg.nr, 4);
+  launch_tails(tp, S, st);
+  ++g_launches;
+}
+
+// One block for all groups.  Inputs / outputs are device pointers for the whole batch.
+int ProcessDevice(rfm_decoder* d, const void* d_in, size_t in_stride, bool u8, unsigned n, float* d_audio,
+                  size_t audio_stride, uint32_t* n_audio_floats, cudaStream_t user, bool host_staged)
+{
+  if (n == 0)
+  {
+    if (n_audio_floats)
+      *n_audio_floats = 0;
+    return RFM_OK;
+  }
+  if (n > d->maxn)
+    return Fail(RFM_ERR_INVALID, "n exceeds max_block_len");
+  if (n < d->plan.in_order)
+    return Fail(RFM_ERR_UNSUPPORTED, "blocks shorter than the input FIR order (8*downsample) are not supported");
+  BlockGeom bg;
+  int rc = PlanBlock(d, n, &bg);
+  if (rc != RFM_OK)
+    return rc;
+  if (2 * (size_t)bg.na > audio_stride)
+    return Fail(RFM_ERR_OVERFLOW, "audio_stride smaller than the floats produced per stream");
+  RFM_CUDA(cudaSetDevice(d->device));
+
+  // drain the RDS bit buffers before they could overflow
+  const unsigned worst_bits = bg.nr / 8 + 4; // >= 8 samples per bit at every supported rate; overflow is checked
+  if (d->pending_bits_bound + worst_bits > d->bits_cap)
+  {
+    rc = DrainBits(d);
+    if (rc != RFM_OK)
+      return rc;
+  }
+
+  cudaStream_t base = d->main_stream;
+  if (!host_staged)
+  {
+    // fork: internal work must see everything already enqueued on the user's stream
+    RFM_CUDA(cudaEventRecord(d->ev_fork, user));
+    RFM_CUDA(cudaStreamWaitEvent(base, d->ev_fork, 0));
+  }
+  // NCO oscillator table for this block (shared by all streams)
+  OscParams op;
+  op.oscV = d->oscV.p; op.osc_hist = d->osc_hist; op.nb = bg.nb; op.osc1 = d->osc1.p;
+  op.cosv = d->plan.rds_osc.cosv; op.sinv = d->plan.rds_osc.sinv;
+  launch_osc(op, base);
+  ++g_launches;
+  RFM_CUDA(cudaEventRecord(d->ev_osc, base));
+
+  const size_t esz = u8 ? 2 : 8;
+  for (auto& g : d->groups)
+  {
+    RFM_CUDA(cudaStreamWaitEvent(g.stream, d->ev_osc, 0));
+    const unsigned char* in_g = reinterpret_cast<const unsigned char*>(d_in) + (size_t)g.s0 * in_stride * esz;
+    float* audio_g = d_audio + (size_t)g.s0 * audio_stride;
+    const void* in_dev = in_g;
+    float* audio_dev = audio_g;
+    size_t in_stride_dev = in_stride, audio_stride_dev = audio_stride;
+    if (host_staged)
+    {
+      // host pointers: copy this group's rows in, run, copy its audio out, all on the group's stream
+      RFM_CUDA(cudaMemcpy2DAsync(g.in_stage.p, (size_t)d->maxn * esz, in_g, in_stride * esz, (size_t)n * esz, g.S,
+                                 cudaMemcpyHostToDevice, g.stream));
+      in_dev = g.in_stage.p;
+      in_stride_dev = d->maxn;
+      audio_dev = g.audio_stage.p;
+      audio_stride_dev = d->audio_cap;
+    }
+    EnqueueGroup(d, g, in_dev, in_stride_dev, u8, bg, audio_dev, audio_stride_dev);
+    if (host_staged)
+      RFM_CUDA(cudaMemcpy2DAsync(audio_g, audio_stride * sizeof(float), g.audio_stage.p,
+                                 (size_t)d->audio_cap * sizeof(float), (size_t)2 * bg.na * sizeof(float), g.S,
+                                 cudaMemcpyDeviceToHost, g.stream));
+    RFM_CUDA(cudaEventRecord(g.done, g.stream));
+    RFM_CUDA(cudaStreamWaitEvent(base, g.done, 0));
+  }
+  // carry the oscillator table history once every group has consumed it
+  TailParams tp;
+  tp.count = 1;
+  tp.d[0] = {d->oscV.p, 0, d->osc_hist, bg.nb, 8, 1};
+  launch_tails(tp, 1, base);
+  ++g_launches;
+  if (!host_staged)
+  {
+    RFM_CUDA(cudaEventRecord(d->ev_join, base));
+    RFM_CUDA(cudaStreamWaitEvent(user, d->ev_join, 0));
+  }
+  RFM_CUDA(cudaGetLastError());
+
+  // advance the lock-step state
+  d->tuner_idx = (d->tuner_idx + n) % kTunerTable;
+  d->in_pos = bg.in_pos_next;
+  d->a_pos = bg.a_pos_next;
+  d->lp_g = (d->lp_g + bg.na) % (unsigned)d->plan.lp_coef.size();
+  d->rlp_g = (d->rlp_g + bg.nr) % (unsigned)d->plan.rlp_coef.size();
+  d->mf_g = (d->mf_g + bg.nr) % (unsigned)d->plan.mf_coef.size();
+  d->pending_bits_bound += worst_bits;
+  d->last_n = n; d->last_nb = bg.nb; d->last_na = bg.na; d->last_nr = bg.nr;
+  memcpy(d->last_hb_n, bg.hb_n, sizeof(bg.hb_n));
+  if (n_audio_floats)
+    *n_audio_floats = 2 * bg.na;
+  if (host_staged)
+    RFM_CUDA(cudaStreamSynchronize(base));
+  return RFM_OK;
+}
+
+Group* FindGroup(rfm_decoder* d, unsigned stream, unsigned* local)
+{
+  for (auto& g : d->groups)
+    if (stream >= g.s0 && stream < g.s0 + g.S)
+    {
+      *local = stream - g.s0;
+      return &g;
+    }
+  return nullptr;
+}
+
+int SyncAll(rfm_decoder* d)
+{
+  RFM_CUDA(cudaSetDevice(d->device));
+  for (auto& g : d->groups)
+    if (g.stream)
+      RFM_CUDA(cudaStreamSynchronize(g.stream));
+  RFM_CUDA(cudaStreamSynchronize(d->main_stream));
+  return RFM_OK;
+}
+
+} // namespace
+
+extern "C"
+{
+
+const char* rfm_last_error(void) { return g_err.c_str(); }
+const char* rfm_version(void) { return "radiofm_b200 0.1 (sm_100a)"; }
+uint64_t rfm_launch_count(void) { return g_launches.load(); }
+
+void rfm_config_default(rfm_config* c)
+{
+  memset(c, 0, sizeof(*c));
+  c->sample_rate_if = 1.0e6;       // RadioReceiver.cpp:184
+  c->tuning_offset = -0.15e6;      // RadioReceiver.cpp:237,297
+  c->sample_rate_pcm = 48000.0;    // OUTPUT_SAMPLERATE
+  c->bandwidth_pcm = 15000.0;
+  c->downsample = 4;               // RadioReceiver.cpp:285
+  c->us_deemphasis = 0;
+  c->n_streams = 1;
+  c->max_block_len = 65536;        // cRtlSdrSource::default_block_length
+  c->device = -1;
+  c->n_groups = 0;
+}
+
+int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out)
+{
+  if (!cfg || !out)
+    return Fail(RFM_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->n_streams == 0 || cfg->downsample == 0 || cfg->max_block_len == 0 || cfg->sample_rate_if <= 0 ||
+      cfg->sample_rate_pcm <= 0)
+    return Fail(RFM_ERR_INVALID, "invalid configuration");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return Fail(RFM_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+  int dev = cfg->device;
+  if (dev < 0)
+    RFM_CUDA(cudaGetDevice(&dev));
+  if (dev >= ndev)
+    return Fail(RFM_ERR_INVALID, "device ordinal out of range");
+  cudaDeviceProp prop;
+  RFM_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10)
+    return Fail(RFM_ERR_NO_DEVICE, std::string("kernels are built for sm_100a only; device is ") + prop.name);
+  RFM_CUDA(cudaSetDevice(dev));
+
+  rfm_decoder* d = new rfm_decoder;
+  d->cfg = *cfg;
+  d->device = dev;
+  d->S = cfg->n_streams;
+  d->maxn = cfg->max_block_len;
+  d->plan = PlanDecoder(cfg->sample_rate_if, cfg->tuning_offset, cfg->sample_rate_pcm, cfg->bandwidth_pcm,
+                        cfg->downsample, cfg->us_deemphasis != 0);
+  const DecoderPlan& p = d->plan;
+  auto bail = [&](int code, const std::string& m) {
+    FreeDecoder(d);
+    return Fail(code, m);
+  };
+  if (p.rds_stages.empty() || p.rds_stages.size() > kMaxDecStages)
+    return bail(RFM_ERR_UNSUPPORTED, "baseband rate outside the supported range (RDS decimation chain empty)");
+  if (p.a_order > 512 || p.in_order > 512 || p.a_order < 2)
+    return bail(RFM_ERR_UNSUPPORTED, "filter order outside the supported range (<= 512)");
+  if (p.mf_coef.size() < 2 || p.rlp_coef.size() > kMaxFirTapsDev)
+    return bail(RFM_ERR_UNSUPPORTED, "RDS filter length outside the supported range");
+
+  const unsigned ds = p.downsample;
+  d->nb_max = (d->maxn + ds - 1) / ds + 1;
+  d->na_max = (unsigned)(d->nb_max / p.a_ratio) + 4;
+  d->nr_max = d->nb_max; // generous: halved per stage below
+  d->z_stride = AlignUp(d->nb_max, 16);
+  d->a_stride = AlignUp(p.a_order + d->nb_max, 32);
+  d->lp_stride = AlignUp((unsigned)p.lp_coef.size() - 1 + d->na_max, 32);
+  unsigned m = d->nb_max;
+  for (size_t k = 0; k < p.rds_stages.size(); ++k)
+  {
+    d->hb_stride[k] = AlignUp(StageHist(p.rds_stages[k]) + m, 16);
+    m = m / 2 + 1;
+  }
+  d->nr_max = m;
+  d->nr_stride = AlignUp(d->nr_max, 16);
+  d->rlp_stride = AlignUp((unsigned)p.rlp_coef.size() - 1 + d->nr_max, 16);
+  d->mf_stride = AlignUp((unsigned)p.mf_coef.size() - 1 + d->nr_max, 32);
+  d->osc_hist = StageHist(p.rds_stages[0]);
+  d->bits_cap = 4096;
+  d->audio_cap = AlignUp(2 * d->na_max, 32);
+
+#define RFM_TRY(expr)                                                                                    \
+  do                                                                                                     \
+  {                                                                                                      \
+    cudaError_t e_ = (expr);                                                                             \
+    if (e_ != cudaSuccess)                                                                               \
+      return bail(RFM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));                    \
+  } while (0)
+
+  RFM_TRY(Upload(d->d_lut, p.u8lut, 256));
+  RFM_TRY(Upload(d->d_tuner, p.tuner, 2 * kTunerTable));
+  RFM_TRY(Upload(d->d_in_coeff, p.in_coeff.data(), p.in_coeff.size()));
+  RFM_TRY(Upload(d->d_a_coeff, p.a_coeff.data(), p.a_coeff.size()));
+  RFM_TRY(Upload(d->d_lp_coef, p.lp_coef.data(), p.lp_coef.size()));
+  RFM_TRY(Upload(d->d_rlp_coef, p.rlp_coef.data(), p.rlp_coef.size()));
+  RFM_TRY(Upload(d->d_mf_coef, p.mf_coef.data(), p.mf_coef.size()));
+  for (size_t k = 0; k < p.rds_stages.size(); ++k)
+  {
+    if (p.rds_stages[k].h)
+      RFM_TRY(Upload(d->d_hb[k], p.rds_stages[k].h, (size_t)p.rds_stages[k].len));
+    else
+      RFM_TRY(d->d_hb[k].Alloc(4));
+  }
+  RFM_TRY(d->oscV.Alloc((size_t)d->osc_hist + d->nb_max));
+  {
+    const float one[2] = {1.0f, 0.0f}; // m_Osc1 initial unit vector, DownConvert.cpp:283-284
+    RFM_TRY(Upload(d->osc1, one, 2));
+  }
+  RFM_TRY(cudaStreamCreateWithFlags(&d->main_stream, cudaStreamNonBlocking));
+  RFM_TRY(cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming));
+  RFM_TRY(cudaEventCreateWithFlags(&d->ev_osc, cudaEventDisableTiming));
+  RFM_TRY(cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming));
+
+  unsigned G = cfg->n_groups;
+  if (G == 0)
+    G = std::min(8u, std::max(1u, d->S / 256));
+  G = std::min(G, d->S);
+  d->groups.resize(G);
+  const size_t esz_max = 8; // cf32 input
+  for (unsigned gi = 0; gi < G; ++gi)
+  {
+    Group& g = d->groups[gi];
+    g.s0 = (unsigned)((uint64_t)d->S * gi / G);
+    g.S = (unsigned)((uint64_t)d->S * (gi + 1) / G) - g.s0;
+    const size_t S = g.S;
+    RFM_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    RFM_TRY(cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
+    RFM_TRY(g.tail.Alloc(S * p.in_order));
+    RFM_TRY(g.z.Alloc(S * d->z_stride));
+    RFM_TRY(g.bbV.Alloc(S * d->a_stride));
+    RFM_TRY(g.rawV.Alloc(S * d->a_stride));
+    for (size_t k = 1; k < p.rds_stages.size(); ++k)
+      RFM_TRY(g.hbV[k].Alloc(S * d->hb_stride[k]));
+    RFM_TRY(g.rlpV.Alloc(S * d->rlp_stride));
+    RFM_TRY(g.rlp_out.Alloc(S * d->nr_stride));
+    RFM_TRY(g.mfV.Alloc(S * d->mf_stride));
+    RFM_TRY(g.mf_out.Alloc(S * d->nr_stride));
+    RFM_TRY(g.bits.Alloc(S * d->bits_cap));
+    RFM_TRY(g.bit_count.Alloc(S));
+    RFM_TRY(g.lpS.Alloc(S * d->lp_stride));
+    RFM_TRY(g.lpM.Alloc(S * d->lp_stride));
+    RFM_TRY(g.fS.Alloc(S * d->na_max));
+    RFM_TRY(g.fM.Alloc(S * d->na_max));
+    RFM_TRY(g.state.Alloc(S * SF_COUNT));
+    RFM_TRY(ResetGroupState(d, g, true));
+  }
+  (void)esz_max;
+  d->sync.resize(d->S);
+  d->host_bits.resize(d->S);
+  RFM_TRY(cudaDeviceSynchronize());
+#undef RFM_TRY
+  *out = d;
+  return RFM_OK;
+}
+
+void rfm_decoder_destroy(rfm_decoder* d) { FreeDecoder(d); }
+
+int rfm_decoder_reset(rfm_decoder* d)
+{
+  if (!d)
+    return Fail(RFM_ERR_INVALID, "null decoder");
+  int rc = SyncAll(d);
+  if (rc != RFM_OK)
+    return rc;
+  rc = DrainBits(d); // bits sliced before the reset belong to the old decoder state
+  if (rc != RFM_OK)
+    return rc;
+  for (auto& g : d->groups)
+    RFM_CUDA(ResetGroupState(d, g, false));
+  d->rlp_g = 0; // InitLPFilter / InitConstFir reset m_State (FirFilter.cpp:145,319)
+  d->mf_g = 0;
+  for (auto& s : d->sync)
+    s.Reset();
+  return RFM_OK;
+}
+
+uint32_t rfm_decoder_max_audio_floats(const rfm_decoder* d, uint32_t n)
+{
+  if (!d)
+    return 0;
+  const unsigned nb = (n + d->plan.downsample - 1) / d->plan.downsample + 1;
+  return 2 * ((unsigned)(nb / d->plan.a_ratio) + 4);
+}
+
+static int EnsureStaging(rfm_decoder* d, bool u8)
+{
+  const size_t esz = u8 ? 2 : 8;
+  for (auto& g : d->groups)
+  {
+    const size_t need = (size_t)g.S * d->maxn * esz;
+    if (g.in_stage.n < need)
+    {
+      g.in_stage.Free();
+      RFM_CUDA(g.in_stage.Alloc(need));
+    }
+    if (g.audio_stage.n == 0)
+      RFM_CUDA(g.audio_stage.Alloc((size_t)g.S * d->audio_cap));
+  }
+  return RFM_OK;
+}
+
+int rfm_decoder_process_u8(rfm_decoder* d, const uint8_t* iq, uint32_t n, float* audio, size_t audio_stride,
+                           uint32_t* n_audio_floats)
+{
+  if (!d || !iq || !audio)
+    return Fail(RFM_ERR_INVALID, "null argument");
+  RFM_CUDA(cudaSetDevice(d->device));
+  int rc = EnsureStaging(d, true);
+  if (rc != RFM_OK)
+    return rc;
+  return ProcessDevice(d, iq, n, true, n, audio, audio_stride, n_audio_floats, d->main_stream, true);
+}
+
+int rfm_decoder_process_cf32(rfm_decoder* d, const float* iq, uint32_t n, float* audio, size_t audio_stride,
+                             uint32_t* n_audio_floats)
+{
+  if (!d || !iq || !audio)
+    return Fail(RFM_ERR_INVALID, "null argument");
+  RFM_CUDA(cudaSetDevice(d->device));
+  int rc = EnsureStaging(d, false);
+  if (rc != RFM_OK)
+    return rc;
+  return ProcessDevice(d, iq, n, false, n, audio, audio_stride, n_audio_floats, d->main_stream, true);
+}
+
+int rfm_decoder_process_u8_device(rfm_decoder* d, const uint8_t* d_iq, size_t iq_stride, uint32_t n, float* d_audio,
+                                  size_t audio_stride, uint32_t* n_audio_floats, void* cuda_stream)
+{
+  if (!d || !d_iq || !d_audio || iq_stride < n)
+    return Fail(RFM_ERR_INVALID, "bad argument");
+  return ProcessDevice(d, d_iq, iq_stride, true, n, d_audio, audio_stride, n_audio_floats,
+                       static_cast<cudaStream_t>(cuda_stream), false);
+}
+
+int rfm_decoder_process_cf32_device(rfm_decoder* d, const float* d_iq, size_t iq_stride, uint32_t n, float* d_audio,
+                                    size_t audio_stride, uint32_t* n_audio_floats, void* cuda_stream)
+{
+  if (!d || !d_iq || !d_audio || iq_stride < n)
+    return Fail(RFM_ERR_INVALID, "bad argument");
+  return ProcessDevice(d, d_iq, iq_stride, false, n, d_audio, audio_stride, n_audio_floats,
+                       static_cast<cudaStream_t>(cuda_stream), false);
+}
+
+int rfm_decoder_rds_take_groups(rfm_decoder* d, uint32_t stream, uint16_t* groups, uint32_t max_groups,
+                                uint32_t* n_groups)
+{
+  if (!d || stream >= d->S || !n_groups)
+    return Fail(RFM_ERR_INVALID, "bad argument");
+  int rc = SyncAll(d);
+  if (rc == RFM_OK)
+    rc = DrainBits(d);
+  if (rc != RFM_OK)
+    return rc;
+  auto& g = d->sync[stream].Groups();
+  const uint32_t n = std::min<uint32_t>((uint32_t)(g.size() / 4), max_groups);
+  if (groups && n)
+    memcpy(groups, g.data(), (size_t)n * 4 * sizeof(uint16_t));
+  g.erase(g.begin(), g.begin() + (size_t)n * 4);
+  *n_groups = n;
+  return RFM_OK;
+}
+
+int rfm_decoder_rds_take_bits(rfm_decoder* d, uint32_t stream, uint8_t* bits, uint32_t max_bits, uint32_t* n_bits)
+{
+  if (!d || stream >= d->S || !n_bits)
+    return Fail(RFM_ERR_INVALID, "bad argument");
+  int rc = SyncAll(d);
+  if (rc == RFM_OK)
+    rc = DrainBits(d);
+  if (rc != RFM_OK)
+    return rc;
+  auto& b = d->host_bits[stream];
+  const uint32_t n = std::min<uint32_t>((uint32_t)b.size(), max_bits);
+  if (bits && n)
+    memcpy(bits, b.data(), n);
+  b.erase(b.begin(), b.begin() + n);
+  *n_bits = n;
+  return RFM_OK;
+}
+
+int rfm_decoder_get_status(rfm_decoder* d, uint32_t stream, rfm_stream_status* out)
+{
+  if (!d || stream >= d->S || !out)
+    return Fail(RFM_ERR_INVALID, "bad argument");
+  unsigned ls = 0;
+  Group* g = FindGroup(d, stream, &ls);
+  RFM_CUDA(cudaSetDevice(d->device));
+  RFM_CUDA(cudaStreamSynchronize(g->stream));
+  RFM_CUDA(cudaStreamSynchronize(d->main_stream));
+  float v[SF_COUNT];
+  RFM_CUDA(cudaMemcpy2D(v, sizeof(float), g->state.p + ls, (size_t)g->S * sizeof(float), sizeof(float), SF_COUNT,
+                        cudaMemcpyDeviceToHost));
+  int stereo;
+  memcpy(&stereo, &v[SF_STEREO], 4);
+  out->stereo_detected = stereo;
+  out->interface_level = v[SF_IF_LEVEL];
+  out->baseband_level = v[SF_BB_LEVEL];
+  out->baseband_mean = v[SF_BB_MEAN];
+  out->pilot_level = 2 * v[SF_PILOT_LEVEL];                                       // FmDecode.h:77
+  const float tuned = -d->plan.tuning_shift * d->plan.fs_if / float(kTunerTable); // FmDecode.h:148
+  out->tuning_offset = tuned + v[SF_BB_MEAN] * d->plan.freq_dev;
+  return RFM_OK;
+}
+
+int rfm_decoder_constants(const rfm_decoder* d, double* s, uint32_t max)
+{
+  if (!d || !s || max < 51)
+    return Fail(RFM_ERR_INVALID, "bad argument");
+  const DecoderPlan& p = d->plan;
+  int i = 0;
+  s[i++] = p.fs_if; s[i++] = p.fs_bb; s[i++] = p.tuning_shift; s[i++] = p.demod_gain;
+  s[i++] = p.nco_lo; s[i++] = p.nco_hi; s[i++] = p.pll_alpha; s[i++] = p.pll_beta; s[i++] = p.de_alpha;
+  s[i++] = p.pilot.minfreq; s[i++] = p.pilot.maxfreq; s[i++] = p.pilot.b0; s[i++] = p.pilot.a1; s[i++] = p.pilot.a2;
+  s[i++] = p.pilot.lb0; s[i++] = p.pilot.lb1; s[i++] = p.pilot.freq0; s[i++] = p.pilot.minsignal;
+  s[i++] = p.pilot.lock_delay;
+  s[i++] = p.in_order; s[i++] = p.downsample; s[i++] = p.a_order; s[i++] = p.a_ratio;
+  s[i++] = p.rds_rate; s[i++] = p.rpll_lo; s[i++] = p.rpll_hi; s[i++] = p.rpll_alpha; s[i++] = p.rpll_beta;
+  s[i++] = (double)p.mf_coef.size(); s[i++] = (double)p.rlp_coef.size();
+  s[i++] = p.rds_osc.inc; s[i++] = p.rds_osc.cosv; s[i++] = p.rds_osc.sinv;
+  s[i++] = p.rsync.A1; s[i++] = p.rsync.A2; s[i++] = p.rsync.B0; s[i++] = p.rsync.B1; s[i++] = p.rsync.B2;
+  s[i++] = p.notch.A1; s[i++] = p.notch.A2; s[i++] = p.notch.B0; s[i++] = p.notch.B1; s[i++] = p.notch.B2;
+  s[i++] = (double)p.lp_coef.size();
+  s[i++] = (double)p.rds_stages.size();
+  for (size_t k = 0; k < 6; ++k)
+    s[i++] = k < p.rds_stages.size() ? p.rds_stages[k].len : 0;
+  return i;
+}
+
+int rfm_decoder_table(const rfm_decoder* d, int which, float* out, uint32_t max_floats, uint32_t* n)
+{
+  if (!d || !n)
+    return Fail(RFM_ERR_INVALID, "bad argument");
+  const DecoderPlan& p = d->plan;
+  const float* src = nullptr;
+  size_t cnt = 0;
+  switch (which)
+  {
+    case 0: src = p.tuner; cnt = 2 * kTunerTable; break;
+    case 1: src = p.in_coeff.data(); cnt = p.in_coeff.size(); break;
+    case 2: src = p.a_coeff.data(); cnt = p.a_coeff.size(); break;
+    case 3: src = p.rlp_coef.data(); cnt = p.rlp_coef.size(); break;
+    case 4: src = p.mf_coef.data(); cnt = p.mf_coef.size(); break;
+    case 5: src = p.lp_coef.data(); cnt = p.lp_coef.size(); break;
+    default: return Fail(RFM_ERR_INVALID, "unknown table");
+  }
+  cnt = std::min<size_t>(cnt, max_floats);
+  if (out)
+    memcpy(out, src, cnt * sizeof(float));
+  *n = (uint32_t)cnt;
+  return RFM_OK;
+}
+
+int rfm_decoder_tap(rfm_decoder* d, const char* name, uint32_t stream, float* out, uint32_t max_floats,
+                    uint32_t* n_floats)
+{
+  if (!d || !name || stream >= d->S || !out || !n_floats)
+    return Fail(RFM_ERR_INVALID, "bad argument");
+  int rc = SyncAll(d);
+  if (rc != RFM_OK)
+    return rc;
+  unsigned ls = 0;
+  Group* g = FindGroup(d, stream, &ls);
+  const DecoderPlan& p = d->plan;
+  const std::string nm(name);
+  const void* src = nullptr;
+  size_t cnt = 0; // floats
+  if (nm == "demod_in") { src = g->z.p + (size_t)ls * d->z_stride; cnt = 2 * (size_t)d->last_nb; }
+  else if (nm == "baseband") { src = g->bbV.p + (size_t)ls * d->a_stride + p.a_order; cnt = d->last_nb; }
+  else if (nm == "rawstereo") { src = g->rawV.p + (size_t)ls * d->a_stride + p.a_order; cnt = d->last_nb; }
+  else if (nm == "mono_rs") { src = g->lpM.p + (size_t)ls * d->lp_stride + p.lp_coef.size() - 1; cnt = d->last_na; }
+  else if (nm == "stereo_rs") { src = g->lpS.p + (size_t)ls * d->lp_stride + p.lp_coef.size() - 1; cnt = d->last_na; }
+  else if (nm == "lp_stereo") { src = g->fS.p + (size_t)ls * d->na_max; cnt = d->last_na; }
+  else if (nm == "lp_mono") { src = g->fM.p + (size_t)ls * d->na_max; cnt = d->last_na; }
+  else if (nm == "rds_dec") { src = g->rlpV.p + (size_t)ls * d->rlp_stride + p.rlp_coef.size() - 1; cnt = 2 * (size_t)d->last_nr; }
+  else if (nm == "rds_lp") { src = g->rlp_out.p + (size_t)ls * d->nr_stride; cnt = 2 * (size_t)d->last_nr; }
+  else if (nm == "rds_pll") { src = g->mfV.p + (size_t)ls * d->mf_stride + p.mf_coef.size() - 1; cnt = d->last_nr; }
+  else if (nm == "rds_mf") { src = g->mf_out.p + (size_t)ls * d->nr_stride; cnt = d->last_nr; }
+  else
+    return Fail(RFM_ERR_INVALID, "unknown tap name");
+  if (cnt > max_floats)
+    return Fail(RFM_ERR_OVERFLOW, "tap buffer too small");
+  RFM_CUDA(cudaMemcpy(out, src, cnt * sizeof(float), cudaMemcpyDeviceToHost));
+  *n_floats = (uint32_t)cnt;
+  return RFM_OK;
+}
+
+// ---- host-only RDS block sync ---------------------------------------------------------------------------
+struct rfm_rdssync
+{
+  RdsBlockSync s;
+};
+
+int rfm_rdssync_create(rfm_rdssync** out)
+{
+  if (!out)
+    return Fail(RFM_ERR_INVALID, "null argument");
+  *out = new rfm_rdssync;
+  return RFM_OK;
+}
+void rfm_rdssync_destroy(rfm_rdssync* s) { delete s; }
+void rfm_rdssync_reset(rfm_rdssync* s)
+{
+  if (s)
+    s->s.Reset();
+}
+int rfm_rdssync_push_bits(rfm_rdssync* s, const uint8_t* bits, uint32_t n)
+{
+  if (!s || (!bits && n))
+    return Fail(RFM_ERR_INVALID, "bad argument");
+  for (uint32_t i = 0; i < n; ++i)
+    s->s.PushBit(bits[i] & 1);
+  return RFM_OK;
+}
+int rfm_rdssync_take_groups(rfm_rdssync* s, uint16_t* groups, uint32_t max_groups, uint32_t* n_groups)
+{
+  if (!s || !n_groups)
+    return Fail(RFM_ERR_INVALID, "bad argument");
+  auto& g = s->s.Groups();
+  const uint32_t n = std::min<uint32_t>((uint32_t)(g.size() / 4), max_groups);
+  if (groups && n)
+    memcpy(groups, g.data(), (size_t)n * 4 * sizeof(uint16_t));
+  g.erase(g.begin(), g.begin() + (size_t)n * 4);
+  *n_groups = n;
+  return RFM_OK;
+}
+uint32_t rfm_rds_check_block(uint32_t word26, uint32_t offset_syndrome, int use_fec, uint32_t* corrected)
+{
+  uint32_t w = word26;
+  const uint32_t syn = RdsCheckBlock(&w, offset_syndrome, use_fec != 0);
+  if (corrected)
+    *corrected = w;
+  return syn;
+}
+
+} // extern "C"

@@ -1,0 +1,864 @@
+// rfm_kernels.cu -- hand-written sm_100a kernels for the IQ -> audio (+RDS) chain.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo ...
+// All arithmetic that feeds the reference's rounding-sensitive recurrences goes through the
+// individually rounded helpers of rfm_math.cuh in the reference's operation order, so the
+// results are bit-identical to the CPU chain ("Numerics").
+//
+// Kernel map (SURVEY.md section 7 / 8a rows in brackets):
+//   k_front        [a1 a3 a5]   u8 -> LUT -> fine-tuner rotate -> Lanczos FIR / ds; tile of outputs
+//                               per CTA, input + halo staged in shared memory
+//   k_front_tail   [a5 state]   last `order` tuned samples -> m_stateComplex
+//   k_bb_lanes     [a4 a6 a13 a15 a16] one lane per stream: IF meter, FM-demod PLL + DC tracker,
+//                               baseband meters, 19 kHz pilot PLL, 38 kHz demux multiply
+//   k_resample     [a14 x2]     fractional Lanczos resampler, mono + stereo share taps
+//   k_rotfir       [a8 a10 a17] cFirFilter (rotating summation start), real / pair / complex
+//   k_audio_tail   [a18 a19 a20] deemphasis + notch + L/R matrix, one lane per stream
+//   k_osc          [a7 NCO]     quadrature-oscillator table for the block (same for every stream)
+//   k_halfband     [a7]         mix + half-band / 11-tap / CIC3 decimate-by-2 stages
+//   k_rds_pll      [a9]         Costas loop, one lane per stream
+//   k_rds_slice    [a11]        bit-clock resonator + peak slicer + differential decode
+//   k_tails                     V-buffer history carry
+#include "rfm_kernels.cuh"
+
+#include <assert.h>
+
+namespace rfm
+{
+
+static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
+
+// ==================================================================================================
+// front end
+// ==================================================================================================
+constexpr unsigned kFrontTile = 128; // outputs per CTA == threads per CTA
+
+// fine-tuned sample i of this block: (u8 -> float) * table[(idx0 + i) mod 64]
+// RTL_SDR_Source.cpp:207-211, FmDecode.cpp:66-82 (std::complex product: ac-bd, ad+bc)
+template <bool U8>
+__device__ __forceinline__ float2 tuned_sample(const void* __restrict__ row, unsigned i, unsigned idx0,
+                                               const float* lut, const float2* tuner)
+{
+  float are, aim;
+  if (U8)
+  {
+    const uchar2 u = reinterpret_cast<const uchar2*>(row)[i];
+    are = lut[u.x];
+    aim = lut[u.y];
+  }
+  else
+  {
+    const float2 f = reinterpret_cast<const float2*>(row)[i];
+    are = f.x;
+    aim = f.y;
+  }
+  const float2 b = tuner[(idx0 + i) & 63u];
+  float2 o;
+  o.x = subf(mulf(are, b.x), mulf(aim, b.y));
+  o.y = addf(mulf(are, b.y), mulf(aim, b.x));
+  return o;
+}
+
+template <bool U8>
+__global__ void __launch_bounds__(kFrontTile) k_front(FrontParams p)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* s_lut = reinterpret_cast<float*>(smem_raw);
+  float2* s_tuner = reinterpret_cast<float2*>(s_lut + 256);
+  float* s_coef = reinterpret_cast<float*>(s_tuner + 64);
+  const unsigned coef_n = (p.order + 2 + 1) & ~1u;
+  float2* X = reinterpret_cast<float2*>(s_coef + coef_n);
+
+  const unsigned tid = threadIdx.x;
+  const unsigned s = blockIdx.y;
+  const unsigned o0 = blockIdx.x * kFrontTile;
+  const unsigned nt = min(kFrontTile, p.nout - o0);
+
+  for (unsigned i = tid; i < 256; i += kFrontTile)
+    s_lut[i] = p.lut[i];
+  if (tid < 64)
+    s_tuner[tid] = reinterpret_cast<const float2*>(p.tuner)[tid];
+  for (unsigned i = tid; i < p.order + 2; i += kFrontTile)
+    s_coef[i] = p.coeff[i];
+  __syncthreads();
+
+  // V = tail(order) ++ block(n); this tile needs V[vlo .. vlo + count)
+  const unsigned vlo = p.p0 + o0 * p.ds;
+  const unsigned count = (nt - 1) * p.ds + p.order;
+  const size_t esz = U8 ? 2 : 8;
+  const unsigned char* row = reinterpret_cast<const unsigned char*>(p.in) + (size_t)s * p.in_stride * esz;
+  const float2* tail = reinterpret_cast<const float2*>(p.tail) + (size_t)s * p.order;
+  for (unsigned v = tid; v < count; v += kFrontTile)
+  {
+    const unsigned V = vlo + v;
+    X[v] = (V < p.order) ? tail[V] : tuned_sample<U8>(row, V - p.order, p.idx0, s_lut, s_tuner);
+  }
+  __syncthreads();
+
+  if (tid < nt)
+  {
+    // y = sum_{j=1..order} x[p - j] * c[j], ascending j, complex x real (DownConvert.cpp:112-129)
+    const float2* xp = X + tid * p.ds + p.order;
+    float yr = 0.0f, yi = 0.0f;
+    for (unsigned j = 1; j <= p.order; ++j)
+    {
+      const float2 x = xp[-(int)j];
+      const float c = s_coef[j];
+      yr = addf(yr, mulf(x.x, c));
+      yi = addf(yi, mulf(x.y, c));
+    }
+    reinterpret_cast<float2*>(p.z)[(size_t)s * p.z_stride + o0 + tid] = make_float2(yr, yi);
+  }
+}
+
+template <bool U8>
+__global__ void __launch_bounds__(256) k_front_tail(FrontParams p)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* tmp = reinterpret_cast<float2*>(smem_raw);
+  const unsigned s = blockIdx.x;
+  const size_t esz = U8 ? 2 : 8;
+  const unsigned char* row = reinterpret_cast<const unsigned char*>(p.in) + (size_t)s * p.in_stride * esz;
+  float2* tail = reinterpret_cast<float2*>(p.tail) + (size_t)s * p.order;
+  const float2* tuner = reinterpret_cast<const float2*>(p.tuner);
+  for (unsigned k = threadIdx.x; k < p.order; k += blockDim.x)
+  {
+    const unsigned V = p.n + k; // new tail = V[n .. n + order)
+    tmp[k] = (V < p.order) ? tail[V] : tuned_sample<U8>(row, V - p.order, p.idx0, p.lut, tuner);
+  }
+  __syncthreads();
+  for (unsigned k = threadIdx.x; k < p.order; k += blockDim.x)
+    tail[k] = tmp[k];
+}
+
+void launch_front(const FrontParams& p, bool u8, cudaStream_t st)
+{
+  if (p.nout == 0 || p.S == 0)
+    return;
+  const unsigned coef_n = (p.order + 2 + 1) & ~1u;
+  const size_t smem = (256 + 128 + coef_n) * sizeof(float) + ((size_t)(kFrontTile - 1) * p.ds + p.order) * sizeof(float2);
+  dim3 grid(cdiv(p.nout, kFrontTile), p.S);
+  if (u8)
+  {
+    cudaFuncSetAttribute(k_front<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_front<true><<<grid, kFrontTile, smem, st>>>(p);
+  }
+  else
+  {
+    cudaFuncSetAttribute(k_front<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_front<false><<<grid, kFrontTile, smem, st>>>(p);
+  }
+}
+
+void launch_front_tail(const FrontParams& p, bool u8, cudaStream_t st)
+{
+  if (p.S == 0 || p.n == 0)
+    return;
+  const size_t smem = (size_t)p.order * sizeof(float2);
+  if (u8)
+    k_front_tail<true><<<p.S, 256, smem, st>>>(p);
+  else
+    k_front_tail<false><<<p.S, 256, smem, st>>>(p);
+}
+
+// ==================================================================================================
+// baseband lanes
+// ==================================================================================================
+struct DemodState
+{
+  float phase, incr, dc;
+};
+
+// cFmDecoder::PhaseLockedLoop, FmDecode.cpp:361-415
+__device__ __forceinline__ float demod_step(DemodState& st, float2 x, const DemodConst& k)
+{
+  float Sin, Cos;
+  rfm_sincos(st.phase, &Sin, &Cos);
+  const float dre = subf(mulf(Cos, x.x), mulf(Sin, x.y));
+  const float dim = addf(mulf(Cos, x.y), mulf(Sin, x.x));
+  const float err = negf(rfm_atan2f(dim, dre));
+  st.incr = addf(st.incr, mulf(k.beta, err));
+  if (st.incr < k.lo)
+    st.incr = k.lo;
+  if (st.incr > k.hi)
+    st.incr = k.hi;
+  st.phase = addf(st.phase, addf(st.incr, mulf(k.alpha, err)));
+  if ((double)st.phase >= RFM_K_2PI)
+    st.phase = d2f(rfm_fmod_2pi_small((double)st.phase));
+  while (st.phase < 0.0f)
+    st.phase = d2f(addd((double)st.phase, RFM_K_2PI));
+  const float pinc = mulf(2.0f, st.incr);
+  st.dc = d2f(addd(muld(1 - 0.0001, (double)st.dc), muld(0.0001, (double)pinc)));
+  return mulf(subf(pinc, st.dc), k.gain);
+}
+
+struct PilotState
+{
+  float phase, freq, i1, i2, q1, q2, x1, level;
+};
+
+// cPilotPhaseLock::Process loop body, FmDecode.cpp:149-216; returns sin(2 phi)
+__device__ __forceinline__ float pilot_step(PilotState& st, float x, const PilotConstDev& k)
+{
+  float ps, pc;
+  rfm_sincos(st.phase, &ps, &pc);
+  const float out = mulf(mulf(2.0f, ps), pc);
+  float pi = mulf(ps, x);
+  float pq = mulf(pc, x);
+  pi = subf(subf(mulf(k.b0, pi), mulf(k.a1, st.i1)), mulf(k.a2, st.i2));
+  pq = subf(subf(mulf(k.b0, pq), mulf(k.a1, st.q1)), mulf(k.a2, st.q2));
+  st.i2 = st.i1;
+  st.i1 = pi;
+  st.q2 = st.q1;
+  st.q1 = pq;
+  float err;
+  if (pi > absf(pq))
+    err = divf(pq, pi);
+  else if (pq > 0.0f)
+    err = 1.0f;
+  else
+    err = -1.0f;
+  st.level = (pi < st.level) ? pi : st.level;
+  st.freq = addf(st.freq, addf(mulf(k.lb0, err), mulf(k.lb1, st.x1)));
+  st.x1 = err;
+  const float t = (st.freq < k.maxfreq) ? st.freq : k.maxfreq;
+  st.freq = (k.minfreq < t) ? t : k.minfreq;
+  st.phase = addf(st.phase, st.freq);
+  if ((double)st.phase > RFM_K_2PI)
+    st.phase = d2f(subd((double)st.phase, RFM_K_2PI));
+  return out;
+}
+
+constexpr unsigned kLaneTile = 32;
+
+template <bool U8>
+__global__ void __launch_bounds__(32) k_bb_lanes(LanesParams p)
+{
+  __shared__ float2 zt[32][kLaneTile + 1];
+  __shared__ float bt[32][kLaneTile + 1];
+  __shared__ float rt[32][kLaneTile + 1];
+
+  const unsigned lane = threadIdx.x;
+  const unsigned s0 = blockIdx.x * 32;
+  const unsigned s = s0 + lane;
+  const bool valid = s < p.S;
+  const unsigned S = p.S;
+  float* st = p.state;
+
+  DemodState dm = {0.f, 0.f, 0.f};
+  PilotState pl = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 1000.0f};
+  float vsum = 0.0f, vsumsq = 0.0f;
+  if (valid)
+  {
+    // --- IF level: RMSLevelApprox over the first ceil(n/64) tuned samples, FmDecode.cpp:427,505-519
+    const FrontParams& f = p.front;
+    const unsigned cnt = (f.n + 63) / 64;
+    const size_t esz = U8 ? 2 : 8;
+    const unsigned char* row = reinterpret_cast<const unsigned char*>(f.in) + (size_t)s * f.in_stride * esz;
+    const float2* tuner = reinterpret_cast<const float2*>(f.tuner);
+    float level = 0.0f;
+    for (unsigned i = 0; i < cnt; ++i)
+    {
+      const float2 t = tuned_sample<U8>(row, i, f.idx0, f.lut, tuner);
+      level = addf(level, addf(mulf(t.x, t.x), mulf(t.y, t.y)));
+    }
+    const float rms = sqrtf_rn(divf(level, (float)cnt));
+    st[SF_IF_LEVEL * S + s] = addf(mulf(0.95f, st[SF_IF_LEVEL * S + s]), mulf(0.05f, rms));
+
+    dm.phase = st[SF_DEMOD_PHASE * S + s];
+    dm.incr = st[SF_DEMOD_INCR * S + s];
+    dm.dc = st[SF_DEMOD_DC * S + s];
+    pl.phase = st[SF_PILOT_PHASE * S + s];
+    pl.freq = st[SF_PILOT_FREQ * S + s];
+    pl.i1 = st[SF_PILOT_I1 * S + s];
+    pl.i2 = st[SF_PILOT_I2 * S + s];
+    pl.q1 = st[SF_PILOT_Q1 * S + s];
+    pl.q2 = st[SF_PILOT_Q2 * S + s];
+    pl.x1 = st[SF_PILOT_X1 * S + s];
+    pl.level = 1000.0f; // FmDecode.cpp:147
+  }
+
+  const float2* z = reinterpret_cast<const float2*>(p.z);
+  for (unsigned t0 = 0; t0 < p.nb; t0 += kLaneTile)
+  {
+    const unsigned tn = min(kLaneTile, p.nb - t0);
+    // coalesced tile load: row r of the tile is stream s0 + r
+    for (unsigned r = 0; r < 32; ++r)
+      if (s0 + r < S && lane < tn)
+        zt[r][lane] = z[(size_t)(s0 + r) * p.z_stride + t0 + lane];
+    __syncwarp();
+    if (valid)
+    {
+      for (unsigned k = 0; k < tn; ++k)
+      {
+        const float bb = demod_step(dm, zt[lane][k], p.demod);
+        vsum = addf(vsum, bb);                       // SamplesMeanRMS, FmDecode.cpp:522-539
+        vsumsq = addf(vsumsq, mulf(bb, bb));
+        const float p38 = pilot_step(pl, bb, p.pilot);
+        bt[lane][k] = bb;
+        rt[lane][k] = mulf(p38, mulf(2.0f, bb));     // FmDecode.cpp:455-456
+      }
+    }
+    __syncwarp();
+    for (unsigned r = 0; r < 32; ++r)
+      if (s0 + r < S && lane < tn)
+      {
+        const size_t o = (size_t)(s0 + r) * p.a_stride + p.a_hist + t0 + lane;
+        p.bbV[o] = bt[r][lane];
+        p.rawV[o] = rt[r][lane];
+      }
+    __syncwarp();
+  }
+
+  if (valid)
+  {
+    st[SF_DEMOD_PHASE * S + s] = dm.phase;
+    st[SF_DEMOD_INCR * S + s] = dm.incr;
+    st[SF_DEMOD_DC * S + s] = dm.dc;
+    st[SF_PILOT_PHASE * S + s] = pl.phase;
+    st[SF_PILOT_FREQ * S + s] = pl.freq;
+    st[SF_PILOT_I1 * S + s] = pl.i1;
+    st[SF_PILOT_I2 * S + s] = pl.i2;
+    st[SF_PILOT_Q1 * S + s] = pl.q1;
+    st[SF_PILOT_Q2 * S + s] = pl.q2;
+    st[SF_PILOT_X1 * S + s] = pl.x1;
+    st[SF_PILOT_LEVEL * S + s] = pl.level;
+    // lock detector, FmDecode.cpp:219-228
+    int lock_cnt = __float_as_int(st[SF_PILOT_LOCKCNT * S + s]);
+    if (mulf(2.0f, pl.level) > p.pilot.minsignal)
+    {
+      if (lock_cnt < p.pilot.lock_delay)
+        lock_cnt += (int)p.nb;
+    }
+    else
+      lock_cnt = 0;
+    st[SF_PILOT_LOCKCNT * S + s] = __int_as_float(lock_cnt);
+    st[SF_STEREO * S + s] = __int_as_float(lock_cnt >= p.pilot.lock_delay ? 1 : 0);
+    // baseband meters, FmDecode.cpp:439-442
+    const float mean = divf(vsum, (float)p.nb);
+    const float rms = sqrtf_rn(divf(vsumsq, (float)p.nb));
+    st[SF_BB_MEAN * S + s] = addf(mulf(0.95f, st[SF_BB_MEAN * S + s]), mulf(0.05f, mean));
+    st[SF_BB_LEVEL * S + s] = addf(mulf(0.95f, st[SF_BB_LEVEL * S + s]), mulf(0.05f, rms));
+  }
+}
+
+void launch_bb_lanes(const LanesParams& p, bool u8, cudaStream_t st)
+{
+  if (p.S == 0 || p.nb == 0)
+    return;
+  if (u8)
+    k_bb_lanes<true><<<cdiv(p.S, 32), 32, 0, st>>>(p);
+  else
+    k_bb_lanes<false><<<cdiv(p.S, 32), 32, 0, st>>>(p);
+}
+
+// ==================================================================================================
+// fractional resampler (mono + stereo), DownConvert.cpp:195-233
+// ==================================================================================================
+constexpr unsigned kResTile = 64;
+
+__device__ __forceinline__ float res_pos(float p0, float pstep, unsigned i)
+{
+  return addf(p0, mulf((float)i, pstep)); // pf = p + i * pstep, DownConvert.cpp:224
+}
+
+__global__ void __launch_bounds__(kResTile) k_resample(ResampleParams p, unsigned max_span)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* s_coef = reinterpret_cast<float*>(smem_raw);
+  float* Xm = s_coef + p.order + 2;
+  float* Xs = Xm + max_span;
+
+  const unsigned tid = threadIdx.x;
+  const unsigned s = blockIdx.y;
+  const unsigned i0 = blockIdx.x * kResTile;
+  const unsigned i1 = min(i0 + kResTile, p.na) - 1;
+
+  for (unsigned i = tid; i < p.order + 2; i += kResTile)
+    s_coef[i] = p.coeff[i];
+
+  const unsigned lo = (unsigned)__float2int_rz(res_pos(p.pos_frac, p.pstep, i0));
+  const unsigned hi = (unsigned)__float2int_rz(res_pos(p.pos_frac, p.pstep, i1)) + p.order;
+  const unsigned span = hi - lo + 1;
+  const float* bb = p.bbV + (size_t)s * p.a_stride;
+  const float* raw = p.rawV + (size_t)s * p.a_stride;
+  for (unsigned v = tid; v < span; v += kResTile)
+  {
+    Xm[v] = bb[lo + v];
+    Xs[v] = raw[lo + v];
+  }
+  __syncthreads();
+
+  const unsigned i = i0 + tid;
+  if (i <= i1)
+  {
+    const float pf = res_pos(p.pos_frac, p.pstep, i);
+    const unsigned pi = (unsigned)__float2int_rz(pf);
+    const float k1 = subf(pf, (float)pi);
+    const float k0 = subf(1.0f, k1);
+    // y = sum_{j=0..order} (c[j] k0 + c[j+1] k1) * V[order + pi - j]
+    const unsigned base = pi - lo + p.order;
+    float ym = 0.0f, ys = 0.0f;
+    float cj = s_coef[0];
+    for (unsigned j = 0; j <= p.order; ++j)
+    {
+      const float cn = s_coef[j + 1];
+      const float k = addf(mulf(cj, k0), mulf(cn, k1));
+      ym = addf(ym, mulf(k, Xm[base - j]));
+      ys = addf(ys, mulf(k, Xs[base - j]));
+      cj = cn;
+    }
+    p.lpM[(size_t)s * p.lp_stride + p.lp_hist + i] = ym;
+    p.lpS[(size_t)s * p.lp_stride + p.lp_hist + i] = ys;
+  }
+}
+
+void launch_resample(const ResampleParams& p, cudaStream_t st)
+{
+  if (p.na == 0 || p.S == 0)
+    return;
+  const unsigned max_span = (unsigned)((float)kResTile * p.pstep) + p.order + 8;
+  const size_t smem = (size_t)(p.order + 2 + 2 * max_span) * sizeof(float);
+  cudaFuncSetAttribute(k_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dim3 grid(cdiv(p.na, kResTile), p.S);
+  k_resample<<<grid, kResTile, smem, st>>>(p, max_span);
+}
+
+// ==================================================================================================
+// cFirFilter::Process / ProcessTwo, FirFilter.cpp:330-413
+// y[g] = sum over j = 0..N-1 of h[k_j] x[g - k_j],  k_j = (g + j) mod N: the circular delay line is
+// walked in buffer order, so the first tap of the sum rotates with the running sample count g.
+// ==================================================================================================
+constexpr unsigned kFirTile = 128;
+
+template <int MODE> // 0 real, 1 real pair, 2 complex
+__global__ void __launch_bounds__(kFirTile) k_rotfir(RotFirParams p)
+{
+  __shared__ float s_coef[kMaxFirTapsDev];
+  const unsigned tid = threadIdx.x;
+  for (unsigned i = tid; i < p.taps; i += kFirTile)
+    s_coef[i] = p.coef[i];
+  __syncthreads();
+  const unsigned s = blockIdx.y;
+  const unsigned i = blockIdx.x * kFirTile + tid;
+  if (i >= p.n)
+    return;
+  const unsigned N = p.taps;
+  unsigned k = (p.g0 + i) % N;
+  const size_t base = (size_t)s * p.in_stride + (N - 1) + i; // V index of x[g]
+  if (MODE == 2)
+  {
+    const float2* x = reinterpret_cast<const float2*>(p.inA);
+    float2 v = x[base - k];
+    float ar = mulf(s_coef[k], v.x), ai = mulf(s_coef[k], v.y);
+    for (unsigned j = 1; j < N; ++j)
+    {
+      k = (k + 1 == N) ? 0 : k + 1;
+      v = x[base - k];
+      ar = addf(ar, mulf(s_coef[k], v.x));
+      ai = addf(ai, mulf(s_coef[k], v.y));
+    }
+    reinterpret_cast<float2*>(p.outA)[(size_t)s * p.out_stride + p.out_off + i] = make_float2(ar, ai);
+  }
+  else
+  {
+    float a = mulf(s_coef[k], p.inA[base - k]);
+    float b = (MODE == 1) ? mulf(s_coef[k], p.inB[base - k]) : 0.0f;
+    for (unsigned j = 1; j < N; ++j)
+    {
+      k = (k + 1 == N) ? 0 : k + 1;
+      a = addf(a, mulf(s_coef[k], p.inA[base - k]));
+      if (MODE == 1)
+        b = addf(b, mulf(s_coef[k], p.inB[base - k]));
+    }
+    p.outA[(size_t)s * p.out_stride + p.out_off + i] = a;
+    if (MODE == 1)
+      p.outB[(size_t)s * p.out_stride + p.out_off + i] = b;
+  }
+}
+
+void launch_rotfir(const RotFirParams& p, cudaStream_t st)
+{
+  if (p.n == 0 || p.S == 0)
+    return;
+  dim3 grid(cdiv(p.n, kFirTile), p.S);
+  if (p.cplx)
+    k_rotfir<2><<<grid, kFirTile, 0, st>>>(p);
+  else if (p.inB)
+    k_rotfir<1><<<grid, kFirTile, 0, st>>>(p);
+  else
+    k_rotfir<0><<<grid, kFirTile, 0, st>>>(p);
+}
+
+// ==================================================================================================
+// audio tail lanes: deemphasis (FmDecode.cpp:348-359), notch (IirFilter.cpp:89-105),
+// matrix (FmDecode.cpp:473-499)
+// ==================================================================================================
+__device__ __forceinline__ float biquad_step(const BiquadDev& c, float x, float& w1, float& w2)
+{
+  const float w0 = subf(subf(x, mulf(c.A1, w1)), mulf(c.A2, w2));
+  const float y = addf(addf(mulf(c.B0, w0), mulf(c.B1, w1)), mulf(c.B2, w2));
+  w2 = w1;
+  w1 = w0;
+  return y;
+}
+
+__global__ void __launch_bounds__(32) k_audio_tail(AudioTailParams p)
+{
+  const unsigned s = blockIdx.x * 32 + threadIdx.x;
+  if (s >= p.S)
+    return;
+  const unsigned S = p.S;
+  float* st = p.state;
+  float de_re = st[SF_DE_RE * S + s], de_im = st[SF_DE_IM * S + s];
+  float w1a = st[SF_NOTCH_W1A * S + s], w2a = st[SF_NOTCH_W2A * S + s];
+  float w1b = st[SF_NOTCH_W1B * S + s], w2b = st[SF_NOTCH_W2B * S + s];
+  const bool stereo = __float_as_int(st[SF_STEREO * S + s]) != 0;
+  const float alpha = p.de_alpha;
+  const float one_m = subf(1.0f, alpha);
+  const float* inS = p.inS + (size_t)s * p.in_stride;
+  const float* inM = p.inM + (size_t)s * p.in_stride;
+  float2* out = reinterpret_cast<float2*>(p.audio + (size_t)s * p.audio_stride);
+  for (unsigned i = 0; i < p.na; ++i)
+  {
+    de_re = addf(mulf(one_m, de_re), mulf(alpha, inS[i]));
+    const float a = mulf(de_re, 2.0f);
+    de_im = addf(mulf(one_m, de_im), mulf(alpha, inM[i]));
+    const float b = mulf(de_im, 2.0f);
+    const float sd = biquad_step(p.notch, a, w1a, w2a);
+    const float m = biquad_step(p.notch, b, w1b, w2b);
+    float2 o;
+    if (stereo)
+    {
+      o.x = mulf(addf(m, sd), 0.5f);
+      o.y = mulf(subf(m, sd), 0.5f);
+    }
+    else
+    {
+      o.x = mulf(m, 0.5f);
+      o.y = o.x;
+    }
+    out[i] = o;
+  }
+  st[SF_DE_RE * S + s] = de_re;
+  st[SF_DE_IM * S + s] = de_im;
+  st[SF_NOTCH_W1A * S + s] = w1a;
+  st[SF_NOTCH_W2A * S + s] = w2a;
+  st[SF_NOTCH_W1B * S + s] = w1b;
+  st[SF_NOTCH_W2B * S + s] = w2b;
+}
+
+void launch_audio_tail(const AudioTailParams& p, cudaStream_t st)
+{
+  if (p.S == 0 || p.na == 0)
+    return;
+  k_audio_tail<<<cdiv(p.S, 32), 32, 0, st>>>(p);
+}
+
+// ==================================================================================================
+// RDS: NCO_OSC table, DownConvert.cpp:438-442 -- identical for every stream of the decoder
+// ==================================================================================================
+__global__ void k_osc(OscParams p)
+{
+  if (threadIdx.x != 0 || blockIdx.x != 0)
+    return;
+  float o1r = p.osc1[0], o1i = p.osc1[1];
+  float2* out = reinterpret_cast<float2*>(p.oscV) + p.osc_hist;
+  for (unsigned i = 0; i < p.nb; ++i)
+  {
+    const float orr = subf(mulf(o1r, p.cosv), mulf(o1i, p.sinv));
+    const float oi = addf(mulf(o1i, p.cosv), mulf(o1r, p.sinv));
+    const float gn = d2f(subd(1.95, (double)addf(mulf(o1r, o1r), mulf(o1i, o1i))));
+    o1r = mulf(gn, orr);
+    o1i = mulf(gn, oi);
+    out[i] = make_float2(orr, oi);
+  }
+  p.osc1[0] = o1r;
+  p.osc1[1] = o1i;
+}
+
+void launch_osc(const OscParams& p, cudaStream_t st)
+{
+  if (p.nb == 0)
+    return;
+  k_osc<<<1, 32, 0, st>>>(p);
+}
+
+// ==================================================================================================
+// decimate-by-2 stages, DownConvert.cpp:516-550 (generic), :589-688 (11-tap), :709-727 (CIC3)
+// ==================================================================================================
+constexpr unsigned kHbTile = 128;
+
+template <bool MIX>
+struct HbIn
+{
+  const HalfBandParams& p;
+  const float2* row;
+  const float* bb;
+  const float2* osc;
+  __device__ HbIn(const HalfBandParams& pp, unsigned s, unsigned hist) : p(pp)
+  {
+    row = reinterpret_cast<const float2*>(pp.in) + (size_t)s * pp.in_stride;
+    bb = pp.bbV + (size_t)s * pp.a_stride + (pp.a_hist - hist);
+    osc = reinterpret_cast<const float2*>(pp.oscV) + (pp.osc_hist - hist);
+  }
+  __device__ __forceinline__ float2 operator()(unsigned v) const
+  {
+    if (!MIX)
+      return row[v];
+    // real baseband x NCO phasor, imaginary input exactly +0 (RDSProcess.cpp:122-123, DownConvert.cpp:464-465)
+    const float b = bb[v];
+    const float2 o = osc[v];
+    float2 r;
+    r.x = subf(mulf(b, o.x), mulf(0.0f, o.y));
+    r.y = addf(mulf(b, o.y), mulf(0.0f, o.x));
+    return r;
+  }
+};
+
+template <bool MIX, int KIND>
+__global__ void __launch_bounds__(kHbTile) k_halfband(HalfBandParams p)
+{
+  __shared__ float s_h[64];
+  const unsigned tid = threadIdx.x;
+  if (KIND != 2)
+  {
+    for (unsigned i = tid; i < p.len; i += kHbTile)
+      s_h[i] = p.h[i];
+    __syncthreads();
+  }
+  const unsigned s = blockIdx.y;
+  const unsigned k = blockIdx.x * kHbTile + tid;
+  if (k >= p.n_in / 2)
+    return;
+  const unsigned hist = (KIND == 2) ? 2 : p.len - 1;
+  HbIn<MIX> V(p, s, hist);
+  float2 acc;
+  if (KIND == 0)
+  {
+    const unsigned i = 2 * k;
+    const unsigned L = p.len;
+    float2 x = V(i);
+    acc.x = mulf(x.x, s_h[0]);
+    acc.y = mulf(x.y, s_h[0]);
+    for (unsigned j = 0; j < L; j += 2)
+    {
+      x = V(i + j);
+      acc.x = addf(acc.x, mulf(x.x, s_h[j]));
+      acc.y = addf(acc.y, mulf(x.y, s_h[j]));
+    }
+    const unsigned c = (L - 1) / 2;
+    x = V(i + c);
+    acc.x = addf(acc.x, mulf(x.x, s_h[c]));
+    acc.y = addf(acc.y, mulf(x.y, s_h[c]));
+  }
+  else if (KIND == 1)
+  {
+    const unsigned i = 2 * k;
+    const int idx[7] = {0, 2, 4, 5, 6, 8, 10};
+    float2 x = V(i);
+    acc.x = mulf(s_h[0], x.x);
+    acc.y = mulf(s_h[0], x.y);
+#pragma unroll
+    for (int t = 1; t < 7; ++t)
+    {
+      x = V(i + idx[t]);
+      acc.x = addf(acc.x, mulf(s_h[idx[t]], x.x));
+      acc.y = addf(acc.y, mulf(s_h[idx[t]], x.y));
+    }
+  }
+  else
+  {
+    const float2 xeven = V(2 * k), xodd = V(2 * k + 1), even = V(2 * k + 2), odd = V(2 * k + 3);
+    acc.x = d2f(muld(.125, addd((double)addf(odd.x, xeven.x), muld(3.0, (double)addf(xodd.x, even.x)))));
+    acc.y = d2f(muld(.125, addd((double)addf(odd.y, xeven.y), muld(3.0, (double)addf(xodd.y, even.y)))));
+  }
+  reinterpret_cast<float2*>(p.out)[(size_t)s * p.out_stride + p.out_off + k] = acc;
+}
+
+void launch_halfband(const HalfBandParams& p, cudaStream_t st)
+{
+  if (p.S == 0 || p.n_in < 2)
+    return;
+  dim3 grid(cdiv(p.n_in / 2, kHbTile), p.S);
+#define RFM_HB(MIX, KIND) k_halfband<MIX, KIND><<<grid, kHbTile, 0, st>>>(p)
+  if (p.mix)
+  {
+    if (p.kind == 0) RFM_HB(true, 0);
+    else if (p.kind == 1) RFM_HB(true, 1);
+    else RFM_HB(true, 2);
+  }
+  else
+  {
+    if (p.kind == 0) RFM_HB(false, 0);
+    else if (p.kind == 1) RFM_HB(false, 1);
+    else RFM_HB(false, 2);
+  }
+#undef RFM_HB
+}
+
+// ==================================================================================================
+// RDS Costas loop, RDSProcess.cpp:187-270
+// ==================================================================================================
+__device__ __forceinline__ float arctan2_approx(float y, float x)
+{
+  if (x == 0.0f)
+  {
+    if (y > 0.0f)
+      return d2f(RFM_K_PI2);
+    if (y == 0.0f)
+      return 0.0f;
+    return d2f(-RFM_K_PI2);
+  }
+  float angle;
+  const float z = divf(y, x);
+  if (absf(z) < 1.0f)
+  {
+    angle = d2f(divd((double)z, addd(1.0, muld(muld(0.2854, (double)z), (double)z))));
+    if (x < 0.0f)
+    {
+      if (y < 0.0f)
+        return d2f(subd((double)angle, RFM_K_PI));
+      return d2f(addd((double)angle, RFM_K_PI));
+    }
+  }
+  else
+  {
+    angle = d2f(subd(RFM_K_PI2, divd((double)z, addd((double)mulf(z, z), 0.2854))));
+    if (y < 0.0f)
+      return d2f(subd((double)angle, RFM_K_PI));
+  }
+  return angle;
+}
+
+__global__ void __launch_bounds__(32) k_rds_pll(RdsPllParams p)
+{
+  const unsigned s = blockIdx.x * 32 + threadIdx.x;
+  if (s >= p.S)
+    return;
+  const unsigned S = p.S;
+  float phase = p.state[SF_RPLL_PHASE * S + s];
+  float freq = p.state[SF_RPLL_FREQ * S + s];
+  const float2* in = reinterpret_cast<const float2*>(p.in) + (size_t)s * p.in_stride;
+  float* out = p.out + (size_t)s * p.out_stride + p.out_off;
+  for (unsigned i = 0; i < p.nr; ++i)
+  {
+    float Sin, Cos;
+    rfm_sincos(phase, &Sin, &Cos);
+    const float2 x = in[i];
+    const float tre = subf(mulf(Cos, x.x), mulf(Sin, x.y));
+    const float tim = addf(mulf(Cos, x.y), mulf(Sin, x.x));
+    const float err = negf(arctan2_approx(tim, tre));
+    freq = addf(freq, mulf(p.beta, err));
+    if (freq > p.hi)
+      freq = p.hi;
+    else if (freq < p.lo)
+      freq = p.lo;
+    phase = addf(phase, addf(freq, mulf(p.alpha, err)));
+    out[i] = tim;
+  }
+  phase = rfm_fmodf_small(phase, d2f(RFM_K_2PI)); // RDSProcess.cpp:269
+  p.state[SF_RPLL_PHASE * S + s] = phase;
+  p.state[SF_RPLL_FREQ * S + s] = freq;
+}
+
+void launch_rds_pll(const RdsPllParams& p, cudaStream_t st)
+{
+  if (p.S == 0 || p.nr == 0)
+    return;
+  k_rds_pll<<<cdiv(p.S, 32), 32, 0, st>>>(p);
+}
+
+// ==================================================================================================
+// bit clock + slicer, RDSProcess.cpp:137-179
+// ==================================================================================================
+__global__ void __launch_bounds__(32) k_rds_slice(RdsSliceParams p)
+{
+  const unsigned s = blockIdx.x * 32 + threadIdx.x;
+  if (s >= p.S)
+    return;
+  const unsigned S = p.S;
+  float* st = p.state;
+  float w1 = st[SF_RSYNC_W1 * S + s], w2 = st[SF_RSYNC_W2 * S + s];
+  float last_sync = st[SF_RS_LASTSYNC * S + s], last_slope = st[SF_RS_LASTSLOPE * S + s];
+  float last_data = st[SF_RS_LASTDATA * S + s];
+  int last_bit = __float_as_int(st[SF_RS_LASTBIT * S + s]);
+  unsigned cnt = p.bit_count[s];
+  const float* in = p.in + (size_t)s * p.in_stride;
+  uint8_t* bits = p.bits + (size_t)s * p.bits_cap;
+  for (unsigned i = 0; i < p.nr; ++i)
+  {
+    const float d = in[i];
+    const float mag = mulf(d, d);
+    const float sync = biquad_step(p.sync, mag, w1, w2);
+    const float slope = subf(sync, last_sync);
+    last_sync = sync;
+    if (slope < 0.0f && mulf(last_slope, slope) < 0.0f)
+    {
+      const int bit = (last_data >= 0.0f) ? 1 : 0;
+      if (cnt < p.bits_cap)
+        bits[cnt] = (uint8_t)(bit ^ last_bit);
+      ++cnt;
+      last_bit = bit;
+    }
+    last_data = d;
+    last_slope = slope;
+  }
+  p.bit_count[s] = cnt;
+  st[SF_RSYNC_W1 * S + s] = w1;
+  st[SF_RSYNC_W2 * S + s] = w2;
+  st[SF_RS_LASTSYNC * S + s] = last_sync;
+  st[SF_RS_LASTSLOPE * S + s] = last_slope;
+  st[SF_RS_LASTDATA * S + s] = last_data;
+  st[SF_RS_LASTBIT * S + s] = __int_as_float(last_bit);
+}
+
+void launch_rds_slice(const RdsSliceParams& p, cudaStream_t st)
+{
+  if (p.S == 0 || p.nr == 0)
+    return;
+  k_rds_slice<<<cdiv(p.S, 32), 32, 0, st>>>(p);
+}
+
+// ==================================================================================================
+// history carry: row = [hist | n]  ->  first `hist` elements := last `hist` elements
+// ==================================================================================================
+template <typename T>
+__device__ __forceinline__ void tail_row(T* row, unsigned hist, unsigned n)
+{
+  // hist <= 2 * blockDim.x (checked on the host); values are read before any is written, so the
+  // overlapping case n < hist is handled too (memmove semantics).
+  T v0, v1;
+  const unsigned a = threadIdx.x, b = threadIdx.x + blockDim.x;
+  if (a < hist)
+    v0 = row[n + a];
+  if (b < hist)
+    v1 = row[n + b];
+  __syncthreads();
+  if (a < hist)
+    row[a] = v0;
+  if (b < hist)
+    row[b] = v1;
+}
+
+__global__ void __launch_bounds__(256) k_tails(TailParams p)
+{
+  const TailDesc d = p.d[blockIdx.y];
+  if (blockIdx.x >= d.rows)
+    return;
+  unsigned char* row = reinterpret_cast<unsigned char*>(d.base) + (size_t)blockIdx.x * d.stride_bytes;
+  if (d.elem == 8)
+    tail_row(reinterpret_cast<uint2*>(row), d.hist, d.n);
+  else
+    tail_row(reinterpret_cast<uint32_t*>(row), d.hist, d.n);
+}
+
+void launch_tails(const TailParams& p, unsigned S, cudaStream_t st)
+{
+  if (p.count == 0 || S == 0)
+    return;
+  dim3 grid(S, p.count);
+  k_tails<<<grid, 256, 0, st>>>(p);
+}
+
+} // namespace rfm

@@ -1,0 +1,239 @@
+// rfm_kernels.cuh -- launch interface of the sm_100a kernels (rfm_kernels.cu).
+//
+// Data layout (all batched [stream][time], one row per IQ stream, everything resident in HBM):
+//   * "V buffers": a stage's input row is  [ H history samples | n new samples ]  so that a FIR tile
+//     can read across the block boundary without branching; the producer writes at offset H and
+//     k_tails moves the last H samples to the front after the consumer has run
+//     (the reference's m_state / m_pHBFirBuf / m_cZBuf carry, DownConvert.cpp:135-153,544-547).
+//   * per-stream scalar state (PLL registers, IIR delays, meters) lives in SoA float arrays.
+//   * state that depends only on the number of samples processed (fine-tuner index, decimator
+//     phase, fractional resampler position, FIR rotation, NCO-oscillator phasor) is identical for
+//     all streams of a decoder and is tracked once (host scalars / one device table).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rfm_math.cuh"
+
+namespace rfm
+{
+
+constexpr unsigned kMaxFirTapsDev = 80; // >= cFirFilter MAX_NUMCOEF (75)
+
+struct DemodConst
+{
+  float gain, lo, hi, alpha, beta;
+};
+
+struct PilotConstDev
+{
+  float minfreq, maxfreq, b0, a1, a2, lb0, lb1, minsignal;
+  int lock_delay;
+};
+
+struct BiquadDev
+{
+  float A1, A2, B0, B1, B2;
+};
+
+// ---- per-stream scalar state, SoA: state[field * S + stream] --------------------------------------
+enum StateField
+{
+  SF_DEMOD_PHASE = 0,
+  SF_DEMOD_INCR,
+  SF_DEMOD_DC,
+  SF_IF_LEVEL,
+  SF_BB_MEAN,
+  SF_BB_LEVEL,
+  SF_PILOT_PHASE,
+  SF_PILOT_FREQ,
+  SF_PILOT_I1,
+  SF_PILOT_I2,
+  SF_PILOT_Q1,
+  SF_PILOT_Q2,
+  SF_PILOT_X1,
+  SF_PILOT_LEVEL,
+  SF_PILOT_LOCKCNT, // int bits
+  SF_STEREO,        // int bits: m_StereoDetected of the last block
+  SF_DE_RE,
+  SF_DE_IM,
+  SF_NOTCH_W1A,
+  SF_NOTCH_W2A,
+  SF_NOTCH_W1B,
+  SF_NOTCH_W2B,
+  SF_RPLL_PHASE,
+  SF_RPLL_FREQ,
+  SF_RSYNC_W1,
+  SF_RSYNC_W2,
+  SF_RS_LASTSYNC,
+  SF_RS_LASTSLOPE,
+  SF_RS_LASTDATA,
+  SF_RS_LASTBIT, // int bits
+  SF_COUNT
+};
+
+// ---- front end: (u8 | cf32) -> fine tuner -> Lanczos FIR / ds -----------------------------------------
+struct FrontParams
+{
+  const void* in;          // u8 [S][in_stride][2] or cf32 [S][in_stride]
+  size_t in_stride;        // samples per row
+  unsigned n;              // new samples per stream
+  unsigned S;
+  unsigned order, ds;
+  unsigned p0;             // m_pos_int: position of the first output inside this block
+  unsigned nout;           // outputs per stream
+  unsigned idx0;           // fine-tuner table index of sample 0
+  const float* lut;        // [256]
+  const float* tuner;      // [64][2]
+  const float* coeff;      // [order + 2]
+  cf32* tail;              // [S][order] tuned history (m_stateComplex)
+  cf32* z;                 // [S][z_stride] FIR output
+  size_t z_stride;
+};
+void launch_front(const FrontParams& p, bool u8, cudaStream_t st);
+void launch_front_tail(const FrontParams& p, bool u8, cudaStream_t st);
+
+// ---- baseband lanes: IF meter, FM-demod PLL, DC tracker, BB meters, pilot PLL, 38 kHz demux multiply --
+struct LanesParams
+{
+  FrontParams front;       // for the IF level meter (first ceil(n/64) tuned samples)
+  const cf32* z;
+  size_t z_stride;
+  unsigned nb;             // baseband samples per stream
+  unsigned S;
+  float* state;            // [SF_COUNT][S]
+  DemodConst demod;
+  PilotConstDev pilot;
+  float* bbV;              // [S][a_stride]: history a_hist, then nb new baseband samples
+  float* rawV;             // same layout, pilot-demodulated L-R
+  size_t a_stride;
+  unsigned a_hist;
+};
+void launch_bb_lanes(const LanesParams& p, bool u8, cudaStream_t st);
+
+// ---- audio: fractional Lanczos resampler (mono + stereo share the interpolated taps) -------------------
+struct ResampleParams
+{
+  const float* bbV;
+  const float* rawV;
+  size_t a_stride;
+  unsigned order;          // V history length == order
+  unsigned nb, S, na;
+  float pos_frac, pstep;
+  const float* coeff;      // [order + 2]
+  float* lpS;              // [S][lp_stride]: history (lp_taps - 1), then na new samples (stereo diff)
+  float* lpM;              // same, mono
+  size_t lp_stride;
+  unsigned lp_hist;
+};
+void launch_resample(const ResampleParams& p, cudaStream_t st);
+
+// ---- cFirFilter with rotating summation start (real pair / complex / real) ------------------------------
+struct RotFirParams
+{
+  const float* inA;        // V rows: history (taps - 1) then n
+  const float* inB;        // second channel or nullptr
+  size_t in_stride;        // in elements (float, or cf32 when cplx)
+  float* outA;
+  float* outB;
+  size_t out_stride;
+  unsigned out_off;        // element offset inside the output row (history of the consumer)
+  unsigned n, S, taps;
+  unsigned g0;             // samples filtered since the last (re)initialisation, mod taps
+  const float* coef;       // [taps]
+  int cplx;                // 1: rows are cf32, same taps for re and im
+};
+void launch_rotfir(const RotFirParams& p, cudaStream_t st);
+
+// ---- audio tail lanes: deemphasis, 19 kHz notch, L/R matrix -------------------------------------------
+struct AudioTailParams
+{
+  const float* inS;
+  const float* inM;
+  size_t in_stride;
+  unsigned na, S;
+  float* state;
+  float de_alpha;
+  BiquadDev notch;
+  float* audio;            // [S][audio_stride] interleaved L,R
+  size_t audio_stride;
+};
+void launch_audio_tail(const AudioTailParams& p, cudaStream_t st);
+
+// ---- RDS: NCO oscillator table, half-band chain, PLL, slicer ------------------------------------------
+struct OscParams
+{
+  cf32* oscV;              // [osc_hist + nb]
+  unsigned osc_hist, nb;
+  float* osc1;             // [2] carried phasor m_Osc1
+  float cosv, sinv;
+};
+void launch_osc(const OscParams& p, cudaStream_t st);
+
+struct HalfBandParams
+{
+  // stage input: either a cf32 V buffer, or (mix != 0) bbV x oscV formed on the fly
+  const cf32* in;
+  size_t in_stride;
+  const float* bbV;
+  size_t a_stride;
+  unsigned a_hist;
+  const cf32* oscV;
+  unsigned osc_hist;
+  int mix;
+  int kind;                // 0 generic half-band, 1 fixed 11-tap, 2 CIC3
+  unsigned len;            // taps (history = len - 1; CIC3: 2)
+  unsigned n_in, S;
+  const float* h;          // device taps [len]
+  cf32* out;               // next stage V buffer
+  size_t out_stride;
+  unsigned out_off;
+};
+void launch_halfband(const HalfBandParams& p, cudaStream_t st);
+
+struct RdsPllParams
+{
+  const cf32* in;          // [S][in_stride]
+  size_t in_stride;
+  unsigned nr, S;
+  float* state;
+  float lo, hi, alpha, beta;
+  float* out;              // matched-filter V buffer
+  size_t out_stride;
+  unsigned out_off;
+};
+void launch_rds_pll(const RdsPllParams& p, cudaStream_t st);
+
+struct RdsSliceParams
+{
+  const float* in;         // matched filter output [S][in_stride]
+  size_t in_stride;
+  unsigned nr, S;
+  float* state;
+  BiquadDev sync;
+  uint8_t* bits;           // [S][bits_cap]
+  unsigned bits_cap;
+  unsigned* bit_count;     // [S] running count (appended across blocks until drained)
+};
+void launch_rds_slice(const RdsSliceParams& p, cudaStream_t st);
+
+// ---- history carry for V buffers -------------------------------------------------------------------------
+struct TailDesc
+{
+  void* base;
+  size_t stride_bytes;     // row stride
+  unsigned hist;           // elements of history
+  unsigned n;              // new elements this block
+  unsigned elem;           // element size in bytes (4 or 8)
+  unsigned rows;           // S, or 1 for shared tables
+};
+constexpr int kMaxTailDesc = 12;
+struct TailParams
+{
+  TailDesc d[kMaxTailDesc];
+  int count;
+};
+void launch_tails(const TailParams& p, unsigned S, cudaStream_t st);
+
+} // namespace rfm
