@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native IQ -> audio (+RDS) chain.
+
+    python bench.py --gpus N --steps K --warmup W            (driver contract; torchrun for N > 1)
+    python bench.py --impl reference ...                      (the reference's own CPU chain, same workload)
+
+Workload (BASELINE.json configs[3], the one the metric is quoted on; fits one GPU): a batch of 4096 independent
+synthetic 2.4 MS/s u8 IQ streams (stereo + RDS stations), full chain.  One step = one 65472-sample block of every
+stream (268 M complex samples).  Multi-GPU: streams shard across ranks with no collective (weak scaling:
+4096 streams per GPU); torch.distributed is used only for the barrier and the max-over-ranks timing.
+
+value  : complex MS/s with the IQ blocks already resident in HBM (device-pointer C-ABI entry point).
+e2e    : the same through the host-buffer C-ABI call (rfm_decoder_process_u8): pinned host IQ in, audio out,
+         H2D / D2H inside the timed region, RDS bits drained to the host block-sync at the end.
+"""
+from __future__ import annotations
+
+import argparse
+import concurrent.futures as cf
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FS, DS, BLK = 2.4e6, 11, 65472          # 2.4 MS/s, downsample 11, block 65472
+STREAMS_PER_GPU = 4096
+BYTES_PER_SAMPLE = 2.0 + 8.0 * 48000.0 / FS   # u8 I,Q in + f32 L,R out = 2.160 B / complex sample
+METRIC = "demodulated complex MS/s per GPU (stereo+RDS) at 1/2/4/8 B200; % of HBM roofline"
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 and len(r) >= 7] or [r for _, r in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        f = lambda v: float(v) if v.replace(".", "", 1).isdigit() else None
+        sm = [f(r[0]) for r in rows if f(r[0]) is not None]
+        pw = [f(r[2]) for r in rows if f(r[2]) is not None]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": f(rows[0][1]),
+                "power_w_max": max(pw) if pw else None, "samples": len(rows), "reasons": reasons}
+
+
+# --------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own chain (oracle/_ref, compiled from /root/reference by oracle/Makefile) or, where
+# that library did not travel, the oracle's plain-C restatement.  One decoder per thread, all host cores.
+# --------------------------------------------------------------------------------------------------------------
+def cpu_chain():
+    from oracle import ref, port
+    if ref.available():
+        return "reference", lambda: ref.RefFmDecoder(FS, -0.15 * FS, downsample=DS)
+    return "port", lambda: port.OracleFmDecoder(FS, -0.15 * FS, downsample=DS)
+
+
+def cpu_input(n_blocks: int) -> np.ndarray:
+    from __graft_entry__ import load_package
+    load_package()
+    import importlib
+    synth = importlib.import_module("radiofm_b200.synth")
+    iq, _ = synth.make_station_u8(FS, n_blocks * BLK, stream_id=0)
+    return iq.reshape(n_blocks, BLK, 2)
+
+
+def cpu_step(decoders, iq, pool, blocks_per_thread, b0):
+    def work(k):
+        d = decoders[k]
+        for j in range(blocks_per_thread):
+            d.process_u8(iq[(b0 + j) % iq.shape[0]])
+    list(pool.map(work, range(len(decoders))))
+    return len(decoders) * blocks_per_thread * BLK
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    kind, make = cpu_chain()
+    cores = len(os.sched_getaffinity(0))
+    iq = cpu_input(8)
+    decoders = [make() for _ in range(cores)]
+    bpt = 8   # blocks per thread per step: ~0.2 s of CPU work per thread per step
+    with cf.ThreadPoolExecutor(cores) as pool:
+        for w in range(args.warmup):
+            cpu_step(decoders, iq, pool, bpt, w * bpt)
+        t0 = time.perf_counter()
+        samples = 0
+        for k in range(args.steps):
+            samples += cpu_step(decoders, iq, pool, bpt, (args.warmup + k) * bpt)
+        dt = time.perf_counter() - t0
+    v = samples / dt / 1e6
+    peak, how = load_peaks()
+    sample = f"{cores} threads x 1 stream x {bpt} blocks of {BLK} IQ samples per step (ctypes releases the GIL)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "MS/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": v, "unit": "MS/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": v, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def workload_config(n_gpus):
+    return {"workload": f"C4: {STREAMS_PER_GPU} independent 2.4 MS/s u8 IQ streams per GPU (stereo+RDS stations), "
+                        f"one {BLK}-sample block of every stream per step",
+            "streams_per_gpu": STREAMS_PER_GPU, "fs_if": FS, "downsample": DS, "block_len": BLK,
+            "sharding": f"streams sharded over {n_gpus} GPU(s), no collective",
+            "l2": "per-step input (536 MB u8) is larger than L2 (126 MB); a different block every step"}
+
+
+def cpu_baseline_leg():
+    kind, make = cpu_chain()
+    cores = len(os.sched_getaffinity(0))
+    iq = cpu_input(8)
+    decoders = [make() for _ in range(cores)]
+    with cf.ThreadPoolExecutor(cores) as pool:
+        cpu_step(decoders, iq, pool, 2, 0)
+        t0 = time.perf_counter()
+        samples, b = 0, 0
+        while time.perf_counter() - t0 < 10.0:
+            samples += cpu_step(decoders, iq, pool, 8, b)
+            b += 8
+        dt = time.perf_counter() - t0
+    return {"value": samples / dt / 1e6, "unit": "MS/s", "cores": cores, "kind": kind,
+            "sample": f"{cores} threads, one decoder each, same 2.4 MS/s stereo+RDS blocks of {BLK} samples, "
+                      f"{samples // BLK} blocks in {dt:.1f} s"}
+
+
+# --------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from __graft_entry__ import load_package
+    rfm = load_package()
+    import importlib
+    synth_device = importlib.import_module("radiofm_b200.synth_device")
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    S = args.streams
+    K, W = args.steps, args.warmup
+    nres = min(K + W, args.resident_blocks)
+    iq = synth_device.make_batch_u8(torch, S, FS, nres * BLK, dev, first_stream=rank * S)
+    torch.cuda.synchronize()
+    dec = rfm.FmDecoderBatch(FS, -0.15 * FS, downsample=DS, n_streams=S, max_block_len=BLK, device=local,
+                             n_groups=args.groups)
+    stride = dec.max_audio_floats(BLK)
+    audio = torch.zeros((S, stride), dtype=torch.float32, device=dev)
+    stream = torch.cuda.Stream()
+    esz = 2  # bytes per u8 IQ sample
+
+    def step_device(i):
+        b = i % nres
+        return dec.process_u8_device(iq.data_ptr() + b * BLK * esz, nres * BLK, BLK, audio.data_ptr(), stride,
+                                     stream.cuda_stream)
+
+    # ---- value: inputs resident in HBM
+    with torch.cuda.stream(stream):
+        for i in range(W):
+            step_device(i)
+    barrier()
+    dec.set_profiling(True)
+    launches0 = rfm.launch_count()
+    clocks = ClockSampler(local)
+    time.sleep(0.25)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        nfl = 0
+        for i in range(K):
+            nfl = step_device(W + i)
+        e1.record(stream)
+    barrier()
+    t1 = time.perf_counter()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clk = clocks.stop(t0, t1)
+    launches = rfm.launch_count() - launches0
+    prof = dec.profile()
+    dec.set_profiling(False)
+    value = world * S * BLK * K / (ms * 1e-3) / 1e6
+
+    # dominant kernel by accumulated device time
+    top = max(prof.items(), key=lambda kv: kv[1][0]) if prof else ("none", (0.0, 0))
+    top_name, (top_ms, top_n) = top
+    peak, how = load_peaks()
+    n_groups = max(1, round(top_n / max(K, 1)))
+    units_per_launch = S * BLK / n_groups
+    avg_ms = top_ms / max(top_n, 1)
+    achieved = BYTES_PER_SAMPLE * units_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": how,
+                "avg_launch_ms": avg_ms, "launches": top_n, "units_per_launch": units_per_launch,
+                "algorithmic_bytes_per_unit": BYTES_PER_SAMPLE,
+                "chain_achieved": BYTES_PER_SAMPLE * value * 1e6 / 1e9 / world,
+                "chain_frac": BYTES_PER_SAMPLE * value * 1e6 / 1e9 / world / peak,
+                "kernel_ms_per_step": {k: round(v[0] / K, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
+
+    # ---- e2e: host buffers through the public host-pointer entry point
+    import ctypes as C
+    nh = min(nres, 2)
+    h_iq = torch.empty((nh, S, BLK, 2), dtype=torch.uint8).pin_memory()
+    h_iq.copy_(iq.view(S, nres, BLK, 2)[:, :nh].permute(1, 0, 2, 3))
+    h_audio = torch.empty((S, stride), dtype=torch.float32).pin_memory()
+    torch.cuda.synchronize()
+    kout = C.c_uint32(0)
+    lib = rfm.lib()
+
+    def step_host(i):
+        rc = lib.rfm_decoder_process_u8(dec._h, C.cast(h_iq[i % nh].data_ptr(), C.POINTER(C.c_uint8)), BLK,
+                                        C.cast(h_audio.data_ptr(), C.POINTER(C.c_float)), stride, C.byref(kout))
+        if rc != 0:
+            raise RuntimeError(lib.rfm_last_error().decode())
+
+    for i in range(max(1, W // 2)):
+        step_host(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        step_host(i)
+    groups = dec.take_groups(0)   # drains the RDS bits of every stream to the host block-sync
+    torch.cuda.synchronize()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e = {"value": world * S * BLK * K / dt / 1e6, "unit": "MS/s", "h2d_bytes_per_step": S * BLK * 2,
+           "d2h_bytes_per_step": S * int(kout.value) * 4, "ms_per_step": dt / K * 1e3,
+           "api": "rfm_decoder_process_u8 (pinned host IQ in, host audio out) + rfm_decoder_rds_take_groups"}
+
+    cpu = cpu_baseline_leg() if (rank == 0 and world == 1 and not args.no_cpu) else None
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "MS/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": workload_config(world), "roofline": roofline,
+                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
+                "audio_floats_per_stream_per_step": nfl}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU)
+    ap.add_argument("--groups", type=int, default=0)
+    ap.add_argument("--resident-blocks", type=int, default=12)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -121,6 +121,21 @@ RFM_API int rfm_decoder_get_status(rfm_decoder* d, uint32_t stream, rfm_stream_s
  * Same index list as oracle/ref_harness.cpp:ref_fm_constants / ref_fm_table. */
 RFM_API int rfm_decoder_constants(const rfm_decoder* d, double* out, uint32_t max);
 RFM_API int rfm_decoder_table(const rfm_decoder* d, int which, float* out, uint32_t max_floats, uint32_t* n);
+/* The same, host-only (no device needed): the planner that restates the reference constructors
+ * (cFmDecoder ctor FmDecode.cpp:237-314, cRDSRxSignalProcessor ctor RDSProcess.cpp:43-88).
+ * table: 0 fine-tuner, 1 input Lanczos taps, 2 audio Lanczos taps, 3 RDS LP, 4 RDS matched filter,
+ * 5 audio LP, 6 u8 -> float LUT (RTL_SDR_Source.cpp:207-211). */
+RFM_API int rfm_plan_constants(const rfm_config* cfg, double* out, uint32_t max);
+RFM_API int rfm_plan_table(const rfm_config* cfg, int which, float* out, uint32_t max_floats, uint32_t* n);
+
+/* Per-kernel device timing for the roofline report: while on, every kernel launch is bracketed by CUDA events
+ * on the stream it is launched on.  set_profiling() also clears the accumulated totals.  profile_read()
+ * enumerates kernels: returns RFM_OK and fills name / total_ms / launches for index 0..k-1, 1 past the end
+ * (index 0 synchronises and collects).  No reference counterpart (the reference only has commented-out
+ * StartPerformance()/StopPerformance() hooks, DownConvert.cpp:418,487). */
+RFM_API int rfm_decoder_set_profiling(rfm_decoder* d, int on);
+RFM_API int rfm_decoder_profile_read(rfm_decoder* d, uint32_t index, char* name, uint32_t name_cap,
+                                     double* total_ms, uint64_t* launches);
 
 /* Debug taps of the last block, copied to host (rows of n_streams).  name: demod_in baseband rawstereo
  * mono_rs stereo_rs lp rds_dec rds_lp rds_pll rds_mf.  Returns floats per stream in *n_floats. */

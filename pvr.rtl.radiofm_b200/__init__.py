@@ -44,7 +44,8 @@ EXPORTED_SYMBOLS = (
     "rfm_decoder_destroy", "rfm_decoder_reset", "rfm_decoder_max_audio_floats", "rfm_decoder_process_u8",
     "rfm_decoder_process_cf32", "rfm_decoder_process_u8_device", "rfm_decoder_process_cf32_device",
     "rfm_decoder_rds_take_groups", "rfm_decoder_rds_take_bits", "rfm_decoder_get_status",
-    "rfm_decoder_constants", "rfm_decoder_table", "rfm_decoder_tap", "rfm_rdssync_create",
+    "rfm_decoder_constants", "rfm_decoder_table", "rfm_plan_constants", "rfm_plan_table", "rfm_decoder_set_profiling",
+    "rfm_decoder_profile_read", "rfm_decoder_tap", "rfm_rdssync_create",
     "rfm_rdssync_destroy", "rfm_rdssync_reset", "rfm_rdssync_push_bits", "rfm_rdssync_take_groups",
     "rfm_rds_check_block",
 )
@@ -93,6 +94,11 @@ def lib():
         L.rfm_decoder_get_status.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(RfmStreamStatus)]
         L.rfm_decoder_constants.argtypes = [C.c_void_p, _f64p, C.c_uint32]
         L.rfm_decoder_table.argtypes = [C.c_void_p, C.c_int, _f32p, C.c_uint32, _u32p]
+        L.rfm_plan_constants.argtypes = [C.POINTER(RfmConfig), _f64p, C.c_uint32]
+        L.rfm_plan_table.argtypes = [C.POINTER(RfmConfig), C.c_int, _f32p, C.c_uint32, _u32p]
+        L.rfm_decoder_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        L.rfm_decoder_profile_read.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_uint32, _f64p,
+                                               C.POINTER(C.c_uint64)]
         L.rfm_decoder_tap.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, _f32p, C.c_uint32, _u32p]
         L.rfm_rdssync_create.argtypes = [C.POINTER(C.c_void_p)]
         L.rfm_rdssync_destroy.argtypes = [C.c_void_p]
@@ -121,17 +127,42 @@ def launch_count() -> int:
 _COMPLEX_TAPS = {"demod_in", "rds_dec", "rds_lp"}
 
 
+def _config(fs_if, tuning_offset, fs_pcm=48000.0, bw_pcm=15000.0, downsample=1, usver=False, n_streams=1,
+            max_block_len=65536, device=-1, n_groups=0) -> RfmConfig:
+    cfg = RfmConfig()
+    lib().rfm_config_default(C.byref(cfg))
+    cfg.sample_rate_if, cfg.tuning_offset, cfg.sample_rate_pcm, cfg.bandwidth_pcm = fs_if, tuning_offset, fs_pcm, bw_pcm
+    cfg.downsample, cfg.us_deemphasis, cfg.n_streams = downsample, int(usver), n_streams
+    cfg.max_block_len, cfg.device, cfg.n_groups = max_block_len, device, n_groups
+    return cfg
+
+
+def plan_constants(fs_if, tuning_offset, fs_pcm=48000.0, bw_pcm=15000.0, downsample=1, usver=False) -> np.ndarray:
+    """Host-only planner output (no device needed); index list = oracle's rfo_constants / ref_fm_constants."""
+    cfg = _config(fs_if, tuning_offset, fs_pcm, bw_pcm, downsample, usver)
+    s = np.zeros(64, dtype=np.float64)
+    rc = lib().rfm_plan_constants(C.byref(cfg), _p(s, _f64p), 64)
+    if rc < 0:
+        _check(rc)
+    return s
+
+
+def plan_table(which: int, fs_if, tuning_offset, fs_pcm=48000.0, bw_pcm=15000.0, downsample=1, usver=False) -> np.ndarray:
+    cfg = _config(fs_if, tuning_offset, fs_pcm, bw_pcm, downsample, usver)
+    out = np.zeros(4096, dtype=np.float32)
+    k = C.c_uint32(0)
+    _check(lib().rfm_plan_table(C.byref(cfg), which, _p(out, _f32p), out.size, C.byref(k)))
+    return out[:k.value].copy()
+
+
 class FmDecoderBatch:
     """n_streams x cFmDecoder (FmDecode.h:99-165) on one B200."""
 
     def __init__(self, fs_if: float, tuning_offset: float, fs_pcm: float = 48000.0, bw_pcm: float = 15000.0,
                  downsample: int = 1, usver: bool = False, n_streams: int = 1, max_block_len: int = 65536,
                  device: int = -1, n_groups: int = 0):
-        cfg = RfmConfig()
-        lib().rfm_config_default(C.byref(cfg))
-        cfg.sample_rate_if, cfg.tuning_offset, cfg.sample_rate_pcm, cfg.bandwidth_pcm = fs_if, tuning_offset, fs_pcm, bw_pcm
-        cfg.downsample, cfg.us_deemphasis, cfg.n_streams = downsample, int(usver), n_streams
-        cfg.max_block_len, cfg.device, cfg.n_groups = max_block_len, device, n_groups
+        cfg = _config(fs_if, tuning_offset, fs_pcm, bw_pcm, downsample, usver, n_streams, max_block_len, device,
+                      n_groups)
         self.n_streams = n_streams
         self._h = C.c_void_p()
         _check(lib().rfm_decoder_create(C.byref(cfg), C.byref(self._h)))
@@ -205,6 +236,24 @@ class FmDecoderBatch:
         return {"stereo": bool(s.stereo_detected), "if_level": np.float32(s.interface_level),
                 "bb_level": np.float32(s.baseband_level), "bb_mean": np.float32(s.baseband_mean),
                 "pilot_level": np.float32(s.pilot_level), "tuning_offset": np.float32(s.tuning_offset)}
+
+    def set_profiling(self, on: bool):
+        _check(lib().rfm_decoder_set_profiling(self._h, int(on)))
+
+    def profile(self) -> dict:
+        """{kernel name: (total device ms, launches)} accumulated since set_profiling(True)."""
+        out = {}
+        name = C.create_string_buffer(64)
+        ms, cnt = C.c_double(0), C.c_uint64(0)
+        i = 0
+        while True:
+            rc = lib().rfm_decoder_profile_read(self._h, i, name, 64, C.byref(ms), C.byref(cnt))
+            if rc == 1:
+                break
+            _check(rc)
+            out[name.value.decode()] = (ms.value, int(cnt.value))
+            i += 1
+        return out
 
     def constants(self) -> np.ndarray:
         s = np.zeros(64, dtype=np.float64)

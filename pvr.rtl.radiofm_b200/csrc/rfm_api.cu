@@ -69,9 +69,19 @@ struct DevBuf
   }
 };
 
+// Optional per-kernel timing: CUDA event pairs recorded around every launch on the stream the kernel is
+// launched on (bench.py's roofline leg).  Off by default.
+constexpr int kMaxProfKinds = 24;
+struct ProfSlot
+{
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+  size_t used = 0;
+};
+
 struct Group
 {
   unsigned s0 = 0, S = 0;
+  ProfSlot prof[kMaxProfKinds];
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
   DevBuf<cf32> tail, z;
@@ -104,6 +114,11 @@ struct rfm_decoder
   DevBuf<cf32> oscV;
   DevBuf<float> osc1;
   std::vector<Group> groups;
+  bool profiling = false;
+  const char* prof_names[kMaxProfKinds] = {nullptr};
+  double prof_ms[kMaxProfKinds] = {0};
+  uint64_t prof_count[kMaxProfKinds] = {0};
+  ProfSlot main_prof[kMaxProfKinds];
   cudaStream_t main_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_osc = nullptr, ev_join = nullptr;
   // lock-step state (identical for every stream)
@@ -124,6 +139,8 @@ struct rfm_decoder
 namespace
 {
 
+void ProfFree(ProfSlot* slots);
+
 void FreeDecoder(rfm_decoder* d)
 {
   if (!d)
@@ -137,6 +154,7 @@ void FreeDecoder(rfm_decoder* d)
     for (auto& b : g.hbV) b.Free();
     g.rlpV.Free(); g.rlp_out.Free(); g.mfV.Free(); g.mf_out.Free(); g.bits.Free(); g.bit_count.Free();
     g.lpS.Free(); g.lpM.Free(); g.fS.Free(); g.fM.Free(); g.state.Free(); g.in_stage.Free(); g.audio_stage.Free();
+    ProfFree(g.prof);
     if (g.done)
       cudaEventDestroy(g.done);
     if (g.stream)
@@ -146,6 +164,7 @@ void FreeDecoder(rfm_decoder* d)
   d->d_rlp_coef.Free(); d->d_mf_coef.Free();
   for (auto& b : d->d_hb) b.Free();
   d->oscV.Free(); d->osc1.Free();
+  ProfFree(d->main_prof);
   for (cudaEvent_t e : {d->ev_fork, d->ev_osc, d->ev_join})
     if (e)
       cudaEventDestroy(e);
@@ -160,6 +179,86 @@ cudaError_t Upload(DevBuf<float>& b, const float* src, size_t n)
   if (e == cudaSuccess && n)
     e = cudaMemcpy(b.p, src, n * sizeof(float), cudaMemcpyHostToDevice);
   return e;
+}
+
+int ProfKind(rfm_decoder* d, const char* name)
+{
+  for (int i = 0; i < kMaxProfKinds; ++i)
+  {
+    if (!d->prof_names[i])
+    {
+      d->prof_names[i] = name;
+      return i;
+    }
+    if (d->prof_names[i] == name || strcmp(d->prof_names[i], name) == 0)
+      return i;
+  }
+  return kMaxProfKinds - 1;
+}
+
+struct ProfScope
+{
+  cudaEvent_t stop = nullptr;
+  cudaStream_t st;
+  ProfScope(rfm_decoder* d, ProfSlot* slots, const char* name, cudaStream_t stream) : st(stream)
+  {
+    if (!d->profiling)
+      return;
+    ProfSlot& sl = slots[ProfKind(d, name)];
+    if (sl.used == sl.ev.size())
+    {
+      cudaEvent_t a, b;
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      sl.ev.emplace_back(a, b);
+    }
+    cudaEventRecord(sl.ev[sl.used].first, st);
+    stop = sl.ev[sl.used].second;
+    ++sl.used;
+  }
+  ~ProfScope()
+  {
+    if (stop)
+      cudaEventRecord(stop, st);
+  }
+};
+#define RFM_PROF(slots, name, stream, call)            \
+  do                                                   \
+  {                                                    \
+    ProfScope ps_(d, slots, name, stream);             \
+    call;                                              \
+  } while (0)
+
+void ProfCollect(rfm_decoder* d, ProfSlot* slots)
+{
+  for (int k = 0; k < kMaxProfKinds; ++k)
+  {
+    ProfSlot& sl = slots[k];
+    for (size_t i = 0; i < sl.used; ++i)
+    {
+      float ms = 0.0f;
+      if (cudaEventElapsedTime(&ms, sl.ev[i].first, sl.ev[i].second) == cudaSuccess)
+      {
+        d->prof_ms[k] += ms;
+        d->prof_count[k] += 1;
+      }
+    }
+    sl.used = 0;
+  }
+}
+
+void ProfFree(ProfSlot* slots)
+{
+  for (int k = 0; k < kMaxProfKinds; ++k)
+  {
+    for (auto& e : slots[k].ev)
+    {
+      cudaEventDestroy(e.first);
+      cudaEventDestroy(e.second);
+    }
+    slots[k].ev.clear();
+    slots[k].used = 0;
+  }
 }
 
 unsigned StageHist(const HalfBandStage& s) { return s.len == 3 ? 2u : (unsigned)s.len - 1; }
@@ -279,7 +378,7 @@ void EnqueueGroup(rfm_decoder* d, Group& g, const void* d_in, size_t in_stride, 
   fp.in = d_in; fp.in_stride = in_stride; fp.n = bg.n; fp.S = S; fp.order = p.in_order; fp.ds = p.downsample;
   fp.p0 = d->in_pos; fp.nout = bg.nb; fp.idx0 = d->tuner_idx; fp.lut = d->d_lut.p; fp.tuner = d->d_tuner.p;
   fp.coeff = d->d_in_coeff.p; fp.tail = g.tail.p; fp.z = g.z.p; fp.z_stride = d->z_stride;
-  launch_front(fp, u8, st);
+  RFM_PROF(g.prof, "k_front", st, launch_front(fp, u8, st));
 
   LanesParams lp;
   lp.front = fp; lp.z = g.z.p; lp.z_stride = d->z_stride; lp.nb = bg.nb; lp.S = S; lp.state = g.state.p;
@@ -287,8 +386,8 @@ void EnqueueGroup(rfm_decoder* d, Group& g, const void* d_in, size_t in_stride, 
   lp.pilot = {p.pilot.minfreq, p.pilot.maxfreq, p.pilot.b0, p.pilot.a1, p.pilot.a2, p.pilot.lb0, p.pilot.lb1,
               p.pilot.minsignal, p.pilot.lock_delay};
   lp.bbV = g.bbV.p; lp.rawV = g.rawV.p; lp.a_stride = d->a_stride; lp.a_hist = a_hist;
-  launch_bb_lanes(lp, u8, st);
-  launch_front_tail(fp, u8, st); // after the lanes kernel: its IF meter reads the same input block
+  RFM_PROF(g.prof, "k_bb_lanes", st, launch_bb_lanes(lp, u8, st));
+  RFM_PROF(g.prof, "k_front_tail", st, launch_front_tail(fp, u8, st)); // after the lanes kernel: its IF meter reads the same input block
   g_launches += 3;
 
   // ---- audio branch
@@ -296,19 +395,19 @@ void EnqueueGroup(rfm_decoder* d, Group& g, const void* d_in, size_t in_stride, 
   rp.bbV = g.bbV.p; rp.rawV = g.rawV.p; rp.a_stride = d->a_stride; rp.order = p.a_order; rp.nb = bg.nb; rp.S = S;
   rp.na = bg.na; rp.pos_frac = d->a_pos; rp.pstep = p.a_pstep; rp.coeff = d->d_a_coeff.p; rp.lpS = g.lpS.p;
   rp.lpM = g.lpM.p; rp.lp_stride = d->lp_stride; rp.lp_hist = lp_taps - 1;
-  launch_resample(rp, st);
+  RFM_PROF(g.prof, "k_resample", st, launch_resample(rp, st));
 
   RotFirParams f29;
   f29.inA = g.lpS.p; f29.inB = g.lpM.p; f29.in_stride = d->lp_stride; f29.outA = g.fS.p; f29.outB = g.fM.p;
   f29.out_stride = d->na_max; f29.out_off = 0; f29.n = bg.na; f29.S = S; f29.taps = lp_taps; f29.g0 = d->lp_g;
   f29.coef = d->d_lp_coef.p; f29.cplx = 0;
-  launch_rotfir(f29, st);
+  RFM_PROF(g.prof, "k_rotfir_lp29", st, launch_rotfir(f29, st));
 
   AudioTailParams at;
   at.inS = g.fS.p; at.inM = g.fM.p; at.in_stride = d->na_max; at.na = bg.na; at.S = S; at.state = g.state.p;
   at.de_alpha = p.de_alpha; at.notch = {p.notch.A1, p.notch.A2, p.notch.B0, p.notch.B1, p.notch.B2};
   at.audio = d_audio; at.audio_stride = audio_stride;
-  launch_audio_tail(at, st);
+  RFM_PROF(g.prof, "k_audio_tail", st, launch_audio_tail(at, st));
   g_launches += 3;
 
   // ---- RDS branch
@@ -332,7 +431,7 @@ void EnqueueGroup(rfm_decoder* d, Group& g, const void* d_in, size_t in_stride, 
     {
       hp.out = g.rlpV.p; hp.out_stride = d->rlp_stride; hp.out_off = rlp_taps - 1;
     }
-    launch_halfband(hp, st);
+    RFM_PROF(g.prof, "k_halfband", st, launch_halfband(hp, st));
     ++g_launches;
   }
   RotFirParams frl;
@@ -340,25 +439,25 @@ void EnqueueGroup(rfm_decoder* d, Group& g, const void* d_in, size_t in_stride, 
   frl.outA = reinterpret_cast<float*>(g.rlp_out.p); frl.outB = nullptr; frl.out_stride = d->nr_stride;
   frl.out_off = 0; frl.n = bg.nr; frl.S = S; frl.taps = rlp_taps; frl.g0 = d->rlp_g; frl.coef = d->d_rlp_coef.p;
   frl.cplx = 1;
-  launch_rotfir(frl, st);
+  RFM_PROF(g.prof, "k_rotfir_rdslp", st, launch_rotfir(frl, st));
 
   RdsPllParams pp;
   pp.in = g.rlp_out.p; pp.in_stride = d->nr_stride; pp.nr = bg.nr; pp.S = S; pp.state = g.state.p;
   pp.lo = p.rpll_lo; pp.hi = p.rpll_hi; pp.alpha = p.rpll_alpha; pp.beta = p.rpll_beta;
   pp.out = g.mfV.p; pp.out_stride = d->mf_stride; pp.out_off = mf_taps - 1;
-  launch_rds_pll(pp, st);
+  RFM_PROF(g.prof, "k_rds_pll", st, launch_rds_pll(pp, st));
 
   RotFirParams fmf;
   fmf.inA = g.mfV.p; fmf.inB = nullptr; fmf.in_stride = d->mf_stride; fmf.outA = g.mf_out.p; fmf.outB = nullptr;
   fmf.out_stride = d->nr_stride; fmf.out_off = 0; fmf.n = bg.nr; fmf.S = S; fmf.taps = mf_taps; fmf.g0 = d->mf_g;
   fmf.coef = d->d_mf_coef.p; fmf.cplx = 0;
-  launch_rotfir(fmf, st);
+  RFM_PROF(g.prof, "k_rotfir_rdsmf", st, launch_rotfir(fmf, st));
 
   RdsSliceParams sp;
   sp.in = g.mf_out.p; sp.in_stride = d->nr_stride; sp.nr = bg.nr; sp.S = S; sp.state = g.state.p;
   sp.sync = {p.rsync.A1, p.rsync.A2, p.rsync.B0, p.rsync.B1, p.rsync.B2};
   sp.bits = g.bits.p; sp.bits_cap = d->bits_cap; sp.bit_count = g.bit_count.p;
-  launch_rds_slice(sp, st);
+  RFM_PROF(g.prof, "k_rds_slice", st, launch_rds_slice(sp, st));
   g_launches += 4;
 
   // ---- history carry of every V buffer of this group
@@ -377,7 +476,7 @@ void EnqueueGroup(rfm_decoder* d, Group& g, const void* d_in, size_t in_stride, 
     add(g.hbV[k].p, d->hb_stride[k], StageHist(p.rds_stages[k]), bg.hb_n[k], 8);
   add(g.rlpV.p, d->rlp_stride, rlp_taps - 1, bg.nr, 8);
   add(g.mfV.p, d->mf_stride, mf_taps - 1, bg.nr, 4);
-  launch_tails(tp, S, st);
+  RFM_PROF(g.prof, "k_tails", st, launch_tails(tp, S, st));
   ++g_launches;
 }
 
@@ -423,7 +522,7 @@ int ProcessDevice(rfm_decoder* d, const void* d_in, size_t in_stride, bool u8, u
   OscParams op;
   op.oscV = d->oscV.p; op.osc_hist = d->osc_hist; op.nb = bg.nb; op.osc1 = d->osc1.p;
   op.cosv = d->plan.rds_osc.cosv; op.sinv = d->plan.rds_osc.sinv;
-  launch_osc(op, base);
+  RFM_PROF(d->main_prof, "k_osc", base, launch_osc(op, base));
   ++g_launches;
   RFM_CUDA(cudaEventRecord(d->ev_osc, base));
 
@@ -458,7 +557,7 @@ int ProcessDevice(rfm_decoder* d, const void* d_in, size_t in_stride, bool u8, u
   TailParams tp;
   tp.count = 1;
   tp.d[0] = {d->oscV.p, 0, d->osc_hist, bg.nb, 8, 1};
-  launch_tails(tp, 1, base);
+  RFM_PROF(d->main_prof, "k_tails", base, launch_tails(tp, 1, base));
   ++g_launches;
   if (!host_staged)
   {
@@ -814,11 +913,10 @@ int rfm_decoder_get_status(rfm_decoder* d, uint32_t stream, rfm_stream_status* o
   return RFM_OK;
 }
 
-int rfm_decoder_constants(const rfm_decoder* d, double* s, uint32_t max)
+static int PlanConstants(const DecoderPlan& p, double* s, uint32_t max)
 {
-  if (!d || !s || max < 51)
+  if (!s || max < 51)
     return Fail(RFM_ERR_INVALID, "bad argument");
-  const DecoderPlan& p = d->plan;
   int i = 0;
   s[i++] = p.fs_if; s[i++] = p.fs_bb; s[i++] = p.tuning_shift; s[i++] = p.demod_gain;
   s[i++] = p.nco_lo; s[i++] = p.nco_hi; s[i++] = p.pll_alpha; s[i++] = p.pll_beta; s[i++] = p.de_alpha;
@@ -838,11 +936,10 @@ int rfm_decoder_constants(const rfm_decoder* d, double* s, uint32_t max)
   return i;
 }
 
-int rfm_decoder_table(const rfm_decoder* d, int which, float* out, uint32_t max_floats, uint32_t* n)
+static int PlanTable(const DecoderPlan& p, int which, float* out, uint32_t max_floats, uint32_t* n)
 {
-  if (!d || !n)
+  if (!n)
     return Fail(RFM_ERR_INVALID, "bad argument");
-  const DecoderPlan& p = d->plan;
   const float* src = nullptr;
   size_t cnt = 0;
   switch (which)
@@ -853,12 +950,88 @@ int rfm_decoder_table(const rfm_decoder* d, int which, float* out, uint32_t max_
     case 3: src = p.rlp_coef.data(); cnt = p.rlp_coef.size(); break;
     case 4: src = p.mf_coef.data(); cnt = p.mf_coef.size(); break;
     case 5: src = p.lp_coef.data(); cnt = p.lp_coef.size(); break;
+    case 6: src = p.u8lut; cnt = 256; break;
     default: return Fail(RFM_ERR_INVALID, "unknown table");
   }
   cnt = std::min<size_t>(cnt, max_floats);
   if (out)
     memcpy(out, src, cnt * sizeof(float));
   *n = (uint32_t)cnt;
+  return RFM_OK;
+}
+
+static int PlanFromConfig(const rfm_config* cfg, DecoderPlan* plan)
+{
+  if (!cfg || cfg->downsample == 0 || cfg->sample_rate_if <= 0 || cfg->sample_rate_pcm <= 0)
+    return Fail(RFM_ERR_INVALID, "invalid configuration");
+  *plan = PlanDecoder(cfg->sample_rate_if, cfg->tuning_offset, cfg->sample_rate_pcm, cfg->bandwidth_pcm,
+                      cfg->downsample, cfg->us_deemphasis != 0);
+  return RFM_OK;
+}
+
+int rfm_plan_constants(const rfm_config* cfg, double* s, uint32_t max)
+{
+  DecoderPlan plan;
+  const int rc = PlanFromConfig(cfg, &plan);
+  return rc != RFM_OK ? rc : PlanConstants(plan, s, max);
+}
+
+int rfm_plan_table(const rfm_config* cfg, int which, float* out, uint32_t max_floats, uint32_t* n)
+{
+  DecoderPlan plan;
+  const int rc = PlanFromConfig(cfg, &plan);
+  return rc != RFM_OK ? rc : PlanTable(plan, which, out, max_floats, n);
+}
+
+int rfm_decoder_constants(const rfm_decoder* d, double* s, uint32_t max)
+{
+  if (!d)
+    return Fail(RFM_ERR_INVALID, "bad argument");
+  return PlanConstants(d->plan, s, max);
+}
+
+int rfm_decoder_table(const rfm_decoder* d, int which, float* out, uint32_t max_floats, uint32_t* n)
+{
+  if (!d)
+    return Fail(RFM_ERR_INVALID, "bad argument");
+  return PlanTable(d->plan, which, out, max_floats, n);
+}
+
+int rfm_decoder_set_profiling(rfm_decoder* d, int on)
+{
+  if (!d)
+    return Fail(RFM_ERR_INVALID, "null decoder");
+  int rc = SyncAll(d);
+  if (rc != RFM_OK)
+    return rc;
+  for (auto& g : d->groups)
+    ProfCollect(d, g.prof);
+  ProfCollect(d, d->main_prof);
+  memset(d->prof_ms, 0, sizeof(d->prof_ms));
+  memset(d->prof_count, 0, sizeof(d->prof_count));
+  d->profiling = on != 0;
+  return RFM_OK;
+}
+
+int rfm_decoder_profile_read(rfm_decoder* d, uint32_t index, char* name, uint32_t name_cap, double* total_ms,
+                             uint64_t* launches)
+{
+  if (!d || !name || name_cap == 0 || !total_ms || !launches)
+    return Fail(RFM_ERR_INVALID, "bad argument");
+  if (index == 0)
+  {
+    int rc = SyncAll(d);
+    if (rc != RFM_OK)
+      return rc;
+    for (auto& g : d->groups)
+      ProfCollect(d, g.prof);
+    ProfCollect(d, d->main_prof);
+  }
+  if (index >= (uint32_t)kMaxProfKinds || !d->prof_names[index])
+    return 1; // end of list
+  snprintf(name, name_cap, "%s", d->prof_names[index]);
+  *total_ms = d->prof_ms[index];
+  *launches = d->prof_count[index];
   return RFM_OK;
 }
 

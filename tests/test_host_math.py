@@ -1,0 +1,96 @@
+"""rfm_math.cuh is __host__ __device__: compile the very same header with g++ (test-only shim, never shipped)
+and pin its restated libm routines on the CPU: rfm_atan2f == glibc atan2f bit for bit; rfm_sincos ==
+float(sin/cos(double)) (what x87 fsincos -> float gives); the fmod helpers == libm."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+SHIM = r'''
+#include "rfm_math.cuh"
+#include <math.h>
+extern "C" {
+unsigned long long cmp_atan2f(const float* y, const float* x, unsigned n) {
+  unsigned long long bad = 0;
+  for (unsigned i = 0; i < n; ++i) {
+    float a = rfm::rfm_atan2f(y[i], x[i]), b = atan2f(y[i], x[i]);
+    bad += rfm::f2u(a) != rfm::f2u(b) && !(a != a && b != b);
+  }
+  return bad;
+}
+unsigned long long cmp_sincos(const float* p, unsigned n) {
+  unsigned long long bad = 0;
+  for (unsigned i = 0; i < n; ++i) {
+    float s, c; rfm::rfm_sincos(p[i], &s, &c);
+    bad += rfm::f2u(s) != rfm::f2u((float)sin((double)p[i]));
+    bad += rfm::f2u(c) != rfm::f2u((float)cos((double)p[i]));
+  }
+  return bad;
+}
+unsigned long long cmp_fmod(const float* p, unsigned n) {
+  unsigned long long bad = 0;
+  const float twopif = (float)RFM_K_2PI;
+  for (unsigned i = 0; i < n; ++i) {
+    bad += rfm::f2u(rfm::rfm_fmodf_small(p[i], twopif)) != rfm::f2u(fmodf(p[i], twopif));
+    double x = fabs((double)p[i]);
+    if (x < 2 * RFM_K_2PI) bad += rfm::rfm_fmod_2pi_small(x) != fmod(x, RFM_K_2PI);
+  }
+  return bad;
+}
+}
+'''
+
+
+@pytest.fixture(scope="module")
+def shim(tmp_path_factory):
+    d = tmp_path_factory.mktemp("mathshim")
+    src = d / "shim.cpp"
+    src.write_text(SHIM)
+    so = d / "shim.so"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++",
+                           "-I", os.path.join(ROOT, "pvr.rtl.radiofm_b200", "csrc"), str(src), "-o", str(so), "-lm"])
+    L = C.CDLL(str(so))
+    for f in (L.cmp_atan2f, L.cmp_sincos, L.cmp_fmod):
+        f.restype = C.c_ulonglong
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def test_atan2f_bit_exact_vs_glibc(shim):
+    rng = np.random.default_rng(1)
+    n = 4_000_000
+    for sy, sx in ((1.0, 1.0), (1e-3, 1.0), (1.0, 1e-4), (1e-20, 1e20), (0.5, -0.5)):
+        y = (rng.standard_normal(n) * sy).astype(np.float32)
+        x = (rng.standard_normal(n) * sx).astype(np.float32)
+        assert shim.cmp_atan2f(_p(y), _p(x), n) == 0
+    # every binade of atanf through atan2f(y, 1) and signed zeros / infinities
+    bits = np.arange(0, 0x7f800001, 997, dtype=np.uint32)
+    y = np.concatenate([bits.view(np.float32), (bits | 0x80000000).view(np.float32)])
+    x = np.ones_like(y)
+    assert shim.cmp_atan2f(_p(y), _p(x), y.size) == 0
+    sp = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, 1e-45, 3e38], dtype=np.float32)
+    yy, xx = [np.ascontiguousarray(v.ravel()) for v in np.meshgrid(sp, sp)]
+    assert shim.cmp_atan2f(_p(yy), _p(xx), yy.size) == 0
+
+
+def test_sincos_is_rounded_double_sincos(shim):
+    rng = np.random.default_rng(2)
+    n = 8_000_000
+    p = (rng.random(n) * 6.6 - 0.2).astype(np.float32)          # the PLL phases live in [0, 2 pi]
+    assert shim.cmp_sincos(_p(p), n) == 0
+    p = (rng.standard_normal(n) * 300.0).astype(np.float32)     # far outside, still exact
+    assert shim.cmp_sincos(_p(p), n) == 0
+
+
+def test_fmod_helpers(shim):
+    rng = np.random.default_rng(3)
+    n = 2_000_000
+    p = (rng.standard_normal(n) * 20.0).astype(np.float32)
+    assert shim.cmp_fmod(_p(p), n) == 0
