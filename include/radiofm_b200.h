@@ -142,6 +142,15 @@ RFM_API int rfm_decoder_profile_read(rfm_decoder* d, uint32_t index, char* name,
 RFM_API int rfm_decoder_tap(rfm_decoder* d, const char* name, uint32_t stream, float* out, uint32_t max_floats,
                             uint32_t* n_floats);
 
+/* Test hooks (no reference counterpart): evaluate one of the scalar building blocks of the kernels on the DEVICE for
+ * n host operands; out2 receives two floats per element.  op: 0 rfm_sincos (sin, cos) 1 sincos fast core
+ * 2 sincos generic 3 atan2f(a, b) 4 branch-free atan2f (+flag) 5 atan2f generic 6 branch-free a / b (+flag)
+ * 7 __fdiv_rn 8 / 9 branch-free demod / pilot phase wrap (+flag) 10 both exact wraps 11 RDS arctan2 approximation
+ * (RDSProcess.cpp:187-217) 12 fmodf.  rfm_div_selftest: branch-free division vs __fdiv_rn over `pairs` random
+ * operand pairs generated on the device. */
+RFM_API int rfm_math_probe(int op, const float* a, const float* b, float* out2, uint32_t n);
+RFM_API int rfm_div_selftest(uint64_t seed, uint64_t pairs, uint64_t* mismatches, uint64_t* tested);
+
 /* ------------------------------------------------------------------------------------------------
  * RDS block synchronisation / FEC on explicit bits (host integer code, RDSProcess.cpp:272-431)
  * ---------------------------------------------------------------------------------------------- */

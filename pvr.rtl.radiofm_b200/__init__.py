@@ -47,7 +47,7 @@ EXPORTED_SYMBOLS = (
     "rfm_decoder_constants", "rfm_decoder_table", "rfm_plan_constants", "rfm_plan_table", "rfm_decoder_set_profiling",
     "rfm_decoder_profile_read", "rfm_decoder_tap", "rfm_rdssync_create",
     "rfm_rdssync_destroy", "rfm_rdssync_reset", "rfm_rdssync_push_bits", "rfm_rdssync_take_groups",
-    "rfm_rds_check_block",
+    "rfm_rds_check_block", "rfm_math_probe", "rfm_div_selftest",
 )
 
 
@@ -105,6 +105,8 @@ def lib():
         L.rfm_rdssync_reset.argtypes = [C.c_void_p]
         L.rfm_rdssync_push_bits.argtypes = [C.c_void_p, _u8p, C.c_uint32]
         L.rfm_rdssync_take_groups.argtypes = [C.c_void_p, _u16p, C.c_uint32, _u32p]
+        L.rfm_math_probe.argtypes = [C.c_int, _f32p, _f32p, _f32p, C.c_uint32]
+        L.rfm_div_selftest.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.rfm_rds_check_block.restype = C.c_uint32
         L.rfm_rds_check_block.argtypes = [C.c_uint32, C.c_uint32, C.c_int, _u32p]
         _lib = L
@@ -302,6 +304,25 @@ class RdsBlockSync:
         k = C.c_uint32(0)
         _check(lib().rfm_rdssync_take_groups(self._h, _p(out, _u16p), max_groups, C.byref(k)))
         return out[:k.value].copy()
+
+
+def math_probe(op: int, a: np.ndarray, b: np.ndarray | None = None) -> np.ndarray:
+    """Evaluate a scalar building block of the kernels on the device; returns [n, 2] float32 (see radiofm_b200.h)."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    out = np.zeros((a.size, 2), dtype=np.float32)
+    pb = None
+    if b is not None:
+        b = np.ascontiguousarray(b, dtype=np.float32)
+        assert b.size == a.size
+        pb = _p(b, _f32p)
+    _check(lib().rfm_math_probe(op, _p(a, _f32p), pb, _p(out, _f32p), a.size))
+    return out
+
+
+def div_selftest(pairs: int, seed: int = 1) -> tuple[int, int]:
+    m, t = C.c_uint64(0), C.c_uint64(0)
+    _check(lib().rfm_div_selftest(seed, pairs, C.byref(m), C.byref(t)))
+    return int(m.value), int(t.value)
 
 
 def rds_check_block(word26: int, offset_syndrome: int, use_fec: bool):

@@ -381,14 +381,15 @@ void EnqueueGroup(rfm_decoder* d, Group& g, const void* d_in, size_t in_stride, 
   RFM_PROF(g.prof, "k_front", st, launch_front(fp, u8, st));
 
   LanesParams lp;
-  lp.front = fp; lp.z = g.z.p; lp.z_stride = d->z_stride; lp.nb = bg.nb; lp.S = S; lp.state = g.state.p;
+  lp.z = g.z.p; lp.z_stride = d->z_stride; lp.nb = bg.nb; lp.S = S; lp.state = g.state.p;
   lp.demod = {p.demod_gain, p.nco_lo, p.nco_hi, p.pll_alpha, p.pll_beta};
   lp.pilot = {p.pilot.minfreq, p.pilot.maxfreq, p.pilot.b0, p.pilot.a1, p.pilot.a2, p.pilot.lb0, p.pilot.lb1,
               p.pilot.minsignal, p.pilot.lock_delay};
   lp.bbV = g.bbV.p; lp.rawV = g.rawV.p; lp.a_stride = d->a_stride; lp.a_hist = a_hist;
-  RFM_PROF(g.prof, "k_bb_lanes", st, launch_bb_lanes(lp, u8, st));
+  RFM_PROF(g.prof, "k_if_level", st, launch_if_level(fp, g.state.p, u8, st));
+  RFM_PROF(g.prof, "k_bb_lanes", st, launch_bb_lanes(lp, st));
   RFM_PROF(g.prof, "k_front_tail", st, launch_front_tail(fp, u8, st)); // after the lanes kernel: its IF meter reads the same input block
-  g_launches += 3;
+  g_launches += 4;
 
   // ---- audio branch
   ResampleParams rp;
@@ -500,6 +501,8 @@ int ProcessDevice(rfm_decoder* d, const void* d_in, size_t in_stride, bool u8, u
     return rc;
   if (2 * (size_t)bg.na > audio_stride)
     return Fail(RFM_ERR_OVERFLOW, "audio_stride smaller than the floats produced per stream");
+  if (!host_staged && ((audio_stride & 1u) || (reinterpret_cast<uintptr_t>(d_audio) & 7u)))
+    return Fail(RFM_ERR_INVALID, "device audio rows must be 8-byte aligned (even audio_stride): L,R pairs are stored as float2");
   RFM_CUDA(cudaSetDevice(d->device));
 
   // drain the RDS bit buffers before they could overflow

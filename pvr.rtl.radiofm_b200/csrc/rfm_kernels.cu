@@ -162,194 +162,282 @@ void launch_front_tail(const FrontParams& p, bool u8, cudaStream_t st)
 }
 
 // ==================================================================================================
-// baseband lanes
+// lane kernels: one lane per stream, sequential in time (nonlinear recurrences).  Common plumbing:
+// a warp owns 32 streams and walks the block in tiles of 32 samples; tiles move between HBM and shared memory
+// with coalesced row accesses (cp.async for the next tile while the current one is computed) and are read /
+// written by the lanes column-wise ([row][33] pitch: conflict-free).
 // ==================================================================================================
-struct DemodState
-{
-  float phase, incr, dc;
-};
+constexpr unsigned kLT = 32;
 
-// cFmDecoder::PhaseLockedLoop, FmDecode.cpp:361-415
-__device__ __forceinline__ float demod_step(DemodState& st, float2 x, const DemodConst& k)
+__device__ __forceinline__ void cp_async_4(void* smem, const void* gmem)
 {
-  float Sin, Cos;
-  rfm_sincos(st.phase, &Sin, &Cos);
-  const float dre = subf(mulf(Cos, x.x), mulf(Sin, x.y));
-  const float dim = addf(mulf(Cos, x.y), mulf(Sin, x.x));
-  const float err = negf(rfm_atan2f(dim, dre));
-  st.incr = addf(st.incr, mulf(k.beta, err));
-  if (st.incr < k.lo)
-    st.incr = k.lo;
-  if (st.incr > k.hi)
-    st.incr = k.hi;
-  st.phase = addf(st.phase, addf(st.incr, mulf(k.alpha, err)));
-  if ((double)st.phase >= RFM_K_2PI)
-    st.phase = d2f(rfm_fmod_2pi_small((double)st.phase));
-  while (st.phase < 0.0f)
-    st.phase = d2f(addd((double)st.phase, RFM_K_2PI));
-  const float pinc = mulf(2.0f, st.incr);
-  st.dc = d2f(addd(muld(1 - 0.0001, (double)st.dc), muld(0.0001, (double)pinc)));
-  return mulf(subf(pinc, st.dc), k.gain);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void* smem, const void* gmem)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// rows s0 .. s0+31 of a [S][stride] array, columns t0 .. t0+31 -> dst[row][col]
+__device__ __forceinline__ void tile_load_async(float (*dst)[kLT + 1], const float* base, size_t stride, unsigned s0,
+                                                unsigned S, unsigned t0, unsigned n, unsigned lane)
+{
+  if (t0 + lane < n)
+  {
+    const unsigned rows = min(32u, S - s0);
+    const float* g = base + (size_t)s0 * stride + t0 + lane;
+    for (unsigned r = 0; r < rows; ++r, g += stride)
+      cp_async_4(&dst[r][lane], g);
+  }
+}
+__device__ __forceinline__ void tile_load_async(float2 (*dst)[kLT + 1], const float2* base, size_t stride, unsigned s0,
+                                                unsigned S, unsigned t0, unsigned n, unsigned lane)
+{
+  if (t0 + lane < n)
+  {
+    const unsigned rows = min(32u, S - s0);
+    const float2* g = base + (size_t)s0 * stride + t0 + lane;
+    for (unsigned r = 0; r < rows; ++r, g += stride)
+      cp_async_8(&dst[r][lane], g);
+  }
+}
+template <typename T>
+__device__ __forceinline__ void tile_store(T* base, size_t stride, unsigned s0, unsigned S, unsigned t0, unsigned n,
+                                           unsigned lane, const T (*src)[kLT + 1])
+{
+  if (t0 + lane < n)
+  {
+    const unsigned rows = min(32u, S - s0);
+    T* g = base + (size_t)s0 * stride + t0 + lane;
+    for (unsigned r = 0; r < rows; ++r, g += stride)
+      *g = src[r][lane];
+  }
 }
 
-struct PilotState
-{
-  float phase, freq, i1, i2, q1, q2, x1, level;
-};
+// named barriers (producer / consumer hand-off between the two warps of k_bb_lanes)
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-// cPilotPhaseLock::Process loop body, FmDecode.cpp:149-216; returns sin(2 phi)
-__device__ __forceinline__ float pilot_step(PilotState& st, float x, const PilotConstDev& k)
-{
-  float ps, pc;
-  rfm_sincos(st.phase, &ps, &pc);
-  const float out = mulf(mulf(2.0f, ps), pc);
-  float pi = mulf(ps, x);
-  float pq = mulf(pc, x);
-  pi = subf(subf(mulf(k.b0, pi), mulf(k.a1, st.i1)), mulf(k.a2, st.i2));
-  pq = subf(subf(mulf(k.b0, pq), mulf(k.a1, st.q1)), mulf(k.a2, st.q2));
-  st.i2 = st.i1;
-  st.i1 = pi;
-  st.q2 = st.q1;
-  st.q1 = pq;
-  float err;
-  if (pi > absf(pq))
-    err = divf(pq, pi);
-  else if (pq > 0.0f)
-    err = 1.0f;
-  else
-    err = -1.0f;
-  st.level = (pi < st.level) ? pi : st.level;
-  st.freq = addf(st.freq, addf(mulf(k.lb0, err), mulf(k.lb1, st.x1)));
-  st.x1 = err;
-  const float t = (st.freq < k.maxfreq) ? st.freq : k.maxfreq;
-  st.freq = (k.minfreq < t) ? t : k.minfreq;
-  st.phase = addf(st.phase, st.freq);
-  if ((double)st.phase > RFM_K_2PI)
-    st.phase = d2f(subd((double)st.phase, RFM_K_2PI));
-  return out;
-}
-
-constexpr unsigned kLaneTile = 32;
-
+// --------------------------------------------------------------------------------------------------
+// IF level meter: RMSLevelApprox over the first ceil(n/64) tuned samples, FmDecode.cpp:427,505-519
+// --------------------------------------------------------------------------------------------------
 template <bool U8>
-__global__ void __launch_bounds__(32) k_bb_lanes(LanesParams p)
+__global__ void __launch_bounds__(128) k_if_level(FrontParams f, float* state)
 {
-  __shared__ float2 zt[32][kLaneTile + 1];
-  __shared__ float bt[32][kLaneTile + 1];
-  __shared__ float rt[32][kLaneTile + 1];
+  const unsigned s = blockIdx.x * 128 + threadIdx.x;
+  if (s >= f.S)
+    return;
+  const unsigned cnt = (f.n + 63) / 64;
+  const size_t esz = U8 ? 2 : 8;
+  const unsigned char* row = reinterpret_cast<const unsigned char*>(f.in) + (size_t)s * f.in_stride * esz;
+  const float2* tuner = reinterpret_cast<const float2*>(f.tuner);
+  float level = 0.0f;
+  for (unsigned i = 0; i < cnt; ++i)
+  {
+    const float2 t = tuned_sample<U8>(row, i, f.idx0, f.lut, tuner);
+    level = addf(level, addf(mulf(t.x, t.x), mulf(t.y, t.y)));
+  }
+  const float rms = sqrtf_rn(divf(level, (float)cnt));
+  float* lv = state + (size_t)SF_IF_LEVEL * f.S + s;
+  *lv = addf(mulf(0.95f, *lv), mulf(0.05f, rms));
+}
 
-  const unsigned lane = threadIdx.x;
+void launch_if_level(const FrontParams& p, float* state, bool u8, cudaStream_t st)
+{
+  if (p.S == 0 || p.n == 0)
+    return;
+  if (u8)
+    k_if_level<true><<<cdiv(p.S, 128), 128, 0, st>>>(p, state);
+  else
+    k_if_level<false><<<cdiv(p.S, 128), 128, 0, st>>>(p, state);
+}
+
+// --------------------------------------------------------------------------------------------------
+// baseband lanes: warp 0 = FM-demodulator PLL (FmDecode.cpp:361-409), warp 1 = DC tracker + output scaling
+// (:410-412), baseband meters (:439-442), 19 kHz pilot PLL (:143-229) and the 38 kHz demux multiply (:455-456).
+// The two recurrences of a stream are independent except that the pilot PLL consumes the demodulator's output,
+// so they run as a two-stage pipeline on two warps (two SM sub-partitions): a tile of NCO increments goes
+// through a 2-slot shared-memory ring guarded by named barriers.  Per-sample cost is max(demod, pilot)
+// instead of the sum.
+// --------------------------------------------------------------------------------------------------
+struct LanesSmem
+{
+  float2 zin[2][32][kLT + 1];
+  float ring[2][32][kLT + 1];
+  float bbt[32][kLT + 1];
+  float rawt[32][kLT + 1];
+};
+
+__global__ void __launch_bounds__(64) k_bb_lanes(LanesParams p)
+{
+  __shared__ LanesSmem sm;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned role = threadIdx.x >> 5;
   const unsigned s0 = blockIdx.x * 32;
   const unsigned s = s0 + lane;
   const bool valid = s < p.S;
   const unsigned S = p.S;
   float* st = p.state;
+  const unsigned ntiles = (p.nb + kLT - 1) / kLT;
+  enum { BAR_FULL = 1, BAR_EMPTY = 3 };
 
-  DemodState dm = {0.f, 0.f, 0.f};
-  PilotState pl = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 1000.0f};
-  float vsum = 0.0f, vsumsq = 0.0f;
-  if (valid)
+  if (role == 0)
   {
-    // --- IF level: RMSLevelApprox over the first ceil(n/64) tuned samples, FmDecode.cpp:427,505-519
-    const FrontParams& f = p.front;
-    const unsigned cnt = (f.n + 63) / 64;
-    const size_t esz = U8 ? 2 : 8;
-    const unsigned char* row = reinterpret_cast<const unsigned char*>(f.in) + (size_t)s * f.in_stride * esz;
-    const float2* tuner = reinterpret_cast<const float2*>(f.tuner);
-    float level = 0.0f;
-    for (unsigned i = 0; i < cnt; ++i)
-    {
-      const float2 t = tuned_sample<U8>(row, i, f.idx0, f.lut, tuner);
-      level = addf(level, addf(mulf(t.x, t.x), mulf(t.y, t.y)));
-    }
-    const float rms = sqrtf_rn(divf(level, (float)cnt));
-    st[SF_IF_LEVEL * S + s] = addf(mulf(0.95f, st[SF_IF_LEVEL * S + s]), mulf(0.05f, rms));
-
-    dm.phase = st[SF_DEMOD_PHASE * S + s];
-    dm.incr = st[SF_DEMOD_INCR * S + s];
-    dm.dc = st[SF_DEMOD_DC * S + s];
-    pl.phase = st[SF_PILOT_PHASE * S + s];
-    pl.freq = st[SF_PILOT_FREQ * S + s];
-    pl.i1 = st[SF_PILOT_I1 * S + s];
-    pl.i2 = st[SF_PILOT_I2 * S + s];
-    pl.q1 = st[SF_PILOT_Q1 * S + s];
-    pl.q2 = st[SF_PILOT_Q2 * S + s];
-    pl.x1 = st[SF_PILOT_X1 * S + s];
-    pl.level = 1000.0f; // FmDecode.cpp:147
-  }
-
-  const float2* z = reinterpret_cast<const float2*>(p.z);
-  for (unsigned t0 = 0; t0 < p.nb; t0 += kLaneTile)
-  {
-    const unsigned tn = min(kLaneTile, p.nb - t0);
-    // coalesced tile load: row r of the tile is stream s0 + r
-    for (unsigned r = 0; r < 32; ++r)
-      if (s0 + r < S && lane < tn)
-        zt[r][lane] = z[(size_t)(s0 + r) * p.z_stride + t0 + lane];
-    __syncwarp();
+    // ---------------- producer: FM demodulator PLL ----------------
+    DemodState dm = {0.f, 0.f};
     if (valid)
     {
-      for (unsigned k = 0; k < tn; ++k)
-      {
-        const float bb = demod_step(dm, zt[lane][k], p.demod);
-        vsum = addf(vsum, bb);                       // SamplesMeanRMS, FmDecode.cpp:522-539
-        vsumsq = addf(vsumsq, mulf(bb, bb));
-        const float p38 = pilot_step(pl, bb, p.pilot);
-        bt[lane][k] = bb;
-        rt[lane][k] = mulf(p38, mulf(2.0f, bb));     // FmDecode.cpp:455-456
-      }
+      dm.phase = st[SF_DEMOD_PHASE * S + s];
+      dm.incr = st[SF_DEMOD_INCR * S + s];
     }
-    __syncwarp();
-    for (unsigned r = 0; r < 32; ++r)
-      if (s0 + r < S && lane < tn)
-      {
-        const size_t o = (size_t)(s0 + r) * p.a_stride + p.a_hist + t0 + lane;
-        p.bbV[o] = bt[r][lane];
-        p.rawV[o] = rt[r][lane];
-      }
-    __syncwarp();
-  }
-
-  if (valid)
-  {
-    st[SF_DEMOD_PHASE * S + s] = dm.phase;
-    st[SF_DEMOD_INCR * S + s] = dm.incr;
-    st[SF_DEMOD_DC * S + s] = dm.dc;
-    st[SF_PILOT_PHASE * S + s] = pl.phase;
-    st[SF_PILOT_FREQ * S + s] = pl.freq;
-    st[SF_PILOT_I1 * S + s] = pl.i1;
-    st[SF_PILOT_I2 * S + s] = pl.i2;
-    st[SF_PILOT_Q1 * S + s] = pl.q1;
-    st[SF_PILOT_Q2 * S + s] = pl.q2;
-    st[SF_PILOT_X1 * S + s] = pl.x1;
-    st[SF_PILOT_LEVEL * S + s] = pl.level;
-    // lock detector, FmDecode.cpp:219-228
-    int lock_cnt = __float_as_int(st[SF_PILOT_LOCKCNT * S + s]);
-    if (mulf(2.0f, pl.level) > p.pilot.minsignal)
+    const float2* z = reinterpret_cast<const float2*>(p.z);
+    tile_load_async(sm.zin[0], z, p.z_stride, s0, S, 0, p.nb, lane);
+    cp_async_commit();
+    for (unsigned t = 0; t < ntiles; ++t)
     {
-      if (lock_cnt < p.pilot.lock_delay)
-        lock_cnt += (int)p.nb;
+      const unsigned b = t & 1u, t0 = t * kLT;
+      const unsigned tn = min(kLT, p.nb - t0);
+      if (t + 1 < ntiles)
+        tile_load_async(sm.zin[b ^ 1u], z, p.z_stride, s0, S, t0 + kLT, p.nb, lane);
+      cp_async_commit();
+      cp_async_wait<1>();
+      __syncwarp();
+      if (t >= 2)
+        bar_sync(BAR_EMPTY + b, 64);
+      // branch-free fast path; if any lane raised the sticky flag the tile is replayed with the exact routines
+      const DemodState tile_start = dm;
+      bool bad = false;
+      if (valid)
+      {
+        for (unsigned k = 0; k < tn; ++k)
+        {
+          const float2 x = sm.zin[b][lane][k];
+          demod_step_fast(dm, x.x, x.y, p.demod, bad);
+          sm.ring[b][lane][k] = dm.incr;
+        }
+      }
+      if (__any_sync(0xffffffffu, bad))
+      {
+        dm = tile_start;
+        if (valid)
+        {
+          for (unsigned k = 0; k < tn; ++k)
+          {
+            const float2 x = sm.zin[b][lane][k];
+            demod_step(dm, x.x, x.y, p.demod);
+            sm.ring[b][lane][k] = dm.incr;
+          }
+        }
+      }
+      __threadfence_block();
+      bar_arrive(BAR_FULL + b, 64);
+      __syncwarp();
     }
-    else
-      lock_cnt = 0;
-    st[SF_PILOT_LOCKCNT * S + s] = __int_as_float(lock_cnt);
-    st[SF_STEREO * S + s] = __int_as_float(lock_cnt >= p.pilot.lock_delay ? 1 : 0);
-    // baseband meters, FmDecode.cpp:439-442
-    const float mean = divf(vsum, (float)p.nb);
-    const float rms = sqrtf_rn(divf(vsumsq, (float)p.nb));
-    st[SF_BB_MEAN * S + s] = addf(mulf(0.95f, st[SF_BB_MEAN * S + s]), mulf(0.05f, mean));
-    st[SF_BB_LEVEL * S + s] = addf(mulf(0.95f, st[SF_BB_LEVEL * S + s]), mulf(0.05f, rms));
+    if (valid)
+    {
+      st[SF_DEMOD_PHASE * S + s] = dm.phase;
+      st[SF_DEMOD_INCR * S + s] = dm.incr;
+    }
+  }
+  else
+  {
+    // ---------------- consumer: DC tracker, meters, pilot PLL, demux multiply ----------------
+    PilotState pl = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 1000.0f};
+    float dc = 0.0f, vsum = 0.0f, vsumsq = 0.0f;
+    if (valid)
+    {
+      dc = st[SF_DEMOD_DC * S + s];
+      pl.phase = st[SF_PILOT_PHASE * S + s];
+      pl.freq = st[SF_PILOT_FREQ * S + s];
+      pl.i1 = st[SF_PILOT_I1 * S + s];
+      pl.i2 = st[SF_PILOT_I2 * S + s];
+      pl.q1 = st[SF_PILOT_Q1 * S + s];
+      pl.q2 = st[SF_PILOT_Q2 * S + s];
+      pl.x1 = st[SF_PILOT_X1 * S + s];
+      pl.level = 1000.0f; // FmDecode.cpp:147
+    }
+    for (unsigned t = 0; t < ntiles; ++t)
+    {
+      const unsigned b = t & 1u, t0 = t * kLT;
+      const unsigned tn = min(kLT, p.nb - t0);
+      bar_sync(BAR_FULL + b, 64);
+      const PilotState pl_start = pl;
+      const float dc_start = dc, vsum_start = vsum, vsumsq_start = vsumsq;
+      bool bad = false;
+      if (valid)
+      {
+        for (unsigned k = 0; k < tn; ++k)
+        {
+          const float bb = demod_output(sm.ring[b][lane][k], dc, p.demod.gain);
+          vsum = addf(vsum, bb);                       // SamplesMeanRMS, FmDecode.cpp:522-539
+          vsumsq = addf(vsumsq, mulf(bb, bb));
+          const float p38 = pilot_step_fast(pl, bb, p.pilot, bad);
+          sm.bbt[lane][k] = bb;
+          sm.rawt[lane][k] = mulf(p38, mulf(2.0f, bb)); // FmDecode.cpp:455-456
+        }
+      }
+      if (__any_sync(0xffffffffu, bad))
+      {
+        pl = pl_start; dc = dc_start; vsum = vsum_start; vsumsq = vsumsq_start;
+        if (valid)
+        {
+          for (unsigned k = 0; k < tn; ++k)
+          {
+            const float bb = demod_output(sm.ring[b][lane][k], dc, p.demod.gain);
+            vsum = addf(vsum, bb);
+            vsumsq = addf(vsumsq, mulf(bb, bb));
+            const float p38 = pilot_step(pl, bb, p.pilot);
+            sm.bbt[lane][k] = bb;
+            sm.rawt[lane][k] = mulf(p38, mulf(2.0f, bb));
+          }
+        }
+      }
+      if (t + 2 < ntiles)
+        bar_arrive(BAR_EMPTY + b, 64);
+      __syncwarp();
+      tile_store(p.bbV + p.a_hist, p.a_stride, s0, S, t0, p.nb, lane, sm.bbt);
+      tile_store(p.rawV + p.a_hist, p.a_stride, s0, S, t0, p.nb, lane, sm.rawt);
+      __syncwarp();
+    }
+    if (valid)
+    {
+      st[SF_DEMOD_DC * S + s] = dc;
+      st[SF_PILOT_PHASE * S + s] = pl.phase;
+      st[SF_PILOT_FREQ * S + s] = pl.freq;
+      st[SF_PILOT_I1 * S + s] = pl.i1;
+      st[SF_PILOT_I2 * S + s] = pl.i2;
+      st[SF_PILOT_Q1 * S + s] = pl.q1;
+      st[SF_PILOT_Q2 * S + s] = pl.q2;
+      st[SF_PILOT_X1 * S + s] = pl.x1;
+      st[SF_PILOT_LEVEL * S + s] = pl.level;
+      // lock detector, FmDecode.cpp:219-228
+      int lock_cnt = __float_as_int(st[SF_PILOT_LOCKCNT * S + s]);
+      if (mulf(2.0f, pl.level) > p.pilot.minsignal)
+      {
+        if (lock_cnt < p.pilot.lock_delay)
+          lock_cnt += (int)p.nb;
+      }
+      else
+        lock_cnt = 0;
+      st[SF_PILOT_LOCKCNT * S + s] = __int_as_float(lock_cnt);
+      st[SF_STEREO * S + s] = __int_as_float(lock_cnt >= p.pilot.lock_delay ? 1 : 0);
+      // baseband meters, FmDecode.cpp:439-442
+      const float mean = divf(vsum, (float)p.nb);
+      const float rms = sqrtf_rn(divf(vsumsq, (float)p.nb));
+      st[SF_BB_MEAN * S + s] = addf(mulf(0.95f, st[SF_BB_MEAN * S + s]), mulf(0.05f, mean));
+      st[SF_BB_LEVEL * S + s] = addf(mulf(0.95f, st[SF_BB_LEVEL * S + s]), mulf(0.05f, rms));
+    }
   }
 }
 
-void launch_bb_lanes(const LanesParams& p, bool u8, cudaStream_t st)
+void launch_bb_lanes(const LanesParams& p, cudaStream_t st)
 {
   if (p.S == 0 || p.nb == 0)
     return;
-  if (u8)
-    k_bb_lanes<true><<<cdiv(p.S, 32), 32, 0, st>>>(p);
-  else
-    k_bb_lanes<false><<<cdiv(p.S, 32), 32, 0, st>>>(p);
+  k_bb_lanes<<<cdiv(p.S, 32), 64, 0, st>>>(p);
 }
 
 // ==================================================================================================
@@ -494,58 +582,86 @@ void launch_rotfir(const RotFirParams& p, cudaStream_t st)
 // audio tail lanes: deemphasis (FmDecode.cpp:348-359), notch (IirFilter.cpp:89-105),
 // matrix (FmDecode.cpp:473-499)
 // ==================================================================================================
-__device__ __forceinline__ float biquad_step(const BiquadDev& c, float x, float& w1, float& w2)
+struct AudioTailSmem
 {
-  const float w0 = subf(subf(x, mulf(c.A1, w1)), mulf(c.A2, w2));
-  const float y = addf(addf(mulf(c.B0, w0), mulf(c.B1, w1)), mulf(c.B2, w2));
-  w2 = w1;
-  w1 = w0;
-  return y;
-}
+  float inS[2][32][kLT + 1];
+  float inM[2][32][kLT + 1];
+  float2 out[32][kLT + 1];
+};
 
 __global__ void __launch_bounds__(32) k_audio_tail(AudioTailParams p)
 {
-  const unsigned s = blockIdx.x * 32 + threadIdx.x;
-  if (s >= p.S)
-    return;
+  __shared__ AudioTailSmem sm;
+  const unsigned lane = threadIdx.x;
+  const unsigned s0 = blockIdx.x * 32;
+  const unsigned s = s0 + lane;
+  const bool valid = s < p.S;
   const unsigned S = p.S;
   float* st = p.state;
-  float de_re = st[SF_DE_RE * S + s], de_im = st[SF_DE_IM * S + s];
-  float w1a = st[SF_NOTCH_W1A * S + s], w2a = st[SF_NOTCH_W2A * S + s];
-  float w1b = st[SF_NOTCH_W1B * S + s], w2b = st[SF_NOTCH_W2B * S + s];
-  const bool stereo = __float_as_int(st[SF_STEREO * S + s]) != 0;
+  float de_re = 0.f, de_im = 0.f, w1a = 0.f, w2a = 0.f, w1b = 0.f, w2b = 0.f;
+  bool stereo = false;
+  if (valid)
+  {
+    de_re = st[SF_DE_RE * S + s]; de_im = st[SF_DE_IM * S + s];
+    w1a = st[SF_NOTCH_W1A * S + s]; w2a = st[SF_NOTCH_W2A * S + s];
+    w1b = st[SF_NOTCH_W1B * S + s]; w2b = st[SF_NOTCH_W2B * S + s];
+    stereo = __float_as_int(st[SF_STEREO * S + s]) != 0;
+  }
   const float alpha = p.de_alpha;
   const float one_m = subf(1.0f, alpha);
-  const float* inS = p.inS + (size_t)s * p.in_stride;
-  const float* inM = p.inM + (size_t)s * p.in_stride;
-  float2* out = reinterpret_cast<float2*>(p.audio + (size_t)s * p.audio_stride);
-  for (unsigned i = 0; i < p.na; ++i)
+  const unsigned ntiles = (p.na + kLT - 1) / kLT;
+  tile_load_async(sm.inS[0], p.inS, p.in_stride, s0, S, 0, p.na, lane);
+  tile_load_async(sm.inM[0], p.inM, p.in_stride, s0, S, 0, p.na, lane);
+  cp_async_commit();
+  for (unsigned t = 0; t < ntiles; ++t)
   {
-    de_re = addf(mulf(one_m, de_re), mulf(alpha, inS[i]));
-    const float a = mulf(de_re, 2.0f);
-    de_im = addf(mulf(one_m, de_im), mulf(alpha, inM[i]));
-    const float b = mulf(de_im, 2.0f);
-    const float sd = biquad_step(p.notch, a, w1a, w2a);
-    const float m = biquad_step(p.notch, b, w1b, w2b);
-    float2 o;
-    if (stereo)
+    const unsigned b = t & 1u, t0 = t * kLT;
+    const unsigned tn = min(kLT, p.na - t0);
+    if (t + 1 < ntiles)
     {
-      o.x = mulf(addf(m, sd), 0.5f);
-      o.y = mulf(subf(m, sd), 0.5f);
+      tile_load_async(sm.inS[b ^ 1u], p.inS, p.in_stride, s0, S, t0 + kLT, p.na, lane);
+      tile_load_async(sm.inM[b ^ 1u], p.inM, p.in_stride, s0, S, t0 + kLT, p.na, lane);
     }
-    else
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncwarp();
+    if (valid)
     {
-      o.x = mulf(m, 0.5f);
-      o.y = o.x;
+      for (unsigned k = 0; k < tn; ++k)
+      {
+        de_re = addf(mulf(one_m, de_re), mulf(alpha, sm.inS[b][lane][k]));
+        const float a = mulf(de_re, 2.0f);
+        de_im = addf(mulf(one_m, de_im), mulf(alpha, sm.inM[b][lane][k]));
+        const float bm = mulf(de_im, 2.0f);
+        const float sd = biquad_step(p.notch, a, w1a, w2a);
+        const float m = biquad_step(p.notch, bm, w1b, w2b);
+        float2 o;
+        if (stereo)
+        {
+          o.x = mulf(addf(m, sd), 0.5f);
+          o.y = mulf(subf(m, sd), 0.5f);
+        }
+        else
+        {
+          o.x = mulf(m, 0.5f);
+          o.y = o.x;
+        }
+        sm.out[lane][k] = o;
+      }
     }
-    out[i] = o;
+    __syncwarp();
+    tile_store(reinterpret_cast<float2*>(p.audio), p.audio_stride / 2, s0, S, t0, p.na, lane, sm.out);
+    __syncwarp();
   }
-  st[SF_DE_RE * S + s] = de_re;
-  st[SF_DE_IM * S + s] = de_im;
-  st[SF_NOTCH_W1A * S + s] = w1a;
-  st[SF_NOTCH_W2A * S + s] = w2a;
-  st[SF_NOTCH_W1B * S + s] = w1b;
-  st[SF_NOTCH_W2B * S + s] = w2b;
+  if (valid)
+  {
+    st[SF_DE_RE * S + s] = de_re;
+    st[SF_DE_IM * S + s] = de_im;
+    st[SF_NOTCH_W1A * S + s] = w1a;
+    st[SF_NOTCH_W2A * S + s] = w2a;
+    st[SF_NOTCH_W1B * S + s] = w1b;
+    st[SF_NOTCH_W2B * S + s] = w2b;
+  }
 }
 
 void launch_audio_tail(const AudioTailParams& p, cudaStream_t st)
@@ -700,66 +816,57 @@ void launch_halfband(const HalfBandParams& p, cudaStream_t st)
 // ==================================================================================================
 // RDS Costas loop, RDSProcess.cpp:187-270
 // ==================================================================================================
-__device__ __forceinline__ float arctan2_approx(float y, float x)
+struct RdsPllSmem
 {
-  if (x == 0.0f)
-  {
-    if (y > 0.0f)
-      return d2f(RFM_K_PI2);
-    if (y == 0.0f)
-      return 0.0f;
-    return d2f(-RFM_K_PI2);
-  }
-  float angle;
-  const float z = divf(y, x);
-  if (absf(z) < 1.0f)
-  {
-    angle = d2f(divd((double)z, addd(1.0, muld(muld(0.2854, (double)z), (double)z))));
-    if (x < 0.0f)
-    {
-      if (y < 0.0f)
-        return d2f(subd((double)angle, RFM_K_PI));
-      return d2f(addd((double)angle, RFM_K_PI));
-    }
-  }
-  else
-  {
-    angle = d2f(subd(RFM_K_PI2, divd((double)z, addd((double)mulf(z, z), 0.2854))));
-    if (y < 0.0f)
-      return d2f(subd((double)angle, RFM_K_PI));
-  }
-  return angle;
-}
+  float2 in[2][32][kLT + 1];
+  float out[32][kLT + 1];
+};
 
 __global__ void __launch_bounds__(32) k_rds_pll(RdsPllParams p)
 {
-  const unsigned s = blockIdx.x * 32 + threadIdx.x;
-  if (s >= p.S)
-    return;
+  __shared__ RdsPllSmem sm;
+  const unsigned lane = threadIdx.x;
+  const unsigned s0 = blockIdx.x * 32;
+  const unsigned s = s0 + lane;
+  const bool valid = s < p.S;
   const unsigned S = p.S;
-  float phase = p.state[SF_RPLL_PHASE * S + s];
-  float freq = p.state[SF_RPLL_FREQ * S + s];
-  const float2* in = reinterpret_cast<const float2*>(p.in) + (size_t)s * p.in_stride;
-  float* out = p.out + (size_t)s * p.out_stride + p.out_off;
-  for (unsigned i = 0; i < p.nr; ++i)
+  float phase = 0.f, freq = 0.f;
+  if (valid)
   {
-    float Sin, Cos;
-    rfm_sincos(phase, &Sin, &Cos);
-    const float2 x = in[i];
-    const float tre = subf(mulf(Cos, x.x), mulf(Sin, x.y));
-    const float tim = addf(mulf(Cos, x.y), mulf(Sin, x.x));
-    const float err = negf(arctan2_approx(tim, tre));
-    freq = addf(freq, mulf(p.beta, err));
-    if (freq > p.hi)
-      freq = p.hi;
-    else if (freq < p.lo)
-      freq = p.lo;
-    phase = addf(phase, addf(freq, mulf(p.alpha, err)));
-    out[i] = tim;
+    phase = p.state[SF_RPLL_PHASE * S + s];
+    freq = p.state[SF_RPLL_FREQ * S + s];
   }
-  phase = rfm_fmodf_small(phase, d2f(RFM_K_2PI)); // RDSProcess.cpp:269
-  p.state[SF_RPLL_PHASE * S + s] = phase;
-  p.state[SF_RPLL_FREQ * S + s] = freq;
+  const float2* in = reinterpret_cast<const float2*>(p.in);
+  const unsigned ntiles = (p.nr + kLT - 1) / kLT;
+  tile_load_async(sm.in[0], in, p.in_stride, s0, S, 0, p.nr, lane);
+  cp_async_commit();
+  for (unsigned t = 0; t < ntiles; ++t)
+  {
+    const unsigned b = t & 1u, t0 = t * kLT;
+    const unsigned tn = min(kLT, p.nr - t0);
+    if (t + 1 < ntiles)
+      tile_load_async(sm.in[b ^ 1u], in, p.in_stride, s0, S, t0 + kLT, p.nr, lane);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncwarp();
+    if (valid)
+    {
+      for (unsigned k = 0; k < tn; ++k)
+      {
+        const float2 x = sm.in[b][lane][k];
+        sm.out[lane][k] = rds_pll_step(phase, freq, x.x, x.y, p.lo, p.hi, p.alpha, p.beta);
+      }
+    }
+    __syncwarp();
+    tile_store(p.out + p.out_off, p.out_stride, s0, S, t0, p.nr, lane, sm.out);
+    __syncwarp();
+  }
+  if (valid)
+  {
+    phase = rfm_fmodf_small(phase, d2f(RFM_K_2PI)); // RDSProcess.cpp:269
+    p.state[SF_RPLL_PHASE * S + s] = phase;
+    p.state[SF_RPLL_FREQ * S + s] = freq;
+  }
 }
 
 void launch_rds_pll(const RdsPllParams& p, cudaStream_t st)
@@ -774,43 +881,70 @@ void launch_rds_pll(const RdsPllParams& p, cudaStream_t st)
 // ==================================================================================================
 __global__ void __launch_bounds__(32) k_rds_slice(RdsSliceParams p)
 {
-  const unsigned s = blockIdx.x * 32 + threadIdx.x;
-  if (s >= p.S)
-    return;
+  __shared__ float tin[2][32][kLT + 1];
+  const unsigned lane = threadIdx.x;
+  const unsigned s0 = blockIdx.x * 32;
+  const unsigned s = s0 + lane;
+  const bool valid = s < p.S;
   const unsigned S = p.S;
   float* st = p.state;
-  float w1 = st[SF_RSYNC_W1 * S + s], w2 = st[SF_RSYNC_W2 * S + s];
-  float last_sync = st[SF_RS_LASTSYNC * S + s], last_slope = st[SF_RS_LASTSLOPE * S + s];
-  float last_data = st[SF_RS_LASTDATA * S + s];
-  int last_bit = __float_as_int(st[SF_RS_LASTBIT * S + s]);
-  unsigned cnt = p.bit_count[s];
-  const float* in = p.in + (size_t)s * p.in_stride;
-  uint8_t* bits = p.bits + (size_t)s * p.bits_cap;
-  for (unsigned i = 0; i < p.nr; ++i)
+  float w1 = 0.f, w2 = 0.f, last_sync = 0.f, last_slope = 0.f, last_data = 0.f;
+  int last_bit = 0;
+  unsigned cnt = 0;
+  if (valid)
   {
-    const float d = in[i];
-    const float mag = mulf(d, d);
-    const float sync = biquad_step(p.sync, mag, w1, w2);
-    const float slope = subf(sync, last_sync);
-    last_sync = sync;
-    if (slope < 0.0f && mulf(last_slope, slope) < 0.0f)
-    {
-      const int bit = (last_data >= 0.0f) ? 1 : 0;
-      if (cnt < p.bits_cap)
-        bits[cnt] = (uint8_t)(bit ^ last_bit);
-      ++cnt;
-      last_bit = bit;
-    }
-    last_data = d;
-    last_slope = slope;
+    w1 = st[SF_RSYNC_W1 * S + s]; w2 = st[SF_RSYNC_W2 * S + s];
+    last_sync = st[SF_RS_LASTSYNC * S + s]; last_slope = st[SF_RS_LASTSLOPE * S + s];
+    last_data = st[SF_RS_LASTDATA * S + s];
+    last_bit = __float_as_int(st[SF_RS_LASTBIT * S + s]);
+    cnt = p.bit_count[s];
   }
-  p.bit_count[s] = cnt;
-  st[SF_RSYNC_W1 * S + s] = w1;
-  st[SF_RSYNC_W2 * S + s] = w2;
-  st[SF_RS_LASTSYNC * S + s] = last_sync;
-  st[SF_RS_LASTSLOPE * S + s] = last_slope;
-  st[SF_RS_LASTDATA * S + s] = last_data;
-  st[SF_RS_LASTBIT * S + s] = __int_as_float(last_bit);
+  uint8_t* bits = p.bits + (size_t)s * p.bits_cap;
+  const unsigned ntiles = (p.nr + kLT - 1) / kLT;
+  tile_load_async(tin[0], p.in, p.in_stride, s0, S, 0, p.nr, lane);
+  cp_async_commit();
+  for (unsigned t = 0; t < ntiles; ++t)
+  {
+    const unsigned b = t & 1u, t0 = t * kLT;
+    const unsigned tn = min(kLT, p.nr - t0);
+    if (t + 1 < ntiles)
+      tile_load_async(tin[b ^ 1u], p.in, p.in_stride, s0, S, t0 + kLT, p.nr, lane);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncwarp();
+    if (valid)
+    {
+      for (unsigned k = 0; k < tn; ++k)
+      {
+        const float d = tin[b][lane][k];
+        const float mag = mulf(d, d);
+        const float sync = biquad_step(p.sync, mag, w1, w2);
+        const float slope = subf(sync, last_sync);
+        last_sync = sync;
+        if (slope < 0.0f && mulf(last_slope, slope) < 0.0f)
+        {
+          const int bit = (last_data >= 0.0f) ? 1 : 0;
+          if (cnt < p.bits_cap)
+            bits[cnt] = (uint8_t)(bit ^ last_bit);
+          ++cnt;
+          last_bit = bit;
+        }
+        last_data = d;
+        last_slope = slope;
+      }
+    }
+    __syncwarp();
+  }
+  if (valid)
+  {
+    p.bit_count[s] = cnt;
+    st[SF_RSYNC_W1 * S + s] = w1;
+    st[SF_RSYNC_W2 * S + s] = w2;
+    st[SF_RS_LASTSYNC * S + s] = last_sync;
+    st[SF_RS_LASTSLOPE * S + s] = last_slope;
+    st[SF_RS_LASTDATA * S + s] = last_data;
+    st[SF_RS_LASTBIT * S + s] = __int_as_float(last_bit);
+  }
 }
 
 void launch_rds_slice(const RdsSliceParams& p, cudaStream_t st)

@@ -15,27 +15,12 @@
 #include <stdint.h>
 
 #include "rfm_math.cuh"
+#include "rfm_steps.cuh"
 
 namespace rfm
 {
 
 constexpr unsigned kMaxFirTapsDev = 80; // >= cFirFilter MAX_NUMCOEF (75)
-
-struct DemodConst
-{
-  float gain, lo, hi, alpha, beta;
-};
-
-struct PilotConstDev
-{
-  float minfreq, maxfreq, b0, a1, a2, lb0, lb1, minsignal;
-  int lock_delay;
-};
-
-struct BiquadDev
-{
-  float A1, A2, B0, B1, B2;
-};
 
 // ---- per-stream scalar state, SoA: state[field * S + stream] --------------------------------------
 enum StateField
@@ -95,9 +80,10 @@ void launch_front(const FrontParams& p, bool u8, cudaStream_t st);
 void launch_front_tail(const FrontParams& p, bool u8, cudaStream_t st);
 
 // ---- baseband lanes: IF meter, FM-demod PLL, DC tracker, BB meters, pilot PLL, 38 kHz demux multiply --
+void launch_if_level(const FrontParams& p, float* state, bool u8, cudaStream_t st);
+
 struct LanesParams
 {
-  FrontParams front;       // for the IF level meter (first ceil(n/64) tuned samples)
   const cf32* z;
   size_t z_stride;
   unsigned nb;             // baseband samples per stream
@@ -110,7 +96,7 @@ struct LanesParams
   size_t a_stride;
   unsigned a_hist;
 };
-void launch_bb_lanes(const LanesParams& p, bool u8, cudaStream_t st);
+void launch_bb_lanes(const LanesParams& p, cudaStream_t st);
 
 // ---- audio: fractional Lanczos resampler (mono + stereo share the interpolated taps) -------------------
 struct ResampleParams

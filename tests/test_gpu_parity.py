@@ -264,3 +264,65 @@ def test_full_size_batch_4096_streams(rfm, port, synth):
     bits = {k: oracles[k].take_bits() for k in range(K)}
     for s in (0, 1, 17, 2047, 4095):
         assert np.array_equal(d.take_bits(s), bits[perm[s]])
+
+
+def test_device_math_probes(rfm):
+    """What the GPU computes for the scalar building blocks (rfm_math.cuh), element by element against libm:
+    sin/cos == float(sin/cos(double)) [== x87 fsincos -> float], atan2f == glibc atan2f, phase wraps == the
+    reference's double expressions, and the branch-free variants == the exact ones wherever they do not flag."""
+    import ctypes as C
+    libm = C.CDLL("libm.so.6")
+    libm.atan2f.restype = C.c_float
+    libm.atan2f.argtypes = [C.c_float, C.c_float]
+    rng = np.random.default_rng(21)
+    n = 2_000_000
+    ph = np.concatenate([(rng.random(n) * 7.0 - 0.2), rng.standard_normal(n // 4) * 40.0]).astype(np.float32)
+    want = np.stack([np.sin(ph.astype(np.float64)).astype(np.float32), np.cos(ph.astype(np.float64)).astype(np.float32)], 1)
+    for op in (0, 2):
+        assert bits_equal(rfm.math_probe(op, ph), want), op
+    core = np.abs(ph) < 16
+    assert bits_equal(rfm.math_probe(1, ph[core]), want[core])
+    # atan2f: scalar form, generic form and branch-free form against glibc
+    m = 300_000
+    y = np.concatenate([rng.standard_normal(m), rng.standard_normal(m) * 1e-3, rng.standard_normal(m)]).astype(np.float32)
+    x = np.concatenate([rng.standard_normal(m), rng.standard_normal(m), rng.standard_normal(m) * 1e-4]).astype(np.float32)
+    ref = np.array([libm.atan2f(a, b) for a, b in zip(y.tolist(), x.tolist())], dtype=np.float32)
+    assert bits_equal(rfm.math_probe(3, y, x)[:, 0], ref)
+    assert bits_equal(rfm.math_probe(5, y, x)[:, 0], ref)
+    fast = rfm.math_probe(4, y, x)
+    ok = fast[:, 1] == 0
+    assert ok.mean() > 0.999 and bits_equal(fast[ok, 0], ref[ok])
+    sp = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, 1e-45, 3e38, np.nan, 1e-39, 5e19, 2e-20], dtype=np.float32)
+    yy, xx = [np.ascontiguousarray(v.ravel()) for v in np.meshgrid(sp, sp)]
+    ref = np.array([libm.atan2f(a, b) for a, b in zip(yy.tolist(), xx.tolist())], dtype=np.float32)
+    got = rfm.math_probe(3, yy, xx)[:, 0]
+    assert np.all((got.view(np.uint32) == ref.view(np.uint32)) | (np.isnan(got) & np.isnan(ref)))
+    fast = rfm.math_probe(4, yy, xx)
+    okf = fast[:, 1] == 0
+    assert np.array_equal(fast[okf, 0].view(np.uint32), ref[okf].view(np.uint32))
+    # branch-free division == __fdiv_rn inside the exponent window (1e9 pairs on the device + structured operands)
+    bad, tested = rfm.div_selftest(1_000_000_000)
+    assert tested > 300_000_000 and bad == 0, (bad, tested)
+    a = (rng.standard_normal(n) * 10.0 ** rng.integers(-20, 20, n)).astype(np.float32)
+    b = (rng.standard_normal(n) * 10.0 ** rng.integers(-20, 20, n)).astype(np.float32)
+    a[:1000] = 0.0
+    a[1000:2000] = -0.0
+    b[::7] = 1.0
+    q = rfm.math_probe(6, a, b)
+    okd = q[:, 1] == 0
+    assert okd.mean() > 0.5 and bits_equal(q[okd, 0], rfm.math_probe(7, a, b)[okd, 0])
+    assert bits_equal(q[okd, 0], (a[okd].astype(np.float64) / b[okd].astype(np.float64)).astype(np.float32))
+    # phase wraps
+    p = (rng.random(n) * 20.0 - 7.0).astype(np.float32)
+    pd = p.astype(np.float64)
+    two_pi = 2.0 * 3.14159265358979323846
+    dem = np.where(pd >= two_pi, np.fmod(pd, two_pi), pd).astype(np.float32)
+    dem = np.where(dem < 0, (dem.astype(np.float64) + two_pi).astype(np.float32), dem)
+    pil = np.where(pd > two_pi, pd - two_pi, pd).astype(np.float32)
+    dom = (p >= -6.0) & (p < 12.5)
+    ex = rfm.math_probe(10, p)
+    assert bits_equal(ex[dom, 0], dem[dom]) and bits_equal(ex[dom & (p > 0), 1], pil[dom & (p > 0)])
+    f8, f9 = rfm.math_probe(8, p), rfm.math_probe(9, p)
+    assert np.array_equal(f8[:, 1] == 0, dom) and bits_equal(f8[dom, 0], dem[dom])
+    d9 = (p < 12.5) & (p > 0)
+    assert bits_equal(f9[d9, 0], pil[d9])

@@ -31,6 +31,36 @@ unsigned long long cmp_sincos(const float* p, unsigned n) {
   }
   return bad;
 }
+unsigned long long cmp_wraps(const float* p, unsigned n) {
+  unsigned long long bad = 0;
+  for (unsigned i = 0; i < n; ++i) {
+    float a = p[i];
+    if ((double)a >= RFM_K_2PI) a = (float)fmod((double)a, RFM_K_2PI);   // FmDecode.cpp:404-409
+    while (a < 0.0f) a = (float)(a + RFM_K_2PI);
+    bad += rfm::f2u(rfm::rfm_wrap_demod(p[i])) != rfm::f2u(a);
+    float b = p[i];
+    if (b > RFM_K_2PI) b = (float)(b - RFM_K_2PI);                        // FmDecode.cpp:203-205
+    if (p[i] > 0.0f) bad += rfm::f2u(rfm::rfm_wrap_pilot(p[i])) != rfm::f2u(b);
+  }
+  return bad;
+}
+unsigned long long cmp_sincos_generic(const float* p, unsigned n) {
+  unsigned long long bad = 0;
+  for (unsigned i = 0; i < n; ++i) {
+    float s, c; rfm::rfm_sincos_generic(p[i], &s, &c);
+    bad += rfm::f2u(s) != rfm::f2u((float)sin((double)p[i]));
+    bad += rfm::f2u(c) != rfm::f2u((float)cos((double)p[i]));
+  }
+  return bad;
+}
+unsigned long long cmp_atan2f_generic(const float* y, const float* x, unsigned n) {
+  unsigned long long bad = 0;
+  for (unsigned i = 0; i < n; ++i) {
+    float a = rfm::rfm_atan2f_generic(y[i], x[i]), b = atan2f(y[i], x[i]);
+    bad += rfm::f2u(a) != rfm::f2u(b) && !(a != a && b != b);
+  }
+  return bad;
+}
 unsigned long long cmp_fmod(const float* p, unsigned n) {
   unsigned long long bad = 0;
   const float twopif = (float)RFM_K_2PI;
@@ -54,7 +84,7 @@ def shim(tmp_path_factory):
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++",
                            "-I", os.path.join(ROOT, "pvr.rtl.radiofm_b200", "csrc"), str(src), "-o", str(so), "-lm"])
     L = C.CDLL(str(so))
-    for f in (L.cmp_atan2f, L.cmp_sincos, L.cmp_fmod):
+    for f in (L.cmp_atan2f, L.cmp_sincos, L.cmp_fmod, L.cmp_wraps, L.cmp_sincos_generic, L.cmp_atan2f_generic):
         f.restype = C.c_ulonglong
     return L
 
@@ -75,9 +105,13 @@ def test_atan2f_bit_exact_vs_glibc(shim):
     y = np.concatenate([bits.view(np.float32), (bits | 0x80000000).view(np.float32)])
     x = np.ones_like(y)
     assert shim.cmp_atan2f(_p(y), _p(x), y.size) == 0
-    sp = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, 1e-45, 3e38], dtype=np.float32)
+    sp = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, 1e-45, 3e38, 1e-39, 2e-20, 5e19], dtype=np.float32)
     yy, xx = [np.ascontiguousarray(v.ravel()) for v in np.meshgrid(sp, sp)]
     assert shim.cmp_atan2f(_p(yy), _p(xx), yy.size) == 0
+    assert shim.cmp_atan2f_generic(_p(yy), _p(xx), yy.size) == 0
+    y = rng.standard_normal(n).astype(np.float32)
+    x = rng.standard_normal(n).astype(np.float32)
+    assert shim.cmp_atan2f_generic(_p(y), _p(x), n) == 0
 
 
 def test_sincos_is_rounded_double_sincos(shim):
@@ -85,8 +119,33 @@ def test_sincos_is_rounded_double_sincos(shim):
     n = 8_000_000
     p = (rng.random(n) * 6.6 - 0.2).astype(np.float32)          # the PLL phases live in [0, 2 pi]
     assert shim.cmp_sincos(_p(p), n) == 0
-    p = (rng.standard_normal(n) * 300.0).astype(np.float32)     # far outside, still exact
+    p = (rng.standard_normal(n) * 300.0).astype(np.float32)     # far outside (generic path), still exact
     assert shim.cmp_sincos(_p(p), n) == 0
+    p = (rng.random(n) * 32.0 - 16.0).astype(np.float32)
+    assert shim.cmp_sincos_generic(_p(p), n) == 0
+    # the floats next to k * pi/2 (worst cases of the argument reduction) and the zeros
+    k = np.arange(-10, 11, dtype=np.float64) * (np.pi / 2)
+    near = np.concatenate([np.nextafter(k.astype(np.float32), np.float32(s)) for s in (-100, 100)] + [k.astype(np.float32),
+                          np.array([0.0, -0.0], dtype=np.float32)])
+    assert shim.cmp_sincos(_p(np.ascontiguousarray(near)), near.size) == 0
+
+
+def test_phase_wraps_equal_the_double_expressions(shim):
+    """tools/exhaustive_math.cpp enumerates every float of the domain; here a dense random + boundary subset."""
+    rng = np.random.default_rng(4)
+    n = 4_000_000
+    p = (rng.random(n) * 18.4 - 6.0).astype(np.float32)
+    assert shim.cmp_wraps(_p(p), n) == 0
+    two_pi = np.float32(6.2831855)
+    edge = [two_pi]
+    for _ in range(64):
+        edge.append(np.nextafter(edge[-1], np.float32(100)))
+    lo = [np.float32(6.283185)]
+    for _ in range(64):
+        lo.append(np.nextafter(lo[-1], np.float32(-100)))
+    tiny = -np.float32(2.0) ** -np.arange(1, 140, dtype=np.float32)
+    e = np.ascontiguousarray(np.concatenate([np.array(edge + lo, dtype=np.float32), tiny, -np.array(edge, dtype=np.float32) + 1]))
+    assert shim.cmp_wraps(_p(e), e.size) == 0
 
 
 def test_fmod_helpers(shim):
