@@ -88,14 +88,22 @@ RFM_API int rfm_decoder_process_u8(rfm_decoder* d, const uint8_t* iq, uint32_t n
 RFM_API int rfm_decoder_process_cf32(rfm_decoder* d, const float* iq, uint32_t n, float* audio,
                                      size_t audio_stride, uint32_t* n_audio_floats);
 
-/* Same with device-resident buffers; work is enqueued on `cuda_stream` (cudaStream_t) and the call
- * returns without synchronising.  iq_stride is in samples per stream row. */
+/* Same with device-resident buffers.  The call only ENQUEUES the block: it is ordered after everything already
+ * submitted to `cuda_stream` (cudaStream_t), runs on the decoder's own streams (so that consecutive blocks
+ * pipeline: the PLL lanes of block k+1 overlap the FIR stages of block k) and returns at once.  The caller
+ * orders its own work after the results with rfm_decoder_wait(), or blocks with rfm_decoder_synchronize();
+ * d_iq must stay untouched until then.  iq_stride is in samples per stream row; d_audio rows must be 8-byte
+ * aligned (even audio_stride). */
 RFM_API int rfm_decoder_process_u8_device(rfm_decoder* d, const uint8_t* d_iq, size_t iq_stride, uint32_t n,
                                           float* d_audio, size_t audio_stride, uint32_t* n_audio_floats,
                                           void* cuda_stream);
 RFM_API int rfm_decoder_process_cf32_device(rfm_decoder* d, const float* d_iq, size_t iq_stride, uint32_t n,
                                             float* d_audio, size_t audio_stride, uint32_t* n_audio_floats,
                                             void* cuda_stream);
+
+/* Make `cuda_stream` wait for every block enqueued so far (no host blocking) / block the host until done. */
+RFM_API int rfm_decoder_wait(rfm_decoder* d, void* cuda_stream);
+RFM_API int rfm_decoder_synchronize(rfm_decoder* d);
 
 /* RDS output of cRDSRxSignalProcessor (RDSProcess.cpp:168 ProcessNewRdsBit sequence, :312,355
  * DecodeRDS(uint16_t[4]) groups).  Bits are the differentially decoded data bits in arrival order.

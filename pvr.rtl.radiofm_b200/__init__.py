@@ -42,7 +42,8 @@ class RfmStreamStatus(C.Structure):
 EXPORTED_SYMBOLS = (
     "rfm_last_error", "rfm_version", "rfm_launch_count", "rfm_config_default", "rfm_decoder_create",
     "rfm_decoder_destroy", "rfm_decoder_reset", "rfm_decoder_max_audio_floats", "rfm_decoder_process_u8",
-    "rfm_decoder_process_cf32", "rfm_decoder_process_u8_device", "rfm_decoder_process_cf32_device",
+    "rfm_decoder_process_cf32", "rfm_decoder_process_u8_device", "rfm_decoder_process_cf32_device", "rfm_decoder_wait",
+    "rfm_decoder_synchronize",
     "rfm_decoder_rds_take_groups", "rfm_decoder_rds_take_bits", "rfm_decoder_get_status",
     "rfm_decoder_constants", "rfm_decoder_table", "rfm_plan_constants", "rfm_plan_table", "rfm_decoder_set_profiling",
     "rfm_decoder_profile_read", "rfm_decoder_tap", "rfm_rdssync_create",
@@ -89,6 +90,8 @@ def lib():
                                                     C.c_size_t, _u32p, C.c_void_p]
         L.rfm_decoder_process_cf32_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p,
                                                       C.c_size_t, _u32p, C.c_void_p]
+        L.rfm_decoder_wait.argtypes = [C.c_void_p, C.c_void_p]
+        L.rfm_decoder_synchronize.argtypes = [C.c_void_p]
         L.rfm_decoder_rds_take_groups.argtypes = [C.c_void_p, C.c_uint32, _u16p, C.c_uint32, _u32p]
         L.rfm_decoder_rds_take_bits.argtypes = [C.c_void_p, C.c_uint32, _u8p, C.c_uint32, _u32p]
         L.rfm_decoder_get_status.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(RfmStreamStatus)]
@@ -218,6 +221,13 @@ class FmDecoderBatch:
                                                      C.c_void_p(d_audio_ptr), audio_stride, C.byref(k),
                                                      C.c_void_p(cuda_stream)))
         return int(k.value)
+
+    def wait(self, cuda_stream: int = 0):
+        """Order `cuda_stream` after every block enqueued so far (device entry points only enqueue)."""
+        _check(lib().rfm_decoder_wait(self._h, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        _check(lib().rfm_decoder_synchronize(self._h))
 
     # ---- RDS / telemetry ----
     def take_groups(self, stream: int = 0, max_groups: int = 4096) -> np.ndarray:

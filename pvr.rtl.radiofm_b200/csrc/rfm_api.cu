@@ -1,14 +1,16 @@
 // rfm_api.cu -- C ABI (include/radiofm_b200.h) over the sm_100a kernels: decoder handle, HBM buffers,
 // per-block launch schedule, stream-group pipelining, RDS bit drain.
 //
-// Execution model.  One decoder = n_streams independent IQ streams processed in lock step.  The
-// streams are split into G groups; each group owns a full set of V buffers and a CUDA stream, and runs
-// the per-block kernel chain
-//     front -> bb_lanes -> { resample -> lp29 -> audio_tail } , { halfband* -> rds lp -> rds pll ->
-//     matched filter -> slicer } -> tails
-// The chains of different groups overlap on the device, so the latency-bound one-lane-per-stream
-// kernels (PLLs: nonlinear recurrences that cannot be parallelised in time) of one group hide behind
-// the throughput-bound FIR kernels of the others.
+// Execution model.  One decoder = n_streams independent IQ streams processed in lock step, split into G groups
+// (G = 1 unless asked otherwise; the host-pointer entry points use groups to overlap H2D / compute / D2H).
+// Each group owns two CUDA streams and runs every block as a two-stage software pipeline:
+//     stage A (stream sA):  if_level, front (u8 -> tune -> FIR / ds), bb_lanes (demod PLL || pilot PLL)
+//     stage B (stream sB):  { resample -> lp29 -> audio_tail }, { halfband* -> rds lp -> rds pll -> matched
+//                           filter -> slicer }, tails
+// Stage A of block k+1 runs while stage B of block k is still in flight: the one-lane-per-stream PLL kernel
+// (nonlinear recurrences, latency-bound, 1-2 warps per SM) hides behind the throughput-bound FIR kernels.
+// What stage A hands to stage B (baseband / L-R rows, stereo flag) is double-buffered by block parity; the
+// NCO-oscillator table of the RDS mixer (identical for all streams) is produced one block ahead on its own stream.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -82,10 +84,11 @@ struct Group
 {
   unsigned s0 = 0, S = 0;
   ProfSlot prof[kMaxProfKinds];
-  cudaStream_t stream = nullptr;
-  cudaEvent_t done = nullptr;
+  cudaStream_t sA = nullptr, sB = nullptr;
+  cudaEvent_t ev_lanes[2] = {nullptr, nullptr}; // stage A of the block with this parity finished
+  cudaEvent_t ev_rest[2] = {nullptr, nullptr};  // stage B ...
   DevBuf<cf32> tail, z;
-  DevBuf<float> bbV, rawV;
+  DevBuf<float> bbV[2], rawV[2];
   DevBuf<cf32> hbV[kMaxDecStages]; // input V buffer of stage k (k >= 1); stage 0 reads bbV x oscV
   DevBuf<cf32> rlpV, rlp_out;
   DevBuf<float> mfV, mf_out;
@@ -111,16 +114,18 @@ struct rfm_decoder
   // plan tables on the device
   DevBuf<float> d_lut, d_tuner, d_in_coeff, d_a_coeff, d_lp_coef, d_rlp_coef, d_mf_coef;
   DevBuf<float> d_hb[kMaxDecStages];
-  DevBuf<cf32> oscV;
+  DevBuf<cf32> oscV[2];
   DevBuf<float> osc1;
+  cudaStream_t s_osc = nullptr;
+  cudaEvent_t ev_osc[2] = {nullptr, nullptr};
+  uint64_t block_index = 0; // blocks enqueued so far; parity selects the double buffers
   std::vector<Group> groups;
   bool profiling = false;
   const char* prof_names[kMaxProfKinds] = {nullptr};
   double prof_ms[kMaxProfKinds] = {0};
   uint64_t prof_count[kMaxProfKinds] = {0};
   ProfSlot main_prof[kMaxProfKinds];
-  cudaStream_t main_stream = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_osc = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // lock-step state (identical for every stream)
   unsigned tuner_idx = 0, in_pos = 0;
   float a_pos = 0.0f;
@@ -148,28 +153,38 @@ void FreeDecoder(rfm_decoder* d)
   cudaSetDevice(d->device);
   for (auto& g : d->groups)
   {
-    if (g.stream)
-      cudaStreamSynchronize(g.stream);
-    g.tail.Free(); g.z.Free(); g.bbV.Free(); g.rawV.Free();
+    for (cudaStream_t st : {g.sA, g.sB})
+      if (st)
+        cudaStreamSynchronize(st);
+    g.tail.Free(); g.z.Free();
+    for (int b = 0; b < 2; ++b)
+    {
+      g.bbV[b].Free();
+      g.rawV[b].Free();
+    }
     for (auto& b : g.hbV) b.Free();
     g.rlpV.Free(); g.rlp_out.Free(); g.mfV.Free(); g.mf_out.Free(); g.bits.Free(); g.bit_count.Free();
     g.lpS.Free(); g.lpM.Free(); g.fS.Free(); g.fM.Free(); g.state.Free(); g.in_stage.Free(); g.audio_stage.Free();
     ProfFree(g.prof);
-    if (g.done)
-      cudaEventDestroy(g.done);
-    if (g.stream)
-      cudaStreamDestroy(g.stream);
+    for (cudaEvent_t e : {g.ev_lanes[0], g.ev_lanes[1], g.ev_rest[0], g.ev_rest[1]})
+      if (e)
+        cudaEventDestroy(e);
+    for (cudaStream_t st : {g.sA, g.sB})
+      if (st)
+        cudaStreamDestroy(st);
   }
   d->d_lut.Free(); d->d_tuner.Free(); d->d_in_coeff.Free(); d->d_a_coeff.Free(); d->d_lp_coef.Free();
   d->d_rlp_coef.Free(); d->d_mf_coef.Free();
   for (auto& b : d->d_hb) b.Free();
-  d->oscV.Free(); d->osc1.Free();
+  if (d->s_osc)
+    cudaStreamSynchronize(d->s_osc);
+  d->oscV[0].Free(); d->oscV[1].Free(); d->osc1.Free();
   ProfFree(d->main_prof);
-  for (cudaEvent_t e : {d->ev_fork, d->ev_osc, d->ev_join})
+  for (cudaEvent_t e : {d->ev_fork, d->ev_osc[0], d->ev_osc[1], d->ev_join})
     if (e)
       cudaEventDestroy(e);
-  if (d->main_stream)
-    cudaStreamDestroy(d->main_stream);
+  if (d->s_osc)
+    cudaStreamDestroy(d->s_osc);
   delete d;
 }
 
@@ -272,7 +287,7 @@ cudaError_t ResetGroupState(rfm_decoder* d, Group& g, bool initial)
   if (e != cudaSuccess)
     return e;
   auto zero = [&](int f) { std::fill(st.begin() + (size_t)f * S, st.begin() + (size_t)(f + 1) * S, 0.0f); };
-  zero(SF_STEREO); zero(SF_IF_LEVEL); zero(SF_BB_MEAN); zero(SF_BB_LEVEL); zero(SF_DEMOD_DC);
+  zero(SF_STEREO); zero(SF_STEREO1); zero(SF_IF_LEVEL); zero(SF_BB_MEAN); zero(SF_BB_LEVEL); zero(SF_DEMOD_DC);
   zero(SF_DEMOD_INCR); zero(SF_DEMOD_PHASE);
   zero(SF_RPLL_PHASE); zero(SF_RPLL_FREQ); zero(SF_RSYNC_W1); zero(SF_RSYNC_W2); zero(SF_RS_LASTSYNC);
   zero(SF_RS_LASTSLOPE); zero(SF_RS_LASTDATA); zero(SF_RS_LASTBIT);
@@ -298,7 +313,7 @@ int DrainBits(rfm_decoder* d)
     return RFM_OK;
   for (auto& g : d->groups)
   {
-    RFM_CUDA(cudaStreamSynchronize(g.stream));
+    RFM_CUDA(cudaStreamSynchronize(g.sB));
     d->h_counts.resize(g.S);
     RFM_CUDA(cudaMemcpy(d->h_counts.data(), g.bit_count.p, g.S * sizeof(unsigned), cudaMemcpyDeviceToHost));
     unsigned mx = 0;
@@ -362,39 +377,55 @@ int PlanBlock(const rfm_decoder* d, unsigned n, BlockGeom* g)
   return RFM_OK;
 }
 
-// Enqueue the whole per-block chain of one group on its stream.
-void EnqueueGroup(rfm_decoder* d, Group& g, const void* d_in, size_t in_stride, bool u8, const BlockGeom& bg,
-                  float* d_audio, size_t audio_stride)
+// Stage A of one block for one group (stream sA): IF meter, front end, history hand-over, PLL lanes.
+void EnqueueStageA(rfm_decoder* d, Group& g, const void* d_in, size_t in_stride, bool u8, const BlockGeom& bg,
+                   unsigned par)
 {
   const DecoderPlan& p = d->plan;
-  cudaStream_t st = g.stream;
+  cudaStream_t st = g.sA;
   const unsigned S = g.S;
   const unsigned a_hist = p.a_order;
-  const unsigned lp_taps = (unsigned)p.lp_coef.size(), rlp_taps = (unsigned)p.rlp_coef.size();
-  const unsigned mf_taps = (unsigned)p.mf_coef.size();
-  const unsigned nst = (unsigned)p.rds_stages.size();
 
   FrontParams fp;
   fp.in = d_in; fp.in_stride = in_stride; fp.n = bg.n; fp.S = S; fp.order = p.in_order; fp.ds = p.downsample;
   fp.p0 = d->in_pos; fp.nout = bg.nb; fp.idx0 = d->tuner_idx; fp.lut = d->d_lut.p; fp.tuner = d->d_tuner.p;
   fp.coeff = d->d_in_coeff.p; fp.tail = g.tail.p; fp.z = g.z.p; fp.z_stride = d->z_stride;
+  RFM_PROF(g.prof, "k_if_level", st, launch_if_level(fp, g.state.p, u8, st));
   RFM_PROF(g.prof, "k_front", st, launch_front(fp, u8, st));
+  RFM_PROF(g.prof, "k_front_tail", st, launch_front_tail(fp, u8, st));
+
+  // history of the baseband / L-R rows: last a_hist samples of the previous block (other parity) -> head of this one
+  TailParams tp;
+  tp.count = 2;
+  tp.d[0] = {g.bbV[par ^ 1u].p, g.bbV[par].p, d->a_stride * sizeof(float), a_hist, d->last_nb, 4, S};
+  tp.d[1] = {g.rawV[par ^ 1u].p, g.rawV[par].p, d->a_stride * sizeof(float), a_hist, d->last_nb, 4, S};
+  RFM_PROF(g.prof, "k_tails", st, launch_tails(tp, S, st));
 
   LanesParams lp;
   lp.z = g.z.p; lp.z_stride = d->z_stride; lp.nb = bg.nb; lp.S = S; lp.state = g.state.p;
   lp.demod = {p.demod_gain, p.nco_lo, p.nco_hi, p.pll_alpha, p.pll_beta};
   lp.pilot = {p.pilot.minfreq, p.pilot.maxfreq, p.pilot.b0, p.pilot.a1, p.pilot.a2, p.pilot.lb0, p.pilot.lb1,
               p.pilot.minsignal, p.pilot.lock_delay};
-  lp.bbV = g.bbV.p; lp.rawV = g.rawV.p; lp.a_stride = d->a_stride; lp.a_hist = a_hist;
-  RFM_PROF(g.prof, "k_if_level", st, launch_if_level(fp, g.state.p, u8, st));
+  lp.bbV = g.bbV[par].p; lp.rawV = g.rawV[par].p; lp.a_stride = d->a_stride; lp.a_hist = a_hist; lp.parity = par;
   RFM_PROF(g.prof, "k_bb_lanes", st, launch_bb_lanes(lp, st));
-  RFM_PROF(g.prof, "k_front_tail", st, launch_front_tail(fp, u8, st)); // after the lanes kernel: its IF meter reads the same input block
-  g_launches += 4;
+  g_launches += 5;
+}
+
+// Stage B of one block for one group (stream sB): audio branch, RDS branch, history carry of its own buffers.
+void EnqueueStageB(rfm_decoder* d, Group& g, const BlockGeom& bg, unsigned par, float* d_audio, size_t audio_stride)
+{
+  const DecoderPlan& p = d->plan;
+  cudaStream_t st = g.sB;
+  const unsigned S = g.S;
+  const unsigned a_hist = p.a_order;
+  const unsigned lp_taps = (unsigned)p.lp_coef.size(), rlp_taps = (unsigned)p.rlp_coef.size();
+  const unsigned mf_taps = (unsigned)p.mf_coef.size();
+  const unsigned nst = (unsigned)p.rds_stages.size();
 
   // ---- audio branch
   ResampleParams rp;
-  rp.bbV = g.bbV.p; rp.rawV = g.rawV.p; rp.a_stride = d->a_stride; rp.order = p.a_order; rp.nb = bg.nb; rp.S = S;
-  rp.na = bg.na; rp.pos_frac = d->a_pos; rp.pstep = p.a_pstep; rp.coeff = d->d_a_coeff.p; rp.lpS = g.lpS.p;
+  rp.bbV = g.bbV[par].p; rp.rawV = g.rawV[par].p; rp.a_stride = d->a_stride; rp.order = p.a_order; rp.nb = bg.nb;
+  rp.S = S; rp.na = bg.na; rp.pos_frac = d->a_pos; rp.pstep = p.a_pstep; rp.coeff = d->d_a_coeff.p; rp.lpS = g.lpS.p;
   rp.lpM = g.lpM.p; rp.lp_stride = d->lp_stride; rp.lp_hist = lp_taps - 1;
   RFM_PROF(g.prof, "k_resample", st, launch_resample(rp, st));
 
@@ -407,7 +438,7 @@ void EnqueueGroup(rfm_decoder* d, Group& g, const void* d_in, size_t in_stride, 
   AudioTailParams at;
   at.inS = g.fS.p; at.inM = g.fM.p; at.in_stride = d->na_max; at.na = bg.na; at.S = S; at.state = g.state.p;
   at.de_alpha = p.de_alpha; at.notch = {p.notch.A1, p.notch.A2, p.notch.B0, p.notch.B1, p.notch.B2};
-  at.audio = d_audio; at.audio_stride = audio_stride;
+  at.audio = d_audio; at.audio_stride = audio_stride; at.parity = par;
   RFM_PROF(g.prof, "k_audio_tail", st, launch_audio_tail(at, st));
   g_launches += 3;
 
@@ -420,8 +451,8 @@ void EnqueueGroup(rfm_decoder* d, Group& g, const void* d_in, size_t in_stride, 
     hp.mix = (k == 0);
     hp.in = (k == 0) ? nullptr : g.hbV[k].p;
     hp.in_stride = d->hb_stride[k];
-    hp.bbV = g.bbV.p; hp.a_stride = d->a_stride; hp.a_hist = a_hist;
-    hp.oscV = d->oscV.p; hp.osc_hist = d->osc_hist;
+    hp.bbV = g.bbV[par].p; hp.a_stride = d->a_stride; hp.a_hist = a_hist;
+    hp.oscV = d->oscV[par].p; hp.osc_hist = d->osc_hist;
     hp.kind = hs.len == 3 ? 2 : (hs.fixed11 ? 1 : 0);
     hp.len = (unsigned)hs.len; hp.n_in = bg.hb_n[k]; hp.S = S; hp.h = d->d_hb[k].p;
     if (k + 1 < nst)
@@ -461,16 +492,14 @@ void EnqueueGroup(rfm_decoder* d, Group& g, const void* d_in, size_t in_stride, 
   RFM_PROF(g.prof, "k_rds_slice", st, launch_rds_slice(sp, st));
   g_launches += 4;
 
-  // ---- history carry of every V buffer of this group
+  // ---- in-place history carry of the stage-B buffers
   TailParams tp;
   tp.count = 0;
   auto add = [&](void* base, size_t stride_elems, unsigned hist, unsigned n, unsigned elem) {
     if (hist == 0)
       return;
-    tp.d[tp.count++] = {base, stride_elems * elem, hist, n, elem, S};
+    tp.d[tp.count++] = {base, base, stride_elems * elem, hist, n, elem, S};
   };
-  add(g.bbV.p, d->a_stride, a_hist, bg.nb, 4);
-  add(g.rawV.p, d->a_stride, a_hist, bg.nb, 4);
   add(g.lpS.p, d->lp_stride, lp_taps - 1, bg.na, 4);
   add(g.lpM.p, d->lp_stride, lp_taps - 1, bg.na, 4);
   for (unsigned k = 1; k < nst; ++k)
@@ -481,7 +510,8 @@ void EnqueueGroup(rfm_decoder* d, Group& g, const void* d_in, size_t in_stride, 
   ++g_launches;
 }
 
-// One block for all groups.  Inputs / outputs are device pointers for the whole batch.
+// One block for all groups.  Inputs / outputs are device pointers for the whole batch (host pointers when
+// host_staged).  Work is only enqueued; the device entry points return without waiting (rfm_decoder_wait).
 int ProcessDevice(rfm_decoder* d, const void* d_in, size_t in_stride, bool u8, unsigned n, float* d_audio,
                   size_t audio_stride, uint32_t* n_audio_floats, cudaStream_t user, bool host_staged)
 {
@@ -514,58 +544,59 @@ int ProcessDevice(rfm_decoder* d, const void* d_in, size_t in_stride, bool u8, u
       return rc;
   }
 
-  cudaStream_t base = d->main_stream;
+  const unsigned par = (unsigned)(d->block_index & 1u);
   if (!host_staged)
+    RFM_CUDA(cudaEventRecord(d->ev_fork, user)); // stage A must see what is already enqueued on the caller's stream
+
+  // NCO oscillator table of this block (shared by all streams), on its own stream: it only depends on the
+  // sample count, so it runs ahead of the data.
+  for (auto& g : d->groups)
+    RFM_CUDA(cudaStreamWaitEvent(d->s_osc, g.ev_rest[par], 0)); // readers of oscV[par] two blocks ago
   {
-    // fork: internal work must see everything already enqueued on the user's stream
-    RFM_CUDA(cudaEventRecord(d->ev_fork, user));
-    RFM_CUDA(cudaStreamWaitEvent(base, d->ev_fork, 0));
+    TailParams tp;
+    tp.count = 1;
+    tp.d[0] = {d->oscV[par ^ 1u].p, d->oscV[par].p, 0, d->osc_hist, d->last_nb, 8, 1};
+    RFM_PROF(d->main_prof, "k_tails", d->s_osc, launch_tails(tp, 1, d->s_osc));
+    OscParams op;
+    op.oscV = d->oscV[par].p; op.osc_hist = d->osc_hist; op.nb = bg.nb; op.osc1 = d->osc1.p;
+    op.cosv = d->plan.rds_osc.cosv; op.sinv = d->plan.rds_osc.sinv;
+    RFM_PROF(d->main_prof, "k_osc", d->s_osc, launch_osc(op, d->s_osc));
+    g_launches += 2;
+    RFM_CUDA(cudaEventRecord(d->ev_osc[par], d->s_osc));
   }
-  // NCO oscillator table for this block (shared by all streams)
-  OscParams op;
-  op.oscV = d->oscV.p; op.osc_hist = d->osc_hist; op.nb = bg.nb; op.osc1 = d->osc1.p;
-  op.cosv = d->plan.rds_osc.cosv; op.sinv = d->plan.rds_osc.sinv;
-  RFM_PROF(d->main_prof, "k_osc", base, launch_osc(op, base));
-  ++g_launches;
-  RFM_CUDA(cudaEventRecord(d->ev_osc, base));
 
   const size_t esz = u8 ? 2 : 8;
   for (auto& g : d->groups)
   {
-    RFM_CUDA(cudaStreamWaitEvent(g.stream, d->ev_osc, 0));
     const unsigned char* in_g = reinterpret_cast<const unsigned char*>(d_in) + (size_t)g.s0 * in_stride * esz;
     float* audio_g = d_audio + (size_t)g.s0 * audio_stride;
     const void* in_dev = in_g;
     float* audio_dev = audio_g;
     size_t in_stride_dev = in_stride, audio_stride_dev = audio_stride;
+    // ---- stage A
+    if (!host_staged)
+      RFM_CUDA(cudaStreamWaitEvent(g.sA, d->ev_fork, 0));
+    RFM_CUDA(cudaStreamWaitEvent(g.sA, g.ev_rest[par], 0)); // stage B of block k-2 has released the parity buffers
     if (host_staged)
     {
-      // host pointers: copy this group's rows in, run, copy its audio out, all on the group's stream
       RFM_CUDA(cudaMemcpy2DAsync(g.in_stage.p, (size_t)d->maxn * esz, in_g, in_stride * esz, (size_t)n * esz, g.S,
-                                 cudaMemcpyHostToDevice, g.stream));
+                                 cudaMemcpyHostToDevice, g.sA));
       in_dev = g.in_stage.p;
       in_stride_dev = d->maxn;
       audio_dev = g.audio_stage.p;
       audio_stride_dev = d->audio_cap;
     }
-    EnqueueGroup(d, g, in_dev, in_stride_dev, u8, bg, audio_dev, audio_stride_dev);
+    EnqueueStageA(d, g, in_dev, in_stride_dev, u8, bg, par);
+    RFM_CUDA(cudaEventRecord(g.ev_lanes[par], g.sA));
+    // ---- stage B
+    RFM_CUDA(cudaStreamWaitEvent(g.sB, g.ev_lanes[par], 0));
+    RFM_CUDA(cudaStreamWaitEvent(g.sB, d->ev_osc[par], 0));
+    EnqueueStageB(d, g, bg, par, audio_dev, audio_stride_dev);
     if (host_staged)
       RFM_CUDA(cudaMemcpy2DAsync(audio_g, audio_stride * sizeof(float), g.audio_stage.p,
                                  (size_t)d->audio_cap * sizeof(float), (size_t)2 * bg.na * sizeof(float), g.S,
-                                 cudaMemcpyDeviceToHost, g.stream));
-    RFM_CUDA(cudaEventRecord(g.done, g.stream));
-    RFM_CUDA(cudaStreamWaitEvent(base, g.done, 0));
-  }
-  // carry the oscillator table history once every group has consumed it
-  TailParams tp;
-  tp.count = 1;
-  tp.d[0] = {d->oscV.p, 0, d->osc_hist, bg.nb, 8, 1};
-  RFM_PROF(d->main_prof, "k_tails", base, launch_tails(tp, 1, base));
-  ++g_launches;
-  if (!host_staged)
-  {
-    RFM_CUDA(cudaEventRecord(d->ev_join, base));
-    RFM_CUDA(cudaStreamWaitEvent(user, d->ev_join, 0));
+                                 cudaMemcpyDeviceToHost, g.sB));
+    RFM_CUDA(cudaEventRecord(g.ev_rest[par], g.sB));
   }
   RFM_CUDA(cudaGetLastError());
 
@@ -579,10 +610,15 @@ int ProcessDevice(rfm_decoder* d, const void* d_in, size_t in_stride, bool u8, u
   d->pending_bits_bound += worst_bits;
   d->last_n = n; d->last_nb = bg.nb; d->last_na = bg.na; d->last_nr = bg.nr;
   memcpy(d->last_hb_n, bg.hb_n, sizeof(bg.hb_n));
+  d->block_index += 1;
   if (n_audio_floats)
     *n_audio_floats = 2 * bg.na;
   if (host_staged)
-    RFM_CUDA(cudaStreamSynchronize(base));
+    for (auto& g : d->groups)
+    {
+      RFM_CUDA(cudaStreamSynchronize(g.sA));
+      RFM_CUDA(cudaStreamSynchronize(g.sB));
+    }
   return RFM_OK;
 }
 
@@ -601,9 +637,10 @@ int SyncAll(rfm_decoder* d)
 {
   RFM_CUDA(cudaSetDevice(d->device));
   for (auto& g : d->groups)
-    if (g.stream)
-      RFM_CUDA(cudaStreamSynchronize(g.stream));
-  RFM_CUDA(cudaStreamSynchronize(d->main_stream));
+    for (cudaStream_t st : {g.sA, g.sB})
+      if (st)
+        RFM_CUDA(cudaStreamSynchronize(st));
+  RFM_CUDA(cudaStreamSynchronize(d->s_osc));
   return RFM_OK;
 }
 
@@ -715,19 +752,21 @@ int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out)
     else
       RFM_TRY(d->d_hb[k].Alloc(4));
   }
-  RFM_TRY(d->oscV.Alloc((size_t)d->osc_hist + d->nb_max));
+  RFM_TRY(d->oscV[0].Alloc((size_t)d->osc_hist + d->nb_max));
+  RFM_TRY(d->oscV[1].Alloc((size_t)d->osc_hist + d->nb_max));
   {
     const float one[2] = {1.0f, 0.0f}; // m_Osc1 initial unit vector, DownConvert.cpp:283-284
     RFM_TRY(Upload(d->osc1, one, 2));
   }
-  RFM_TRY(cudaStreamCreateWithFlags(&d->main_stream, cudaStreamNonBlocking));
+  RFM_TRY(cudaStreamCreateWithFlags(&d->s_osc, cudaStreamNonBlocking));
   RFM_TRY(cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming));
-  RFM_TRY(cudaEventCreateWithFlags(&d->ev_osc, cudaEventDisableTiming));
+  RFM_TRY(cudaEventCreateWithFlags(&d->ev_osc[0], cudaEventDisableTiming));
+  RFM_TRY(cudaEventCreateWithFlags(&d->ev_osc[1], cudaEventDisableTiming));
   RFM_TRY(cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming));
 
   unsigned G = cfg->n_groups;
   if (G == 0)
-    G = std::min(8u, std::max(1u, d->S / 256));
+    G = 1;
   G = std::min(G, d->S);
   d->groups.resize(G);
   const size_t esz_max = 8; // cf32 input
@@ -737,12 +776,20 @@ int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out)
     g.s0 = (unsigned)((uint64_t)d->S * gi / G);
     g.S = (unsigned)((uint64_t)d->S * (gi + 1) / G) - g.s0;
     const size_t S = g.S;
-    RFM_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
-    RFM_TRY(cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
+    RFM_TRY(cudaStreamCreateWithFlags(&g.sA, cudaStreamNonBlocking));
+    RFM_TRY(cudaStreamCreateWithFlags(&g.sB, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b)
+    {
+      RFM_TRY(cudaEventCreateWithFlags(&g.ev_lanes[b], cudaEventDisableTiming));
+      RFM_TRY(cudaEventCreateWithFlags(&g.ev_rest[b], cudaEventDisableTiming));
+    }
     RFM_TRY(g.tail.Alloc(S * p.in_order));
     RFM_TRY(g.z.Alloc(S * d->z_stride));
-    RFM_TRY(g.bbV.Alloc(S * d->a_stride));
-    RFM_TRY(g.rawV.Alloc(S * d->a_stride));
+    for (int b = 0; b < 2; ++b)
+    {
+      RFM_TRY(g.bbV[b].Alloc(S * d->a_stride));
+      RFM_TRY(g.rawV[b].Alloc(S * d->a_stride));
+    }
     for (size_t k = 1; k < p.rds_stages.size(); ++k)
       RFM_TRY(g.hbV[k].Alloc(S * d->hb_stride[k]));
     RFM_TRY(g.rlpV.Alloc(S * d->rlp_stride));
@@ -822,7 +869,7 @@ int rfm_decoder_process_u8(rfm_decoder* d, const uint8_t* iq, uint32_t n, float*
   int rc = EnsureStaging(d, true);
   if (rc != RFM_OK)
     return rc;
-  return ProcessDevice(d, iq, n, true, n, audio, audio_stride, n_audio_floats, d->main_stream, true);
+  return ProcessDevice(d, iq, n, true, n, audio, audio_stride, n_audio_floats, nullptr, true);
 }
 
 int rfm_decoder_process_cf32(rfm_decoder* d, const float* iq, uint32_t n, float* audio, size_t audio_stride,
@@ -834,7 +881,7 @@ int rfm_decoder_process_cf32(rfm_decoder* d, const float* iq, uint32_t n, float*
   int rc = EnsureStaging(d, false);
   if (rc != RFM_OK)
     return rc;
-  return ProcessDevice(d, iq, n, false, n, audio, audio_stride, n_audio_floats, d->main_stream, true);
+  return ProcessDevice(d, iq, n, false, n, audio, audio_stride, n_audio_floats, nullptr, true);
 }
 
 int rfm_decoder_process_u8_device(rfm_decoder* d, const uint8_t* d_iq, size_t iq_stride, uint32_t n, float* d_audio,
@@ -853,6 +900,28 @@ int rfm_decoder_process_cf32_device(rfm_decoder* d, const float* d_iq, size_t iq
     return Fail(RFM_ERR_INVALID, "bad argument");
   return ProcessDevice(d, d_iq, iq_stride, false, n, d_audio, audio_stride, n_audio_floats,
                        static_cast<cudaStream_t>(cuda_stream), false);
+}
+
+int rfm_decoder_wait(rfm_decoder* d, void* cuda_stream)
+{
+  if (!d)
+    return Fail(RFM_ERR_INVALID, "null decoder");
+  RFM_CUDA(cudaSetDevice(d->device));
+  cudaStream_t user = static_cast<cudaStream_t>(cuda_stream);
+  for (auto& g : d->groups)
+    for (cudaStream_t st : {g.sA, g.sB})
+    {
+      RFM_CUDA(cudaEventRecord(d->ev_join, st));
+      RFM_CUDA(cudaStreamWaitEvent(user, d->ev_join, 0));
+    }
+  return RFM_OK;
+}
+
+int rfm_decoder_synchronize(rfm_decoder* d)
+{
+  if (!d)
+    return Fail(RFM_ERR_INVALID, "null decoder");
+  return SyncAll(d);
 }
 
 int rfm_decoder_rds_take_groups(rfm_decoder* d, uint32_t stream, uint16_t* groups, uint32_t max_groups,
@@ -899,13 +968,13 @@ int rfm_decoder_get_status(rfm_decoder* d, uint32_t stream, rfm_stream_status* o
   unsigned ls = 0;
   Group* g = FindGroup(d, stream, &ls);
   RFM_CUDA(cudaSetDevice(d->device));
-  RFM_CUDA(cudaStreamSynchronize(g->stream));
-  RFM_CUDA(cudaStreamSynchronize(d->main_stream));
+  RFM_CUDA(cudaStreamSynchronize(g->sA));
+  RFM_CUDA(cudaStreamSynchronize(g->sB));
   float v[SF_COUNT];
   RFM_CUDA(cudaMemcpy2D(v, sizeof(float), g->state.p + ls, (size_t)g->S * sizeof(float), sizeof(float), SF_COUNT,
                         cudaMemcpyDeviceToHost));
   int stereo;
-  memcpy(&stereo, &v[SF_STEREO], 4);
+  memcpy(&stereo, &v[SF_STEREO + ((d->block_index + 1) & 1u)], 4); // parity of the last block
   out->stereo_detected = stereo;
   out->interface_level = v[SF_IF_LEVEL];
   out->baseband_level = v[SF_BB_LEVEL];
@@ -1050,11 +1119,12 @@ int rfm_decoder_tap(rfm_decoder* d, const char* name, uint32_t stream, float* ou
   Group* g = FindGroup(d, stream, &ls);
   const DecoderPlan& p = d->plan;
   const std::string nm(name);
+  const unsigned lastpar = (unsigned)((d->block_index + 1) & 1u);
   const void* src = nullptr;
   size_t cnt = 0; // floats
   if (nm == "demod_in") { src = g->z.p + (size_t)ls * d->z_stride; cnt = 2 * (size_t)d->last_nb; }
-  else if (nm == "baseband") { src = g->bbV.p + (size_t)ls * d->a_stride + p.a_order; cnt = d->last_nb; }
-  else if (nm == "rawstereo") { src = g->rawV.p + (size_t)ls * d->a_stride + p.a_order; cnt = d->last_nb; }
+  else if (nm == "baseband") { src = g->bbV[lastpar].p + (size_t)ls * d->a_stride + p.a_order; cnt = d->last_nb; }
+  else if (nm == "rawstereo") { src = g->rawV[lastpar].p + (size_t)ls * d->a_stride + p.a_order; cnt = d->last_nb; }
   else if (nm == "mono_rs") { src = g->lpM.p + (size_t)ls * d->lp_stride + p.lp_coef.size() - 1; cnt = d->last_na; }
   else if (nm == "stereo_rs") { src = g->lpS.p + (size_t)ls * d->lp_stride + p.lp_coef.size() - 1; cnt = d->last_na; }
   else if (nm == "lp_stereo") { src = g->fS.p + (size_t)ls * d->na_max; cnt = d->last_na; }

@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(64) k_bb_lanes(LanesParams p)
       else
         lock_cnt = 0;
       st[SF_PILOT_LOCKCNT * S + s] = __int_as_float(lock_cnt);
-      st[SF_STEREO * S + s] = __int_as_float(lock_cnt >= p.pilot.lock_delay ? 1 : 0);
+      st[(SF_STEREO + p.parity) * S + s] = __int_as_float(lock_cnt >= p.pilot.lock_delay ? 1 : 0);
       // baseband meters, FmDecode.cpp:439-442
       const float mean = divf(vsum, (float)p.nb);
       const float rms = sqrtf_rn(divf(vsumsq, (float)p.nb));
@@ -605,7 +605,7 @@ __global__ void __launch_bounds__(32) k_audio_tail(AudioTailParams p)
     de_re = st[SF_DE_RE * S + s]; de_im = st[SF_DE_IM * S + s];
     w1a = st[SF_NOTCH_W1A * S + s]; w2a = st[SF_NOTCH_W2A * S + s];
     w1b = st[SF_NOTCH_W1B * S + s]; w2b = st[SF_NOTCH_W2B * S + s];
-    stereo = __float_as_int(st[SF_STEREO * S + s]) != 0;
+    stereo = __float_as_int(st[(SF_STEREO + p.parity) * S + s]) != 0;
   }
   const float alpha = p.de_alpha;
   const float one_m = subf(1.0f, alpha);
@@ -958,7 +958,7 @@ void launch_rds_slice(const RdsSliceParams& p, cudaStream_t st)
 // history carry: row = [hist | n]  ->  first `hist` elements := last `hist` elements
 // ==================================================================================================
 template <typename T>
-__device__ __forceinline__ void tail_row(T* row, unsigned hist, unsigned n)
+__device__ __forceinline__ void tail_row(const T* row, T* dst, unsigned hist, unsigned n)
 {
   // hist <= 2 * blockDim.x (checked on the host); values are read before any is written, so the
   // overlapping case n < hist is handled too (memmove semantics).
@@ -970,9 +970,9 @@ __device__ __forceinline__ void tail_row(T* row, unsigned hist, unsigned n)
     v1 = row[n + b];
   __syncthreads();
   if (a < hist)
-    row[a] = v0;
+    dst[a] = v0;
   if (b < hist)
-    row[b] = v1;
+    dst[b] = v1;
 }
 
 __global__ void __launch_bounds__(256) k_tails(TailParams p)
@@ -980,11 +980,12 @@ __global__ void __launch_bounds__(256) k_tails(TailParams p)
   const TailDesc d = p.d[blockIdx.y];
   if (blockIdx.x >= d.rows)
     return;
-  unsigned char* row = reinterpret_cast<unsigned char*>(d.base) + (size_t)blockIdx.x * d.stride_bytes;
+  const unsigned char* row = reinterpret_cast<const unsigned char*>(d.base) + (size_t)blockIdx.x * d.stride_bytes;
+  unsigned char* dst = reinterpret_cast<unsigned char*>(d.dst) + (size_t)blockIdx.x * d.stride_bytes;
   if (d.elem == 8)
-    tail_row(reinterpret_cast<uint2*>(row), d.hist, d.n);
+    tail_row(reinterpret_cast<const uint2*>(row), reinterpret_cast<uint2*>(dst), d.hist, d.n);
   else
-    tail_row(reinterpret_cast<uint32_t*>(row), d.hist, d.n);
+    tail_row(reinterpret_cast<const uint32_t*>(row), reinterpret_cast<uint32_t*>(dst), d.hist, d.n);
 }
 
 void launch_tails(const TailParams& p, unsigned S, cudaStream_t st)

@@ -40,7 +40,8 @@ enum StateField
   SF_PILOT_X1,
   SF_PILOT_LEVEL,
   SF_PILOT_LOCKCNT, // int bits
-  SF_STEREO,        // int bits: m_StereoDetected of the last block
+  SF_STEREO,        // int bits: m_StereoDetected of the last block (even blocks)
+  SF_STEREO1,       // ... odd blocks (the lanes of block k+1 overlap the audio tail of block k)
   SF_DE_RE,
   SF_DE_IM,
   SF_NOTCH_W1A,
@@ -95,6 +96,7 @@ struct LanesParams
   float* rawV;             // same layout, pilot-demodulated L-R
   size_t a_stride;
   unsigned a_hist;
+  unsigned parity;         // selects SF_STEREO / SF_STEREO1
 };
 void launch_bb_lanes(const LanesParams& p, cudaStream_t st);
 
@@ -144,6 +146,7 @@ struct AudioTailParams
   BiquadDev notch;
   float* audio;            // [S][audio_stride] interleaved L,R
   size_t audio_stride;
+  unsigned parity;         // selects SF_STEREO / SF_STEREO1
 };
 void launch_audio_tail(const AudioTailParams& p, cudaStream_t st);
 
@@ -207,8 +210,9 @@ void launch_rds_slice(const RdsSliceParams& p, cudaStream_t st);
 // ---- history carry for V buffers -------------------------------------------------------------------------
 struct TailDesc
 {
-  void* base;
-  size_t stride_bytes;     // row stride
+  void* base;              // source rows: [hist | n]
+  void* dst;               // destination rows (== base for an in-place carry)
+  size_t stride_bytes;     // row stride (same for both)
   unsigned hist;           // elements of history
   unsigned n;              // new elements this block
   unsigned elem;           // element size in bytes (4 or 8)

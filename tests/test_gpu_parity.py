@@ -236,6 +236,7 @@ def test_device_pointer_entry_point(rfm, port):
             t_in = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(x, (S,) + x.shape))).cuda(non_blocking=False)
             t_out = torch.zeros((S, stride), dtype=torch.float32, device="cuda")
             k = d.process_u8_device(t_in.data_ptr(), blk, blk, t_out.data_ptr(), stride, st.cuda_stream)
+            d.wait(st.cuda_stream)   # the call only enqueues; order the read-back after the results
             out = t_out.cpu().numpy()
         a_o = o.process_u8(x)
         for s in range(S):
