@@ -221,7 +221,7 @@ def run_b200(args):
             step_device(i)
         dec.wait(stream.cuda_stream)
     barrier()
-    dec.set_profiling(True)
+    dec.set_profiling(not args.no_prof)
     launches0 = rfm.launch_count()
     clocks = ClockSampler(local)
     time.sleep(0.25)
@@ -263,6 +263,10 @@ def run_b200(args):
     # ---- e2e: host buffers through the public host-pointer entry point (its own decoder: stream groups overlap
     # the H2D copy of one group with the kernels / D2H of the others)
     import ctypes as C
+    if args.no_e2e:
+        if rank == 0:
+            print(json.dumps({"value": value, "ms_per_step": ms / K, "kernel_ms_per_step": roofline["kernel_ms_per_step"]}))
+        return
     dec.close()
     dec = rfm.FmDecoderBatch(FS, -0.15 * FS, downsample=DS, n_streams=S, max_block_len=BLK, device=local,
                              n_groups=args.host_groups)
@@ -317,6 +321,8 @@ def main():
     ap.add_argument("--host-groups", type=int, default=8)
     ap.add_argument("--resident-blocks", type=int, default=12)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-prof", action="store_true", help="do not bracket kernels with CUDA events (roofline leg off)")
+    ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

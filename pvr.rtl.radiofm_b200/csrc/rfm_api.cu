@@ -3,17 +3,20 @@
 //
 // Execution model.  One decoder = n_streams independent IQ streams processed in lock step, split into G groups
 // (G = 1 unless asked otherwise; the host-pointer entry points use groups to overlap H2D / compute / D2H).
-// Each group owns two CUDA streams and runs every block as a two-stage software pipeline:
-//     stage A (stream sA):  if_level, front (u8 -> tune -> FIR / ds), bb_lanes (demod PLL || pilot PLL)
+// Each group owns three CUDA streams and runs every block as a three-stage software pipeline:
+//     stage F (stream sF):  if_level, front (u8 -> tune -> FIR / ds)
+//     stage A (stream sA, high priority):  bb_lanes (demod PLL || pilot PLL)
 //     stage B (stream sB):  { resample -> lp29 -> audio_tail }, { halfband* -> rds lp -> rds pll -> matched
 //                           filter -> slicer }, tails
-// Stage A of block k+1 runs while stage B of block k is still in flight: the one-lane-per-stream PLL kernel
-// (nonlinear recurrences, latency-bound, 1-2 warps per SM) hides behind the throughput-bound FIR kernels.
-// What stage A hands to stage B (baseband / L-R rows, stereo flag) is double-buffered by block parity; the
-// NCO-oscillator table of the RDS mixer (identical for all streams) is produced one block ahead on its own stream.
+// While the lanes of block k run, the front end of block k+1 and stage B of block k-1 are in flight: the
+// one-lane-per-stream PLL kernel (nonlinear recurrences, latency-bound, 2 warps per SM) is the long pole and hides
+// the throughput-bound FIR kernels.  Everything handed from one stage to the next (decimated IQ, baseband / L-R
+// rows, stereo flag) is double-buffered by block parity; the NCO-oscillator table of the RDS mixer (identical for
+// all streams) is produced ahead on its own stream.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -84,10 +87,11 @@ struct Group
 {
   unsigned s0 = 0, S = 0;
   ProfSlot prof[kMaxProfKinds];
-  cudaStream_t sA = nullptr, sB = nullptr;
-  cudaEvent_t ev_lanes[2] = {nullptr, nullptr}; // stage A of the block with this parity finished
+  cudaStream_t sF = nullptr, sA = nullptr, sB = nullptr; // front / lanes / rest
+  cudaEvent_t ev_front[2] = {nullptr, nullptr}; // front end of the block with this parity finished
+  cudaEvent_t ev_lanes[2] = {nullptr, nullptr}; // PLL lanes ...
   cudaEvent_t ev_rest[2] = {nullptr, nullptr};  // stage B ...
-  DevBuf<cf32> tail, z;
+  DevBuf<cf32> tail, z[2];
   DevBuf<float> bbV[2], rawV[2];
   DevBuf<cf32> hbV[kMaxDecStages]; // input V buffer of stage k (k >= 1); stage 0 reads bbV x oscV
   DevBuf<cf32> rlpV, rlp_out;
@@ -153,10 +157,10 @@ void FreeDecoder(rfm_decoder* d)
   cudaSetDevice(d->device);
   for (auto& g : d->groups)
   {
-    for (cudaStream_t st : {g.sA, g.sB})
+    for (cudaStream_t st : {g.sF, g.sA, g.sB})
       if (st)
         cudaStreamSynchronize(st);
-    g.tail.Free(); g.z.Free();
+    g.tail.Free(); g.z[0].Free(); g.z[1].Free();
     for (int b = 0; b < 2; ++b)
     {
       g.bbV[b].Free();
@@ -166,10 +170,10 @@ void FreeDecoder(rfm_decoder* d)
     g.rlpV.Free(); g.rlp_out.Free(); g.mfV.Free(); g.mf_out.Free(); g.bits.Free(); g.bit_count.Free();
     g.lpS.Free(); g.lpM.Free(); g.fS.Free(); g.fM.Free(); g.state.Free(); g.in_stage.Free(); g.audio_stage.Free();
     ProfFree(g.prof);
-    for (cudaEvent_t e : {g.ev_lanes[0], g.ev_lanes[1], g.ev_rest[0], g.ev_rest[1]})
+    for (cudaEvent_t e : {g.ev_front[0], g.ev_front[1], g.ev_lanes[0], g.ev_lanes[1], g.ev_rest[0], g.ev_rest[1]})
       if (e)
         cudaEventDestroy(e);
-    for (cudaStream_t st : {g.sA, g.sB})
+    for (cudaStream_t st : {g.sF, g.sA, g.sB})
       if (st)
         cudaStreamDestroy(st);
   }
@@ -377,22 +381,38 @@ int PlanBlock(const rfm_decoder* d, unsigned n, BlockGeom* g)
   return RFM_OK;
 }
 
-// Stage A of one block for one group (stream sA): IF meter, front end, history hand-over, PLL lanes.
-void EnqueueStageA(rfm_decoder* d, Group& g, const void* d_in, size_t in_stride, bool u8, const BlockGeom& bg,
+// timing experiments only (results are wrong when a stage is skipped): RFM_DEBUG_SKIP=front,lanes,rest
+bool DebugSkip(const char* what)
+{
+  static const char* env = getenv("RFM_DEBUG_SKIP");
+  return env && strstr(env, what);
+}
+
+// Stage F of one block for one group (stream sF): IF meter, front end.
+void EnqueueStageF(rfm_decoder* d, Group& g, const void* d_in, size_t in_stride, bool u8, const BlockGeom& bg,
                    unsigned par)
+{
+  const DecoderPlan& p = d->plan;
+  cudaStream_t st = g.sF;
+  const unsigned S = g.S;
+
+  FrontParams fp;
+  fp.in = d_in; fp.in_stride = in_stride; fp.n = bg.n; fp.S = S; fp.order = p.in_order; fp.ds = p.downsample;
+  fp.p0 = d->in_pos; fp.nout = bg.nb; fp.idx0 = d->tuner_idx; fp.lut = d->d_lut.p; fp.tuner = d->d_tuner.p;
+  fp.coeff = d->d_in_coeff.p; fp.coeff_host = p.in_coeff.data(); fp.tail = g.tail.p; fp.z = g.z[par].p; fp.z_stride = d->z_stride;
+  RFM_PROF(g.prof, "k_if_level", st, launch_if_level(fp, g.state.p, u8, st));
+  RFM_PROF(g.prof, "k_front", st, launch_front(fp, u8, st));
+  RFM_PROF(g.prof, "k_front_tail", st, launch_front_tail(fp, u8, st));
+  g_launches += 3;
+}
+
+// Stage A of one block for one group (stream sA): history hand-over, PLL lanes.
+void EnqueueStageA(rfm_decoder* d, Group& g, const BlockGeom& bg, unsigned par)
 {
   const DecoderPlan& p = d->plan;
   cudaStream_t st = g.sA;
   const unsigned S = g.S;
   const unsigned a_hist = p.a_order;
-
-  FrontParams fp;
-  fp.in = d_in; fp.in_stride = in_stride; fp.n = bg.n; fp.S = S; fp.order = p.in_order; fp.ds = p.downsample;
-  fp.p0 = d->in_pos; fp.nout = bg.nb; fp.idx0 = d->tuner_idx; fp.lut = d->d_lut.p; fp.tuner = d->d_tuner.p;
-  fp.coeff = d->d_in_coeff.p; fp.tail = g.tail.p; fp.z = g.z.p; fp.z_stride = d->z_stride;
-  RFM_PROF(g.prof, "k_if_level", st, launch_if_level(fp, g.state.p, u8, st));
-  RFM_PROF(g.prof, "k_front", st, launch_front(fp, u8, st));
-  RFM_PROF(g.prof, "k_front_tail", st, launch_front_tail(fp, u8, st));
 
   // history of the baseband / L-R rows: last a_hist samples of the previous block (other parity) -> head of this one
   TailParams tp;
@@ -402,13 +422,13 @@ void EnqueueStageA(rfm_decoder* d, Group& g, const void* d_in, size_t in_stride,
   RFM_PROF(g.prof, "k_tails", st, launch_tails(tp, S, st));
 
   LanesParams lp;
-  lp.z = g.z.p; lp.z_stride = d->z_stride; lp.nb = bg.nb; lp.S = S; lp.state = g.state.p;
+  lp.z = g.z[par].p; lp.z_stride = d->z_stride; lp.nb = bg.nb; lp.S = S; lp.state = g.state.p;
   lp.demod = {p.demod_gain, p.nco_lo, p.nco_hi, p.pll_alpha, p.pll_beta};
   lp.pilot = {p.pilot.minfreq, p.pilot.maxfreq, p.pilot.b0, p.pilot.a1, p.pilot.a2, p.pilot.lb0, p.pilot.lb1,
               p.pilot.minsignal, p.pilot.lock_delay};
   lp.bbV = g.bbV[par].p; lp.rawV = g.rawV[par].p; lp.a_stride = d->a_stride; lp.a_hist = a_hist; lp.parity = par;
   RFM_PROF(g.prof, "k_bb_lanes", st, launch_bb_lanes(lp, st));
-  g_launches += 5;
+  g_launches += 2;
 }
 
 // Stage B of one block for one group (stream sB): audio branch, RDS branch, history carry of its own buffers.
@@ -573,25 +593,33 @@ int ProcessDevice(rfm_decoder* d, const void* d_in, size_t in_stride, bool u8, u
     const void* in_dev = in_g;
     float* audio_dev = audio_g;
     size_t in_stride_dev = in_stride, audio_stride_dev = audio_stride;
-    // ---- stage A
+    // ---- stage F
     if (!host_staged)
-      RFM_CUDA(cudaStreamWaitEvent(g.sA, d->ev_fork, 0));
-    RFM_CUDA(cudaStreamWaitEvent(g.sA, g.ev_rest[par], 0)); // stage B of block k-2 has released the parity buffers
+      RFM_CUDA(cudaStreamWaitEvent(g.sF, d->ev_fork, 0));
+    RFM_CUDA(cudaStreamWaitEvent(g.sF, g.ev_lanes[par], 0)); // the lanes of block k-2 have released z[par]
     if (host_staged)
     {
       RFM_CUDA(cudaMemcpy2DAsync(g.in_stage.p, (size_t)d->maxn * esz, in_g, in_stride * esz, (size_t)n * esz, g.S,
-                                 cudaMemcpyHostToDevice, g.sA));
+                                 cudaMemcpyHostToDevice, g.sF));
       in_dev = g.in_stage.p;
       in_stride_dev = d->maxn;
       audio_dev = g.audio_stage.p;
       audio_stride_dev = d->audio_cap;
     }
-    EnqueueStageA(d, g, in_dev, in_stride_dev, u8, bg, par);
+    if (!DebugSkip("front"))
+      EnqueueStageF(d, g, in_dev, in_stride_dev, u8, bg, par);
+    RFM_CUDA(cudaEventRecord(g.ev_front[par], g.sF));
+    // ---- stage A
+    RFM_CUDA(cudaStreamWaitEvent(g.sA, g.ev_front[par], 0));
+    RFM_CUDA(cudaStreamWaitEvent(g.sA, g.ev_rest[par], 0)); // stage B of block k-2 has released the parity buffers
+    if (!DebugSkip("lanes"))
+      EnqueueStageA(d, g, bg, par);
     RFM_CUDA(cudaEventRecord(g.ev_lanes[par], g.sA));
     // ---- stage B
     RFM_CUDA(cudaStreamWaitEvent(g.sB, g.ev_lanes[par], 0));
     RFM_CUDA(cudaStreamWaitEvent(g.sB, d->ev_osc[par], 0));
-    EnqueueStageB(d, g, bg, par, audio_dev, audio_stride_dev);
+    if (!DebugSkip("rest"))
+      EnqueueStageB(d, g, bg, par, audio_dev, audio_stride_dev);
     if (host_staged)
       RFM_CUDA(cudaMemcpy2DAsync(audio_g, audio_stride * sizeof(float), g.audio_stage.p,
                                  (size_t)d->audio_cap * sizeof(float), (size_t)2 * bg.na * sizeof(float), g.S,
@@ -615,10 +643,7 @@ int ProcessDevice(rfm_decoder* d, const void* d_in, size_t in_stride, bool u8, u
     *n_audio_floats = 2 * bg.na;
   if (host_staged)
     for (auto& g : d->groups)
-    {
-      RFM_CUDA(cudaStreamSynchronize(g.sA));
-      RFM_CUDA(cudaStreamSynchronize(g.sB));
-    }
+      RFM_CUDA(cudaStreamSynchronize(g.sB)); // the last stage: everything before it has completed too
   return RFM_OK;
 }
 
@@ -637,7 +662,7 @@ int SyncAll(rfm_decoder* d)
 {
   RFM_CUDA(cudaSetDevice(d->device));
   for (auto& g : d->groups)
-    for (cudaStream_t st : {g.sA, g.sB})
+    for (cudaStream_t st : {g.sF, g.sA, g.sB})
       if (st)
         RFM_CUDA(cudaStreamSynchronize(st));
   RFM_CUDA(cudaStreamSynchronize(d->s_osc));
@@ -776,15 +801,22 @@ int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out)
     g.s0 = (unsigned)((uint64_t)d->S * gi / G);
     g.S = (unsigned)((uint64_t)d->S * (gi + 1) / G) - g.s0;
     const size_t S = g.S;
-    RFM_TRY(cudaStreamCreateWithFlags(&g.sA, cudaStreamNonBlocking));
-    RFM_TRY(cudaStreamCreateWithFlags(&g.sB, cudaStreamNonBlocking));
+    {
+      int prio_lo = 0, prio_hi = 0; // the latency-bound lanes kernel gets its CTAs placed first
+      RFM_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+      RFM_TRY(cudaStreamCreateWithPriority(&g.sA, cudaStreamNonBlocking, prio_hi));
+      RFM_TRY(cudaStreamCreateWithPriority(&g.sF, cudaStreamNonBlocking, prio_lo));
+      RFM_TRY(cudaStreamCreateWithPriority(&g.sB, cudaStreamNonBlocking, prio_lo));
+    }
     for (int b = 0; b < 2; ++b)
     {
+      RFM_TRY(cudaEventCreateWithFlags(&g.ev_front[b], cudaEventDisableTiming));
       RFM_TRY(cudaEventCreateWithFlags(&g.ev_lanes[b], cudaEventDisableTiming));
       RFM_TRY(cudaEventCreateWithFlags(&g.ev_rest[b], cudaEventDisableTiming));
     }
     RFM_TRY(g.tail.Alloc(S * p.in_order));
-    RFM_TRY(g.z.Alloc(S * d->z_stride));
+    RFM_TRY(g.z[0].Alloc(S * d->z_stride));
+    RFM_TRY(g.z[1].Alloc(S * d->z_stride));
     for (int b = 0; b < 2; ++b)
     {
       RFM_TRY(g.bbV[b].Alloc(S * d->a_stride));
@@ -909,7 +941,7 @@ int rfm_decoder_wait(rfm_decoder* d, void* cuda_stream)
   RFM_CUDA(cudaSetDevice(d->device));
   cudaStream_t user = static_cast<cudaStream_t>(cuda_stream);
   for (auto& g : d->groups)
-    for (cudaStream_t st : {g.sA, g.sB})
+    for (cudaStream_t st : {g.sF, g.sA, g.sB})
     {
       RFM_CUDA(cudaEventRecord(d->ev_join, st));
       RFM_CUDA(cudaStreamWaitEvent(user, d->ev_join, 0));
@@ -968,6 +1000,7 @@ int rfm_decoder_get_status(rfm_decoder* d, uint32_t stream, rfm_stream_status* o
   unsigned ls = 0;
   Group* g = FindGroup(d, stream, &ls);
   RFM_CUDA(cudaSetDevice(d->device));
+  RFM_CUDA(cudaStreamSynchronize(g->sF));
   RFM_CUDA(cudaStreamSynchronize(g->sA));
   RFM_CUDA(cudaStreamSynchronize(g->sB));
   float v[SF_COUNT];
@@ -1122,7 +1155,7 @@ int rfm_decoder_tap(rfm_decoder* d, const char* name, uint32_t stream, float* ou
   const unsigned lastpar = (unsigned)((d->block_index + 1) & 1u);
   const void* src = nullptr;
   size_t cnt = 0; // floats
-  if (nm == "demod_in") { src = g->z.p + (size_t)ls * d->z_stride; cnt = 2 * (size_t)d->last_nb; }
+  if (nm == "demod_in") { src = g->z[lastpar].p + (size_t)ls * d->z_stride; cnt = 2 * (size_t)d->last_nb; }
   else if (nm == "baseband") { src = g->bbV[lastpar].p + (size_t)ls * d->a_stride + p.a_order; cnt = d->last_nb; }
   else if (nm == "rawstereo") { src = g->rawV[lastpar].p + (size_t)ls * d->a_stride + p.a_order; cnt = d->last_nb; }
   else if (nm == "mono_rs") { src = g->lpM.p + (size_t)ls * d->lp_stride + p.lp_coef.size() - 1; cnt = d->last_na; }

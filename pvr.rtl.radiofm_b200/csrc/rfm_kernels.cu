@@ -22,6 +22,7 @@
 #include "rfm_kernels.cuh"
 
 #include <assert.h>
+#include <string.h>
 
 namespace rfm
 {
@@ -131,10 +132,210 @@ __global__ void __launch_bounds__(256) k_front_tail(FrontParams p)
     tail[k] = tmp[k];
 }
 
+// --------------------------------------------------------------------------------------------------
+// Register-tiled front end for the decimations the reference's caller produces (ds = 1, 4, 5, 11; order = 8 ds).
+//   * a CTA of 128 threads makes 512 consecutive outputs of one stream; every thread owns R = 4 consecutive outputs;
+//   * the tuned input window ((512-1) ds + order samples) is formed once in shared memory.  u8 -> float uses the
+//     exact two-FMA form of the reference's double expression (rfm_u8_to_float, all 256 codes checked), so no
+//     table lookups; the 8 fine-tuner phasors a thread needs are loop-invariant registers;
+//   * the FIR walks the thread's window from the newest sample down: each sample is loaded ONCE (LDS.64) and feeds
+//     up to R accumulators, each of which therefore receives its taps in ascending j -- the reference's
+//     summation order (DownConvert.cpp:112-129); products and sums are individually rounded (no FMA);
+//   * taps come from the kernel-parameter constant bank with compile-time offsets (no loads);
+//   * the window is stored with one padding slot per R*ds samples: thread stride R*ds+1 (odd) float2 ->
+//     conflict-free 64-bit shared loads.
+// --------------------------------------------------------------------------------------------------
+struct FrontCoef
+{
+  float c[92]; // c[j], j = 0 .. order + 1 (order <= 88)
+};
+
+// float(double(u) / 127.5 - 1.0) (RTL_SDR_Source.cpp:207-211) without a table: t = u * 0x1.01p-7 - 1 is exact, the
+// second FMA adds the low part of 1/127.5 and rounds once.  Equal to the reference expression for all 256 codes
+// (tests/test_abi_host.py::test_u8_conversion_formula, and the GPU parity tests through the whole chain).
+__device__ __forceinline__ float rfm_u8_to_float(unsigned word, unsigned byte_sel)
+{
+  const float m = __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540u + byte_sel)); // 2^23 + u
+  const float u = __fsub_rn(m, 8388608.0f);
+  const float t = __fmaf_rn(u, 0x1.01p-7f, -1.0f);
+  return __fmaf_rn(u, 0x1.010102p-23f, t);
+}
+
+template <int DS>
+struct FrontGeom
+{
+  static constexpr int R = 4, T = 128, ORDER = 8 * DS, OB = T * R, SEG = R * DS;
+  static constexpr int W = (OB - 1) * DS + ORDER;          // window samples
+  static constexpr int WIN = ORDER + DS * (R - 1);         // samples one thread touches
+  static constexpr int WP = W + (W - 1) / SEG + 1;         // padded window
+  __host__ __device__ static constexpr int pos(int w) { return w + w / SEG; }
+};
+
+template <bool U8, int DS>
+__global__ void __launch_bounds__(128) k_front_tiled(FrontParams p, FrontCoef cf)
+{
+  using G = FrontGeom<DS>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* X = reinterpret_cast<float2*>(smem_raw);
+
+  const unsigned tid = threadIdx.x;
+  const unsigned s = blockIdx.y;
+  const unsigned o0 = blockIdx.x * G::OB;
+  const unsigned nt = min((unsigned)G::OB, p.nout - o0);
+  // V = tail(order) ++ block(n); this CTA needs V[vlo .. vlo + count)
+  const unsigned vlo = p.p0 + o0 * DS;
+  const unsigned count = (nt - 1) * DS + G::ORDER;
+  const float2* tuner = reinterpret_cast<const float2*>(p.tuner);
+
+  // ---- window: history part (first CTA of a row only)
+  if (vlo < (unsigned)G::ORDER)
+  {
+    const float2* tail = reinterpret_cast<const float2*>(p.tail) + (size_t)s * G::ORDER;
+    for (unsigned V = vlo + tid; V < (unsigned)G::ORDER && V - vlo < count; V += G::T)
+      X[G::pos((int)(V - vlo))] = tail[V];
+  }
+  // ---- window: new samples i in [i_lo, i_hi) of this block, sample i lands at w = i + order - vlo
+  const int i_lo = max(0, (int)vlo - G::ORDER);
+  const int i_hi = min((int)p.n, (int)(vlo + count) - G::ORDER);
+  if (U8)
+  {
+    const unsigned char* row = reinterpret_cast<const unsigned char*>(p.in) + (size_t)s * p.in_stride * 2;
+    // 16-byte chunks of 8 samples, aligned in memory: chunk c holds samples k0 + 8c .. k0 + 8c + 7
+    const int k0 = (int)(((16u - (unsigned)(reinterpret_cast<uintptr_t>(row) & 15u)) & 15u) >> 1);
+    const int c_lo = (i_lo - k0) >= 0 ? (i_lo - k0) / 8 : -(((k0 - i_lo) + 7) / 8);
+    // a thread's chunks are 128 chunks = 1024 samples apart: its 8 tuner phasors never change
+    float2 tw[8];
+    const int ib0 = k0 + 8 * (c_lo + (int)tid);
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      tw[e] = tuner[(p.idx0 + (unsigned)(ib0 + e)) & 63u];
+    for (int ib = ib0; ib < i_hi; ib += 8 * G::T)
+    {
+      uint4 raw;
+      if (ib >= 0 && ib + 8 <= (int)p.n)
+        raw = *reinterpret_cast<const uint4*>(row + 2 * (size_t)ib);
+      else
+      {
+        unsigned short h[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          h[e] = (ib + e >= 0 && ib + e < (int)p.n) ? *reinterpret_cast<const unsigned short*>(row + 2 * (size_t)(ib + e)) : (unsigned short)0;
+        raw.x = h[0] | ((unsigned)h[1] << 16); raw.y = h[2] | ((unsigned)h[3] << 16);
+        raw.z = h[4] | ((unsigned)h[5] << 16); raw.w = h[6] | ((unsigned)h[7] << 16);
+      }
+      const unsigned wd[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+      {
+        const int i = ib + e;
+        if (i >= i_lo && i < i_hi)
+        {
+          const unsigned word = wd[e >> 1];
+          const float are = rfm_u8_to_float(word, (e & 1) ? 2u : 0u);
+          const float aim = rfm_u8_to_float(word, (e & 1) ? 3u : 1u);
+          float2 o;
+          o.x = subf(mulf(are, tw[e].x), mulf(aim, tw[e].y));   // FmDecode.cpp:66-82
+          o.y = addf(mulf(are, tw[e].y), mulf(aim, tw[e].x));
+          X[G::pos(i + G::ORDER - (int)vlo)] = o;
+        }
+      }
+    }
+  }
+  else
+  {
+    const float2* row = reinterpret_cast<const float2*>(p.in) + (size_t)s * p.in_stride;
+    for (int i = i_lo + (int)tid; i < i_hi; i += G::T)
+    {
+      const float2 a = row[i];
+      const float2 b = tuner[(p.idx0 + (unsigned)i) & 63u];
+      float2 o;
+      o.x = subf(mulf(a.x, b.x), mulf(a.y, b.y));
+      o.y = addf(mulf(a.x, b.y), mulf(a.y, b.x));
+      X[G::pos(i + G::ORDER - (int)vlo)] = o;
+    }
+  }
+  __syncthreads();
+
+  // ---- FIR: outputs tid*R .. tid*R + R-1; thread window w = SEG*tid + (WIN-1) - u, u = 0 .. WIN-1 (newest first)
+  if (tid * G::R >= nt)
+    return;
+  float2 acc[G::R];
+#pragma unroll
+  for (int i = 0; i < G::R; ++i)
+    acc[i] = make_float2(0.0f, 0.0f);
+  const float2* xt = X + tid * (G::SEG + 1);
+#pragma unroll
+  for (int u = 0; u < G::WIN; ++u)
+  {
+    const int wl = G::WIN - 1 - u; // local window index; pos(SEG*tid + wl) = (SEG+1)*tid + wl + wl/SEG
+    const float2 v = xt[wl + wl / G::SEG];
+#pragma unroll
+    for (int i = 0; i < G::R; ++i)
+    {
+      const int j = u + 1 - DS * (G::R - 1 - i); // tap of output i that meets this sample
+      if (j >= 1 && j <= G::ORDER)
+      {
+        acc[i].x = addf(acc[i].x, mulf(v.x, cf.c[j]));
+        acc[i].y = addf(acc[i].y, mulf(v.y, cf.c[j]));
+      }
+    }
+  }
+  float2* zo = reinterpret_cast<float2*>(p.z) + (size_t)s * p.z_stride + o0 + tid * G::R;
+  if (tid * G::R + G::R <= nt)
+  {
+    reinterpret_cast<float4*>(zo)[0] = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
+    reinterpret_cast<float4*>(zo)[1] = make_float4(acc[2].x, acc[2].y, acc[3].x, acc[3].y);
+  }
+  else
+  {
+#pragma unroll
+    for (int i = 0; i < G::R; ++i)
+      if (tid * G::R + i < nt)
+        zo[i] = acc[i];
+  }
+}
+
+template <bool U8, int DS>
+static void launch_front_tiled(const FrontParams& p, const FrontCoef& cf, cudaStream_t st)
+{
+  using G = FrontGeom<DS>;
+  const size_t smem = (size_t)G::WP * sizeof(float2);
+  static bool attr_done = false; // per instantiation
+  if (!attr_done)
+  {
+    cudaFuncSetAttribute(k_front_tiled<U8, DS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_done = true;
+  }
+  dim3 grid(cdiv(p.nout, G::OB), p.S);
+  k_front_tiled<U8, DS><<<grid, G::T, smem, st>>>(p, cf);
+}
+
 void launch_front(const FrontParams& p, bool u8, cudaStream_t st)
 {
   if (p.nout == 0 || p.S == 0)
     return;
+  const bool tiled = p.order == 8 * p.ds && (p.ds == 1 || p.ds == 4 || p.ds == 5 || p.ds == 11) && p.coeff_host &&
+                     (!u8 || ((reinterpret_cast<uintptr_t>(p.in) | (p.in_stride * 2)) & 1u) == 0);
+  if (tiled)
+  {
+    FrontCoef cf;
+    memset(&cf, 0, sizeof(cf));
+    memcpy(cf.c, p.coeff_host, (p.order + 2) * sizeof(float));
+#define RFM_FT(DS)                                    \
+  if (u8)                                             \
+    launch_front_tiled<true, DS>(p, cf, st);          \
+  else                                                \
+    launch_front_tiled<false, DS>(p, cf, st)
+    switch (p.ds)
+    {
+      case 1: RFM_FT(1); break;
+      case 4: RFM_FT(4); break;
+      case 5: RFM_FT(5); break;
+      default: RFM_FT(11); break;
+    }
+#undef RFM_FT
+    return;
+  }
   const unsigned coef_n = (p.order + 2 + 1) & ~1u;
   const size_t smem = (256 + 128 + coef_n) * sizeof(float) + ((size_t)(kFrontTile - 1) * p.ds + p.order) * sizeof(float2);
   dim3 grid(cdiv(p.nout, kFrontTile), p.S);

@@ -72,7 +72,8 @@ struct FrontParams
   unsigned idx0;           // fine-tuner table index of sample 0
   const float* lut;        // [256]
   const float* tuner;      // [64][2]
-  const float* coeff;      // [order + 2]
+  const float* coeff;      // [order + 2] (device)
+  const float* coeff_host; // the same table on the host (kernel-parameter constant bank of the tiled kernel)
   cf32* tail;              // [S][order] tuned history (m_stateComplex)
   cf32* z;                 // [S][z_stride] FIR output
   size_t z_stride;

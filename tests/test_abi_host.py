@@ -115,3 +115,17 @@ def test_rds_block_sync_matches_golden_bits(rfm):
     s = rfm.RdsBlockSync()
     s.push_bits(g["bits"])
     assert np.array_equal(s.take_groups(), g["groups"])
+
+
+def test_u8_conversion_formula(rfm):
+    """The tiled front-end kernel converts u8 -> float with two FMAs instead of a table (rfm_u8_to_float in
+    rfm_kernels.cu): t = fma(u, 0x1.01p-7, -1) [exact], v = fma(u, 0x1.010102p-23, t).  Emulated here with exact
+    float64 products and a single rounding per FMA; must equal the reference expression for all 256 codes."""
+    u = np.arange(256, dtype=np.float64)
+    a_hi = float.fromhex("0x1.01p-7")
+    a_lo = float.fromhex("0x1.010102p-23")
+    t = u * a_hi - 1.0
+    assert np.array_equal(t, t.astype(np.float32).astype(np.float64))      # first FMA is exact
+    v = (u * a_lo + t).astype(np.float32)                                   # exact in float64, rounded once
+    assert bits_equal(v, rfm.plan_table(6, 1e6, 0.0))
+    assert bits_equal(v, (np.arange(256) / (255.0 / 2.0) - 1.0).astype(np.float32))
