@@ -120,6 +120,9 @@ struct rfm_decoder
   DevBuf<float> d_hb[kMaxDecStages];
   DevBuf<cf32> oscV[2];
   DevBuf<float> osc1;
+  DevBuf<float> res_kk[2]; // per-block interpolated resampler taps, shared by all streams (by parity)
+  DevBuf<int> res_meta[2];
+  unsigned res_lp = 0;
   cudaStream_t s_osc = nullptr;
   cudaEvent_t ev_osc[2] = {nullptr, nullptr};
   uint64_t block_index = 0; // blocks enqueued so far; parity selects the double buffers
@@ -183,6 +186,11 @@ void FreeDecoder(rfm_decoder* d)
   if (d->s_osc)
     cudaStreamSynchronize(d->s_osc);
   d->oscV[0].Free(); d->oscV[1].Free(); d->osc1.Free();
+  for (int b = 0; b < 2; ++b)
+  {
+    d->res_kk[b].Free();
+    d->res_meta[b].Free();
+  }
   ProfFree(d->main_prof);
   for (cudaEvent_t e : {d->ev_fork, d->ev_osc[0], d->ev_osc[1], d->ev_join})
     if (e)
@@ -447,7 +455,8 @@ void EnqueueStageB(rfm_decoder* d, Group& g, const BlockGeom& bg, unsigned par, 
   rp.bbV = g.bbV[par].p; rp.rawV = g.rawV[par].p; rp.a_stride = d->a_stride; rp.order = p.a_order; rp.nb = bg.nb;
   rp.S = S; rp.na = bg.na; rp.pos_frac = d->a_pos; rp.pstep = p.a_pstep; rp.coeff = d->d_a_coeff.p; rp.lpS = g.lpS.p;
   rp.lpM = g.lpM.p; rp.lp_stride = d->lp_stride; rp.lp_hist = lp_taps - 1;
-  RFM_PROF(g.prof, "k_resample", st, launch_resample(rp, st));
+  rp.kk = d->res_kk[par].p; rp.meta = d->res_meta[par].p; rp.lp = d->res_lp;
+  RFM_PROF(g.prof, "k_resample", st, launch_resample_tiled(rp, st));
 
   RotFirParams f29;
   f29.inA = g.lpS.p; f29.inB = g.lpM.p; f29.in_stride = d->lp_stride; f29.outA = g.fS.p; f29.outB = g.fM.p;
@@ -581,7 +590,11 @@ int ProcessDevice(rfm_decoder* d, const void* d_in, size_t in_stride, bool u8, u
     op.oscV = d->oscV[par].p; op.osc_hist = d->osc_hist; op.nb = bg.nb; op.osc1 = d->osc1.p;
     op.cosv = d->plan.rds_osc.cosv; op.sinv = d->plan.rds_osc.sinv;
     RFM_PROF(d->main_prof, "k_osc", d->s_osc, launch_osc(op, d->s_osc));
-    g_launches += 2;
+    ResTapsParams tp2;
+    tp2.pos_frac = d->a_pos; tp2.pstep = d->plan.a_pstep; tp2.na = bg.na; tp2.order = d->plan.a_order;
+    tp2.lp = d->res_lp; tp2.coeff = d->d_a_coeff.p; tp2.kk = d->res_kk[par].p; tp2.meta = d->res_meta[par].p;
+    RFM_PROF(d->main_prof, "k_res_taps", d->s_osc, launch_res_taps(tp2, d->s_osc));
+    g_launches += 3;
     RFM_CUDA(cudaEventRecord(d->ev_osc[par], d->s_osc));
   }
 
@@ -776,6 +789,12 @@ int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out)
       RFM_TRY(Upload(d->d_hb[k], p.rds_stages[k].h, (size_t)p.rds_stages[k].len));
     else
       RFM_TRY(d->d_hb[k].Alloc(4));
+  }
+  d->res_lp = p.a_order + 1 + 3 * ((unsigned)p.a_ratio + 1) + 4;
+  for (int b = 0; b < 2; ++b)
+  {
+    RFM_TRY(d->res_kk[b].Alloc((size_t)(d->na_max / 4 + 2) * d->res_lp * 4));
+    RFM_TRY(d->res_meta[b].Alloc((size_t)(d->na_max / 4 + 2) * 2));
   }
   RFM_TRY(d->oscV[0].Alloc((size_t)d->osc_hist + d->nb_max));
   RFM_TRY(d->oscV[1].Alloc((size_t)d->osc_hist + d->nb_max));

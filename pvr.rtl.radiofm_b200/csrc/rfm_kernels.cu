@@ -713,6 +713,163 @@ void launch_resample(const ResampleParams& p, cudaStream_t st)
   k_resample<<<grid, kResTile, smem, st>>>(p, max_span);
 }
 
+// --------------------------------------------------------------------------------------------------
+// Tiled form.  The output positions pf = p + i * pstep and with them the interpolated taps
+// k[i][j] = c[j] (1 - k1_i) + c[j+1] k1_i are the same for EVERY stream of the decoder (lock-step), so they are
+// formed once per block by k_res_taps (DownConvert.cpp:203-224, same float operations) and shared:
+//   * outputs are handled in groups of 4 consecutive ones; a group's taps are stored against a common time axis
+//     (zero outside an output's own window: adding +-0 leaves the running sum unchanged), 4 taps per time step
+//     as one float4;
+//   * k_resample_tiled: lane = stream (32 streams per CTA, rows staged transposed into shared memory with an odd
+//     pitch), a warp walks one group from the newest sample down -- every output receives its taps in ascending j,
+//     the reference's order (DownConvert.cpp:210-222) -- with one broadcast LDS.128 (4 taps) + 2 LDS (mono / L-R
+//     sample) per 16 individually rounded multiply / add operations.
+// --------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_res_taps(ResTapsParams p)
+{
+  const unsigned g = blockIdx.x;
+  __shared__ int s_pi[4];
+  __shared__ float s_k0[4], s_k1[4];
+  if (threadIdx.x < 4)
+  {
+    const unsigned i = 4 * g + threadIdx.x;
+    const float pf = res_pos(p.pos_frac, p.pstep, i);
+    const int pi = __float2int_rz(pf);
+    const float k1 = subf(pf, (float)pi);
+    s_pi[threadIdx.x] = (i < p.na) ? pi : -1;
+    s_k1[threadIdx.x] = k1;
+    s_k0[threadIdx.x] = subf(1.0f, k1);
+  }
+  __syncthreads();
+  // valid outputs of this group: 0 .. cnt-1 (cnt >= 1)
+  unsigned cnt = 0;
+  for (unsigned r = 0; r < 4; ++r)
+    cnt += s_pi[r] >= 0;
+  const int vlo = s_pi[0];                       // V index (history included) of the oldest sample of output 0
+  const int vhi = (int)p.order + s_pi[cnt - 1];  // newest sample of the last valid output
+  const int L = vhi - vlo + 1;
+  if (threadIdx.x == 0)
+  {
+    p.meta[2 * g] = vlo;
+    p.meta[2 * g + 1] = L;
+  }
+  float4* kk = reinterpret_cast<float4*>(p.kk) + (size_t)g * p.lp;
+  for (int tt = threadIdx.x; tt < (int)p.lp; tt += blockDim.x)
+  {
+    float v[4];
+    for (unsigned r = 0; r < 4; ++r)
+    {
+      const int j = (int)p.order + s_pi[r] - (vlo + tt); // tap of output r that meets V = vlo + tt
+      v[r] = 0.0f;
+      if (s_pi[r] >= 0 && j >= 0 && j <= (int)p.order && tt < L)
+        v[r] = addf(mulf(p.coeff[j], s_k0[r]), mulf(p.coeff[j + 1], s_k1[r]));
+    }
+    kk[tt] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+void launch_res_taps(const ResTapsParams& p, cudaStream_t st)
+{
+  if (p.na == 0)
+    return;
+  k_res_taps<<<cdiv(p.na, 4), 128, 0, st>>>(p);
+}
+
+template <int GB> // groups of 4 outputs per CTA
+__global__ void __launch_bounds__(128) k_resample_tiled(ResampleParams p, unsigned pitch)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* KK = reinterpret_cast<float4*>(smem_raw);                 // [GB][lp]
+  float* Xm = reinterpret_cast<float*>(KK + (size_t)GB * p.lp);     // [32][pitch]
+  float* Xs = Xm + 32 * pitch;
+  __shared__ int s_meta[2 * GB];
+
+  const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const unsigned ngroups = (p.na + 3) / 4;
+  const unsigned g0 = blockIdx.x * GB;
+  const unsigned gn = min((unsigned)GB, ngroups - g0);
+  const unsigned s0 = blockIdx.y * 32;
+  const unsigned rows = min(32u, p.S - s0);
+  if (tid < 2 * gn)
+    s_meta[tid] = p.meta[2 * g0 + tid];
+  __syncthreads();
+  const int v0 = s_meta[0];
+  const int span = s_meta[2 * (gn - 1)] + s_meta[2 * (gn - 1) + 1] - v0; // V range of the CTA
+  // taps of the CTA's groups
+  {
+    const float4* src = reinterpret_cast<const float4*>(p.kk) + (size_t)g0 * p.lp;
+    for (unsigned i = tid; i < gn * p.lp; i += 128)
+      KK[i] = src[i];
+  }
+  // input rows, transposed: warp w stages rows w, w+4, ...
+  for (unsigned r = warp; r < rows; r += 4)
+  {
+    const float* bm = p.bbV + (size_t)(s0 + r) * p.a_stride + v0;
+    const float* bs = p.rawV + (size_t)(s0 + r) * p.a_stride + v0;
+    for (int c = lane; c < span; c += 32)
+    {
+      Xm[r * pitch + c] = bm[c];
+      Xs[r * pitch + c] = bs[c];
+    }
+  }
+  __syncthreads();
+  if (lane >= rows)
+    return;
+  const float* xm = Xm + lane * pitch;
+  const float* xs = Xs + lane * pitch;
+  for (unsigned gi = warp; gi < gn; gi += 4)
+  {
+    const int off = s_meta[2 * gi] - v0;
+    const int L = s_meta[2 * gi + 1];
+    const float4* kk = KK + (size_t)gi * p.lp;
+    float am[4] = {0.f, 0.f, 0.f, 0.f}, as[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int tt = L - 1; tt >= 0; --tt)
+    {
+      const float4 k = kk[tt];
+      const float m = xm[off + tt], sv = xs[off + tt];
+      am[0] = addf(am[0], mulf(k.x, m)); as[0] = addf(as[0], mulf(k.x, sv));
+      am[1] = addf(am[1], mulf(k.y, m)); as[1] = addf(as[1], mulf(k.y, sv));
+      am[2] = addf(am[2], mulf(k.z, m)); as[2] = addf(as[2], mulf(k.z, sv));
+      am[3] = addf(am[3], mulf(k.w, m)); as[3] = addf(as[3], mulf(k.w, sv));
+    }
+    const unsigned i = 4 * (g0 + gi);
+    float* om = p.lpM + (size_t)(s0 + lane) * p.lp_stride + p.lp_hist + i;
+    float* os = p.lpS + (size_t)(s0 + lane) * p.lp_stride + p.lp_hist + i;
+    if (i + 4 <= p.na && ((p.lp_hist | p.lp_stride) & 3u) == 0)
+    {
+      *reinterpret_cast<float4*>(om) = make_float4(am[0], am[1], am[2], am[3]);
+      *reinterpret_cast<float4*>(os) = make_float4(as[0], as[1], as[2], as[3]);
+    }
+    else
+    {
+      for (unsigned r = 0; r < 4 && i + r < p.na; ++r)
+      {
+        om[r] = am[r];
+        os[r] = as[r];
+      }
+    }
+  }
+}
+
+void launch_resample_tiled(const ResampleParams& p, cudaStream_t st)
+{
+  if (p.na == 0 || p.S == 0)
+    return;
+  constexpr int GB = 4; // 16 outputs per CTA
+  const unsigned span_max = (unsigned)(4.0f * GB * p.pstep) + p.order + 40;
+  const unsigned pitch = span_max | 1u;
+  const size_t smem = (size_t)GB * p.lp * sizeof(float4) + (size_t)2 * 32 * pitch * sizeof(float);
+  static size_t attr = 0;
+  if (smem > attr)
+  {
+    cudaFuncSetAttribute(k_resample_tiled<GB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = smem;
+  }
+  dim3 grid(cdiv((p.na + 3) / 4, GB), cdiv(p.S, 32));
+  k_resample_tiled<GB><<<grid, 128, smem, st>>>(p, pitch);
+}
+
 // ==================================================================================================
 // cFirFilter::Process / ProcessTwo, FirFilter.cpp:330-413
 // y[g] = sum over j = 0..N-1 of h[k_j] x[g - k_j],  k_j = (g + j) mod N: the circular delay line is

@@ -115,8 +115,23 @@ struct ResampleParams
   float* lpM;              // same, mono
   size_t lp_stride;
   unsigned lp_hist;
+  // tiled form: per-block tap table shared by all streams (launch_res_taps)
+  const float* kk;         // [groups][lp][4]
+  const int* meta;         // [groups][2]: first V index, length
+  unsigned lp;             // time steps reserved per group (>= order + 1 + 3 * ceil(ratio) + 1)
 };
 void launch_resample(const ResampleParams& p, cudaStream_t st);
+void launch_resample_tiled(const ResampleParams& p, cudaStream_t st);
+
+struct ResTapsParams
+{
+  float pos_frac, pstep;
+  unsigned na, order, lp;
+  const float* coeff;      // [order + 2]
+  float* kk;
+  int* meta;
+};
+void launch_res_taps(const ResTapsParams& p, cudaStream_t st);
 
 // ---- cFirFilter with rotating summation start (real pair / complex / real) ------------------------------
 struct RotFirParams
