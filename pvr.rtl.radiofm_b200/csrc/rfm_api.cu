@@ -87,7 +87,8 @@ struct Group
 {
   unsigned s0 = 0, S = 0;
   ProfSlot prof[kMaxProfKinds];
-  cudaStream_t sF = nullptr, sA = nullptr, sB = nullptr; // front / lanes / rest
+  cudaStream_t sF = nullptr, sA = nullptr, sB = nullptr, sR = nullptr; // front / lanes / audio branch / RDS branch
+  cudaEvent_t ev_rds[2] = {nullptr, nullptr};   // RDS branch of the block with this parity finished
   cudaEvent_t ev_front[2] = {nullptr, nullptr}; // front end of the block with this parity finished
   cudaEvent_t ev_lanes[2] = {nullptr, nullptr}; // PLL lanes ...
   cudaEvent_t ev_rest[2] = {nullptr, nullptr};  // stage B ...
@@ -160,7 +161,7 @@ void FreeDecoder(rfm_decoder* d)
   cudaSetDevice(d->device);
   for (auto& g : d->groups)
   {
-    for (cudaStream_t st : {g.sF, g.sA, g.sB})
+    for (cudaStream_t st : {g.sF, g.sA, g.sB, g.sR})
       if (st)
         cudaStreamSynchronize(st);
     g.tail.Free(); g.z[0].Free(); g.z[1].Free();
@@ -173,10 +174,10 @@ void FreeDecoder(rfm_decoder* d)
     g.rlpV.Free(); g.rlp_out.Free(); g.mfV.Free(); g.mf_out.Free(); g.bits.Free(); g.bit_count.Free();
     g.lpS.Free(); g.lpM.Free(); g.fS.Free(); g.fM.Free(); g.state.Free(); g.in_stage.Free(); g.audio_stage.Free();
     ProfFree(g.prof);
-    for (cudaEvent_t e : {g.ev_front[0], g.ev_front[1], g.ev_lanes[0], g.ev_lanes[1], g.ev_rest[0], g.ev_rest[1]})
+    for (cudaEvent_t e : {g.ev_front[0], g.ev_front[1], g.ev_lanes[0], g.ev_lanes[1], g.ev_rest[0], g.ev_rest[1], g.ev_rds[0], g.ev_rds[1]})
       if (e)
         cudaEventDestroy(e);
-    for (cudaStream_t st : {g.sF, g.sA, g.sB})
+    for (cudaStream_t st : {g.sF, g.sA, g.sB, g.sR})
       if (st)
         cudaStreamDestroy(st);
   }
@@ -469,9 +470,17 @@ void EnqueueStageB(rfm_decoder* d, Group& g, const BlockGeom& bg, unsigned par, 
   at.de_alpha = p.de_alpha; at.notch = {p.notch.A1, p.notch.A2, p.notch.B0, p.notch.B1, p.notch.B2};
   at.audio = d_audio; at.audio_stride = audio_stride; at.parity = par;
   RFM_PROF(g.prof, "k_audio_tail", st, launch_audio_tail(at, st));
-  g_launches += 3;
+  {
+    TailParams tpa;
+    tpa.count = 2;
+    tpa.d[0] = {g.lpS.p, g.lpS.p, d->lp_stride * sizeof(float), lp_taps - 1, bg.na, 4, S};
+    tpa.d[1] = {g.lpM.p, g.lpM.p, d->lp_stride * sizeof(float), lp_taps - 1, bg.na, 4, S};
+    RFM_PROF(g.prof, "k_tails", st, launch_tails(tpa, S, st));
+  }
+  g_launches += 4;
 
-  // ---- RDS branch
+  // ---- RDS branch, on its own stream (its PLL / slicer lane kernels are latency-bound and overlap the audio FIRs)
+  st = g.sR;
   for (unsigned k = 0; k < nst; ++k)
   {
     const HalfBandStage& hs = p.rds_stages[k];
@@ -529,8 +538,6 @@ void EnqueueStageB(rfm_decoder* d, Group& g, const BlockGeom& bg, unsigned par, 
       return;
     tp.d[tp.count++] = {base, base, stride_elems * elem, hist, n, elem, S};
   };
-  add(g.lpS.p, d->lp_stride, lp_taps - 1, bg.na, 4);
-  add(g.lpM.p, d->lp_stride, lp_taps - 1, bg.na, 4);
   for (unsigned k = 1; k < nst; ++k)
     add(g.hbV[k].p, d->hb_stride[k], StageHist(p.rds_stages[k]), bg.hb_n[k], 8);
   add(g.rlpV.p, d->rlp_stride, rlp_taps - 1, bg.nr, 8);
@@ -629,10 +636,15 @@ int ProcessDevice(rfm_decoder* d, const void* d_in, size_t in_stride, bool u8, u
       EnqueueStageA(d, g, bg, par);
     RFM_CUDA(cudaEventRecord(g.ev_lanes[par], g.sA));
     // ---- stage B
-    RFM_CUDA(cudaStreamWaitEvent(g.sB, g.ev_lanes[par], 0));
-    RFM_CUDA(cudaStreamWaitEvent(g.sB, d->ev_osc[par], 0));
+    for (cudaStream_t st : {g.sB, g.sR})
+    {
+      RFM_CUDA(cudaStreamWaitEvent(st, g.ev_lanes[par], 0));
+      RFM_CUDA(cudaStreamWaitEvent(st, d->ev_osc[par], 0));
+    }
     if (!DebugSkip("rest"))
       EnqueueStageB(d, g, bg, par, audio_dev, audio_stride_dev);
+    RFM_CUDA(cudaEventRecord(g.ev_rds[par], g.sR));
+    RFM_CUDA(cudaStreamWaitEvent(g.sB, g.ev_rds[par], 0)); // ev_rest (recorded on sB) covers both branches
     if (host_staged)
       RFM_CUDA(cudaMemcpy2DAsync(audio_g, audio_stride * sizeof(float), g.audio_stage.p,
                                  (size_t)d->audio_cap * sizeof(float), (size_t)2 * bg.na * sizeof(float), g.S,
@@ -675,7 +687,7 @@ int SyncAll(rfm_decoder* d)
 {
   RFM_CUDA(cudaSetDevice(d->device));
   for (auto& g : d->groups)
-    for (cudaStream_t st : {g.sF, g.sA, g.sB})
+    for (cudaStream_t st : {g.sF, g.sA, g.sB, g.sR})
       if (st)
         RFM_CUDA(cudaStreamSynchronize(st));
   RFM_CUDA(cudaStreamSynchronize(d->s_osc));
@@ -826,10 +838,12 @@ int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out)
       RFM_TRY(cudaStreamCreateWithPriority(&g.sA, cudaStreamNonBlocking, prio_hi));
       RFM_TRY(cudaStreamCreateWithPriority(&g.sF, cudaStreamNonBlocking, prio_lo));
       RFM_TRY(cudaStreamCreateWithPriority(&g.sB, cudaStreamNonBlocking, prio_lo));
+      RFM_TRY(cudaStreamCreateWithPriority(&g.sR, cudaStreamNonBlocking, prio_lo));
     }
     for (int b = 0; b < 2; ++b)
     {
       RFM_TRY(cudaEventCreateWithFlags(&g.ev_front[b], cudaEventDisableTiming));
+      RFM_TRY(cudaEventCreateWithFlags(&g.ev_rds[b], cudaEventDisableTiming));
       RFM_TRY(cudaEventCreateWithFlags(&g.ev_lanes[b], cudaEventDisableTiming));
       RFM_TRY(cudaEventCreateWithFlags(&g.ev_rest[b], cudaEventDisableTiming));
     }
@@ -960,7 +974,7 @@ int rfm_decoder_wait(rfm_decoder* d, void* cuda_stream)
   RFM_CUDA(cudaSetDevice(d->device));
   cudaStream_t user = static_cast<cudaStream_t>(cuda_stream);
   for (auto& g : d->groups)
-    for (cudaStream_t st : {g.sF, g.sA, g.sB})
+    for (cudaStream_t st : {g.sF, g.sA, g.sB, g.sR})
     {
       RFM_CUDA(cudaEventRecord(d->ev_join, st));
       RFM_CUDA(cudaStreamWaitEvent(user, d->ev_join, 0));

@@ -428,7 +428,11 @@ __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.ar
 template <bool U8>
 __global__ void __launch_bounds__(128) k_if_level(FrontParams f, float* state)
 {
-  const unsigned s = blockIdx.x * 128 + threadIdx.x;
+  // one warp per stream: the |x|^2 terms are formed in parallel (coalesced), the float sum itself runs in sample
+  // order on lane 0 (the reference's summation order, FmDecode.cpp:505-519)
+  __shared__ float terms[4][1025];
+  const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const unsigned s = blockIdx.x * 4 + warp;
   if (s >= f.S)
     return;
   const unsigned cnt = (f.n + 63) / 64;
@@ -436,14 +440,26 @@ __global__ void __launch_bounds__(128) k_if_level(FrontParams f, float* state)
   const unsigned char* row = reinterpret_cast<const unsigned char*>(f.in) + (size_t)s * f.in_stride * esz;
   const float2* tuner = reinterpret_cast<const float2*>(f.tuner);
   float level = 0.0f;
-  for (unsigned i = 0; i < cnt; ++i)
+  for (unsigned i0 = 0; i0 < cnt; i0 += 1024)
   {
-    const float2 t = tuned_sample<U8>(row, i, f.idx0, f.lut, tuner);
-    level = addf(level, addf(mulf(t.x, t.x), mulf(t.y, t.y)));
+    const unsigned m = min(1024u, cnt - i0);
+    for (unsigned i = lane; i < m; i += 32)
+    {
+      const float2 t = tuned_sample<U8>(row, i0 + i, f.idx0, f.lut, tuner);
+      terms[warp][i] = addf(mulf(t.x, t.x), mulf(t.y, t.y));
+    }
+    __syncwarp();
+    if (lane == 0)
+      for (unsigned i = 0; i < m; ++i)
+        level = addf(level, terms[warp][i]);
+    __syncwarp();
   }
-  const float rms = sqrtf_rn(divf(level, (float)cnt));
-  float* lv = state + (size_t)SF_IF_LEVEL * f.S + s;
-  *lv = addf(mulf(0.95f, *lv), mulf(0.05f, rms));
+  if (lane == 0)
+  {
+    const float rms = sqrtf_rn(divf(level, (float)cnt));
+    float* lv = state + (size_t)SF_IF_LEVEL * f.S + s;
+    *lv = addf(mulf(0.95f, *lv), mulf(0.05f, rms));
+  }
 }
 
 void launch_if_level(const FrontParams& p, float* state, bool u8, cudaStream_t st)
@@ -451,9 +467,9 @@ void launch_if_level(const FrontParams& p, float* state, bool u8, cudaStream_t s
   if (p.S == 0 || p.n == 0)
     return;
   if (u8)
-    k_if_level<true><<<cdiv(p.S, 128), 128, 0, st>>>(p, state);
+    k_if_level<true><<<cdiv(p.S, 4), 128, 0, st>>>(p, state);
   else
-    k_if_level<false><<<cdiv(p.S, 128), 128, 0, st>>>(p, state);
+    k_if_level<false><<<cdiv(p.S, 4), 128, 0, st>>>(p, state);
 }
 
 // --------------------------------------------------------------------------------------------------
@@ -775,8 +791,11 @@ void launch_res_taps(const ResTapsParams& p, cudaStream_t st)
   k_res_taps<<<cdiv(p.na, 4), 128, 0, st>>>(p);
 }
 
+constexpr unsigned kResThreads = 256;
+constexpr unsigned kResWarps = kResThreads / 32;
+
 template <int GB> // groups of 4 outputs per CTA
-__global__ void __launch_bounds__(128) k_resample_tiled(ResampleParams p, unsigned pitch)
+__global__ void __launch_bounds__(kResThreads) k_resample_tiled(ResampleParams p, unsigned pitch)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* KK = reinterpret_cast<float4*>(smem_raw);                 // [GB][lp]
@@ -798,18 +817,34 @@ __global__ void __launch_bounds__(128) k_resample_tiled(ResampleParams p, unsign
   // taps of the CTA's groups
   {
     const float4* src = reinterpret_cast<const float4*>(p.kk) + (size_t)g0 * p.lp;
-    for (unsigned i = tid; i < gn * p.lp; i += 128)
+    for (unsigned i = tid; i < gn * p.lp; i += kResThreads)
       KK[i] = src[i];
   }
-  // input rows, transposed: warp w stages rows w, w+4, ...
-  for (unsigned r = warp; r < rows; r += 4)
+  // input rows, transposed: warp w stages rows w, w + kResWarps, ...; 8 columns x 2 arrays in flight per lane
+  for (unsigned r = warp; r < rows; r += kResWarps)
   {
     const float* bm = p.bbV + (size_t)(s0 + r) * p.a_stride + v0;
     const float* bs = p.rawV + (size_t)(s0 + r) * p.a_stride + v0;
-    for (int c = lane; c < span; c += 32)
+    for (int c0 = 0; c0 < span; c0 += 256)
     {
-      Xm[r * pitch + c] = bm[c];
-      Xs[r * pitch + c] = bs[c];
+      float vm[8], vs[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+      {
+        const int c = c0 + u * 32 + (int)lane;
+        vm[u] = (c < span) ? bm[c] : 0.0f;
+        vs[u] = (c < span) ? bs[c] : 0.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+      {
+        const int c = c0 + u * 32 + (int)lane;
+        if (c < span)
+        {
+          Xm[r * pitch + c] = vm[u];
+          Xs[r * pitch + c] = vs[u];
+        }
+      }
     }
   }
   __syncthreads();
@@ -817,7 +852,7 @@ __global__ void __launch_bounds__(128) k_resample_tiled(ResampleParams p, unsign
     return;
   const float* xm = Xm + lane * pitch;
   const float* xs = Xs + lane * pitch;
-  for (unsigned gi = warp; gi < gn; gi += 4)
+  for (unsigned gi = warp; gi < gn; gi += kResWarps)
   {
     const int off = s_meta[2 * gi] - v0;
     const int L = s_meta[2 * gi + 1];
@@ -852,14 +887,9 @@ __global__ void __launch_bounds__(128) k_resample_tiled(ResampleParams p, unsign
   }
 }
 
-void launch_resample_tiled(const ResampleParams& p, cudaStream_t st)
+template <int GB>
+static void launch_resample_tiled_gb(const ResampleParams& p, unsigned pitch, size_t smem, cudaStream_t st)
 {
-  if (p.na == 0 || p.S == 0)
-    return;
-  constexpr int GB = 4; // 16 outputs per CTA
-  const unsigned span_max = (unsigned)(4.0f * GB * p.pstep) + p.order + 40;
-  const unsigned pitch = span_max | 1u;
-  const size_t smem = (size_t)GB * p.lp * sizeof(float4) + (size_t)2 * 32 * pitch * sizeof(float);
   static size_t attr = 0;
   if (smem > attr)
   {
@@ -867,7 +897,31 @@ void launch_resample_tiled(const ResampleParams& p, cudaStream_t st)
     attr = smem;
   }
   dim3 grid(cdiv((p.na + 3) / 4, GB), cdiv(p.S, 32));
-  k_resample_tiled<GB><<<grid, 128, smem, st>>>(p, pitch);
+  k_resample_tiled<GB><<<grid, kResThreads, smem, st>>>(p, pitch);
+}
+
+void launch_resample_tiled(const ResampleParams& p, cudaStream_t st)
+{
+  if (p.na == 0 || p.S == 0)
+    return;
+  // as many groups of 4 outputs per CTA as fit the shared memory (the halo of `order` samples is amortised over them)
+  auto need = [&](unsigned gb, unsigned* pitch) {
+    const unsigned span_max = (unsigned)(4.0f * gb * p.pstep) + p.order + 12;
+    *pitch = span_max | 1u;
+    return (size_t)gb * p.lp * sizeof(float4) + (size_t)2 * 32 * *pitch * sizeof(float);
+  };
+  const size_t budget = 200 * 1024;
+  unsigned pitch = 0;
+  size_t smem = need(16, &pitch);
+  if (smem <= budget)
+    return launch_resample_tiled_gb<16>(p, pitch, smem, st);
+  smem = need(8, &pitch);
+  if (smem <= budget)
+    return launch_resample_tiled_gb<8>(p, pitch, smem, st);
+  smem = need(4, &pitch);
+  if (smem <= budget)
+    return launch_resample_tiled_gb<4>(p, pitch, smem, st);
+  launch_resample(p, st); // very long filters: untiled form
 }
 
 // ==================================================================================================

@@ -64,7 +64,7 @@ RFM_HD void demod_step_fast(DemodState& st, float xr, float xi, const DemodConst
   const float dim = addf(mulf(Cos, xi), mulf(Sin, xr));
   const float err = negf(rfm_atan2f_fast(dim, dre, bad));
   const float incr = fminf(fmaxf(addf(st.incr, mulf(k.beta, err)), k.lo), k.hi);
-  bad = bad || !(absf(st.phase) < 16.0f);
+  bad = bad | (!(absf(st.phase) < 16.0f));
   st.incr = incr;
   st.phase = rfm_wrap_demod_fast(addf(st.phase, addf(incr, mulf(k.alpha, err))), bad);
 }
@@ -116,7 +116,7 @@ RFM_HD float pilot_step(PilotState& st, float x, const PilotConstDev& k)
 RFM_HD float pilot_step_fast(PilotState& st, float x, const PilotConstDev& k, bool& bad)
 {
   float ps, pc;
-  bad = bad || !(absf(st.phase) < 16.0f);
+  bad = bad | (!(absf(st.phase) < 16.0f));
   rfm_sincos_core(st.phase, &ps, &pc);
   const float out = mulf(mulf(2.0f, ps), pc);
   float pi = mulf(ps, x);
@@ -128,7 +128,7 @@ RFM_HD float pilot_step_fast(PilotState& st, float x, const PilotConstDev& k, bo
   st.q2 = st.q1;
   st.q1 = pq;
   const bool use_div = pi > absf(pq);
-  bad = bad || (use_div && rfm_div_unsafe(pq, pi));
+  bad = bad | (use_div & rfm_div_unsafe(pq, pi));
   const float ediv = rfm_div_fast(pq, pi);
   const float esat = (pq > 0.0f) ? 1.0f : -1.0f;
   const float err = use_div ? ediv : esat;
