@@ -145,6 +145,10 @@ RFM_API int rfm_decoder_set_profiling(rfm_decoder* d, int on);
 RFM_API int rfm_decoder_profile_read(rfm_decoder* d, uint32_t index, char* name, uint32_t name_cap,
                                      double* total_ms, uint64_t* launches);
 
+/* Telemetry of the time-parallel FM-demodulator PLL: number of 192-sample chunks (summed over streams) whose
+ * speculative result had to be recomputed sequentially since the decoder was created. */
+RFM_API int rfm_decoder_demod_repairs(rfm_decoder* d, uint64_t* chunks);
+
 /* Debug taps of the last block, copied to host (rows of n_streams).  name: demod_in baseband rawstereo
  * mono_rs stereo_rs lp rds_dec rds_lp rds_pll rds_mf.  Returns floats per stream in *n_floats. */
 RFM_API int rfm_decoder_tap(rfm_decoder* d, const char* name, uint32_t stream, float* out, uint32_t max_floats,

@@ -43,7 +43,7 @@ EXPORTED_SYMBOLS = (
     "rfm_last_error", "rfm_version", "rfm_launch_count", "rfm_config_default", "rfm_decoder_create",
     "rfm_decoder_destroy", "rfm_decoder_reset", "rfm_decoder_max_audio_floats", "rfm_decoder_process_u8",
     "rfm_decoder_process_cf32", "rfm_decoder_process_u8_device", "rfm_decoder_process_cf32_device", "rfm_decoder_wait",
-    "rfm_decoder_synchronize",
+    "rfm_decoder_synchronize", "rfm_decoder_demod_repairs",
     "rfm_decoder_rds_take_groups", "rfm_decoder_rds_take_bits", "rfm_decoder_get_status",
     "rfm_decoder_constants", "rfm_decoder_table", "rfm_plan_constants", "rfm_plan_table", "rfm_decoder_set_profiling",
     "rfm_decoder_profile_read", "rfm_decoder_tap", "rfm_rdssync_create",
@@ -92,6 +92,7 @@ def lib():
                                                       C.c_size_t, _u32p, C.c_void_p]
         L.rfm_decoder_wait.argtypes = [C.c_void_p, C.c_void_p]
         L.rfm_decoder_synchronize.argtypes = [C.c_void_p]
+        L.rfm_decoder_demod_repairs.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.rfm_decoder_rds_take_groups.argtypes = [C.c_void_p, C.c_uint32, _u16p, C.c_uint32, _u32p]
         L.rfm_decoder_rds_take_bits.argtypes = [C.c_void_p, C.c_uint32, _u8p, C.c_uint32, _u32p]
         L.rfm_decoder_get_status.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(RfmStreamStatus)]
@@ -225,6 +226,11 @@ class FmDecoderBatch:
     def wait(self, cuda_stream: int = 0):
         """Order `cuda_stream` after every block enqueued so far (device entry points only enqueue)."""
         _check(lib().rfm_decoder_wait(self._h, C.c_void_p(cuda_stream)))
+
+    def demod_repairs(self) -> int:
+        v = C.c_uint64(0)
+        _check(lib().rfm_decoder_demod_repairs(self._h, C.byref(v)))
+        return int(v.value)
 
     def synchronize(self):
         _check(lib().rfm_decoder_synchronize(self._h))

@@ -93,6 +93,8 @@ struct Group
   cudaEvent_t ev_lanes[2] = {nullptr, nullptr}; // PLL lanes ...
   cudaEvent_t ev_rest[2] = {nullptr, nullptr};  // stage B ...
   DevBuf<cf32> tail, z[2];
+  DevBuf<float> incr;          // NCO increments, demodulator -> lanes (same stream: single buffer)
+  DevBuf<float2> dm_start, dm_end; // speculative demodulator chunk states
   DevBuf<float> bbV[2], rawV[2];
   DevBuf<cf32> hbV[kMaxDecStages]; // input V buffer of stage k (k >= 1); stage 0 reads bbV x oscV
   DevBuf<cf32> rlpV, rlp_out;
@@ -121,6 +123,7 @@ struct rfm_decoder
   DevBuf<float> d_hb[kMaxDecStages];
   DevBuf<cf32> oscV[2];
   DevBuf<float> osc1;
+  DevBuf<unsigned long long> d_repairs; // demodulator chunks repaired sequentially (telemetry)
   DevBuf<float> res_kk[2]; // per-block interpolated resampler taps, shared by all streams (by parity)
   DevBuf<int> res_meta[2];
   unsigned res_lp = 0;
@@ -164,7 +167,7 @@ void FreeDecoder(rfm_decoder* d)
     for (cudaStream_t st : {g.sF, g.sA, g.sB, g.sR})
       if (st)
         cudaStreamSynchronize(st);
-    g.tail.Free(); g.z[0].Free(); g.z[1].Free();
+    g.tail.Free(); g.z[0].Free(); g.z[1].Free(); g.incr.Free(); g.dm_start.Free(); g.dm_end.Free();
     for (int b = 0; b < 2; ++b)
     {
       g.bbV[b].Free();
@@ -186,7 +189,7 @@ void FreeDecoder(rfm_decoder* d)
   for (auto& b : d->d_hb) b.Free();
   if (d->s_osc)
     cudaStreamSynchronize(d->s_osc);
-  d->oscV[0].Free(); d->oscV[1].Free(); d->osc1.Free();
+  d->oscV[0].Free(); d->oscV[1].Free(); d->osc1.Free(); d->d_repairs.Free();
   for (int b = 0; b < 2; ++b)
   {
     d->res_kk[b].Free();
@@ -430,14 +433,22 @@ void EnqueueStageA(rfm_decoder* d, Group& g, const BlockGeom& bg, unsigned par)
   tp.d[1] = {g.rawV[par ^ 1u].p, g.rawV[par].p, d->a_stride * sizeof(float), a_hist, d->last_nb, 4, S};
   RFM_PROF(g.prof, "k_tails", st, launch_tails(tp, S, st));
 
+  DemodSpecParams dp;
+  dp.z = g.z[par].p; dp.z_stride = d->z_stride; dp.nb = bg.nb; dp.S = S; dp.state = g.state.p;
+  dp.demod = {p.demod_gain, p.nco_lo, p.nco_hi, p.pll_alpha, p.pll_beta};
+  dp.incr = g.incr.p; dp.w_stride = d->z_stride; dp.st_start = g.dm_start.p; dp.st_end = g.dm_end.p;
+  dp.repairs = d->d_repairs.p;
+  RFM_PROF(g.prof, "k_demod_spec", st, launch_demod_spec(dp, st));
+  RFM_PROF(g.prof, "k_demod_fix", st, launch_demod_fix(dp, st));
+
   LanesParams lp;
-  lp.z = g.z[par].p; lp.z_stride = d->z_stride; lp.nb = bg.nb; lp.S = S; lp.state = g.state.p;
-  lp.demod = {p.demod_gain, p.nco_lo, p.nco_hi, p.pll_alpha, p.pll_beta};
+  lp.incr = g.incr.p; lp.w_stride = d->z_stride; lp.nb = bg.nb; lp.S = S; lp.state = g.state.p;
+  lp.demod = dp.demod;
   lp.pilot = {p.pilot.minfreq, p.pilot.maxfreq, p.pilot.b0, p.pilot.a1, p.pilot.a2, p.pilot.lb0, p.pilot.lb1,
               p.pilot.minsignal, p.pilot.lock_delay};
   lp.bbV = g.bbV[par].p; lp.rawV = g.rawV[par].p; lp.a_stride = d->a_stride; lp.a_hist = a_hist; lp.parity = par;
   RFM_PROF(g.prof, "k_bb_lanes", st, launch_bb_lanes(lp, st));
-  g_launches += 2;
+  g_launches += 4;
 }
 
 // Stage B of one block for one group (stream sB): audio branch, RDS branch, history carry of its own buffers.
@@ -802,6 +813,7 @@ int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out)
     else
       RFM_TRY(d->d_hb[k].Alloc(4));
   }
+  RFM_TRY(d->d_repairs.Alloc(1));
   d->res_lp = p.a_order + 1 + 3 * ((unsigned)p.a_ratio + 1) + 4;
   for (int b = 0; b < 2; ++b)
   {
@@ -850,6 +862,9 @@ int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out)
     RFM_TRY(g.tail.Alloc(S * p.in_order));
     RFM_TRY(g.z[0].Alloc(S * d->z_stride));
     RFM_TRY(g.z[1].Alloc(S * d->z_stride));
+    RFM_TRY(g.incr.Alloc(S * d->z_stride));
+    RFM_TRY(g.dm_start.Alloc(S * (size_t)demod_chunks(d->nb_max)));
+    RFM_TRY(g.dm_end.Alloc(S * (size_t)demod_chunks(d->nb_max)));
     for (int b = 0; b < 2; ++b)
     {
       RFM_TRY(g.bbV[b].Alloc(S * d->a_stride));
@@ -979,6 +994,19 @@ int rfm_decoder_wait(rfm_decoder* d, void* cuda_stream)
       RFM_CUDA(cudaEventRecord(d->ev_join, st));
       RFM_CUDA(cudaStreamWaitEvent(user, d->ev_join, 0));
     }
+  return RFM_OK;
+}
+
+int rfm_decoder_demod_repairs(rfm_decoder* d, uint64_t* chunks)
+{
+  if (!d || !chunks)
+    return Fail(RFM_ERR_INVALID, "bad argument");
+  int rc = SyncAll(d);
+  if (rc != RFM_OK)
+    return rc;
+  unsigned long long v = 0;
+  RFM_CUDA(cudaMemcpy(&v, d->d_repairs.p, sizeof(v), cudaMemcpyDeviceToHost));
+  *chunks = v;
   return RFM_OK;
 }
 

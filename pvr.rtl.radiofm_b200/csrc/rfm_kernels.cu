@@ -480,11 +480,256 @@ void launch_if_level(const FrontParams& p, float* state, bool u8, cudaStream_t s
 // through a 2-slot shared-memory ring guarded by named barriers.  Per-sample cost is max(demod, pilot)
 // instead of the sum.
 // --------------------------------------------------------------------------------------------------
+// --------------------------------------------------------------------------------------------------
+// FM-demodulator PLL (FmDecode.cpp:361-409), time-parallel and still bit-exact.
+// The loop is a fast contraction: two copies driven by the same input but started from different states
+// (phase, increment) differ by a factor ~0.58 per sample (poles of the linearised loop), so after a short warm-up
+// they coincide to the last bit.  k_demod_spec cuts the block into chunks of kDemodChunk samples and runs every
+// (stream, chunk) on its own lane: chunk 0 starts from the carried state, chunk c > 0 starts kDemodWarm samples
+// early from a guess (phase 0, carried increment).  It records the state it had at the chunk start and at the
+// chunk end.  k_demod_fix then walks the chunks of a stream in order: where the recorded start state of chunk c is
+// bit-identical to the (now known exact) end state of chunk c-1 the speculative outputs ARE the sequential ones;
+// anywhere else -- in practice never on a tuned station, routinely on pure noise -- the chunk is recomputed
+// sequentially from the exact state.  The result is always exactly the reference's sequential recurrence.
+// --------------------------------------------------------------------------------------------------
+constexpr unsigned kDemodChunk = 192; // multiples of the 32-sample tile
+constexpr unsigned kDemodWarm = 96;
+
+__global__ void __launch_bounds__(32) k_demod_spec(DemodSpecParams p)
+{
+  __shared__ float2 zin[2][32][kLT + 1];
+  __shared__ float wout[32][kLT + 1];
+  const unsigned lane = threadIdx.x;
+  const unsigned s0 = blockIdx.x * 32;
+  const unsigned s = s0 + lane;
+  const unsigned c = blockIdx.y;
+  const bool valid = s < p.S;
+  const unsigned S = p.S;
+  const unsigned t_begin = c * kDemodChunk;
+  const unsigned t_end = min(p.nb, t_begin + kDemodChunk);
+  const unsigned t_start = (c == 0) ? 0u : t_begin - kDemodWarm;
+
+  DemodState dm = {0.f, 0.f};
+  if (valid)
+  {
+    dm.incr = p.state[SF_DEMOD_INCR * S + s];
+    if (c == 0)
+      dm.phase = p.state[SF_DEMOD_PHASE * S + s];
+  }
+  const float2* z = reinterpret_cast<const float2*>(p.z);
+  const unsigned ntiles = (t_end - t_start + kLT - 1) / kLT;
+  tile_load_async(zin[0], z, p.z_stride, s0, S, t_start, t_end, lane);
+  cp_async_commit();
+  for (unsigned t = 0; t < ntiles; ++t)
+  {
+    const unsigned b = t & 1u, t0 = t_start + t * kLT;
+    const unsigned tn = min(kLT, t_end - t0);
+    if (t + 1 < ntiles)
+      tile_load_async(zin[b ^ 1u], z, p.z_stride, s0, S, t0 + kLT, t_end, lane);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncwarp();
+    if (t0 == t_begin && valid)
+      p.st_start[(size_t)c * S + s] = make_float2(dm.phase, dm.incr);
+    const DemodState tile_start = dm;
+    bool bad = false;
+    if (valid)
+    {
+      for (unsigned k = 0; k < tn; ++k)
+      {
+        const float2 x = zin[b][lane][k];
+        demod_step_fast(dm, x.x, x.y, p.demod, bad);
+        wout[lane][k] = dm.incr;
+      }
+    }
+    if (__any_sync(0xffffffffu, bad))
+    {
+      dm = tile_start;
+      if (valid)
+      {
+        for (unsigned k = 0; k < tn; ++k)
+        {
+          const float2 x = zin[b][lane][k];
+          demod_step(dm, x.x, x.y, p.demod);
+          wout[lane][k] = dm.incr;
+        }
+      }
+    }
+    __syncwarp();
+    if (t0 >= t_begin)
+      tile_store(p.incr, p.w_stride, s0, S, t0, t_end, lane, wout);
+    __syncwarp();
+  }
+  if (valid)
+    p.st_end[(size_t)c * S + s] = make_float2(dm.phase, dm.incr);
+}
+
+// Parallel repair pass: every (stream, chunk >= 1) whose assumed start state is not the end state of the previous
+// chunk is recomputed from that end state -- all such chunks at once, one lane each.  A repaired chunk nearly
+// always ends in the state it ended in before (the loop had converged inside the chunk), so one or two passes
+// leave nothing for the sequential k_demod_fix, which remains as the unconditional guarantee.
+__global__ void __launch_bounds__(32) k_demod_repair(DemodSpecParams p)
+{
+  __shared__ float2 zin[2][32][kLT + 1];
+  __shared__ float wout[32][kLT + 1];
+  const unsigned lane = threadIdx.x;
+  const unsigned s0 = blockIdx.x * 32;
+  const unsigned s = s0 + lane;
+  const unsigned c = blockIdx.y + 1;
+  const unsigned S = p.S;
+  const bool valid = s < S;
+  float2 prev_end = make_float2(0.f, 0.f), assumed = prev_end;
+  if (valid)
+  {
+    prev_end = p.st_end[(size_t)(c - 1) * S + s];
+    assumed = p.st_start[(size_t)c * S + s];
+  }
+  const bool mism = valid && (__float_as_uint(assumed.x) != __float_as_uint(prev_end.x) ||
+                              __float_as_uint(assumed.y) != __float_as_uint(prev_end.y));
+  const unsigned rows = __ballot_sync(0xffffffffu, mism);
+  if (rows == 0u)
+    return;
+  if (mism && p.repairs)
+    atomicAdd(p.repairs, 1ull);
+  const unsigned t_begin = c * kDemodChunk;
+  const unsigned t_end = min(p.nb, t_begin + kDemodChunk);
+  DemodState dm = {prev_end.x, prev_end.y};
+  const float2* z = reinterpret_cast<const float2*>(p.z);
+  const unsigned ntiles = (t_end - t_begin + kLT - 1) / kLT;
+  tile_load_async(zin[0], z, p.z_stride, s0, S, t_begin, t_end, lane);
+  cp_async_commit();
+  for (unsigned t = 0; t < ntiles; ++t)
+  {
+    const unsigned b = t & 1u, t0 = t_begin + t * kLT;
+    const unsigned tn = min(kLT, t_end - t0);
+    if (t + 1 < ntiles)
+      tile_load_async(zin[b ^ 1u], z, p.z_stride, s0, S, t0 + kLT, t_end, lane);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncwarp();
+    const DemodState tile_start = dm;
+    bool bad = false;
+    if (mism)
+    {
+      for (unsigned k = 0; k < tn; ++k)
+      {
+        const float2 x = zin[b][lane][k];
+        demod_step_fast(dm, x.x, x.y, p.demod, bad);
+        wout[lane][k] = dm.incr;
+      }
+    }
+    if (__any_sync(0xffffffffu, bad))
+    {
+      dm = tile_start;
+      if (mism)
+      {
+        for (unsigned k = 0; k < tn; ++k)
+        {
+          const float2 x = zin[b][lane][k];
+          demod_step(dm, x.x, x.y, p.demod);
+          wout[lane][k] = dm.incr;
+        }
+      }
+    }
+    __syncwarp();
+    // only the repaired rows are written back
+    if (t0 + lane < t_end)
+      for (unsigned r = 0; r < 32; ++r)
+        if ((rows >> r) & 1u)
+          p.incr[(size_t)(s0 + r) * p.w_stride + t0 + lane] = wout[r][lane];
+    __syncwarp();
+  }
+  if (mism)
+  {
+    p.st_start[(size_t)c * S + s] = prev_end;
+    p.st_end[(size_t)c * S + s] = make_float2(dm.phase, dm.incr);
+  }
+}
+
+__global__ void __launch_bounds__(32) k_demod_fix(DemodSpecParams p)
+{
+  const unsigned s = blockIdx.x * 32 + threadIdx.x;
+  const bool valid = s < p.S;
+  const unsigned S = p.S;
+  const unsigned nchunks = (p.nb + kDemodChunk - 1) / kDemodChunk;
+  float2 cur = make_float2(0.f, 0.f);
+  if (valid)
+    cur = p.st_end[s];
+  const float2* z = reinterpret_cast<const float2*>(p.z) + (size_t)s * p.z_stride;
+  float* w = p.incr + (size_t)s * p.w_stride;
+  for (unsigned c = 1; c < nchunks; ++c)
+  {
+    float2 assumed = cur, end = cur;
+    if (valid)
+    {
+      assumed = p.st_start[(size_t)c * S + s];
+      end = p.st_end[(size_t)c * S + s];
+    }
+    const bool mism = valid && (__float_as_uint(assumed.x) != __float_as_uint(cur.x) ||
+                                __float_as_uint(assumed.y) != __float_as_uint(cur.y));
+    if (__any_sync(0xffffffffu, mism))
+    {
+      if (mism)
+      {
+        if (p.repairs)
+          atomicAdd(p.repairs, 1ull);
+        // the speculation missed for this stream: redo the chunk from the exact state (rare; direct global access)
+        DemodState dm = {cur.x, cur.y};
+        const unsigned t1 = min(p.nb, (c + 1) * kDemodChunk);
+        for (unsigned t = c * kDemodChunk; t < t1; ++t)
+        {
+          const float2 x = z[t];
+          demod_step(dm, x.x, x.y, p.demod);
+          w[t] = dm.incr;
+        }
+        end = make_float2(dm.phase, dm.incr);
+      }
+    }
+    cur = end;
+  }
+  if (valid)
+  {
+    p.state[SF_DEMOD_PHASE * S + s] = cur.x;
+    p.state[SF_DEMOD_INCR * S + s] = cur.y;
+  }
+}
+
+void launch_demod_spec(const DemodSpecParams& p, cudaStream_t st)
+{
+  if (p.S == 0 || p.nb == 0)
+    return;
+  const unsigned nchunks = cdiv(p.nb, kDemodChunk);
+  dim3 grid(cdiv(p.S, 32), nchunks);
+  k_demod_spec<<<grid, 32, 0, st>>>(p);
+}
+
+void launch_demod_fix(const DemodSpecParams& p, cudaStream_t st)
+{
+  if (p.S == 0 || p.nb == 0)
+    return;
+  const unsigned nchunks = cdiv(p.nb, kDemodChunk);
+  if (nchunks > 1)
+  {
+    dim3 grid(cdiv(p.S, 32), nchunks - 1);
+    k_demod_repair<<<grid, 32, 0, st>>>(p);
+    k_demod_repair<<<grid, 32, 0, st>>>(p);
+  }
+  k_demod_fix<<<cdiv(p.S, 32), 32, 0, st>>>(p);
+}
+
+unsigned demod_chunks(unsigned nb) { return cdiv(nb, kDemodChunk); }
+
+// --------------------------------------------------------------------------------------------------
+// baseband lanes: warp 0 = DC tracker + output scaling (FmDecode.cpp:410-412) and baseband meters (:439-442);
+// warp 1 = 19 kHz pilot PLL (:143-229) and the 38 kHz demux multiply (:455-456).  Both are one-lane-per-stream
+// recurrences; the pilot PLL consumes the baseband the first warp produces, so they run as a two-stage pipeline on
+// two warps (two SM sub-partitions): tiles of baseband go through a 2-slot shared-memory ring guarded by named
+// barriers, and the pilot warp -- the long pole of the whole chain -- carries nothing but its own recurrence.
+// --------------------------------------------------------------------------------------------------
 struct LanesSmem
 {
-  float2 zin[2][32][kLT + 1];
-  float ring[2][32][kLT + 1];
-  float bbt[32][kLT + 1];
+  float win[2][32][kLT + 1];   // NCO increments from the demodulator
+  float ring[2][32][kLT + 1];  // baseband, warp 0 -> warp 1
   float rawt[32][kLT + 1];
 };
 
@@ -503,70 +748,55 @@ __global__ void __launch_bounds__(64) k_bb_lanes(LanesParams p)
 
   if (role == 0)
   {
-    // ---------------- producer: FM demodulator PLL ----------------
-    DemodState dm = {0.f, 0.f};
+    // ---------------- producer: DC tracker, output scaling, meters ----------------
+    float dc = 0.0f, vsum = 0.0f, vsumsq = 0.0f;
     if (valid)
-    {
-      dm.phase = st[SF_DEMOD_PHASE * S + s];
-      dm.incr = st[SF_DEMOD_INCR * S + s];
-    }
-    const float2* z = reinterpret_cast<const float2*>(p.z);
-    tile_load_async(sm.zin[0], z, p.z_stride, s0, S, 0, p.nb, lane);
+      dc = st[SF_DEMOD_DC * S + s];
+    tile_load_async(sm.win[0], p.incr, p.w_stride, s0, S, 0, p.nb, lane);
     cp_async_commit();
     for (unsigned t = 0; t < ntiles; ++t)
     {
       const unsigned b = t & 1u, t0 = t * kLT;
       const unsigned tn = min(kLT, p.nb - t0);
       if (t + 1 < ntiles)
-        tile_load_async(sm.zin[b ^ 1u], z, p.z_stride, s0, S, t0 + kLT, p.nb, lane);
+        tile_load_async(sm.win[b ^ 1u], p.incr, p.w_stride, s0, S, t0 + kLT, p.nb, lane);
       cp_async_commit();
       cp_async_wait<1>();
       __syncwarp();
       if (t >= 2)
         bar_sync(BAR_EMPTY + b, 64);
-      // branch-free fast path; if any lane raised the sticky flag the tile is replayed with the exact routines
-      const DemodState tile_start = dm;
-      bool bad = false;
       if (valid)
       {
         for (unsigned k = 0; k < tn; ++k)
         {
-          const float2 x = sm.zin[b][lane][k];
-          demod_step_fast(dm, x.x, x.y, p.demod, bad);
-          sm.ring[b][lane][k] = dm.incr;
-        }
-      }
-      if (__any_sync(0xffffffffu, bad))
-      {
-        dm = tile_start;
-        if (valid)
-        {
-          for (unsigned k = 0; k < tn; ++k)
-          {
-            const float2 x = sm.zin[b][lane][k];
-            demod_step(dm, x.x, x.y, p.demod);
-            sm.ring[b][lane][k] = dm.incr;
-          }
+          const float bb = demod_output(sm.win[b][lane][k], dc, p.demod.gain);
+          vsum = addf(vsum, bb);                       // SamplesMeanRMS, FmDecode.cpp:522-539
+          vsumsq = addf(vsumsq, mulf(bb, bb));
+          sm.ring[b][lane][k] = bb;
         }
       }
       __threadfence_block();
       bar_arrive(BAR_FULL + b, 64);
       __syncwarp();
+      tile_store(p.bbV + p.a_hist, p.a_stride, s0, S, t0, p.nb, lane, sm.ring[b]);
+      __syncwarp();
     }
     if (valid)
     {
-      st[SF_DEMOD_PHASE * S + s] = dm.phase;
-      st[SF_DEMOD_INCR * S + s] = dm.incr;
+      st[SF_DEMOD_DC * S + s] = dc;
+      // baseband meters, FmDecode.cpp:439-442
+      const float mean = divf(vsum, (float)p.nb);
+      const float rms = sqrtf_rn(divf(vsumsq, (float)p.nb));
+      st[SF_BB_MEAN * S + s] = addf(mulf(0.95f, st[SF_BB_MEAN * S + s]), mulf(0.05f, mean));
+      st[SF_BB_LEVEL * S + s] = addf(mulf(0.95f, st[SF_BB_LEVEL * S + s]), mulf(0.05f, rms));
     }
   }
   else
   {
-    // ---------------- consumer: DC tracker, meters, pilot PLL, demux multiply ----------------
+    // ---------------- consumer: pilot PLL, demux multiply ----------------
     PilotState pl = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 1000.0f};
-    float dc = 0.0f, vsum = 0.0f, vsumsq = 0.0f;
     if (valid)
     {
-      dc = st[SF_DEMOD_DC * S + s];
       pl.phase = st[SF_PILOT_PHASE * S + s];
       pl.freq = st[SF_PILOT_FREQ * S + s];
       pl.i1 = st[SF_PILOT_I1 * S + s];
@@ -581,33 +811,27 @@ __global__ void __launch_bounds__(64) k_bb_lanes(LanesParams p)
       const unsigned b = t & 1u, t0 = t * kLT;
       const unsigned tn = min(kLT, p.nb - t0);
       bar_sync(BAR_FULL + b, 64);
+      // branch-free fast path; if any lane raised the sticky flag the tile is replayed with the exact routines
       const PilotState pl_start = pl;
-      const float dc_start = dc, vsum_start = vsum, vsumsq_start = vsumsq;
       bool bad = false;
       if (valid)
       {
         for (unsigned k = 0; k < tn; ++k)
         {
-          const float bb = demod_output(sm.ring[b][lane][k], dc, p.demod.gain);
-          vsum = addf(vsum, bb);                       // SamplesMeanRMS, FmDecode.cpp:522-539
-          vsumsq = addf(vsumsq, mulf(bb, bb));
+          const float bb = sm.ring[b][lane][k];
           const float p38 = pilot_step_fast(pl, bb, p.pilot, bad);
-          sm.bbt[lane][k] = bb;
           sm.rawt[lane][k] = mulf(p38, mulf(2.0f, bb)); // FmDecode.cpp:455-456
         }
       }
       if (__any_sync(0xffffffffu, bad))
       {
-        pl = pl_start; dc = dc_start; vsum = vsum_start; vsumsq = vsumsq_start;
+        pl = pl_start;
         if (valid)
         {
           for (unsigned k = 0; k < tn; ++k)
           {
-            const float bb = demod_output(sm.ring[b][lane][k], dc, p.demod.gain);
-            vsum = addf(vsum, bb);
-            vsumsq = addf(vsumsq, mulf(bb, bb));
+            const float bb = sm.ring[b][lane][k];
             const float p38 = pilot_step(pl, bb, p.pilot);
-            sm.bbt[lane][k] = bb;
             sm.rawt[lane][k] = mulf(p38, mulf(2.0f, bb));
           }
         }
@@ -615,13 +839,11 @@ __global__ void __launch_bounds__(64) k_bb_lanes(LanesParams p)
       if (t + 2 < ntiles)
         bar_arrive(BAR_EMPTY + b, 64);
       __syncwarp();
-      tile_store(p.bbV + p.a_hist, p.a_stride, s0, S, t0, p.nb, lane, sm.bbt);
       tile_store(p.rawV + p.a_hist, p.a_stride, s0, S, t0, p.nb, lane, sm.rawt);
       __syncwarp();
     }
     if (valid)
     {
-      st[SF_DEMOD_DC * S + s] = dc;
       st[SF_PILOT_PHASE * S + s] = pl.phase;
       st[SF_PILOT_FREQ * S + s] = pl.freq;
       st[SF_PILOT_I1 * S + s] = pl.i1;
@@ -641,11 +863,6 @@ __global__ void __launch_bounds__(64) k_bb_lanes(LanesParams p)
         lock_cnt = 0;
       st[SF_PILOT_LOCKCNT * S + s] = __int_as_float(lock_cnt);
       st[(SF_STEREO + p.parity) * S + s] = __int_as_float(lock_cnt >= p.pilot.lock_delay ? 1 : 0);
-      // baseband meters, FmDecode.cpp:439-442
-      const float mean = divf(vsum, (float)p.nb);
-      const float rms = sqrtf_rn(divf(vsumsq, (float)p.nb));
-      st[SF_BB_MEAN * S + s] = addf(mulf(0.95f, st[SF_BB_MEAN * S + s]), mulf(0.05f, mean));
-      st[SF_BB_LEVEL * S + s] = addf(mulf(0.95f, st[SF_BB_LEVEL * S + s]), mulf(0.05f, rms));
     }
   }
 }
@@ -656,6 +873,7 @@ void launch_bb_lanes(const LanesParams& p, cudaStream_t st)
     return;
   k_bb_lanes<<<cdiv(p.S, 32), 64, 0, st>>>(p);
 }
+
 
 // ==================================================================================================
 // fractional resampler (mono + stereo), DownConvert.cpp:195-233

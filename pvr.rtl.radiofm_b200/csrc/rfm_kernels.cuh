@@ -84,10 +84,28 @@ void launch_front_tail(const FrontParams& p, bool u8, cudaStream_t st);
 // ---- baseband lanes: IF meter, FM-demod PLL, DC tracker, BB meters, pilot PLL, 38 kHz demux multiply --
 void launch_if_level(const FrontParams& p, float* state, bool u8, cudaStream_t st);
 
+// ---- FM-demodulator PLL: speculative chunk-parallel pass + exactness check / sequential repair --------------------
+struct DemodSpecParams
+{
+  const cf32* z;           // [S][z_stride] decimated IQ
+  size_t z_stride;
+  unsigned nb, S;
+  float* state;            // [SF_COUNT][S]: SF_DEMOD_PHASE / SF_DEMOD_INCR carried
+  DemodConst demod;
+  float* incr;             // [S][w_stride] NCO increment after every sample
+  size_t w_stride;
+  float2* st_start;        // [chunks][S] state a chunk assumed at its first sample
+  float2* st_end;          // [chunks][S] state after its last sample
+  unsigned long long* repairs; // telemetry: chunks that had to be recomputed sequentially (may be null)
+};
+void launch_demod_spec(const DemodSpecParams& p, cudaStream_t st);
+void launch_demod_fix(const DemodSpecParams& p, cudaStream_t st);
+unsigned demod_chunks(unsigned nb);
+
 struct LanesParams
 {
-  const cf32* z;
-  size_t z_stride;
+  const float* incr;       // [S][w_stride] from the demodulator
+  size_t w_stride;
   unsigned nb;             // baseband samples per stream
   unsigned S;
   float* state;            // [SF_COUNT][S]
