@@ -154,6 +154,28 @@ RFM_API int rfm_decoder_demod_repairs(rfm_decoder* d, uint64_t* chunks);
 RFM_API int rfm_decoder_tap(rfm_decoder* d, const char* name, uint32_t stream, float* out, uint32_t max_floats,
                             uint32_t* n_floats);
 
+/* ------------------------------------------------------------------------------------------------
+ * cFreqShift (FreqShift.h:12-27, FreqShift.cpp:10-76), batched over rows: one NCO per row (stations of one
+ * wideband capture, or independent streams).  Bug-compatible with the reference's x86 branch: float32 phase,
+ * float32 increment float(K_2PI * f / Fs), never wrapped.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rfm_freqshift rfm_freqshift;
+/* cFreqShift(NcoFreq, InRate) per row -- FreqShift.cpp:10-16 */
+RFM_API int rfm_freqshift_create(uint32_t rows, const float* nco_freq, float in_rate, uint32_t max_len, int device,
+                                 rfm_freqshift** out);
+RFM_API void rfm_freqshift_destroy(rfm_freqshift* f);
+/* cFreqShift::Reset -- FreqShift.cpp:18-21 */
+RFM_API int rfm_freqshift_reset(rfm_freqshift* f);
+/* cFreqShift::Process(ComplexType* pInData, unsigned InLength), in place -- FreqShift.cpp:23-76; iq [rows][n][2] host */
+RFM_API int rfm_freqshift_process_cf32(rfm_freqshift* f, float* iq, uint32_t n);
+/* the same fused with cRtlSdrSource::ReadAsyncCB's u8 -> float conversion (RTL_SDR_Source.cpp:207-211): iq is one
+ * shared capture [n][2] (shared_capture != 0: every row mixes the same samples with its own NCO) or [rows][n][2];
+ * out [rows][n][2] float, host */
+RFM_API int rfm_freqshift_process_u8(rfm_freqshift* f, const uint8_t* iq, int shared_capture, uint32_t n, float* out);
+/* device pointers; mode 0: cf32 rows (d_out may alias d_in), 1: one shared u8 capture, 2: u8 rows; strides in samples */
+RFM_API int rfm_freqshift_process_device(rfm_freqshift* f, int mode, const void* d_in, size_t in_stride, float* d_out,
+                                         size_t out_stride, uint32_t n, void* cuda_stream);
+
 /* Test hooks (no reference counterpart): evaluate one of the scalar building blocks of the kernels on the DEVICE for
  * n host operands; out2 receives two floats per element.  op: 0 rfm_sincos (sin, cos) 1 sincos fast core
  * 2 sincos generic 3 atan2f(a, b) 4 branch-free atan2f (+flag) 5 atan2f generic 6 branch-free a / b (+flag)

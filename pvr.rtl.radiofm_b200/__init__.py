@@ -48,7 +48,9 @@ EXPORTED_SYMBOLS = (
     "rfm_decoder_constants", "rfm_decoder_table", "rfm_plan_constants", "rfm_plan_table", "rfm_decoder_set_profiling",
     "rfm_decoder_profile_read", "rfm_decoder_tap", "rfm_rdssync_create",
     "rfm_rdssync_destroy", "rfm_rdssync_reset", "rfm_rdssync_push_bits", "rfm_rdssync_take_groups",
-    "rfm_rds_check_block", "rfm_math_probe", "rfm_div_selftest",
+    "rfm_rds_check_block", "rfm_math_probe", "rfm_div_selftest", "rfm_freqshift_create",
+    "rfm_freqshift_destroy", "rfm_freqshift_reset", "rfm_freqshift_process_cf32", "rfm_freqshift_process_u8",
+    "rfm_freqshift_process_device",
 )
 
 
@@ -111,6 +113,13 @@ def lib():
         L.rfm_rdssync_take_groups.argtypes = [C.c_void_p, _u16p, C.c_uint32, _u32p]
         L.rfm_math_probe.argtypes = [C.c_int, _f32p, _f32p, _f32p, C.c_uint32]
         L.rfm_div_selftest.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.rfm_freqshift_create.argtypes = [C.c_uint32, _f32p, C.c_float, C.c_uint32, C.c_int, C.POINTER(C.c_void_p)]
+        L.rfm_freqshift_destroy.argtypes = [C.c_void_p]
+        L.rfm_freqshift_reset.argtypes = [C.c_void_p]
+        L.rfm_freqshift_process_cf32.argtypes = [C.c_void_p, _f32p, C.c_uint32]
+        L.rfm_freqshift_process_u8.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_uint32, _f32p]
+        L.rfm_freqshift_process_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                                   C.c_uint32, C.c_void_p]
         L.rfm_rds_check_block.restype = C.c_uint32
         L.rfm_rds_check_block.argtypes = [C.c_uint32, C.c_uint32, C.c_int, _u32p]
         _lib = L
@@ -320,6 +329,38 @@ class RdsBlockSync:
         k = C.c_uint32(0)
         _check(lib().rfm_rdssync_take_groups(self._h, _p(out, _u16p), max_groups, C.byref(k)))
         return out[:k.value].copy()
+
+
+class FreqShiftBatch:
+    """rows x cFreqShift (FreqShift.h:12-27): one float32 NCO per row, never wrapped (x86 reference behaviour)."""
+
+    def __init__(self, nco_freq, in_rate: float, max_len: int = 65536, device: int = -1):
+        f = np.ascontiguousarray(np.atleast_1d(nco_freq), dtype=np.float32)
+        self.rows = f.size
+        self._h = C.c_void_p()
+        _check(lib().rfm_freqshift_create(self.rows, _p(f, _f32p), in_rate, max_len, device, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().rfm_freqshift_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reset(self):
+        _check(lib().rfm_freqshift_reset(self._h))
+
+    def process_cf32(self, iq: np.ndarray) -> np.ndarray:
+        iq = np.array(iq, dtype=np.float32, order="C").reshape(self.rows, -1, 2)
+        _check(lib().rfm_freqshift_process_cf32(self._h, _p(iq, _f32p), iq.shape[1]))
+        return iq
+
+    def process_u8(self, iq_u8: np.ndarray, shared_capture: bool) -> np.ndarray:
+        iq_u8 = np.ascontiguousarray(iq_u8, dtype=np.uint8)
+        n = iq_u8.reshape(-1, 2).shape[0] // (1 if shared_capture else self.rows)
+        out = np.empty((self.rows, n, 2), dtype=np.float32)
+        _check(lib().rfm_freqshift_process_u8(self._h, _p(iq_u8, _u8p), int(shared_capture), n, _p(out, _f32p)))
+        return out
 
 
 def math_probe(op: int, a: np.ndarray, b: np.ndarray | None = None) -> np.ndarray:

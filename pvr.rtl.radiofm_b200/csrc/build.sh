@@ -10,7 +10,8 @@ mkdir -p build
 $NVCC $NVFLAGS -c rfm_kernels.cu -o build/rfm_kernels.o
 $NVCC $NVFLAGS -c rfm_api.cu -o build/rfm_api.o
 $NVCC $NVFLAGS -c rfm_probe.cu -o build/rfm_probe.o
+$NVCC $NVFLAGS -c rfm_freqshift.cu -o build/rfm_freqshift.o
 g++ -O2 -std=c++17 -fPIC -fvisibility=hidden -ffp-contract=off -c rfm_plan.cpp -o build/rfm_plan.o
 g++ -O2 -std=c++17 -fPIC -fvisibility=hidden -ffp-contract=off -c rfm_rdssync.cpp -o build/rfm_rdssync.o
-$NVCC $ARCH -shared -o $OUT build/rfm_kernels.o build/rfm_api.o build/rfm_probe.o build/rfm_plan.o build/rfm_rdssync.o -lcudart_static -lpthread -ldl -lrt
+$NVCC $ARCH -shared -o $OUT build/rfm_kernels.o build/rfm_api.o build/rfm_probe.o build/rfm_freqshift.o build/rfm_plan.o build/rfm_rdssync.o -lcudart_static -lpthread -ldl -lrt
 echo "built $(readlink -f $OUT)"

@@ -1,0 +1,106 @@
+// host/FmDecode.h -- cFmDecoder with the reference's signatures (FmDecode.h:99-165), forwarding to the B200 chain
+// through the C ABI (include/radiofm_b200.h).  A maintainer of the add-on replaces `#include "FmDecode.h"` by this
+// header and links libradiofm_b200.so; cRadioReceiver::OpenLiveStream / DemuxRead (RadioReceiver.cpp:296-300,
+// 515-525) keep calling the same constructor, ProcessStream, Reset and getters.  No CPU fallback: construction
+// throws std::runtime_error when no sm_100 device / library is usable.
+//
+// RDS: the reference hands decoded groups to its cRDSGroupDecoder from inside ProcessStream
+// (RDSProcess.cpp:312,355).  Here the groups decoded during a ProcessStream call are delivered, in order and on the
+// calling thread, to the sink set with SetRdsGroupSink() before ProcessStream returns -- e.g.
+//     dec.SetRdsGroupSink([&](uint16_t* blk) { m_Decoder.DecodeRDS(blk); });   // RDSGroupDecoder.h:29
+#pragma once
+
+#include <stdint.h>
+
+#include <functional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/radiofm_b200.h"
+#include "Definitions.h"
+
+#define DEFAULT_BANDWIDTH_PCM 15000 // FmDecode.h:22
+
+class cFmDecoder
+{
+public:
+  cFmDecoder(cRadioReceiver* proc, double sample_rate_if, double tuning_offset, double sample_rate_pcm,
+             double bandwidth_pcm = DEFAULT_BANDWIDTH_PCM, unsigned int downsample = 1, bool USver = false,
+             int cuda_device = -1)
+    : m_proc(proc)
+  {
+    rfm_config cfg;
+    rfm_config_default(&cfg);
+    cfg.sample_rate_if = sample_rate_if;
+    cfg.tuning_offset = tuning_offset;
+    cfg.sample_rate_pcm = sample_rate_pcm;
+    cfg.bandwidth_pcm = bandwidth_pcm;
+    cfg.downsample = downsample;
+    cfg.us_deemphasis = USver ? 1 : 0;
+    cfg.n_streams = 1;
+    cfg.max_block_len = 65536; // FmDecode.cpp:277-282
+    cfg.device = cuda_device;
+    if (rfm_decoder_create(&cfg, &m_dec) != RFM_OK)
+      throw std::runtime_error(std::string("cFmDecoder (B200): ") + rfm_last_error());
+  }
+  virtual ~cFmDecoder() { rfm_decoder_destroy(m_dec); }
+  cFmDecoder(const cFmDecoder&) = delete;
+  cFmDecoder& operator=(const cFmDecoder&) = delete;
+
+  void Reset() { rfm_decoder_reset(m_dec); } // FmDecode.cpp:326-338
+
+  // FmDecode.h:135 -- returns the number of floats written (2 x frames, interleaved L,R)
+  unsigned int ProcessStream(const ComplexType* samples_in, unsigned int samples, float* audio)
+  {
+    uint32_t n_out = 0;
+    const int rc = rfm_decoder_process_cf32(m_dec, reinterpret_cast<const float*>(samples_in), samples, audio,
+                                            2 * (size_t)samples, &n_out);
+    if (rc != RFM_OK)
+      return 0; // the reference has no error channel; rfm_last_error() has the text
+    DeliverGroups();
+    return n_out;
+  }
+  // the same, straight from the RTL-SDR byte stream (skips the u8 -> float expansion of RTL_SDR_Source.cpp:207-211)
+  unsigned int ProcessStreamU8(const uint8_t* iq_u8, unsigned int samples, float* audio)
+  {
+    uint32_t n_out = 0;
+    if (rfm_decoder_process_u8(m_dec, iq_u8, samples, audio, 2 * (size_t)samples, &n_out) != RFM_OK)
+      return 0;
+    DeliverGroups();
+    return n_out;
+  }
+
+  bool StereoDetected() const { return Status().stereo_detected != 0; }       // FmDecode.h:140
+  RealType GetTuningOffset() const { return Status().tuning_offset; }         // FmDecode.h:146-150
+  RealType GetInterfaceLevel() const { return Status().interface_level; }     // FmDecode.h:155
+  RealType GetBasebandLevel() const { return Status().baseband_level; }       // FmDecode.h:160
+  RealType GetPilotLevel() const { return Status().pilot_level; }             // FmDecode.h:165
+
+  void SetRdsGroupSink(std::function<void(uint16_t*)> sink) { m_sink = std::move(sink); }
+  cRadioReceiver* Receiver() const { return m_proc; }
+
+private:
+  rfm_stream_status Status() const
+  {
+    rfm_stream_status s = {};
+    rfm_decoder_get_status(m_dec, 0, &s);
+    return s;
+  }
+  void DeliverGroups()
+  {
+    uint16_t blk[64][4];
+    uint32_t n = 0;
+    do
+    {
+      if (rfm_decoder_rds_take_groups(m_dec, 0, &blk[0][0], 64, &n) != RFM_OK)
+        return;
+      for (uint32_t i = 0; i < n && m_sink; ++i)
+        m_sink(blk[i]);
+    } while (n == 64);
+  }
+
+  cRadioReceiver* m_proc;
+  rfm_decoder* m_dec = nullptr;
+  std::function<void(uint16_t*)> m_sink;
+};
