@@ -4,8 +4,8 @@
 // Execution model.  One decoder = n_streams independent IQ streams processed in lock step, split into G groups
 // (G = 1 unless asked otherwise; the host-pointer entry points use groups to overlap H2D / compute / D2H).
 // Each group owns three CUDA streams and runs every block as a three-stage software pipeline:
-//     stage F (stream sF):  if_level, front (u8 -> tune -> FIR / ds)
-//     stage A (stream sA, high priority):  bb_lanes (demod PLL || pilot PLL)
+//     stage F (stream sF):  if_level, front (u8 -> tune -> FIR / ds), time-parallel FM-demodulator PLL
+//     stage A (stream sA, high priority):  bb_lanes (DC tracker / meters || pilot PLL)
 //     stage B (stream sB):  { resample -> lp29 -> audio_tail }, { halfband* -> rds lp -> rds pll -> matched
 //                           filter -> slicer }, tails
 // While the lanes of block k run, the front end of block k+1 and stage B of block k-1 are in flight: the
@@ -90,10 +90,11 @@ struct Group
   cudaStream_t sF = nullptr, sA = nullptr, sB = nullptr, sR = nullptr; // front / lanes / audio branch / RDS branch
   cudaEvent_t ev_rds[2] = {nullptr, nullptr};   // RDS branch of the block with this parity finished
   cudaEvent_t ev_front[2] = {nullptr, nullptr}; // front end of the block with this parity finished
+  cudaEvent_t ev_demod[2] = {nullptr, nullptr}; // demodulator done: z[parity] may be overwritten
   cudaEvent_t ev_lanes[2] = {nullptr, nullptr}; // PLL lanes ...
   cudaEvent_t ev_rest[2] = {nullptr, nullptr};  // stage B ...
   DevBuf<cf32> tail, z[2];
-  DevBuf<float> incr;          // NCO increments, demodulator -> lanes (same stream: single buffer)
+  DevBuf<float> incr[2];       // NCO increments, demodulator (stage F) -> lanes (stage A), by parity
   DevBuf<float2> dm_start, dm_end; // speculative demodulator chunk states
   DevBuf<float> bbV[2], rawV[2];
   DevBuf<cf32> hbV[kMaxDecStages]; // input V buffer of stage k (k >= 1); stage 0 reads bbV x oscV
@@ -136,7 +137,7 @@ struct rfm_decoder
   double prof_ms[kMaxProfKinds] = {0};
   uint64_t prof_count[kMaxProfKinds] = {0};
   ProfSlot main_prof[kMaxProfKinds];
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_base = nullptr;
   // lock-step state (identical for every stream)
   unsigned tuner_idx = 0, in_pos = 0;
   float a_pos = 0.0f;
@@ -167,7 +168,7 @@ void FreeDecoder(rfm_decoder* d)
     for (cudaStream_t st : {g.sF, g.sA, g.sB, g.sR})
       if (st)
         cudaStreamSynchronize(st);
-    g.tail.Free(); g.z[0].Free(); g.z[1].Free(); g.incr.Free(); g.dm_start.Free(); g.dm_end.Free();
+    g.tail.Free(); g.z[0].Free(); g.z[1].Free(); g.incr[0].Free(); g.incr[1].Free(); g.dm_start.Free(); g.dm_end.Free();
     for (int b = 0; b < 2; ++b)
     {
       g.bbV[b].Free();
@@ -177,9 +178,11 @@ void FreeDecoder(rfm_decoder* d)
     g.rlpV.Free(); g.rlp_out.Free(); g.mfV.Free(); g.mf_out.Free(); g.bits.Free(); g.bit_count.Free();
     g.lpS.Free(); g.lpM.Free(); g.fS.Free(); g.fM.Free(); g.state.Free(); g.in_stage.Free(); g.audio_stage.Free();
     ProfFree(g.prof);
-    for (cudaEvent_t e : {g.ev_front[0], g.ev_front[1], g.ev_lanes[0], g.ev_lanes[1], g.ev_rest[0], g.ev_rest[1], g.ev_rds[0], g.ev_rds[1]})
+    for (cudaEvent_t e : {g.ev_demod[0], g.ev_demod[1], g.ev_front[0], g.ev_front[1], g.ev_lanes[0], g.ev_lanes[1], g.ev_rest[0], g.ev_rest[1], g.ev_rds[0], g.ev_rds[1]})
       if (e)
         cudaEventDestroy(e);
+    if (g.sF == g.sA)
+      g.sF = g.sB = g.sR = nullptr; // RFM_DEBUG_SERIAL aliasing
     for (cudaStream_t st : {g.sF, g.sA, g.sB, g.sR})
       if (st)
         cudaStreamDestroy(st);
@@ -262,6 +265,7 @@ struct ProfScope
 
 void ProfCollect(rfm_decoder* d, ProfSlot* slots)
 {
+  static const bool timeline = getenv("RFM_DEBUG_TIMELINE") != nullptr;
   for (int k = 0; k < kMaxProfKinds; ++k)
   {
     ProfSlot& sl = slots[k];
@@ -272,6 +276,12 @@ void ProfCollect(rfm_decoder* d, ProfSlot* slots)
       {
         d->prof_ms[k] += ms;
         d->prof_count[k] += 1;
+        if (timeline && d->ev_base)
+        {
+          float t0 = 0.0f;
+          if (cudaEventElapsedTime(&t0, d->ev_base, sl.ev[i].first) == cudaSuccess)
+            fprintf(stderr, "TL %-16s %9.4f %9.4f\n", d->prof_names[k], t0, t0 + ms);
+        }
       }
     }
     sl.used = 0;
@@ -415,7 +425,18 @@ void EnqueueStageF(rfm_decoder* d, Group& g, const void* d_in, size_t in_stride,
   RFM_PROF(g.prof, "k_if_level", st, launch_if_level(fp, g.state.p, u8, st));
   RFM_PROF(g.prof, "k_front", st, launch_front(fp, u8, st));
   RFM_PROF(g.prof, "k_front_tail", st, launch_front_tail(fp, u8, st));
-  g_launches += 3;
+
+  // FM-demodulator PLL, time-parallel (throughput work like the front end).  It overwrites incr[par], which the
+  // lanes of block k-2 were reading.
+  cudaStreamWaitEvent(st, g.ev_lanes[par], 0);
+  DemodSpecParams dp;
+  dp.z = g.z[par].p; dp.z_stride = d->z_stride; dp.nb = bg.nb; dp.S = S; dp.state = g.state.p;
+  dp.demod = {p.demod_gain, p.nco_lo, p.nco_hi, p.pll_alpha, p.pll_beta};
+  dp.incr = g.incr[par].p; dp.w_stride = d->z_stride; dp.st_start = g.dm_start.p; dp.st_end = g.dm_end.p;
+  dp.repairs = d->d_repairs.p;
+  RFM_PROF(g.prof, "k_demod_spec", st, launch_demod_spec(dp, st));
+  RFM_PROF(g.prof, "k_demod_fix", st, launch_demod_fix(dp, st));
+  g_launches += 7;
 }
 
 // Stage A of one block for one group (stream sA): history hand-over, PLL lanes.
@@ -433,22 +454,14 @@ void EnqueueStageA(rfm_decoder* d, Group& g, const BlockGeom& bg, unsigned par)
   tp.d[1] = {g.rawV[par ^ 1u].p, g.rawV[par].p, d->a_stride * sizeof(float), a_hist, d->last_nb, 4, S};
   RFM_PROF(g.prof, "k_tails", st, launch_tails(tp, S, st));
 
-  DemodSpecParams dp;
-  dp.z = g.z[par].p; dp.z_stride = d->z_stride; dp.nb = bg.nb; dp.S = S; dp.state = g.state.p;
-  dp.demod = {p.demod_gain, p.nco_lo, p.nco_hi, p.pll_alpha, p.pll_beta};
-  dp.incr = g.incr.p; dp.w_stride = d->z_stride; dp.st_start = g.dm_start.p; dp.st_end = g.dm_end.p;
-  dp.repairs = d->d_repairs.p;
-  RFM_PROF(g.prof, "k_demod_spec", st, launch_demod_spec(dp, st));
-  RFM_PROF(g.prof, "k_demod_fix", st, launch_demod_fix(dp, st));
-
   LanesParams lp;
-  lp.incr = g.incr.p; lp.w_stride = d->z_stride; lp.nb = bg.nb; lp.S = S; lp.state = g.state.p;
-  lp.demod = dp.demod;
+  lp.incr = g.incr[par].p; lp.w_stride = d->z_stride; lp.nb = bg.nb; lp.S = S; lp.state = g.state.p;
+  lp.demod = {p.demod_gain, p.nco_lo, p.nco_hi, p.pll_alpha, p.pll_beta};
   lp.pilot = {p.pilot.minfreq, p.pilot.maxfreq, p.pilot.b0, p.pilot.a1, p.pilot.a2, p.pilot.lb0, p.pilot.lb1,
               p.pilot.minsignal, p.pilot.lock_delay};
   lp.bbV = g.bbV[par].p; lp.rawV = g.rawV[par].p; lp.a_stride = d->a_stride; lp.a_hist = a_hist; lp.parity = par;
   RFM_PROF(g.prof, "k_bb_lanes", st, launch_bb_lanes(lp, st));
-  g_launches += 4;
+  g_launches += 2;
 }
 
 // Stage B of one block for one group (stream sB): audio branch, RDS branch, history carry of its own buffers.
@@ -627,7 +640,7 @@ int ProcessDevice(rfm_decoder* d, const void* d_in, size_t in_stride, bool u8, u
     // ---- stage F
     if (!host_staged)
       RFM_CUDA(cudaStreamWaitEvent(g.sF, d->ev_fork, 0));
-    RFM_CUDA(cudaStreamWaitEvent(g.sF, g.ev_lanes[par], 0)); // the lanes of block k-2 have released z[par]
+    // (z[par] was last read by the demodulator of block k-2, on this same stream)
     if (host_staged)
     {
       RFM_CUDA(cudaMemcpy2DAsync(g.in_stage.p, (size_t)d->maxn * esz, in_g, in_stride * esz, (size_t)n * esz, g.S,
@@ -847,14 +860,24 @@ int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out)
     {
       int prio_lo = 0, prio_hi = 0; // the latency-bound lanes kernel gets its CTAs placed first
       RFM_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+      if (getenv("RFM_DEBUG_NOPRIO"))
+        prio_hi = prio_lo;
+      // sA (demodulator + lanes) is the critical chain, the front end feeds it; the audio / RDS branches have slack
       RFM_TRY(cudaStreamCreateWithPriority(&g.sA, cudaStreamNonBlocking, prio_hi));
-      RFM_TRY(cudaStreamCreateWithPriority(&g.sF, cudaStreamNonBlocking, prio_lo));
+      RFM_TRY(cudaStreamCreateWithPriority(&g.sF, cudaStreamNonBlocking,
+                                           getenv("RFM_DEBUG_FLOW") ? prio_lo : std::min(prio_lo, prio_hi + 1)));
       RFM_TRY(cudaStreamCreateWithPriority(&g.sB, cudaStreamNonBlocking, prio_lo));
       RFM_TRY(cudaStreamCreateWithPriority(&g.sR, cudaStreamNonBlocking, prio_lo));
+      if (getenv("RFM_DEBUG_SERIAL"))
+      { // measurement aid: every stage on ONE stream, so per-kernel event times are isolated durations
+        cudaStreamDestroy(g.sF); cudaStreamDestroy(g.sB); cudaStreamDestroy(g.sR);
+        g.sF = g.sB = g.sR = g.sA;
+      }
     }
     for (int b = 0; b < 2; ++b)
     {
       RFM_TRY(cudaEventCreateWithFlags(&g.ev_front[b], cudaEventDisableTiming));
+      RFM_TRY(cudaEventCreateWithFlags(&g.ev_demod[b], cudaEventDisableTiming));
       RFM_TRY(cudaEventCreateWithFlags(&g.ev_rds[b], cudaEventDisableTiming));
       RFM_TRY(cudaEventCreateWithFlags(&g.ev_lanes[b], cudaEventDisableTiming));
       RFM_TRY(cudaEventCreateWithFlags(&g.ev_rest[b], cudaEventDisableTiming));
@@ -862,7 +885,8 @@ int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out)
     RFM_TRY(g.tail.Alloc(S * p.in_order));
     RFM_TRY(g.z[0].Alloc(S * d->z_stride));
     RFM_TRY(g.z[1].Alloc(S * d->z_stride));
-    RFM_TRY(g.incr.Alloc(S * d->z_stride));
+    RFM_TRY(g.incr[0].Alloc(S * d->z_stride));
+    RFM_TRY(g.incr[1].Alloc(S * d->z_stride));
     RFM_TRY(g.dm_start.Alloc(S * (size_t)demod_chunks(d->nb_max)));
     RFM_TRY(g.dm_end.Alloc(S * (size_t)demod_chunks(d->nb_max)));
     for (int b = 0; b < 2; ++b)
@@ -1176,6 +1200,12 @@ int rfm_decoder_set_profiling(rfm_decoder* d, int on)
   memset(d->prof_ms, 0, sizeof(d->prof_ms));
   memset(d->prof_count, 0, sizeof(d->prof_count));
   d->profiling = on != 0;
+  if (on)
+  {
+    if (!d->ev_base)
+      cudaEventCreate(&d->ev_base);
+    cudaEventRecord(d->ev_base, d->s_osc);
+  }
   return RFM_OK;
 }
 

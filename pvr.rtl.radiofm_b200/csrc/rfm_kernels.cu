@@ -22,6 +22,7 @@
 #include "rfm_kernels.cuh"
 
 #include <assert.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace rfm
@@ -1012,13 +1013,14 @@ void launch_res_taps(const ResTapsParams& p, cudaStream_t st)
 constexpr unsigned kResThreads = 256;
 constexpr unsigned kResWarps = kResThreads / 32;
 
-template <int GB> // groups of 4 outputs per CTA
+// NCH = 2: one CTA makes both channels (mono and L-R share the taps: one broadcast LDS.128 per 16 multiply / add);
+// NCH = 1: blockIdx.z selects the channel (half the shared-memory tile per CTA).
+template <int GB, int NCH> // groups of 4 outputs per CTA
 __global__ void __launch_bounds__(kResThreads) k_resample_tiled(ResampleParams p, unsigned pitch)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* KK = reinterpret_cast<float4*>(smem_raw);                 // [GB][lp]
-  float* Xm = reinterpret_cast<float*>(KK + (size_t)GB * p.lp);     // [32][pitch]
-  float* Xs = Xm + 32 * pitch;
+  float* X = reinterpret_cast<float*>(KK + (size_t)GB * p.lp);      // [NCH][32][pitch]
   __shared__ int s_meta[2 * GB];
 
   const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -1027,118 +1029,128 @@ __global__ void __launch_bounds__(kResThreads) k_resample_tiled(ResampleParams p
   const unsigned gn = min((unsigned)GB, ngroups - g0);
   const unsigned s0 = blockIdx.y * 32;
   const unsigned rows = min(32u, p.S - s0);
+  const float* src[2] = {(NCH == 2 || blockIdx.z == 0) ? p.bbV : p.rawV, p.rawV};
+  float* dst[2] = {(NCH == 2 || blockIdx.z == 0) ? p.lpM : p.lpS, p.lpS};
   if (tid < 2 * gn)
     s_meta[tid] = p.meta[2 * g0 + tid];
   __syncthreads();
   const int v0 = s_meta[0];
   const int span = s_meta[2 * (gn - 1)] + s_meta[2 * (gn - 1) + 1] - v0; // V range of the CTA
-  // taps of the CTA's groups
   {
-    const float4* src = reinterpret_cast<const float4*>(p.kk) + (size_t)g0 * p.lp;
+    const float4* ksrc = reinterpret_cast<const float4*>(p.kk) + (size_t)g0 * p.lp;
     for (unsigned i = tid; i < gn * p.lp; i += kResThreads)
-      KK[i] = src[i];
+      KK[i] = ksrc[i];
   }
-  // input rows, transposed: warp w stages rows w, w + kResWarps, ...; 8 columns x 2 arrays in flight per lane
+  // input rows, transposed: warp w stages rows w, w + kResWarps, ...; 8 columns per array in flight per lane
   for (unsigned r = warp; r < rows; r += kResWarps)
   {
-    const float* bm = p.bbV + (size_t)(s0 + r) * p.a_stride + v0;
-    const float* bs = p.rawV + (size_t)(s0 + r) * p.a_stride + v0;
     for (int c0 = 0; c0 < span; c0 += 256)
     {
-      float vm[8], vs[8];
+      float v[NCH][8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
+      for (int ch = 0; ch < NCH; ++ch)
       {
-        const int c = c0 + u * 32 + (int)lane;
-        vm[u] = (c < span) ? bm[c] : 0.0f;
-        vs[u] = (c < span) ? bs[c] : 0.0f;
-      }
+        const float* b = src[ch] + (size_t)(s0 + r) * p.a_stride + v0;
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
-      {
-        const int c = c0 + u * 32 + (int)lane;
-        if (c < span)
+        for (int u = 0; u < 8; ++u)
         {
-          Xm[r * pitch + c] = vm[u];
-          Xs[r * pitch + c] = vs[u];
+          const int c = c0 + u * 32 + (int)lane;
+          v[ch][u] = (c < span) ? b[c] : 0.0f;
         }
       }
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+        {
+          const int c = c0 + u * 32 + (int)lane;
+          if (c < span)
+            X[(ch * 32 + r) * pitch + c] = v[ch][u];
+        }
     }
   }
   __syncthreads();
   if (lane >= rows)
     return;
-  const float* xm = Xm + lane * pitch;
-  const float* xs = Xs + lane * pitch;
+  const float* x0 = X + lane * pitch;
+  const float* x1 = X + (32 + lane) * pitch;
   for (unsigned gi = warp; gi < gn; gi += kResWarps)
   {
     const int off = s_meta[2 * gi] - v0;
     const int L = s_meta[2 * gi + 1];
     const float4* kk = KK + (size_t)gi * p.lp;
-    float am[4] = {0.f, 0.f, 0.f, 0.f}, as[4] = {0.f, 0.f, 0.f, 0.f};
+    float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
     for (int tt = L - 1; tt >= 0; --tt)
     {
       const float4 k = kk[tt];
-      const float m = xm[off + tt], sv = xs[off + tt];
-      am[0] = addf(am[0], mulf(k.x, m)); as[0] = addf(as[0], mulf(k.x, sv));
-      am[1] = addf(am[1], mulf(k.y, m)); as[1] = addf(as[1], mulf(k.y, sv));
-      am[2] = addf(am[2], mulf(k.z, m)); as[2] = addf(as[2], mulf(k.z, sv));
-      am[3] = addf(am[3], mulf(k.w, m)); as[3] = addf(as[3], mulf(k.w, sv));
+      const float m = x0[off + tt];
+      a[0] = addf(a[0], mulf(k.x, m));
+      a[1] = addf(a[1], mulf(k.y, m));
+      a[2] = addf(a[2], mulf(k.z, m));
+      a[3] = addf(a[3], mulf(k.w, m));
+      if (NCH == 2)
+      {
+        const float sv = x1[off + tt];
+        b[0] = addf(b[0], mulf(k.x, sv));
+        b[1] = addf(b[1], mulf(k.y, sv));
+        b[2] = addf(b[2], mulf(k.z, sv));
+        b[3] = addf(b[3], mulf(k.w, sv));
+      }
     }
     const unsigned i = 4 * (g0 + gi);
-    float* om = p.lpM + (size_t)(s0 + lane) * p.lp_stride + p.lp_hist + i;
-    float* os = p.lpS + (size_t)(s0 + lane) * p.lp_stride + p.lp_hist + i;
-    if (i + 4 <= p.na && ((p.lp_hist | p.lp_stride) & 3u) == 0)
+    const bool vec = i + 4 <= p.na && ((p.lp_hist | p.lp_stride) & 3u) == 0;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch)
     {
-      *reinterpret_cast<float4*>(om) = make_float4(am[0], am[1], am[2], am[3]);
-      *reinterpret_cast<float4*>(os) = make_float4(as[0], as[1], as[2], as[3]);
-    }
-    else
-    {
-      for (unsigned r = 0; r < 4 && i + r < p.na; ++r)
-      {
-        om[r] = am[r];
-        os[r] = as[r];
-      }
+      float* o = dst[ch] + (size_t)(s0 + lane) * p.lp_stride + p.lp_hist + i;
+      const float* acc = ch ? b : a;
+      if (vec)
+        *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      else
+        for (unsigned r = 0; r < 4 && i + r < p.na; ++r)
+          o[r] = acc[r];
     }
   }
 }
 
-template <int GB>
+template <int GB, int NCH>
 static void launch_resample_tiled_gb(const ResampleParams& p, unsigned pitch, size_t smem, cudaStream_t st)
 {
   static size_t attr = 0;
   if (smem > attr)
   {
-    cudaFuncSetAttribute(k_resample_tiled<GB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_resample_tiled<GB, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = smem;
   }
-  dim3 grid(cdiv((p.na + 3) / 4, GB), cdiv(p.S, 32));
-  k_resample_tiled<GB><<<grid, kResThreads, smem, st>>>(p, pitch);
+  dim3 grid(cdiv((p.na + 3) / 4, GB), cdiv(p.S, 32), NCH == 2 ? 1 : 2);
+  k_resample_tiled<GB, NCH><<<grid, kResThreads, smem, st>>>(p, pitch);
 }
 
 void launch_resample_tiled(const ResampleParams& p, cudaStream_t st)
 {
   if (p.na == 0 || p.S == 0)
     return;
-  // as many groups of 4 outputs per CTA as fit the shared memory (the halo of `order` samples is amortised over them)
-  auto need = [&](unsigned gb, unsigned* pitch) {
+  auto need = [&](unsigned gb, unsigned nch, unsigned* pitch) {
     const unsigned span_max = (unsigned)(4.0f * gb * p.pstep) + p.order + 12;
     *pitch = span_max | 1u;
-    return (size_t)gb * p.lp * sizeof(float4) + (size_t)2 * 32 * *pitch * sizeof(float);
+    return (size_t)gb * p.lp * sizeof(float4) + (size_t)nch * 32 * *pitch * sizeof(float);
   };
-  const size_t budget = 200 * 1024;
+  static const int variant = getenv("RFM_RES_VARIANT") ? atoi(getenv("RFM_RES_VARIANT")) : 0;
   unsigned pitch = 0;
-  size_t smem = need(16, &pitch);
-  if (smem <= budget)
-    return launch_resample_tiled_gb<16>(p, pitch, smem, st);
-  smem = need(8, &pitch);
-  if (smem <= budget)
-    return launch_resample_tiled_gb<8>(p, pitch, smem, st);
-  smem = need(4, &pitch);
-  if (smem <= budget)
-    return launch_resample_tiled_gb<4>(p, pitch, smem, st);
+  size_t smem;
+  if (variant == 1 && (smem = need(8, 2, &pitch)) <= 200 * 1024)
+    return launch_resample_tiled_gb<8, 2>(p, pitch, smem, st);
+  if (variant == 2 && (smem = need(8, 1, &pitch)) <= 200 * 1024)
+    return launch_resample_tiled_gb<8, 1>(p, pitch, smem, st);
+  if (variant == 3 && (smem = need(16, 1, &pitch)) <= 200 * 1024)
+    return launch_resample_tiled_gb<16, 1>(p, pitch, smem, st);
+  if ((smem = need(16, 2, &pitch)) <= 200 * 1024)
+    return launch_resample_tiled_gb<16, 2>(p, pitch, smem, st);
+  if ((smem = need(8, 2, &pitch)) <= 200 * 1024)
+    return launch_resample_tiled_gb<8, 2>(p, pitch, smem, st);
+  if ((smem = need(4, 2, &pitch)) <= 200 * 1024)
+    return launch_resample_tiled_gb<4, 2>(p, pitch, smem, st);
   launch_resample(p, st); // very long filters: untiled form
 }
 
