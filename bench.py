@@ -291,10 +291,14 @@ def run_b200(args):
     for i in range(max(1, W // 2)):
         step_host(i)
     barrier()
+    if os.environ.get("RFM_E2E_PROF"):
+        dec.set_profiling(True)
     t0 = time.perf_counter()
     for i in range(K):
         step_host(i)
     groups = dec.take_groups(0)   # drains the RDS bits of every stream to the host block-sync
+    if os.environ.get("RFM_E2E_PROF"):
+        dec.profile()
     torch.cuda.synchronize()
     dt = max_over_ranks(time.perf_counter() - t0)
     barrier()

@@ -23,6 +23,7 @@
 #include <atomic>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/radiofm_b200.h"
@@ -50,6 +51,8 @@ int Fail(int code, const std::string& msg)
     if (e_ != cudaSuccess)                                                                               \
       return Fail(RFM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));                    \
   } while (0)
+
+constexpr size_t kMaxKeptBits = 1u << 16; // raw RDS bits retained per stream between rfm_decoder_rds_take_bits calls
 
 unsigned AlignUp(unsigned v, unsigned a) { return (v + a - 1) / a * a; }
 
@@ -351,16 +354,31 @@ int DrainBits(rfm_decoder* d)
       continue;
     d->h_bits.resize((size_t)g.S * mx);
     RFM_CUDA(cudaMemcpy2D(d->h_bits.data(), mx, g.bits.p, d->bits_cap, mx, g.S, cudaMemcpyDeviceToHost));
-    for (unsigned s = 0; s < g.S; ++s)
-    {
-      const uint8_t* b = d->h_bits.data() + (size_t)s * mx;
-      auto& hb = d->host_bits[g.s0 + s];
-      auto& sy = d->sync[g.s0 + s];
-      for (unsigned i = 0; i < d->h_counts[s]; ++i)
+    // host block sync / FEC (RDSProcess.cpp:272-431): streams are independent -> spread over the host cores
+    auto work = [&](unsigned lo, unsigned hi) {
+      for (unsigned s = lo; s < hi; ++s)
       {
-        hb.push_back(b[i]);
-        sy.PushBit(b[i]);
+        const uint8_t* b = d->h_bits.data() + (size_t)s * mx;
+        const unsigned cnt = d->h_counts[s];
+        auto& hb = d->host_bits[g.s0 + s];
+        if (hb.size() + cnt > kMaxKeptBits) // raw bits are kept for rfm_decoder_rds_take_bits, bounded
+          hb.erase(hb.begin(), hb.begin() + std::min(hb.size(), hb.size() + cnt - kMaxKeptBits));
+        hb.insert(hb.end(), b, b + cnt);
+        auto& sy = d->sync[g.s0 + s];
+        for (unsigned i = 0; i < cnt; ++i)
+          sy.PushBit(b[i]);
       }
+    };
+    const unsigned nthreads = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), std::max(1u, g.S / 64));
+    if (nthreads <= 1)
+      work(0, g.S);
+    else
+    {
+      std::vector<std::thread> pool;
+      for (unsigned t = 0; t < nthreads; ++t)
+        pool.emplace_back(work, (unsigned)((uint64_t)g.S * t / nthreads), (unsigned)((uint64_t)g.S * (t + 1) / nthreads));
+      for (auto& th : pool)
+        th.join();
     }
     RFM_CUDA(cudaMemset(g.bit_count.p, 0, g.S * sizeof(unsigned)));
   }
@@ -643,10 +661,22 @@ int ProcessDevice(rfm_decoder* d, const void* d_in, size_t in_stride, bool u8, u
     // (z[par] was last read by the demodulator of block k-2, on this same stream)
     if (host_staged)
     {
-      RFM_CUDA(cudaMemcpy2DAsync(g.in_stage.p, (size_t)d->maxn * esz, in_g, in_stride * esz, (size_t)n * esz, g.S,
-                                 cudaMemcpyHostToDevice, g.sF));
+      // one contiguous copy when the caller's rows are dense (the usual case): the staging rows are then packed too
+      if (in_stride == n)
+      {
+        {
+          ProfScope ps_(d, g.prof, "copy_h2d", g.sF);
+          RFM_CUDA(cudaMemcpyAsync(g.in_stage.p, in_g, (size_t)g.S * n * esz, cudaMemcpyHostToDevice, g.sF));
+        }
+        in_stride_dev = n;
+      }
+      else
+      {
+        RFM_CUDA(cudaMemcpy2DAsync(g.in_stage.p, (size_t)d->maxn * esz, in_g, in_stride * esz, (size_t)n * esz, g.S,
+                                   cudaMemcpyHostToDevice, g.sF));
+        in_stride_dev = d->maxn;
+      }
       in_dev = g.in_stage.p;
-      in_stride_dev = d->maxn;
       audio_dev = g.audio_stage.p;
       audio_stride_dev = d->audio_cap;
     }
@@ -670,9 +700,12 @@ int ProcessDevice(rfm_decoder* d, const void* d_in, size_t in_stride, bool u8, u
     RFM_CUDA(cudaEventRecord(g.ev_rds[par], g.sR));
     RFM_CUDA(cudaStreamWaitEvent(g.sB, g.ev_rds[par], 0)); // ev_rest (recorded on sB) covers both branches
     if (host_staged)
+    {
+      ProfScope ps_(d, g.prof, "copy_d2h", g.sB);
       RFM_CUDA(cudaMemcpy2DAsync(audio_g, audio_stride * sizeof(float), g.audio_stage.p,
                                  (size_t)d->audio_cap * sizeof(float), (size_t)2 * bg.na * sizeof(float), g.S,
                                  cudaMemcpyDeviceToHost, g.sB));
+    }
     RFM_CUDA(cudaEventRecord(g.ev_rest[par], g.sB));
   }
   RFM_CUDA(cudaGetLastError());

@@ -493,7 +493,7 @@ void launch_if_level(const FrontParams& p, float* state, bool u8, cudaStream_t s
 // anywhere else -- in practice never on a tuned station, routinely on pure noise -- the chunk is recomputed
 // sequentially from the exact state.  The result is always exactly the reference's sequential recurrence.
 // --------------------------------------------------------------------------------------------------
-constexpr unsigned kDemodChunk = 192; // multiples of the 32-sample tile
+constexpr unsigned kDemodChunk = 384; // multiples of the 32-sample tile
 constexpr unsigned kDemodWarm = 96;
 
 __global__ void __launch_bounds__(32) k_demod_spec(DemodSpecParams p)
@@ -712,7 +712,6 @@ void launch_demod_fix(const DemodSpecParams& p, cudaStream_t st)
   if (nchunks > 1)
   {
     dim3 grid(cdiv(p.S, 32), nchunks - 1);
-    k_demod_repair<<<grid, 32, 0, st>>>(p);
     k_demod_repair<<<grid, 32, 0, st>>>(p);
   }
   k_demod_fix<<<cdiv(p.S, 32), 32, 0, st>>>(p);
