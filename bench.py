@@ -306,6 +306,29 @@ def run_b200(args):
            "d2h_bytes_per_step": S * int(kout.value) * 4, "ms_per_step": dt / K * 1e3,
            "api": "rfm_decoder_process_u8 (pinned host IQ in, host audio out) + rfm_decoder_rds_take_groups"}
 
+    # the same with asynchronous submission (rfm_decoder_submit_u8 + rfm_decoder_synchronize): two host input / output
+    # buffers alternate, so the H2D copy of block k+1 overlaps the kernels of block k
+    h_audio2 = torch.empty((2, S, stride), dtype=torch.float32).pin_memory()
+
+    def submit_host(i):
+        rc = lib.rfm_decoder_submit_u8(dec._h, C.cast(h_iq[i % nh].data_ptr(), C.POINTER(C.c_uint8)), BLK,
+                                       C.cast(h_audio2[i % 2].data_ptr(), C.POINTER(C.c_float)), stride, C.byref(kout))
+        if rc != 0:
+            raise RuntimeError(lib.rfm_last_error().decode())
+
+    submit_host(0)
+    dec.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        submit_host(i)
+    dec.synchronize()
+    groups = dec.take_groups(0)
+    dt = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e["async"] = {"value": world * S * BLK * K / dt / 1e6, "unit": "MS/s", "ms_per_step": dt / K * 1e3,
+                    "api": "rfm_decoder_submit_u8 x K + rfm_decoder_synchronize + rfm_decoder_rds_take_groups"}
+
     cpu = cpu_baseline_leg() if (rank == 0 and world == 1 and not args.no_cpu) else None
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "MS/s", "n_gpus": world, "steps": K, "warmup": W,

@@ -88,6 +88,12 @@ RFM_API int rfm_decoder_process_u8(rfm_decoder* d, const uint8_t* iq, uint32_t n
 RFM_API int rfm_decoder_process_cf32(rfm_decoder* d, const float* iq, uint32_t n, float* audio,
                                      size_t audio_stride, uint32_t* n_audio_floats);
 
+/* Asynchronous form of rfm_decoder_process_u8 for batch serving: the block is only enqueued (H2D copy, kernels, D2H
+ * copy), so that the copy of block k+1 overlaps the kernels of block k.  iq should be pinned host memory; iq and
+ * audio must stay valid / untouched until rfm_decoder_synchronize() returns. */
+RFM_API int rfm_decoder_submit_u8(rfm_decoder* d, const uint8_t* iq, uint32_t n, float* audio, size_t audio_stride,
+                                  uint32_t* n_audio_floats);
+
 /* Same with device-resident buffers.  The call only ENQUEUES the block: it is ordered after everything already
  * submitted to `cuda_stream` (cudaStream_t), runs on the decoder's own streams (so that consecutive blocks
  * pipeline: the PLL lanes of block k+1 overlap the FIR stages of block k) and returns at once.  The caller

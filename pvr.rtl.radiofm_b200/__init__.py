@@ -42,7 +42,7 @@ class RfmStreamStatus(C.Structure):
 EXPORTED_SYMBOLS = (
     "rfm_last_error", "rfm_version", "rfm_launch_count", "rfm_config_default", "rfm_decoder_create",
     "rfm_decoder_destroy", "rfm_decoder_reset", "rfm_decoder_max_audio_floats", "rfm_decoder_process_u8",
-    "rfm_decoder_process_cf32", "rfm_decoder_process_u8_device", "rfm_decoder_process_cf32_device", "rfm_decoder_wait",
+    "rfm_decoder_process_cf32", "rfm_decoder_submit_u8", "rfm_decoder_process_u8_device", "rfm_decoder_process_cf32_device", "rfm_decoder_wait",
     "rfm_decoder_synchronize", "rfm_decoder_demod_repairs",
     "rfm_decoder_rds_take_groups", "rfm_decoder_rds_take_bits", "rfm_decoder_get_status",
     "rfm_decoder_constants", "rfm_decoder_table", "rfm_plan_constants", "rfm_plan_table", "rfm_decoder_set_profiling",
@@ -87,6 +87,7 @@ def lib():
         L.rfm_decoder_max_audio_floats.restype = C.c_uint32
         L.rfm_decoder_max_audio_floats.argtypes = [C.c_void_p, C.c_uint32]
         L.rfm_decoder_process_u8.argtypes = [C.c_void_p, _u8p, C.c_uint32, _f32p, C.c_size_t, _u32p]
+        L.rfm_decoder_submit_u8.argtypes = [C.c_void_p, _u8p, C.c_uint32, _f32p, C.c_size_t, _u32p]
         L.rfm_decoder_process_cf32.argtypes = [C.c_void_p, _f32p, C.c_uint32, _f32p, C.c_size_t, _u32p]
         L.rfm_decoder_process_u8_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p,
                                                     C.c_size_t, _u32p, C.c_void_p]

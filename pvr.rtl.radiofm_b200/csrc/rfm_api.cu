@@ -591,7 +591,8 @@ void EnqueueStageB(rfm_decoder* d, Group& g, const BlockGeom& bg, unsigned par, 
 // One block for all groups.  Inputs / outputs are device pointers for the whole batch (host pointers when
 // host_staged).  Work is only enqueued; the device entry points return without waiting (rfm_decoder_wait).
 int ProcessDevice(rfm_decoder* d, const void* d_in, size_t in_stride, bool u8, unsigned n, float* d_audio,
-                  size_t audio_stride, uint32_t* n_audio_floats, cudaStream_t user, bool host_staged)
+                  size_t audio_stride, uint32_t* n_audio_floats, cudaStream_t user, bool host_staged,
+                  bool host_sync = true)
 {
   if (n == 0)
   {
@@ -723,7 +724,7 @@ int ProcessDevice(rfm_decoder* d, const void* d_in, size_t in_stride, bool u8, u
   d->block_index += 1;
   if (n_audio_floats)
     *n_audio_floats = 2 * bg.na;
-  if (host_staged)
+  if (host_staged && host_sync)
     for (auto& g : d->groups)
       RFM_CUDA(cudaStreamSynchronize(g.sB)); // the last stage: everything before it has completed too
   return RFM_OK;
@@ -1019,6 +1020,18 @@ int rfm_decoder_process_cf32(rfm_decoder* d, const float* iq, uint32_t n, float*
   if (rc != RFM_OK)
     return rc;
   return ProcessDevice(d, iq, n, false, n, audio, audio_stride, n_audio_floats, nullptr, true);
+}
+
+int rfm_decoder_submit_u8(rfm_decoder* d, const uint8_t* iq, uint32_t n, float* audio, size_t audio_stride,
+                          uint32_t* n_audio_floats)
+{
+  if (!d || !iq || !audio)
+    return Fail(RFM_ERR_INVALID, "null argument");
+  RFM_CUDA(cudaSetDevice(d->device));
+  int rc = EnsureStaging(d, true);
+  if (rc != RFM_OK)
+    return rc;
+  return ProcessDevice(d, iq, n, true, n, audio, audio_stride, n_audio_floats, nullptr, true, false);
 }
 
 int rfm_decoder_process_u8_device(rfm_decoder* d, const uint8_t* d_iq, size_t iq_stride, uint32_t n, float* d_audio,
