@@ -210,8 +210,32 @@ __global__ void __launch_bounds__(128) k_front_tiled(FrontParams p, FrontCoef cf
 #pragma unroll
     for (int e = 0; e < 8; ++e)
       tw[e] = tuner[(p.idx0 + (unsigned)(ib0 + e)) & 63u];
+    // (kept as a rolled loop: the unrolled FIR below already fills most of the 32 KB instruction cache)
+#pragma unroll 1
     for (int ib = ib0; ib < i_hi; ib += 8 * G::T)
     {
+      if (ib >= i_lo && ib + 8 <= i_hi)
+      {
+        // interior chunk (the common case): one 16-byte load, no per-sample predicates
+        const uint4 raw = *reinterpret_cast<const uint4*>(row + 2 * (size_t)ib);
+        const unsigned wd[4] = {raw.x, raw.y, raw.z, raw.w};
+        const int w0 = ib + G::ORDER - (int)vlo;
+        const int q0 = w0 / G::SEG, rem = w0 - q0 * G::SEG;
+        float2* xo = X + w0 + q0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+        {
+          const unsigned word = wd[e >> 1];
+          const float are = rfm_u8_to_float(word, (e & 1) ? 2u : 0u);
+          const float aim = rfm_u8_to_float(word, (e & 1) ? 3u : 1u);
+          float2 o;
+          o.x = subf(mulf(are, tw[e].x), mulf(aim, tw[e].y));   // FmDecode.cpp:66-82
+          o.y = addf(mulf(are, tw[e].y), mulf(aim, tw[e].x));
+          const int carry = (G::SEG >= 8) ? ((rem + e >= G::SEG) ? 1 : 0) : (rem + e) / G::SEG;
+          xo[e + carry] = o;
+        }
+        continue;
+      }
       uint4 raw;
       if (ib >= 0 && ib + 8 <= (int)p.n)
         raw = *reinterpret_cast<const uint4*>(row + 2 * (size_t)ib);
@@ -235,7 +259,7 @@ __global__ void __launch_bounds__(128) k_front_tiled(FrontParams p, FrontCoef cf
           const float are = rfm_u8_to_float(word, (e & 1) ? 2u : 0u);
           const float aim = rfm_u8_to_float(word, (e & 1) ? 3u : 1u);
           float2 o;
-          o.x = subf(mulf(are, tw[e].x), mulf(aim, tw[e].y));   // FmDecode.cpp:66-82
+          o.x = subf(mulf(are, tw[e].x), mulf(aim, tw[e].y));
           o.y = addf(mulf(are, tw[e].y), mulf(aim, tw[e].x));
           X[G::pos(i + G::ORDER - (int)vlo)] = o;
         }
@@ -493,12 +517,14 @@ void launch_if_level(const FrontParams& p, float* state, bool u8, cudaStream_t s
 // anywhere else -- in practice never on a tuned station, routinely on pure noise -- the chunk is recomputed
 // sequentially from the exact state.  The result is always exactly the reference's sequential recurrence.
 // --------------------------------------------------------------------------------------------------
-constexpr unsigned kDemodChunk = 384; // multiples of the 32-sample tile
+constexpr unsigned kDemodChunk = 192; // multiples of the 32-sample tile
 constexpr unsigned kDemodWarm = 96;
 
 __global__ void __launch_bounds__(32) k_demod_spec(DemodSpecParams p)
 {
-  __shared__ float2 zin[2][32][kLT + 1];
+  // Single-buffered tiles (12.6 KB per warp-CTA): ~17 warps per SM hide the tile-load latency of each other, which
+  // is worth more here than overlapping a warp's own loads (the kernel is issue-bound once enough warps are resident).
+  __shared__ float2 zin[32][kLT + 1];
   __shared__ float wout[32][kLT + 1];
   const unsigned lane = threadIdx.x;
   const unsigned s0 = blockIdx.x * 32;
@@ -519,16 +545,13 @@ __global__ void __launch_bounds__(32) k_demod_spec(DemodSpecParams p)
   }
   const float2* z = reinterpret_cast<const float2*>(p.z);
   const unsigned ntiles = (t_end - t_start + kLT - 1) / kLT;
-  tile_load_async(zin[0], z, p.z_stride, s0, S, t_start, t_end, lane);
-  cp_async_commit();
   for (unsigned t = 0; t < ntiles; ++t)
   {
-    const unsigned b = t & 1u, t0 = t_start + t * kLT;
+    const unsigned t0 = t_start + t * kLT;
     const unsigned tn = min(kLT, t_end - t0);
-    if (t + 1 < ntiles)
-      tile_load_async(zin[b ^ 1u], z, p.z_stride, s0, S, t0 + kLT, t_end, lane);
+    tile_load_async(zin, z, p.z_stride, s0, S, t0, t_end, lane);
     cp_async_commit();
-    cp_async_wait<1>();
+    cp_async_wait<0>();
     __syncwarp();
     if (t0 == t_begin && valid)
       p.st_start[(size_t)c * S + s] = make_float2(dm.phase, dm.incr);
@@ -538,7 +561,7 @@ __global__ void __launch_bounds__(32) k_demod_spec(DemodSpecParams p)
     {
       for (unsigned k = 0; k < tn; ++k)
       {
-        const float2 x = zin[b][lane][k];
+        const float2 x = zin[lane][k];
         demod_step_fast(dm, x.x, x.y, p.demod, bad);
         wout[lane][k] = dm.incr;
       }
@@ -550,7 +573,7 @@ __global__ void __launch_bounds__(32) k_demod_spec(DemodSpecParams p)
       {
         for (unsigned k = 0; k < tn; ++k)
         {
-          const float2 x = zin[b][lane][k];
+          const float2 x = zin[lane][k];
           demod_step(dm, x.x, x.y, p.demod);
           wout[lane][k] = dm.incr;
         }
