@@ -101,7 +101,8 @@ struct Group
   DevBuf<float2> dm_start, dm_end; // speculative demodulator chunk states
   DevBuf<float> bbV[2], rawV[2];
   DevBuf<cf32> hbV[kMaxDecStages]; // input V buffer of stage k (k >= 1); stage 0 reads bbV x oscV
-  DevBuf<cf32> rlpV, rlp_out;
+  DevBuf<cf32> rlpV, rlp_out;   // rlpV: decimator output of the last block (stage tap); rlp_out: RDS LP output
+  DevBuf<cf32> rds_tails;       // fused RDS front: per-stream histories of every stage + LP delay line
   DevBuf<float> mfV, mf_out;
   DevBuf<uint8_t> bits;
   DevBuf<unsigned> bit_count;
@@ -122,6 +123,7 @@ struct rfm_decoder
   unsigned z_stride = 0, a_stride = 0, lp_stride = 0, rlp_stride = 0, mf_stride = 0, nr_stride = 0;
   unsigned hb_stride[kMaxDecStages] = {0};
   unsigned osc_hist = 0, bits_cap = 0, audio_cap = 0;
+  unsigned rds_tail_stride = 0, rds_tail_off[kRfMaxStages + 1] = {0};
   // plan tables on the device
   DevBuf<float> d_lut, d_tuner, d_in_coeff, d_a_coeff, d_lp_coef, d_rlp_coef, d_mf_coef;
   DevBuf<float> d_hb[kMaxDecStages];
@@ -178,7 +180,7 @@ void FreeDecoder(rfm_decoder* d)
       g.rawV[b].Free();
     }
     for (auto& b : g.hbV) b.Free();
-    g.rlpV.Free(); g.rlp_out.Free(); g.mfV.Free(); g.mf_out.Free(); g.bits.Free(); g.bit_count.Free();
+    g.rlpV.Free(); g.rlp_out.Free(); g.rds_tails.Free(); g.mfV.Free(); g.mf_out.Free(); g.bits.Free(); g.bit_count.Free();
     g.lpS.Free(); g.lpM.Free(); g.fS.Free(); g.fM.Free(); g.state.Free(); g.in_stage.Free(); g.audio_stage.Free();
     ProfFree(g.prof);
     for (cudaEvent_t e : {g.ev_demod[0], g.ev_demod[1], g.ev_front[0], g.ev_front[1], g.ev_lanes[0], g.ev_lanes[1], g.ev_rest[0], g.ev_rest[1], g.ev_rds[0], g.ev_rds[1]})
@@ -329,9 +331,15 @@ cudaError_t ResetGroupState(rfm_decoder* d, Group& g, bool initial)
   if (e != cudaSuccess)
     return e;
   // InitLPFilter / InitConstFir clear the delay lines (FirFilter.cpp:138-144,313-319)
-  e = cudaMemset(g.rlpV.p, 0, g.rlpV.n * sizeof(cf32));
-  if (e != cudaSuccess)
-    return e;
+  // the LP delay line is the last segment of every stream's tail row
+  {
+    const unsigned nst = (unsigned)d->plan.rds_stages.size();
+    const unsigned lp_hist = (unsigned)d->plan.rlp_coef.size() - 1;
+    e = cudaMemset2D(g.rds_tails.p + d->rds_tail_off[nst], (size_t)d->rds_tail_stride * sizeof(cf32), 0,
+                     (size_t)lp_hist * sizeof(cf32), S);
+    if (e != cudaSuccess)
+      return e;
+  }
   return cudaMemset(g.mfV.p, 0, g.mfV.n * sizeof(float));
 }
 
@@ -523,35 +531,25 @@ void EnqueueStageB(rfm_decoder* d, Group& g, const BlockGeom& bg, unsigned par, 
 
   // ---- RDS branch, on its own stream (its PLL / slicer lane kernels are latency-bound and overlap the audio FIRs)
   st = g.sR;
+  RdsFrontParams rf;
+  memset(&rf, 0, sizeof(rf));
+  rf.bbV = g.bbV[par].p; rf.a_stride = d->a_stride; rf.a_hist = a_hist;
+  rf.osc = d->oscV[par].p + d->osc_hist; rf.nb = bg.nb; rf.S = S; rf.nst = nst;
   for (unsigned k = 0; k < nst; ++k)
   {
     const HalfBandStage& hs = p.rds_stages[k];
-    HalfBandParams hp;
-    memset(&hp, 0, sizeof(hp));
-    hp.mix = (k == 0);
-    hp.in = (k == 0) ? nullptr : g.hbV[k].p;
-    hp.in_stride = d->hb_stride[k];
-    hp.bbV = g.bbV[par].p; hp.a_stride = d->a_stride; hp.a_hist = a_hist;
-    hp.oscV = d->oscV[par].p; hp.osc_hist = d->osc_hist;
-    hp.kind = hs.len == 3 ? 2 : (hs.fixed11 ? 1 : 0);
-    hp.len = (unsigned)hs.len; hp.n_in = bg.hb_n[k]; hp.S = S; hp.h = d->d_hb[k].p;
-    if (k + 1 < nst)
-    {
-      hp.out = g.hbV[k + 1].p; hp.out_stride = d->hb_stride[k + 1]; hp.out_off = StageHist(p.rds_stages[k + 1]);
-    }
-    else
-    {
-      hp.out = g.rlpV.p; hp.out_stride = d->rlp_stride; hp.out_off = rlp_taps - 1;
-    }
-    RFM_PROF(g.prof, "k_halfband", st, launch_halfband(hp, st));
-    ++g_launches;
+    rf.st[k].kind = hs.len == 3 ? 2 : (hs.fixed11 ? 1 : 0);
+    rf.st[k].len = (unsigned)hs.len;
+    rf.st[k].hist = StageHist(hs);
+    rf.st[k].h = hs.h ? d->d_hb[k].p : nullptr;
+    rf.tail_off[k] = d->rds_tail_off[k];
   }
-  RotFirParams frl;
-  frl.inA = reinterpret_cast<const float*>(g.rlpV.p); frl.inB = nullptr; frl.in_stride = d->rlp_stride;
-  frl.outA = reinterpret_cast<float*>(g.rlp_out.p); frl.outB = nullptr; frl.out_stride = d->nr_stride;
-  frl.out_off = 0; frl.n = bg.nr; frl.S = S; frl.taps = rlp_taps; frl.g0 = d->rlp_g; frl.coef = d->d_rlp_coef.p;
-  frl.cplx = 1;
-  RFM_PROF(g.prof, "k_rotfir_rdslp", st, launch_rotfir(frl, st));
+  rf.tail_off[nst] = d->rds_tail_off[nst];
+  rf.lp_coef = d->d_rlp_coef.p; rf.lp_n = rlp_taps; rf.g0 = d->rlp_g;
+  rf.tails = g.rds_tails.p; rf.tail_stride = d->rds_tail_stride;
+  rf.out = g.rlp_out.p; rf.dec_out = g.rlpV.p; rf.out_stride = d->nr_stride;
+  RFM_PROF(g.prof, "k_rds_front", st, launch_rds_front(rf, st));
+  ++g_launches;
 
   RdsPllParams pp;
   pp.in = g.rlp_out.p; pp.in_stride = d->nr_stride; pp.nr = bg.nr; pp.S = S; pp.state = g.state.p;
@@ -580,9 +578,6 @@ void EnqueueStageB(rfm_decoder* d, Group& g, const BlockGeom& bg, unsigned par, 
       return;
     tp.d[tp.count++] = {base, base, stride_elems * elem, hist, n, elem, S};
   };
-  for (unsigned k = 1; k < nst; ++k)
-    add(g.hbV[k].p, d->hb_stride[k], StageHist(p.rds_stages[k]), bg.hb_n[k], 8);
-  add(g.rlpV.p, d->rlp_stride, rlp_taps - 1, bg.nr, 8);
   add(g.mfV.p, d->mf_stride, mf_taps - 1, bg.nr, 4);
   RFM_PROF(g.prof, "k_tails", st, launch_tails(tp, S, st));
   ++g_launches;
@@ -810,7 +805,7 @@ int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out)
     FreeDecoder(d);
     return Fail(code, m);
   };
-  if (p.rds_stages.empty() || p.rds_stages.size() > kMaxDecStages)
+  if (p.rds_stages.empty() || p.rds_stages.size() > kRfMaxStages)
     return bail(RFM_ERR_UNSUPPORTED, "baseband rate outside the supported range (RDS decimation chain empty)");
   if (p.a_order > 512 || p.in_order > 512 || p.a_order < 2)
     return bail(RFM_ERR_UNSUPPORTED, "filter order outside the supported range (<= 512)");
@@ -835,6 +830,17 @@ int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out)
   d->rlp_stride = AlignUp((unsigned)p.rlp_coef.size() - 1 + d->nr_max, 16);
   d->mf_stride = AlignUp((unsigned)p.mf_coef.size() - 1 + d->nr_max, 32);
   d->osc_hist = StageHist(p.rds_stages[0]);
+  {
+    unsigned off = 0;
+    for (size_t k = 0; k < p.rds_stages.size(); ++k)
+    {
+      d->rds_tail_off[k] = off;
+      off += StageHist(p.rds_stages[k]);
+    }
+    d->rds_tail_off[p.rds_stages.size()] = off;
+    off += (unsigned)p.rlp_coef.size() - 1;
+    d->rds_tail_stride = AlignUp(off, 4);
+  }
   d->bits_cap = 4096;
   d->audio_cap = AlignUp(2 * d->na_max, 32);
 
@@ -928,9 +934,9 @@ int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out)
       RFM_TRY(g.bbV[b].Alloc(S * d->a_stride));
       RFM_TRY(g.rawV[b].Alloc(S * d->a_stride));
     }
-    for (size_t k = 1; k < p.rds_stages.size(); ++k)
-      RFM_TRY(g.hbV[k].Alloc(S * d->hb_stride[k]));
-    RFM_TRY(g.rlpV.Alloc(S * d->rlp_stride));
+
+    RFM_TRY(g.rlpV.Alloc(S * d->nr_stride));
+    RFM_TRY(g.rds_tails.Alloc(S * d->rds_tail_stride));
     RFM_TRY(g.rlp_out.Alloc(S * d->nr_stride));
     RFM_TRY(g.mfV.Alloc(S * d->mf_stride));
     RFM_TRY(g.mf_out.Alloc(S * d->nr_stride));
@@ -1299,7 +1305,7 @@ int rfm_decoder_tap(rfm_decoder* d, const char* name, uint32_t stream, float* ou
   else if (nm == "stereo_rs") { src = g->lpS.p + (size_t)ls * d->lp_stride + p.lp_coef.size() - 1; cnt = d->last_na; }
   else if (nm == "lp_stereo") { src = g->fS.p + (size_t)ls * d->na_max; cnt = d->last_na; }
   else if (nm == "lp_mono") { src = g->fM.p + (size_t)ls * d->na_max; cnt = d->last_na; }
-  else if (nm == "rds_dec") { src = g->rlpV.p + (size_t)ls * d->rlp_stride + p.rlp_coef.size() - 1; cnt = 2 * (size_t)d->last_nr; }
+  else if (nm == "rds_dec") { src = g->rlpV.p + (size_t)ls * d->nr_stride; cnt = 2 * (size_t)d->last_nr; }
   else if (nm == "rds_lp") { src = g->rlp_out.p + (size_t)ls * d->nr_stride; cnt = 2 * (size_t)d->last_nr; }
   else if (nm == "rds_pll") { src = g->mfV.p + (size_t)ls * d->mf_stride + p.mf_coef.size() - 1; cnt = d->last_nr; }
   else if (nm == "rds_mf") { src = g->mf_out.p + (size_t)ls * d->nr_stride; cnt = d->last_nr; }

@@ -1456,6 +1456,245 @@ __global__ void __launch_bounds__(kHbTile) k_halfband(HalfBandParams p)
   reinterpret_cast<float2*>(p.out)[(size_t)s * p.out_stride + p.out_off + k] = acc;
 }
 
+// --------------------------------------------------------------------------------------------------
+// Fused RDS front: NCO mix (DownConvert.cpp:438-442,464-465) -> every decimate-by-2 stage (:516-550, :589-688,
+// :709-727) -> the 2.4 kHz Kaiser LP (cFirFilter::Process complex, FirFilter.cpp:330-350; RDSProcess.cpp:128).
+// One CTA per stream walks the block in tiles of kRfTile baseband samples; every stage lives in a shared-memory
+// "V buffer" [history | tile], so no intermediate ever goes to HBM (the unfused chain wrote and re-read 4 of them).
+// Histories are carried tile to tile in shared memory and block to block in a small per-stream tail row.
+// Arithmetic and summation orders are those of k_halfband / k_rotfir (bit-identical results).
+// --------------------------------------------------------------------------------------------------
+constexpr unsigned kRfTile = 1024;
+constexpr unsigned kRfThreads = 128;
+
+template <int L>
+__device__ __forceinline__ float2 hb_generic(const float* h, const float2* V, unsigned k)
+{
+  const float2* x = V + 2 * k;
+  float2 acc;
+  acc.x = mulf(x[0].x, h[0]);
+  acc.y = mulf(x[0].y, h[0]);
+#pragma unroll
+  for (int j = 0; j < L; j += 2)
+  {
+    acc.x = addf(acc.x, mulf(x[j].x, h[j]));
+    acc.y = addf(acc.y, mulf(x[j].y, h[j]));
+  }
+  constexpr int c = (L - 1) / 2;
+  acc.x = addf(acc.x, mulf(x[c].x, h[c]));
+  acc.y = addf(acc.y, mulf(x[c].y, h[c]));
+  return acc;
+}
+
+__device__ __forceinline__ float2 hb_out(int kind, unsigned L, const float* h, const float2* V, unsigned k)
+{
+  float2 acc;
+  if (kind == 0)
+  {
+    switch (L) // the lengths of filtercoef.h's tables, unrolled
+    {
+      case 11: return hb_generic<11>(h, V, k);
+      case 15: return hb_generic<15>(h, V, k);
+      case 19: return hb_generic<19>(h, V, k);
+      case 23: return hb_generic<23>(h, V, k);
+      case 27: return hb_generic<27>(h, V, k);
+      case 31: return hb_generic<31>(h, V, k);
+      case 35: return hb_generic<35>(h, V, k);
+      case 39: return hb_generic<39>(h, V, k);
+      case 43: return hb_generic<43>(h, V, k);
+      case 47: return hb_generic<47>(h, V, k);
+      case 51: return hb_generic<51>(h, V, k);
+      default: break;
+    }
+    const unsigned i = 2 * k;
+    float2 x = V[i];
+    acc.x = mulf(x.x, h[0]);
+    acc.y = mulf(x.y, h[0]);
+    for (unsigned j = 0; j < L; j += 2)
+    {
+      x = V[i + j];
+      acc.x = addf(acc.x, mulf(x.x, h[j]));
+      acc.y = addf(acc.y, mulf(x.y, h[j]));
+    }
+    const unsigned c = (L - 1) / 2;
+    x = V[i + c];
+    acc.x = addf(acc.x, mulf(x.x, h[c]));
+    acc.y = addf(acc.y, mulf(x.y, h[c]));
+  }
+  else if (kind == 1)
+  {
+    const unsigned i = 2 * k;
+    const int idx[7] = {0, 2, 4, 5, 6, 8, 10};
+    float2 x = V[i];
+    acc.x = mulf(h[0], x.x);
+    acc.y = mulf(h[0], x.y);
+#pragma unroll
+    for (int t = 1; t < 7; ++t)
+    {
+      x = V[i + idx[t]];
+      acc.x = addf(acc.x, mulf(h[idx[t]], x.x));
+      acc.y = addf(acc.y, mulf(h[idx[t]], x.y));
+    }
+  }
+  else
+  {
+    const float2 xeven = V[2 * k], xodd = V[2 * k + 1], even = V[2 * k + 2], odd = V[2 * k + 3];
+    acc.x = d2f(muld(.125, addd((double)addf(odd.x, xeven.x), muld(3.0, (double)addf(xodd.x, even.x)))));
+    acc.y = d2f(muld(.125, addd((double)addf(odd.y, xeven.y), muld(3.0, (double)addf(xodd.y, even.y)))));
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(kRfThreads) k_rds_front(RdsFrontParams p)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // layout: taps of every stage, LP taps, then the V buffers of stage 0 .. nst-1 and of the LP
+  float* s_h = reinterpret_cast<float*>(smem_raw);
+  unsigned hoff[kRfMaxStages + 1];
+  unsigned acc_f = 0;
+  for (unsigned k = 0; k < p.nst; ++k)
+  {
+    hoff[k] = acc_f;
+    acc_f += (p.st[k].len + 1u) & ~1u;
+  }
+  hoff[p.nst] = acc_f;
+  float* s_lp = s_h + acc_f;
+  acc_f += (p.lp_n + 1u) & ~1u;
+  float2* vbuf = reinterpret_cast<float2*>(s_h + acc_f);
+  float2* B[kRfMaxStages + 1];
+  {
+    unsigned off = 0, n = kRfTile;
+    for (unsigned k = 0; k <= p.nst; ++k)
+    {
+      B[k] = vbuf + off;
+      const unsigned hist = (k < p.nst) ? p.st[k].hist : p.lp_n - 1;
+      off += hist + n;
+      n >>= 1;
+    }
+  }
+  const unsigned tid = threadIdx.x;
+  const unsigned s = blockIdx.x;
+  for (unsigned k = 0; k < p.nst; ++k)
+    for (unsigned i = tid; i < p.st[k].len; i += kRfThreads)
+      s_h[hoff[k] + i] = p.st[k].h ? p.st[k].h[i] : 0.0f;
+  for (unsigned i = tid; i < p.lp_n; i += kRfThreads)
+    s_lp[i] = p.lp_coef[i];
+  // histories from the previous block
+  float2* tails = reinterpret_cast<float2*>(p.tails) + (size_t)s * p.tail_stride;
+  for (unsigned k = 0; k <= p.nst; ++k)
+  {
+    const unsigned hist = (k < p.nst) ? p.st[k].hist : p.lp_n - 1;
+    for (unsigned i = tid; i < hist; i += kRfThreads)
+      B[k][i] = tails[p.tail_off[k] + i];
+  }
+  __syncthreads();
+
+  const float* bb = p.bbV + (size_t)s * p.a_stride + p.a_hist;
+  const float2* osc = reinterpret_cast<const float2*>(p.osc);
+  float2* out = reinterpret_cast<float2*>(p.out) + (size_t)s * p.out_stride;
+  const unsigned N = p.lp_n;
+  unsigned out_base = 0; // LP outputs produced so far in this block
+  for (unsigned t0 = 0; t0 < p.nb; t0 += kRfTile)
+  {
+    const unsigned tn = min(kRfTile, p.nb - t0);
+    // mix: real baseband x NCO phasor, imaginary input exactly +0 (RDSProcess.cpp:122-123)
+    for (unsigned i = tid; i < tn; i += kRfThreads)
+    {
+      const float b = bb[t0 + i];
+      const float2 o = osc[t0 + i];
+      float2 r;
+      r.x = subf(mulf(b, o.x), mulf(0.0f, o.y));
+      r.y = addf(mulf(b, o.y), mulf(0.0f, o.x));
+      B[0][p.st[0].hist + i] = r;
+    }
+    __syncthreads();
+    unsigned n = tn;
+    for (unsigned k = 0; k < p.nst; ++k)
+    {
+      const unsigned nout = n >> 1;
+      const unsigned ohist = (k + 1 < p.nst) ? p.st[k + 1].hist : N - 1;
+      const bool last = (k + 1 == p.nst) && p.dec_out != nullptr;
+      for (unsigned o = tid; o < nout; o += kRfThreads)
+      {
+        const float2 v = hb_out(p.st[k].kind, p.st[k].len, s_h + hoff[k], B[k], o);
+        B[k + 1][ohist + o] = v;
+        if (last) // decimator output (cRDSRxSignalProcessor's m_RdsRaw before the LP), kept for the stage taps
+          reinterpret_cast<float2*>(p.dec_out)[(size_t)s * p.out_stride + out_base + o] = v;
+      }
+      __syncthreads();
+      n = nout;
+    }
+    // LP with cFirFilter's rotating summation start: y[g] = sum_j h[k_j] x[g - k_j], k_j = (g + j) mod N
+    for (unsigned i = tid; i < n; i += kRfThreads)
+    {
+      unsigned k = (p.g0 + out_base + i) % N;
+      const float2* x = B[p.nst] + (N - 1) + i;
+      float2 v = x[-(int)k];
+      float ar = mulf(s_lp[k], v.x), ai = mulf(s_lp[k], v.y);
+      // uniform trip count (the start tap differs per lane): wrap with a compare / select, no modulo
+#pragma unroll 5
+      for (unsigned j = 1; j < N; ++j)
+      {
+        unsigned q = k + j;
+        q = (q >= N) ? q - N : q;
+        v = x[-(int)q];
+        ar = addf(ar, mulf(s_lp[q], v.x));
+        ai = addf(ai, mulf(s_lp[q], v.y));
+      }
+      out[out_base + i] = make_float2(ar, ai);
+    }
+    out_base += n;
+    __syncthreads();
+    // carry the histories: last `hist` entries of [hist | n_k] to the front
+    {
+      unsigned nk = tn;
+      for (unsigned k = 0; k <= p.nst; ++k)
+      {
+        const unsigned hist = (k < p.nst) ? p.st[k].hist : N - 1;
+        float2 v0 = make_float2(0.f, 0.f);
+        if (tid < hist)
+          v0 = B[k][nk + tid];
+        __syncthreads();
+        if (tid < hist)
+          B[k][tid] = v0;
+        nk >>= 1;
+      }
+    }
+    __syncthreads();
+  }
+  for (unsigned k = 0; k <= p.nst; ++k)
+  {
+    const unsigned hist = (k < p.nst) ? p.st[k].hist : p.lp_n - 1;
+    for (unsigned i = tid; i < hist; i += kRfThreads)
+      tails[p.tail_off[k] + i] = B[k][i];
+  }
+}
+
+void launch_rds_front(const RdsFrontParams& p, cudaStream_t st)
+{
+  if (p.S == 0 || p.nb == 0)
+    return;
+  size_t floats = 0;
+  for (unsigned k = 0; k < p.nst; ++k)
+    floats += (p.st[k].len + 1u) & ~1u;
+  floats += (p.lp_n + 1u) & ~1u;
+  size_t f2 = 0;
+  unsigned n = kRfTile;
+  for (unsigned k = 0; k <= p.nst; ++k)
+  {
+    f2 += ((k < p.nst) ? p.st[k].hist : p.lp_n - 1) + n;
+    n >>= 1;
+  }
+  const size_t smem = floats * sizeof(float) + f2 * sizeof(float2);
+  static size_t attr = 0;
+  if (smem > attr)
+  {
+    cudaFuncSetAttribute(k_rds_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = smem;
+  }
+  k_rds_front<<<p.S, kRfThreads, smem, st>>>(p);
+}
+
 void launch_halfband(const HalfBandParams& p, cudaStream_t st)
 {
   if (p.S == 0 || p.n_in < 2)

@@ -215,6 +215,33 @@ struct HalfBandParams
 };
 void launch_halfband(const HalfBandParams& p, cudaStream_t st);
 
+// fused RDS front: mix + decimate-by-2 chain + RDS low-pass, histories carried in a per-stream tail row
+constexpr unsigned kRfMaxStages = 6;
+struct RdsFrontStage
+{
+  int kind;                // 0 generic half-band, 1 fixed 11-tap, 2 CIC3
+  unsigned len, hist;
+  const float* h;          // device taps (nullptr for CIC3)
+};
+struct RdsFrontParams
+{
+  const float* bbV;        // [S][a_stride], new samples at a_hist
+  size_t a_stride;
+  unsigned a_hist;
+  const cf32* osc;         // NCO phasors of this block (first new sample)
+  unsigned nb, S, nst;
+  RdsFrontStage st[kRfMaxStages];
+  const float* lp_coef;    // RDS LP taps (device)
+  unsigned lp_n, g0;       // g0: samples filtered since the LP was (re)initialised, mod lp_n
+  cf32* tails;             // [S][tail_stride]: per-stage histories, then the LP delay line
+  size_t tail_stride;
+  unsigned tail_off[kRfMaxStages + 1];
+  cf32* out;               // [S][out_stride] LP output
+  cf32* dec_out;           // [S][out_stride] decimator output (optional, for the stage taps)
+  size_t out_stride;
+};
+void launch_rds_front(const RdsFrontParams& p, cudaStream_t st);
+
 struct RdsPllParams
 {
   const cf32* in;          // [S][in_stride]
