@@ -35,6 +35,16 @@ STREAMS_PER_GPU = 4096
 BYTES_PER_SAMPLE = 2.0 + 8.0 * 48000.0 / FS   # u8 I,Q in + f32 L,R out = 2.160 B / complex sample
 METRIC = "demodulated complex MS/s per GPU (stereo+RDS) at 1/2/4/8 B200; % of HBM roofline"
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at the C4 workload (4096 streams, one 65472-sample block),
+# from one `ncu --set full` capture per kernel: profiles/r01_ncu_top_kernels.txt
+NCU_TRAFFIC_BYTES = {
+    "k_bb_lanes": 98.313984e6 + 139.291648e6,
+    "k_front": 539.271424e6 + 175.535104e6,
+    "k_demod_spec": 275.005696e6 + 69.869824e6,
+    "k_resample": 204.2816e6 + 33.52192e6,
+    "k_rds_front": 103.283968e6 + 33.89312e6,
+}
+
 
 def load_peaks():
     try:
@@ -255,8 +265,11 @@ def run_b200(args):
     units_per_launch = S * BLK / n_groups
     avg_ms = top_ms / max(top_n, 1)
     achieved = BYTES_PER_SAMPLE * units_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+    traffic = NCU_TRAFFIC_BYTES.get(top_name) if (S == STREAMS_PER_GPU and n_groups == 1) else None
     roofline = {"bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": how,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": how,
+                "note": "the chain is latency-bound (one-lane-per-stream pilot PLL recurrence, k_bb_lanes) and FP32-issue-"
+                        "bound (bit-exact un-fused FIRs), not HBM-bound: see DESIGN.md sections 3, 3.2",
                 "avg_launch_ms": avg_ms, "launches": top_n, "units_per_launch": units_per_launch,
                 "algorithmic_bytes_per_unit": BYTES_PER_SAMPLE,
                 "chain_achieved": BYTES_PER_SAMPLE * value * 1e6 / 1e9 / world,
