@@ -91,15 +91,15 @@ struct Group
   unsigned s0 = 0, S = 0;
   ProfSlot prof[kMaxProfKinds];
   cudaStream_t sF = nullptr, sA = nullptr, sB = nullptr, sR = nullptr; // front / lanes / audio branch / RDS branch
-  cudaEvent_t ev_rds[2] = {nullptr, nullptr};   // RDS branch of the block with this parity finished
+  cudaEvent_t ev_rds[3] = {nullptr, nullptr, nullptr};  // RDS branch of the block finished (mod 3)
   cudaEvent_t ev_front[2] = {nullptr, nullptr}; // front end of the block with this parity finished
   cudaEvent_t ev_demod[2] = {nullptr, nullptr}; // demodulator done: z[parity] may be overwritten
   cudaEvent_t ev_lanes[2] = {nullptr, nullptr}; // PLL lanes ...
-  cudaEvent_t ev_rest[2] = {nullptr, nullptr};  // stage B ...
+  cudaEvent_t ev_rest[3] = {nullptr, nullptr, nullptr}; // stage B ... (by block index mod 3)
   DevBuf<cf32> tail, z[2];
   DevBuf<float> incr[2];       // NCO increments, demodulator (stage F) -> lanes (stage A), by parity
   DevBuf<float2> dm_start, dm_end; // speculative demodulator chunk states
-  DevBuf<float> bbV[2], rawV[2];
+  DevBuf<float> bbV[3], rawV[3]; // lanes -> stage B hand-over: three deep, so stage B of block k has two lane periods
   DevBuf<cf32> hbV[kMaxDecStages]; // input V buffer of stage k (k >= 1); stage 0 reads bbV x oscV
   DevBuf<cf32> rlpV, rlp_out;   // rlpV: decimator output of the last block (stage tap); rlp_out: RDS LP output
   DevBuf<cf32> rds_tails;       // fused RDS front: per-stream histories of every stage + LP delay line
@@ -127,14 +127,14 @@ struct rfm_decoder
   // plan tables on the device
   DevBuf<float> d_lut, d_tuner, d_in_coeff, d_a_coeff, d_lp_coef, d_rlp_coef, d_mf_coef;
   DevBuf<float> d_hb[kMaxDecStages];
-  DevBuf<cf32> oscV[2];
+  DevBuf<cf32> oscV[3];
   DevBuf<float> osc1;
   DevBuf<unsigned long long> d_repairs; // demodulator chunks repaired sequentially (telemetry)
-  DevBuf<float> res_kk[2]; // per-block interpolated resampler taps, shared by all streams (by parity)
-  DevBuf<int> res_meta[2];
+  DevBuf<float> res_kk[3]; // per-block interpolated resampler taps, shared by all streams (by block index mod 3)
+  DevBuf<int> res_meta[3];
   unsigned res_lp = 0;
   cudaStream_t s_osc = nullptr;
-  cudaEvent_t ev_osc[2] = {nullptr, nullptr};
+  cudaEvent_t ev_osc[3] = {nullptr, nullptr, nullptr};
   uint64_t block_index = 0; // blocks enqueued so far; parity selects the double buffers
   std::vector<Group> groups;
   bool profiling = false;
@@ -174,7 +174,7 @@ void FreeDecoder(rfm_decoder* d)
       if (st)
         cudaStreamSynchronize(st);
     g.tail.Free(); g.z[0].Free(); g.z[1].Free(); g.incr[0].Free(); g.incr[1].Free(); g.dm_start.Free(); g.dm_end.Free();
-    for (int b = 0; b < 2; ++b)
+    for (int b = 0; b < 3; ++b)
     {
       g.bbV[b].Free();
       g.rawV[b].Free();
@@ -183,7 +183,7 @@ void FreeDecoder(rfm_decoder* d)
     g.rlpV.Free(); g.rlp_out.Free(); g.rds_tails.Free(); g.mfV.Free(); g.mf_out.Free(); g.bits.Free(); g.bit_count.Free();
     g.lpS.Free(); g.lpM.Free(); g.fS.Free(); g.fM.Free(); g.state.Free(); g.in_stage.Free(); g.audio_stage.Free();
     ProfFree(g.prof);
-    for (cudaEvent_t e : {g.ev_demod[0], g.ev_demod[1], g.ev_front[0], g.ev_front[1], g.ev_lanes[0], g.ev_lanes[1], g.ev_rest[0], g.ev_rest[1], g.ev_rds[0], g.ev_rds[1]})
+    for (cudaEvent_t e : {g.ev_demod[0], g.ev_demod[1], g.ev_front[0], g.ev_front[1], g.ev_lanes[0], g.ev_lanes[1], g.ev_rest[0], g.ev_rest[1], g.ev_rest[2], g.ev_rds[0], g.ev_rds[1], g.ev_rds[2]})
       if (e)
         cudaEventDestroy(e);
     if (g.sF == g.sA)
@@ -197,14 +197,14 @@ void FreeDecoder(rfm_decoder* d)
   for (auto& b : d->d_hb) b.Free();
   if (d->s_osc)
     cudaStreamSynchronize(d->s_osc);
-  d->oscV[0].Free(); d->oscV[1].Free(); d->osc1.Free(); d->d_repairs.Free();
-  for (int b = 0; b < 2; ++b)
+  d->oscV[0].Free(); d->oscV[1].Free(); d->oscV[2].Free(); d->osc1.Free(); d->d_repairs.Free();
+  for (int b = 0; b < 3; ++b)
   {
     d->res_kk[b].Free();
     d->res_meta[b].Free();
   }
   ProfFree(d->main_prof);
-  for (cudaEvent_t e : {d->ev_fork, d->ev_osc[0], d->ev_osc[1], d->ev_join})
+  for (cudaEvent_t e : {d->ev_fork, d->ev_osc[0], d->ev_osc[1], d->ev_osc[2], d->ev_join})
     if (e)
       cudaEventDestroy(e);
   if (d->s_osc)
@@ -318,7 +318,7 @@ cudaError_t ResetGroupState(rfm_decoder* d, Group& g, bool initial)
   if (e != cudaSuccess)
     return e;
   auto zero = [&](int f) { std::fill(st.begin() + (size_t)f * S, st.begin() + (size_t)(f + 1) * S, 0.0f); };
-  zero(SF_STEREO); zero(SF_STEREO1); zero(SF_IF_LEVEL); zero(SF_BB_MEAN); zero(SF_BB_LEVEL); zero(SF_DEMOD_DC);
+  zero(SF_STEREO); zero(SF_STEREO1); zero(SF_STEREO2); zero(SF_IF_LEVEL); zero(SF_BB_MEAN); zero(SF_BB_LEVEL); zero(SF_DEMOD_DC);
   zero(SF_DEMOD_INCR); zero(SF_DEMOD_PHASE);
   zero(SF_RPLL_PHASE); zero(SF_RPLL_FREQ); zero(SF_RSYNC_W1); zero(SF_RSYNC_W2); zero(SF_RS_LASTSYNC);
   zero(SF_RS_LASTSLOPE); zero(SF_RS_LASTDATA); zero(SF_RS_LASTBIT);
@@ -466,7 +466,7 @@ void EnqueueStageF(rfm_decoder* d, Group& g, const void* d_in, size_t in_stride,
 }
 
 // Stage A of one block for one group (stream sA): history hand-over, PLL lanes.
-void EnqueueStageA(rfm_decoder* d, Group& g, const BlockGeom& bg, unsigned par)
+void EnqueueStageA(rfm_decoder* d, Group& g, const BlockGeom& bg, unsigned par, unsigned par3)
 {
   const DecoderPlan& p = d->plan;
   cudaStream_t st = g.sA;
@@ -476,8 +476,9 @@ void EnqueueStageA(rfm_decoder* d, Group& g, const BlockGeom& bg, unsigned par)
   // history of the baseband / L-R rows: last a_hist samples of the previous block (other parity) -> head of this one
   TailParams tp;
   tp.count = 2;
-  tp.d[0] = {g.bbV[par ^ 1u].p, g.bbV[par].p, d->a_stride * sizeof(float), a_hist, d->last_nb, 4, S};
-  tp.d[1] = {g.rawV[par ^ 1u].p, g.rawV[par].p, d->a_stride * sizeof(float), a_hist, d->last_nb, 4, S};
+  const unsigned prev3 = (par3 + 2u) % 3u;
+  tp.d[0] = {g.bbV[prev3].p, g.bbV[par3].p, d->a_stride * sizeof(float), a_hist, d->last_nb, 4, S};
+  tp.d[1] = {g.rawV[prev3].p, g.rawV[par3].p, d->a_stride * sizeof(float), a_hist, d->last_nb, 4, S};
   RFM_PROF(g.prof, "k_tails", st, launch_tails(tp, S, st));
 
   LanesParams lp;
@@ -485,7 +486,7 @@ void EnqueueStageA(rfm_decoder* d, Group& g, const BlockGeom& bg, unsigned par)
   lp.demod = {p.demod_gain, p.nco_lo, p.nco_hi, p.pll_alpha, p.pll_beta};
   lp.pilot = {p.pilot.minfreq, p.pilot.maxfreq, p.pilot.b0, p.pilot.a1, p.pilot.a2, p.pilot.lb0, p.pilot.lb1,
               p.pilot.minsignal, p.pilot.lock_delay};
-  lp.bbV = g.bbV[par].p; lp.rawV = g.rawV[par].p; lp.a_stride = d->a_stride; lp.a_hist = a_hist; lp.parity = par;
+  lp.bbV = g.bbV[par3].p; lp.rawV = g.rawV[par3].p; lp.a_stride = d->a_stride; lp.a_hist = a_hist; lp.parity = par3;
   RFM_PROF(g.prof, "k_bb_lanes", st, launch_bb_lanes(lp, st));
   g_launches += 2;
 }
@@ -618,29 +619,31 @@ int ProcessDevice(rfm_decoder* d, const void* d_in, size_t in_stride, bool u8, u
       return rc;
   }
 
-  const unsigned par = (unsigned)(d->block_index & 1u);
+  const unsigned par = (unsigned)(d->block_index & 1u);  // z / incr (front -> demodulator -> lanes)
+  const unsigned par3 = (unsigned)(d->block_index % 3u); // everything handed to stage B
+  const unsigned prev3 = (par3 + 2u) % 3u;
   if (!host_staged)
     RFM_CUDA(cudaEventRecord(d->ev_fork, user)); // stage A must see what is already enqueued on the caller's stream
 
   // NCO oscillator table of this block (shared by all streams), on its own stream: it only depends on the
   // sample count, so it runs ahead of the data.
   for (auto& g : d->groups)
-    RFM_CUDA(cudaStreamWaitEvent(d->s_osc, g.ev_rest[par], 0)); // readers of oscV[par] two blocks ago
+    RFM_CUDA(cudaStreamWaitEvent(d->s_osc, g.ev_rest[par3], 0)); // readers of oscV[par3] three blocks ago
   {
     TailParams tp;
     tp.count = 1;
-    tp.d[0] = {d->oscV[par ^ 1u].p, d->oscV[par].p, 0, d->osc_hist, d->last_nb, 8, 1};
+    tp.d[0] = {d->oscV[prev3].p, d->oscV[par3].p, 0, d->osc_hist, d->last_nb, 8, 1};
     RFM_PROF(d->main_prof, "k_tails", d->s_osc, launch_tails(tp, 1, d->s_osc));
     OscParams op;
-    op.oscV = d->oscV[par].p; op.osc_hist = d->osc_hist; op.nb = bg.nb; op.osc1 = d->osc1.p;
+    op.oscV = d->oscV[par3].p; op.osc_hist = d->osc_hist; op.nb = bg.nb; op.osc1 = d->osc1.p;
     op.cosv = d->plan.rds_osc.cosv; op.sinv = d->plan.rds_osc.sinv;
     RFM_PROF(d->main_prof, "k_osc", d->s_osc, launch_osc(op, d->s_osc));
     ResTapsParams tp2;
     tp2.pos_frac = d->a_pos; tp2.pstep = d->plan.a_pstep; tp2.na = bg.na; tp2.order = d->plan.a_order;
-    tp2.lp = d->res_lp; tp2.coeff = d->d_a_coeff.p; tp2.kk = d->res_kk[par].p; tp2.meta = d->res_meta[par].p;
+    tp2.lp = d->res_lp; tp2.coeff = d->d_a_coeff.p; tp2.kk = d->res_kk[par3].p; tp2.meta = d->res_meta[par3].p;
     RFM_PROF(d->main_prof, "k_res_taps", d->s_osc, launch_res_taps(tp2, d->s_osc));
     g_launches += 3;
-    RFM_CUDA(cudaEventRecord(d->ev_osc[par], d->s_osc));
+    RFM_CUDA(cudaEventRecord(d->ev_osc[par3], d->s_osc));
   }
 
   const size_t esz = u8 ? 2 : 8;
@@ -681,20 +684,20 @@ int ProcessDevice(rfm_decoder* d, const void* d_in, size_t in_stride, bool u8, u
     RFM_CUDA(cudaEventRecord(g.ev_front[par], g.sF));
     // ---- stage A
     RFM_CUDA(cudaStreamWaitEvent(g.sA, g.ev_front[par], 0));
-    RFM_CUDA(cudaStreamWaitEvent(g.sA, g.ev_rest[par], 0)); // stage B of block k-2 has released the parity buffers
+    RFM_CUDA(cudaStreamWaitEvent(g.sA, g.ev_rest[par3], 0)); // stage B of block k-3 has released bbV / rawV [par3]
     if (!DebugSkip("lanes"))
-      EnqueueStageA(d, g, bg, par);
+      EnqueueStageA(d, g, bg, par, par3);
     RFM_CUDA(cudaEventRecord(g.ev_lanes[par], g.sA));
     // ---- stage B
     for (cudaStream_t st : {g.sB, g.sR})
     {
       RFM_CUDA(cudaStreamWaitEvent(st, g.ev_lanes[par], 0));
-      RFM_CUDA(cudaStreamWaitEvent(st, d->ev_osc[par], 0));
+      RFM_CUDA(cudaStreamWaitEvent(st, d->ev_osc[par3], 0));
     }
     if (!DebugSkip("rest"))
-      EnqueueStageB(d, g, bg, par, audio_dev, audio_stride_dev);
-    RFM_CUDA(cudaEventRecord(g.ev_rds[par], g.sR));
-    RFM_CUDA(cudaStreamWaitEvent(g.sB, g.ev_rds[par], 0)); // ev_rest (recorded on sB) covers both branches
+      EnqueueStageB(d, g, bg, par3, audio_dev, audio_stride_dev);
+    RFM_CUDA(cudaEventRecord(g.ev_rds[par3], g.sR));
+    RFM_CUDA(cudaStreamWaitEvent(g.sB, g.ev_rds[par3], 0)); // ev_rest (recorded on sB) covers both branches
     if (host_staged)
     {
       ProfScope ps_(d, g.prof, "copy_d2h", g.sB);
@@ -702,7 +705,7 @@ int ProcessDevice(rfm_decoder* d, const void* d_in, size_t in_stride, bool u8, u
                                  (size_t)d->audio_cap * sizeof(float), (size_t)2 * bg.na * sizeof(float), g.S,
                                  cudaMemcpyDeviceToHost, g.sB));
     }
-    RFM_CUDA(cudaEventRecord(g.ev_rest[par], g.sB));
+    RFM_CUDA(cudaEventRecord(g.ev_rest[par3], g.sB));
   }
   RFM_CUDA(cudaGetLastError());
 
@@ -868,21 +871,21 @@ int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out)
   }
   RFM_TRY(d->d_repairs.Alloc(1));
   d->res_lp = p.a_order + 1 + 3 * ((unsigned)p.a_ratio + 1) + 4;
-  for (int b = 0; b < 2; ++b)
+  for (int b = 0; b < 3; ++b)
   {
     RFM_TRY(d->res_kk[b].Alloc((size_t)(d->na_max / 4 + 2) * d->res_lp * 4));
     RFM_TRY(d->res_meta[b].Alloc((size_t)(d->na_max / 4 + 2) * 2));
   }
-  RFM_TRY(d->oscV[0].Alloc((size_t)d->osc_hist + d->nb_max));
-  RFM_TRY(d->oscV[1].Alloc((size_t)d->osc_hist + d->nb_max));
+  for (int b = 0; b < 3; ++b)
+    RFM_TRY(d->oscV[b].Alloc((size_t)d->osc_hist + d->nb_max));
   {
     const float one[2] = {1.0f, 0.0f}; // m_Osc1 initial unit vector, DownConvert.cpp:283-284
     RFM_TRY(Upload(d->osc1, one, 2));
   }
   RFM_TRY(cudaStreamCreateWithFlags(&d->s_osc, cudaStreamNonBlocking));
   RFM_TRY(cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming));
-  RFM_TRY(cudaEventCreateWithFlags(&d->ev_osc[0], cudaEventDisableTiming));
-  RFM_TRY(cudaEventCreateWithFlags(&d->ev_osc[1], cudaEventDisableTiming));
+  for (int b = 0; b < 3; ++b)
+    RFM_TRY(cudaEventCreateWithFlags(&d->ev_osc[b], cudaEventDisableTiming));
   RFM_TRY(cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming));
 
   unsigned G = cfg->n_groups;
@@ -903,11 +906,16 @@ int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out)
       if (getenv("RFM_DEBUG_NOPRIO"))
         prio_hi = prio_lo;
       // sA (demodulator + lanes) is the critical chain, the front end feeds it; the audio / RDS branches have slack
-      RFM_TRY(cudaStreamCreateWithPriority(&g.sA, cudaStreamNonBlocking, prio_hi));
-      RFM_TRY(cudaStreamCreateWithPriority(&g.sF, cudaStreamNonBlocking,
-                                           getenv("RFM_DEBUG_FLOW") ? prio_lo : std::min(prio_lo, prio_hi + 1)));
-      RFM_TRY(cudaStreamCreateWithPriority(&g.sB, cudaStreamNonBlocking, prio_lo));
-      RFM_TRY(cudaStreamCreateWithPriority(&g.sR, cudaStreamNonBlocking, prio_lo));
+      const char* flow = getenv("RFM_DEBUG_FLOW");
+      const int mode = flow ? atoi(flow) : 0;
+      int pA = prio_hi, pF = std::min(prio_lo, prio_hi + 1), pB = prio_lo;
+      if (mode == 1) { pF = prio_lo; }
+      if (mode == 2) { pF = prio_lo; pB = std::min(prio_lo, prio_hi + 1); }
+      if (mode == 3) { pA = prio_lo; pF = prio_lo; pB = prio_hi; }
+      RFM_TRY(cudaStreamCreateWithPriority(&g.sA, cudaStreamNonBlocking, pA));
+      RFM_TRY(cudaStreamCreateWithPriority(&g.sF, cudaStreamNonBlocking, pF));
+      RFM_TRY(cudaStreamCreateWithPriority(&g.sB, cudaStreamNonBlocking, pB));
+      RFM_TRY(cudaStreamCreateWithPriority(&g.sR, cudaStreamNonBlocking, pB));
       if (getenv("RFM_DEBUG_SERIAL"))
       { // measurement aid: every stage on ONE stream, so per-kernel event times are isolated durations
         cudaStreamDestroy(g.sF); cudaStreamDestroy(g.sB); cudaStreamDestroy(g.sR);
@@ -918,9 +926,7 @@ int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out)
     {
       RFM_TRY(cudaEventCreateWithFlags(&g.ev_front[b], cudaEventDisableTiming));
       RFM_TRY(cudaEventCreateWithFlags(&g.ev_demod[b], cudaEventDisableTiming));
-      RFM_TRY(cudaEventCreateWithFlags(&g.ev_rds[b], cudaEventDisableTiming));
       RFM_TRY(cudaEventCreateWithFlags(&g.ev_lanes[b], cudaEventDisableTiming));
-      RFM_TRY(cudaEventCreateWithFlags(&g.ev_rest[b], cudaEventDisableTiming));
     }
     RFM_TRY(g.tail.Alloc(S * p.in_order));
     RFM_TRY(g.z[0].Alloc(S * d->z_stride));
@@ -929,10 +935,12 @@ int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out)
     RFM_TRY(g.incr[1].Alloc(S * d->z_stride));
     RFM_TRY(g.dm_start.Alloc(S * (size_t)demod_chunks(d->nb_max)));
     RFM_TRY(g.dm_end.Alloc(S * (size_t)demod_chunks(d->nb_max)));
-    for (int b = 0; b < 2; ++b)
+    for (int b = 0; b < 3; ++b)
     {
       RFM_TRY(g.bbV[b].Alloc(S * d->a_stride));
       RFM_TRY(g.rawV[b].Alloc(S * d->a_stride));
+      RFM_TRY(cudaEventCreateWithFlags(&g.ev_rest[b], cudaEventDisableTiming));
+      RFM_TRY(cudaEventCreateWithFlags(&g.ev_rds[b], cudaEventDisableTiming));
     }
 
     RFM_TRY(g.rlpV.Alloc(S * d->nr_stride));
@@ -1144,7 +1152,7 @@ int rfm_decoder_get_status(rfm_decoder* d, uint32_t stream, rfm_stream_status* o
   RFM_CUDA(cudaMemcpy2D(v, sizeof(float), g->state.p + ls, (size_t)g->S * sizeof(float), sizeof(float), SF_COUNT,
                         cudaMemcpyDeviceToHost));
   int stereo;
-  memcpy(&stereo, &v[SF_STEREO + ((d->block_index + 1) & 1u)], 4); // parity of the last block
+  memcpy(&stereo, &v[SF_STEREO + ((d->block_index + 2) % 3u)], 4); // slot of the last block
   out->stereo_detected = stereo;
   out->interface_level = v[SF_IF_LEVEL];
   out->baseband_level = v[SF_BB_LEVEL];
@@ -1296,11 +1304,12 @@ int rfm_decoder_tap(rfm_decoder* d, const char* name, uint32_t stream, float* ou
   const DecoderPlan& p = d->plan;
   const std::string nm(name);
   const unsigned lastpar = (unsigned)((d->block_index + 1) & 1u);
+  const unsigned lastpar3 = (unsigned)((d->block_index + 2) % 3u);
   const void* src = nullptr;
   size_t cnt = 0; // floats
   if (nm == "demod_in") { src = g->z[lastpar].p + (size_t)ls * d->z_stride; cnt = 2 * (size_t)d->last_nb; }
-  else if (nm == "baseband") { src = g->bbV[lastpar].p + (size_t)ls * d->a_stride + p.a_order; cnt = d->last_nb; }
-  else if (nm == "rawstereo") { src = g->rawV[lastpar].p + (size_t)ls * d->a_stride + p.a_order; cnt = d->last_nb; }
+  else if (nm == "baseband") { src = g->bbV[lastpar3].p + (size_t)ls * d->a_stride + p.a_order; cnt = d->last_nb; }
+  else if (nm == "rawstereo") { src = g->rawV[lastpar3].p + (size_t)ls * d->a_stride + p.a_order; cnt = d->last_nb; }
   else if (nm == "mono_rs") { src = g->lpM.p + (size_t)ls * d->lp_stride + p.lp_coef.size() - 1; cnt = d->last_na; }
   else if (nm == "stereo_rs") { src = g->lpS.p + (size_t)ls * d->lp_stride + p.lp_coef.size() - 1; cnt = d->last_na; }
   else if (nm == "lp_stereo") { src = g->fS.p + (size_t)ls * d->na_max; cnt = d->last_na; }

@@ -41,7 +41,8 @@ enum StateField
   SF_PILOT_LEVEL,
   SF_PILOT_LOCKCNT, // int bits
   SF_STEREO,        // int bits: m_StereoDetected of the last block (even blocks)
-  SF_STEREO1,       // ... odd blocks (the lanes of block k+1 overlap the audio tail of block k)
+  SF_STEREO1,       // ... three slots by block index mod 3 (the lanes of blocks k+1, k+2 overlap the audio tail of block k)
+  SF_STEREO2,
   SF_DE_RE,
   SF_DE_IM,
   SF_NOTCH_W1A,

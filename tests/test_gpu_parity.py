@@ -327,3 +327,62 @@ def test_device_math_probes(rfm):
     assert np.array_equal(f8[:, 1] == 0, dom) and bits_equal(f8[dom, 0], dem[dom])
     d9 = (p < 12.5) & (p > 0)
     assert bits_equal(f9[d9, 0], pil[d9])
+
+
+def test_speculation_misses_and_degenerate_inputs_stay_exact(rfm, port, synth):
+    """The time-parallel FM-demodulator PLL speculates on a contracting loop.  On pure noise the
+    speculation misses routinely and chunks are repaired; on constant input operands hit exact zeros (the sticky-flag
+    replay path of the lane kernels).  Either way the result must stay bit-identical to the sequential reference."""
+    fs, ds, blk = RATES["2.4M"]
+    nblk = 3
+    rng = np.random.default_rng(77)
+    noise = np.clip(np.rint(127.5 + 40 * rng.standard_normal((nblk * blk, 2))), 0, 255).astype(np.uint8)
+    weak = np.clip(np.rint(127.5 + 2.0 * rng.standard_normal((nblk * blk, 2))), 0, 255).astype(np.uint8)
+    const = np.full((nblk * blk, 2), 128, dtype=np.uint8)
+    alt = const.copy()
+    alt[::2, 0] = 127
+    good = station("2.4M", nblk)[0]
+    iqs = np.stack([noise, weak, const, alt, good])
+    S = iqs.shape[0]
+    d = rfm.FmDecoderBatch(fs, -0.15 * fs, downsample=ds, n_streams=S, max_block_len=blk)
+    oracles = [port.OracleFmDecoder(fs, -0.15 * fs, downsample=ds) for _ in range(S)]
+    for b in range(nblk):
+        a = d.process_u8(iqs[:, b * blk:(b + 1) * blk])
+        for s in range(S):
+            r = oracles[s].process_u8(iqs[s, b * blk:(b + 1) * blk])
+            assert bits_equal(a[s], r), (b, s)
+            assert bits_equal(d.tap("baseband", s), oracles[s].tap("baseband")), (b, s)
+            so, sd = oracles[s].status(), d.status(s)
+            assert all(np.float32(so[k]).view(np.uint32) == np.float32(sd[k]).view(np.uint32) or
+                       (np.isnan(so[k]) and np.isnan(sd[k])) for k in so), (b, s, so, sd)
+    for s in range(S):
+        assert np.array_equal(oracles[s].take_bits(), d.take_bits(s))
+    assert d.demod_repairs() > 0, "pure noise is expected to defeat the speculation now and then"
+
+
+def test_async_submit_matches_synchronous_call(rfm, port):
+    """rfm_decoder_submit_u8 (enqueue only, pinned host buffers) over several blocks == the synchronous entry point."""
+    import ctypes as C
+    import torch
+    fs, ds, blk = RATES["1.2M"]
+    S, nblk = 6, 4
+    iq, _ = station("1.2M", nblk)
+    o = port.OracleFmDecoder(fs, -0.15 * fs, downsample=ds)
+    ref = [o.process_u8(iq[b * blk:(b + 1) * blk]) for b in range(nblk)]
+    d = rfm.FmDecoderBatch(fs, -0.15 * fs, downsample=ds, n_streams=S, max_block_len=blk, n_groups=3)
+    stride = d.max_audio_floats(blk)
+    h_in = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(iq.reshape(nblk, 1, blk, 2), (nblk, S, blk, 2)))).pin_memory()
+    h_out = torch.zeros((nblk, S, stride), dtype=torch.float32).pin_memory()
+    k = C.c_uint32(0)
+    ks = []
+    for b in range(nblk):
+        rc = rfm.lib().rfm_decoder_submit_u8(d._h, C.cast(h_in[b].data_ptr(), C.POINTER(C.c_uint8)), blk,
+                                             C.cast(h_out[b].data_ptr(), C.POINTER(C.c_float)), stride, C.byref(k))
+        assert rc == 0, rfm.lib().rfm_last_error()
+        ks.append(k.value)
+    d.synchronize()
+    out = h_out.numpy()
+    for b in range(nblk):
+        for s in range(S):
+            assert bits_equal(out[b, s, :ks[b]], ref[b]), (b, s)
+    assert np.array_equal(d.take_groups(S - 1), o.take_groups())
