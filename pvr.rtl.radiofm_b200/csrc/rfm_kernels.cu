@@ -1063,33 +1063,49 @@ __global__ void __launch_bounds__(kResThreads) k_resample_tiled(ResampleParams p
     for (unsigned i = tid; i < gn * p.lp; i += kResThreads)
       KK[i] = ksrc[i];
   }
-  // input rows, transposed: warp w stages rows w, w + kResWarps, ...; 8 columns per array in flight per lane
+  // input rows, transposed into X[row][col] (odd pitch): warp w stages rows w, w + kResWarps, ...  The rows are read with
+  // 16-byte loads from a 16-byte aligned start (v0 rounded down; the V rows themselves are 128-byte aligned), all
+  // loads of a row in flight together -- the tile load is latency-bound, not bandwidth-bound.
+  const int dv = v0 & 3;               // columns added in front by the alignment
+  const int span_a = span + dv;
+  constexpr int kIt = 5;               // 5 x 128 columns >= the largest tile (pitch <= 640 enforced by the launcher)
   for (unsigned r = warp; r < rows; r += kResWarps)
   {
-    for (int c0 = 0; c0 < span; c0 += 256)
+    float4 v[NCH][kIt];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch)
     {
-      float v[NCH][8];
+      const float* b = src[ch] + (size_t)(s0 + r) * p.a_stride + (v0 - dv);
 #pragma unroll
-      for (int ch = 0; ch < NCH; ++ch)
+      for (int it = 0; it < kIt; ++it)
       {
-        const float* b = src[ch] + (size_t)(s0 + r) * p.a_stride + v0;
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
+        const int c = 4 * ((int)lane + 32 * it);
+        v[ch][it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c + 3 < span_a)
+          v[ch][it] = *reinterpret_cast<const float4*>(b + c);
+        else if (c < span_a)
         {
-          const int c = c0 + u * 32 + (int)lane;
-          v[ch][u] = (c < span) ? b[c] : 0.0f;
+          v[ch][it].x = b[c];
+          if (c + 1 < span_a) v[ch][it].y = b[c + 1];
+          if (c + 2 < span_a) v[ch][it].z = b[c + 2];
         }
       }
-#pragma unroll
-      for (int ch = 0; ch < NCH; ++ch)
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-        {
-          const int c = c0 + u * 32 + (int)lane;
-          if (c < span)
-            X[(ch * 32 + r) * pitch + c] = v[ch][u];
-        }
     }
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+      for (int it = 0; it < kIt; ++it)
+      {
+        const int c = 4 * ((int)lane + 32 * it);
+        float* xr = X + (ch * 32 + r) * pitch + c;
+        if (c < span_a)
+        {
+          xr[0] = v[ch][it].x;
+          if (c + 1 < span_a) xr[1] = v[ch][it].y;
+          if (c + 2 < span_a) xr[2] = v[ch][it].z;
+          if (c + 3 < span_a) xr[3] = v[ch][it].w;
+        }
+      }
   }
   __syncthreads();
   if (lane >= rows)
@@ -1098,7 +1114,7 @@ __global__ void __launch_bounds__(kResThreads) k_resample_tiled(ResampleParams p
   const float* x1 = X + (32 + lane) * pitch;
   for (unsigned gi = warp; gi < gn; gi += kResWarps)
   {
-    const int off = s_meta[2 * gi] - v0;
+    const int off = s_meta[2 * gi] - v0 + dv;
     const int L = s_meta[2 * gi + 1];
     const float4* kk = KK + (size_t)gi * p.lp;
     float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
@@ -1154,8 +1170,10 @@ void launch_resample_tiled(const ResampleParams& p, cudaStream_t st)
   if (p.na == 0 || p.S == 0)
     return;
   auto need = [&](unsigned gb, unsigned nch, unsigned* pitch) {
-    const unsigned span_max = (unsigned)(4.0f * gb * p.pstep) + p.order + 12;
+    const unsigned span_max = (unsigned)(4.0f * gb * p.pstep) + p.order + 16; // + alignment slack of the 16-byte loads
     *pitch = span_max | 1u;
+    if (*pitch > 640)
+      return (size_t)1 << 30; // the staging loop covers 5 x 128 columns
     return (size_t)gb * p.lp * sizeof(float4) + (size_t)nch * 32 * *pitch * sizeof(float);
   };
   static const int variant = getenv("RFM_RES_VARIANT") ? atoi(getenv("RFM_RES_VARIANT")) : 0;
