@@ -457,6 +457,7 @@ void EnqueueStageF(rfm_decoder* d, Group& g, const void* d_in, size_t in_stride,
   cudaStreamWaitEvent(st, g.ev_lanes[par], 0);
   DemodSpecParams dp;
   dp.z = g.z[par].p; dp.z_stride = d->z_stride; dp.nb = bg.nb; dp.S = S; dp.state = g.state.p;
+  dp.warm = p.fs_bb < 225000.0f ? 96u : 160u; // measured miss rates: DESIGN.md 3.1
   dp.demod = {p.demod_gain, p.nco_lo, p.nco_hi, p.pll_alpha, p.pll_beta};
   dp.incr = g.incr[par].p; dp.w_stride = d->z_stride; dp.st_start = g.dm_start.p; dp.st_end = g.dm_end.p;
   dp.repairs = d->d_repairs.p;

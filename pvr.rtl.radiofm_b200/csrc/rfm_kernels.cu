@@ -510,15 +510,15 @@ void launch_if_level(const FrontParams& p, float* state, bool u8, cudaStream_t s
 // The loop is a fast contraction: two copies driven by the same input but started from different states
 // (phase, increment) differ by a factor ~0.58 per sample (poles of the linearised loop), so after a short warm-up
 // they coincide to the last bit.  k_demod_spec cuts the block into chunks of kDemodChunk samples and runs every
-// (stream, chunk) on its own lane: chunk 0 starts from the carried state, chunk c > 0 starts kDemodWarm samples
-// early from a guess (phase 0, carried increment).  It records the state it had at the chunk start and at the
+// (stream, chunk) on its own lane: chunk 0 starts from the carried state, chunk c > 0 starts `warm` samples
+// early from a guess (phase 0, carried increment); the warm-up length is chosen by the host from the baseband rate (96 or 160
+// samples: it only changes how often the repair pass has work).  It records the state it had at the chunk start and at the
 // chunk end.  k_demod_fix then walks the chunks of a stream in order: where the recorded start state of chunk c is
 // bit-identical to the (now known exact) end state of chunk c-1 the speculative outputs ARE the sequential ones;
 // anywhere else -- in practice never on a tuned station, routinely on pure noise -- the chunk is recomputed
 // sequentially from the exact state.  The result is always exactly the reference's sequential recurrence.
 // --------------------------------------------------------------------------------------------------
 constexpr unsigned kDemodChunk = 192; // multiples of the 32-sample tile
-constexpr unsigned kDemodWarm = 96;
 
 __global__ void __launch_bounds__(32) k_demod_spec(DemodSpecParams p)
 {
@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(32) k_demod_spec(DemodSpecParams p)
   const unsigned S = p.S;
   const unsigned t_begin = c * kDemodChunk;
   const unsigned t_end = min(p.nb, t_begin + kDemodChunk);
-  const unsigned t_start = (c == 0) ? 0u : t_begin - kDemodWarm;
+  const unsigned t_start = (c == 0) ? 0u : t_begin - p.warm; // p.warm <= kDemodChunk, multiple of the tile
 
   DemodState dm = {0.f, 0.f};
   if (valid)
@@ -1204,26 +1204,52 @@ constexpr unsigned kFirTile = 128;
 template <int MODE> // 0 real, 1 real pair, 2 complex
 __global__ void __launch_bounds__(kFirTile) k_rotfir(RotFirParams p)
 {
+  // CTA = 128 consecutive outputs of one stream; the input window [taps - 1 | 128] is staged in shared memory
   __shared__ float s_coef[kMaxFirTapsDev];
+  __shared__ float s_a[(MODE == 2 ? 2 : 1) * (kMaxFirTapsDev + kFirTile)];
+  __shared__ float s_b[MODE == 1 ? (kMaxFirTapsDev + kFirTile) : 1];
   const unsigned tid = threadIdx.x;
-  for (unsigned i = tid; i < p.taps; i += kFirTile)
-    s_coef[i] = p.coef[i];
-  __syncthreads();
-  const unsigned s = blockIdx.y;
-  const unsigned i = blockIdx.x * kFirTile + tid;
-  if (i >= p.n)
-    return;
   const unsigned N = p.taps;
-  unsigned k = (p.g0 + i) % N;
-  const size_t base = (size_t)s * p.in_stride + (N - 1) + i; // V index of x[g]
+  const unsigned s = blockIdx.y;
+  const unsigned i0 = blockIdx.x * kFirTile;
+  const unsigned nt = min(kFirTile, p.n - i0);
+  for (unsigned i = tid; i < N; i += kFirTile)
+    s_coef[i] = p.coef[i];
+  const unsigned wlen = N - 1 + nt; // V indices i0 .. i0 + wlen - 1
   if (MODE == 2)
   {
-    const float2* x = reinterpret_cast<const float2*>(p.inA);
-    float2 v = x[base - k];
-    float ar = mulf(s_coef[k], v.x), ai = mulf(s_coef[k], v.y);
+    const float2* x = reinterpret_cast<const float2*>(p.inA) + (size_t)s * p.in_stride + i0;
+    for (unsigned i = tid; i < wlen; i += kFirTile)
+      reinterpret_cast<float2*>(s_a)[i] = x[i];
+  }
+  else
+  {
+    const float* xa = p.inA + (size_t)s * p.in_stride + i0;
+    for (unsigned i = tid; i < wlen; i += kFirTile)
+      s_a[i] = xa[i];
+    if (MODE == 1)
+    {
+      const float* xb = p.inB + (size_t)s * p.in_stride + i0;
+      for (unsigned i = tid; i < wlen; i += kFirTile)
+        s_b[i] = xb[i];
+    }
+  }
+  __syncthreads();
+  if (tid >= nt)
+    return;
+  const unsigned i = i0 + tid;
+  const unsigned k0 = (p.g0 + i) % N;
+  const unsigned base = (N - 1) + tid; // window index of x[g]
+  if (MODE == 2)
+  {
+    const float2* x = reinterpret_cast<const float2*>(s_a);
+    float2 v = x[base - k0];
+    float ar = mulf(s_coef[k0], v.x), ai = mulf(s_coef[k0], v.y);
+#pragma unroll 4
     for (unsigned j = 1; j < N; ++j)
     {
-      k = (k + 1 == N) ? 0 : k + 1;
+      unsigned k = k0 + j;
+      k = (k >= N) ? k - N : k;
       v = x[base - k];
       ar = addf(ar, mulf(s_coef[k], v.x));
       ai = addf(ai, mulf(s_coef[k], v.y));
@@ -1232,14 +1258,17 @@ __global__ void __launch_bounds__(kFirTile) k_rotfir(RotFirParams p)
   }
   else
   {
-    float a = mulf(s_coef[k], p.inA[base - k]);
-    float b = (MODE == 1) ? mulf(s_coef[k], p.inB[base - k]) : 0.0f;
+    float a = mulf(s_coef[k0], s_a[base - k0]);
+    float b = (MODE == 1) ? mulf(s_coef[k0], s_b[base - k0]) : 0.0f;
+#pragma unroll 4
     for (unsigned j = 1; j < N; ++j)
     {
-      k = (k + 1 == N) ? 0 : k + 1;
-      a = addf(a, mulf(s_coef[k], p.inA[base - k]));
+      unsigned k = k0 + j;
+      k = (k >= N) ? k - N : k;
+      const float c = s_coef[k];
+      a = addf(a, mulf(c, s_a[base - k]));
       if (MODE == 1)
-        b = addf(b, mulf(s_coef[k], p.inB[base - k]));
+        b = addf(b, mulf(c, s_b[base - k]));
     }
     p.outA[(size_t)s * p.out_stride + p.out_off + i] = a;
     if (MODE == 1)

@@ -91,6 +91,7 @@ struct DemodSpecParams
   const cf32* z;           // [S][z_stride] decimated IQ
   size_t z_stride;
   unsigned nb, S;
+  unsigned warm;           // speculative warm-up samples (multiple of 32, <= 192)
   float* state;            // [SF_COUNT][S]: SF_DEMOD_PHASE / SF_DEMOD_INCR carried
   DemodConst demod;
   float* incr;             // [S][w_stride] NCO increment after every sample
