@@ -1201,18 +1201,20 @@ void launch_resample_tiled(const ResampleParams& p, cudaStream_t st)
 // ==================================================================================================
 constexpr unsigned kFirTile = 128;
 
+constexpr unsigned kFirOut = 4 * kFirTile; // outputs per CTA (4 per thread, strided by the CTA width)
+
 template <int MODE> // 0 real, 1 real pair, 2 complex
 __global__ void __launch_bounds__(kFirTile) k_rotfir(RotFirParams p)
 {
-  // CTA = 128 consecutive outputs of one stream; the input window [taps - 1 | 128] is staged in shared memory
+  // CTA = 512 consecutive outputs of one stream; the input window [taps - 1 | 512] is staged in shared memory
   __shared__ float s_coef[kMaxFirTapsDev];
-  __shared__ float s_a[(MODE == 2 ? 2 : 1) * (kMaxFirTapsDev + kFirTile)];
-  __shared__ float s_b[MODE == 1 ? (kMaxFirTapsDev + kFirTile) : 1];
+  __shared__ float s_a[(MODE == 2 ? 2 : 1) * (kMaxFirTapsDev + kFirOut)];
+  __shared__ float s_b[MODE == 1 ? (kMaxFirTapsDev + kFirOut) : 1];
   const unsigned tid = threadIdx.x;
   const unsigned N = p.taps;
   const unsigned s = blockIdx.y;
-  const unsigned i0 = blockIdx.x * kFirTile;
-  const unsigned nt = min(kFirTile, p.n - i0);
+  const unsigned i0 = blockIdx.x * kFirOut;
+  const unsigned nt = min(kFirOut, p.n - i0);
   for (unsigned i = tid; i < N; i += kFirTile)
     s_coef[i] = p.coef[i];
   const unsigned wlen = N - 1 + nt; // V indices i0 .. i0 + wlen - 1
@@ -1235,44 +1237,45 @@ __global__ void __launch_bounds__(kFirTile) k_rotfir(RotFirParams p)
     }
   }
   __syncthreads();
-  if (tid >= nt)
-    return;
-  const unsigned i = i0 + tid;
-  const unsigned k0 = (p.g0 + i) % N;
-  const unsigned base = (N - 1) + tid; // window index of x[g]
-  if (MODE == 2)
+  for (unsigned t = tid; t < nt; t += kFirTile)
   {
-    const float2* x = reinterpret_cast<const float2*>(s_a);
-    float2 v = x[base - k0];
-    float ar = mulf(s_coef[k0], v.x), ai = mulf(s_coef[k0], v.y);
-#pragma unroll 4
-    for (unsigned j = 1; j < N; ++j)
+    const unsigned i = i0 + t;
+    const unsigned k0 = (p.g0 + i) % N;
+    const unsigned base = (N - 1) + t; // window index of x[g]
+    if (MODE == 2)
     {
-      unsigned k = k0 + j;
-      k = (k >= N) ? k - N : k;
-      v = x[base - k];
-      ar = addf(ar, mulf(s_coef[k], v.x));
-      ai = addf(ai, mulf(s_coef[k], v.y));
+      const float2* x = reinterpret_cast<const float2*>(s_a);
+      float2 v = x[base - k0];
+      float ar = mulf(s_coef[k0], v.x), ai = mulf(s_coef[k0], v.y);
+#pragma unroll 4
+      for (unsigned j = 1; j < N; ++j)
+      {
+        unsigned k = k0 + j;
+        k = (k >= N) ? k - N : k;
+        v = x[base - k];
+        ar = addf(ar, mulf(s_coef[k], v.x));
+        ai = addf(ai, mulf(s_coef[k], v.y));
+      }
+      reinterpret_cast<float2*>(p.outA)[(size_t)s * p.out_stride + p.out_off + i] = make_float2(ar, ai);
     }
-    reinterpret_cast<float2*>(p.outA)[(size_t)s * p.out_stride + p.out_off + i] = make_float2(ar, ai);
-  }
-  else
-  {
-    float a = mulf(s_coef[k0], s_a[base - k0]);
-    float b = (MODE == 1) ? mulf(s_coef[k0], s_b[base - k0]) : 0.0f;
-#pragma unroll 4
-    for (unsigned j = 1; j < N; ++j)
+    else
     {
-      unsigned k = k0 + j;
-      k = (k >= N) ? k - N : k;
-      const float c = s_coef[k];
-      a = addf(a, mulf(c, s_a[base - k]));
+      float a = mulf(s_coef[k0], s_a[base - k0]);
+      float b = (MODE == 1) ? mulf(s_coef[k0], s_b[base - k0]) : 0.0f;
+#pragma unroll 4
+      for (unsigned j = 1; j < N; ++j)
+      {
+        unsigned k = k0 + j;
+        k = (k >= N) ? k - N : k;
+        const float c = s_coef[k];
+        a = addf(a, mulf(c, s_a[base - k]));
+        if (MODE == 1)
+          b = addf(b, mulf(c, s_b[base - k]));
+      }
+      p.outA[(size_t)s * p.out_stride + p.out_off + i] = a;
       if (MODE == 1)
-        b = addf(b, mulf(c, s_b[base - k]));
+        p.outB[(size_t)s * p.out_stride + p.out_off + i] = b;
     }
-    p.outA[(size_t)s * p.out_stride + p.out_off + i] = a;
-    if (MODE == 1)
-      p.outB[(size_t)s * p.out_stride + p.out_off + i] = b;
   }
 }
 
@@ -1280,7 +1283,7 @@ void launch_rotfir(const RotFirParams& p, cudaStream_t st)
 {
   if (p.n == 0 || p.S == 0)
     return;
-  dim3 grid(cdiv(p.n, kFirTile), p.S);
+  dim3 grid(cdiv(p.n, kFirOut), p.S);
   if (p.cplx)
     k_rotfir<2><<<grid, kFirTile, 0, st>>>(p);
   else if (p.inB)
