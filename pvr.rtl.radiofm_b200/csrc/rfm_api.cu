@@ -100,7 +100,6 @@ struct Group
   DevBuf<float> incr[2];       // NCO increments, demodulator (stage F) -> lanes (stage A), by parity
   DevBuf<float2> dm_start, dm_end; // speculative demodulator chunk states
   DevBuf<float> bbV[3], rawV[3]; // lanes -> stage B hand-over: three deep, so stage B of block k has two lane periods
-  DevBuf<cf32> hbV[kMaxDecStages]; // input V buffer of stage k (k >= 1); stage 0 reads bbV x oscV
   DevBuf<cf32> rlpV, rlp_out;   // rlpV: decimator output of the last block (stage tap); rlp_out: RDS LP output
   DevBuf<cf32> rds_tails;       // fused RDS front: per-stream histories of every stage + LP delay line
   DevBuf<float> mfV, mf_out;
@@ -179,7 +178,6 @@ void FreeDecoder(rfm_decoder* d)
       g.bbV[b].Free();
       g.rawV[b].Free();
     }
-    for (auto& b : g.hbV) b.Free();
     g.rlpV.Free(); g.rlp_out.Free(); g.rds_tails.Free(); g.mfV.Free(); g.mf_out.Free(); g.bits.Free(); g.bit_count.Free();
     g.lpS.Free(); g.lpM.Free(); g.fS.Free(); g.fM.Free(); g.state.Free(); g.in_stage.Free(); g.audio_stage.Free();
     ProfFree(g.prof);

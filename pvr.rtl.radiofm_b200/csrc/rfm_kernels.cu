@@ -15,7 +15,7 @@
 //   k_rotfir       [a8 a10 a17] cFirFilter (rotating summation start), real / pair / complex
 //   k_audio_tail   [a18 a19 a20] deemphasis + notch + L/R matrix, one lane per stream
 //   k_osc          [a7 NCO]     quadrature-oscillator table for the block (same for every stream)
-//   k_halfband     [a7]         mix + half-band / 11-tap / CIC3 decimate-by-2 stages
+//   k_rds_front    [a7 a8]      NCO mix + every decimate-by-2 stage + RDS LP, fused in shared memory
 //   k_rds_pll      [a9]         Costas loop, one lane per stream
 //   k_rds_slice    [a11]        bit-clock resonator + peak slicer + differential decode
 //   k_tails                     V-buffer history carry
@@ -1415,97 +1415,8 @@ void launch_osc(const OscParams& p, cudaStream_t st)
 }
 
 // ==================================================================================================
-// decimate-by-2 stages, DownConvert.cpp:516-550 (generic), :589-688 (11-tap), :709-727 (CIC3)
+// RDS branch: decimate-by-2 stages, DownConvert.cpp:516-550 (generic), :589-688 (11-tap), :709-727 (CIC3)
 // ==================================================================================================
-constexpr unsigned kHbTile = 128;
-
-template <bool MIX>
-struct HbIn
-{
-  const HalfBandParams& p;
-  const float2* row;
-  const float* bb;
-  const float2* osc;
-  __device__ HbIn(const HalfBandParams& pp, unsigned s, unsigned hist) : p(pp)
-  {
-    row = reinterpret_cast<const float2*>(pp.in) + (size_t)s * pp.in_stride;
-    bb = pp.bbV + (size_t)s * pp.a_stride + (pp.a_hist - hist);
-    osc = reinterpret_cast<const float2*>(pp.oscV) + (pp.osc_hist - hist);
-  }
-  __device__ __forceinline__ float2 operator()(unsigned v) const
-  {
-    if (!MIX)
-      return row[v];
-    // real baseband x NCO phasor, imaginary input exactly +0 (RDSProcess.cpp:122-123, DownConvert.cpp:464-465)
-    const float b = bb[v];
-    const float2 o = osc[v];
-    float2 r;
-    r.x = subf(mulf(b, o.x), mulf(0.0f, o.y));
-    r.y = addf(mulf(b, o.y), mulf(0.0f, o.x));
-    return r;
-  }
-};
-
-template <bool MIX, int KIND>
-__global__ void __launch_bounds__(kHbTile) k_halfband(HalfBandParams p)
-{
-  __shared__ float s_h[64];
-  const unsigned tid = threadIdx.x;
-  if (KIND != 2)
-  {
-    for (unsigned i = tid; i < p.len; i += kHbTile)
-      s_h[i] = p.h[i];
-    __syncthreads();
-  }
-  const unsigned s = blockIdx.y;
-  const unsigned k = blockIdx.x * kHbTile + tid;
-  if (k >= p.n_in / 2)
-    return;
-  const unsigned hist = (KIND == 2) ? 2 : p.len - 1;
-  HbIn<MIX> V(p, s, hist);
-  float2 acc;
-  if (KIND == 0)
-  {
-    const unsigned i = 2 * k;
-    const unsigned L = p.len;
-    float2 x = V(i);
-    acc.x = mulf(x.x, s_h[0]);
-    acc.y = mulf(x.y, s_h[0]);
-    for (unsigned j = 0; j < L; j += 2)
-    {
-      x = V(i + j);
-      acc.x = addf(acc.x, mulf(x.x, s_h[j]));
-      acc.y = addf(acc.y, mulf(x.y, s_h[j]));
-    }
-    const unsigned c = (L - 1) / 2;
-    x = V(i + c);
-    acc.x = addf(acc.x, mulf(x.x, s_h[c]));
-    acc.y = addf(acc.y, mulf(x.y, s_h[c]));
-  }
-  else if (KIND == 1)
-  {
-    const unsigned i = 2 * k;
-    const int idx[7] = {0, 2, 4, 5, 6, 8, 10};
-    float2 x = V(i);
-    acc.x = mulf(s_h[0], x.x);
-    acc.y = mulf(s_h[0], x.y);
-#pragma unroll
-    for (int t = 1; t < 7; ++t)
-    {
-      x = V(i + idx[t]);
-      acc.x = addf(acc.x, mulf(s_h[idx[t]], x.x));
-      acc.y = addf(acc.y, mulf(s_h[idx[t]], x.y));
-    }
-  }
-  else
-  {
-    const float2 xeven = V(2 * k), xodd = V(2 * k + 1), even = V(2 * k + 2), odd = V(2 * k + 3);
-    acc.x = d2f(muld(.125, addd((double)addf(odd.x, xeven.x), muld(3.0, (double)addf(xodd.x, even.x)))));
-    acc.y = d2f(muld(.125, addd((double)addf(odd.y, xeven.y), muld(3.0, (double)addf(xodd.y, even.y)))));
-  }
-  reinterpret_cast<float2*>(p.out)[(size_t)s * p.out_stride + p.out_off + k] = acc;
-}
-
 // --------------------------------------------------------------------------------------------------
 // Fused RDS front: NCO mix (DownConvert.cpp:438-442,464-465) -> every decimate-by-2 stage (:516-550, :589-688,
 // :709-727) -> the 2.4 kHz Kaiser LP (cFirFilter::Process complex, FirFilter.cpp:330-350; RDSProcess.cpp:128).
@@ -1743,27 +1654,6 @@ void launch_rds_front(const RdsFrontParams& p, cudaStream_t st)
     attr = smem;
   }
   k_rds_front<<<p.S, kRfThreads, smem, st>>>(p);
-}
-
-void launch_halfband(const HalfBandParams& p, cudaStream_t st)
-{
-  if (p.S == 0 || p.n_in < 2)
-    return;
-  dim3 grid(cdiv(p.n_in / 2, kHbTile), p.S);
-#define RFM_HB(MIX, KIND) k_halfband<MIX, KIND><<<grid, kHbTile, 0, st>>>(p)
-  if (p.mix)
-  {
-    if (p.kind == 0) RFM_HB(true, 0);
-    else if (p.kind == 1) RFM_HB(true, 1);
-    else RFM_HB(true, 2);
-  }
-  else
-  {
-    if (p.kind == 0) RFM_HB(false, 0);
-    else if (p.kind == 1) RFM_HB(false, 1);
-    else RFM_HB(false, 2);
-  }
-#undef RFM_HB
 }
 
 // ==================================================================================================

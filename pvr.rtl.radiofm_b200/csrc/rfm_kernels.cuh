@@ -196,27 +196,6 @@ struct OscParams
 };
 void launch_osc(const OscParams& p, cudaStream_t st);
 
-struct HalfBandParams
-{
-  // stage input: either a cf32 V buffer, or (mix != 0) bbV x oscV formed on the fly
-  const cf32* in;
-  size_t in_stride;
-  const float* bbV;
-  size_t a_stride;
-  unsigned a_hist;
-  const cf32* oscV;
-  unsigned osc_hist;
-  int mix;
-  int kind;                // 0 generic half-band, 1 fixed 11-tap, 2 CIC3
-  unsigned len;            // taps (history = len - 1; CIC3: 2)
-  unsigned n_in, S;
-  const float* h;          // device taps [len]
-  cf32* out;               // next stage V buffer
-  size_t out_stride;
-  unsigned out_off;
-};
-void launch_halfband(const HalfBandParams& p, cudaStream_t st);
-
 // fused RDS front: mix + decimate-by-2 chain + RDS low-pass, histories carried in a per-stream tail row
 constexpr unsigned kRfMaxStages = 6;
 struct RdsFrontStage
