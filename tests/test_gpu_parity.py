@@ -386,3 +386,31 @@ def test_async_submit_matches_synchronous_call(rfm, port):
         for s in range(S):
             assert bits_equal(out[b, s, :ks[b]], ref[b]), (b, s)
     assert np.array_equal(d.take_groups(S - 1), o.take_groups())
+
+
+@pytest.mark.parametrize("fs,ds,blk,kw", [
+    (2.048e6, 9, 65520, {}),                               # decimation the tiled front end is not specialised for
+    (1.0e6, 4, 65536, {"usver": True}),                    # 75 us deemphasis (USver)
+    (1.0e6, 4, 65536, {"bw_pcm": 12000.0}),                # narrower audio bandwidth: other Lanczos / Kaiser tables
+    (1.2e6, 5, 65520, {"tuning_offset": 0.0}),             # no fine-tuner shift
+    (1.2e6, 5, 65520, {"tuning_offset": 93750.0}),         # positive shift (table walks the other way)
+    (960000.0, 4, 65536, {}),
+])
+def test_other_configurations(rfm, port, synth, fs, ds, blk, kw):
+    """Constructor arguments beyond the BASELINE configs (generic front-end kernel, USver, bandwidth, tuning)."""
+    kw = dict(kw)
+    off = kw.pop("tuning_offset", -0.15 * fs)
+    nblk = 3
+    iq, _ = synth.make_station_u8(fs, nblk * blk, stream_id=2, f_off=off)
+    o = port.OracleFmDecoder(fs, off, downsample=ds, **kw)
+    d = rfm.FmDecoderBatch(fs, off, downsample=ds, n_streams=3, max_block_len=blk, n_groups=2, **kw)
+    assert np.array_equal(o.constants()[:51], d.constants()[:51])
+    for b in range(nblk):
+        x = iq[b * blk:(b + 1) * blk]
+        a_o = o.process_u8(x)
+        a_d = d.process_u8(np.broadcast_to(x, (3,) + x.shape))
+        for s in range(3):
+            assert bits_equal(a_d[s], a_o), (b, s)
+        for t in ("demod_in", "baseband", "rds_dec", "rds_lp", "rds_mf"):
+            assert bits_equal(d.tap(t, 2), oracle_tap(o, t)), (t, b)
+    assert np.array_equal(o.take_bits(), d.take_bits(1))
