@@ -210,14 +210,23 @@ __global__ void __launch_bounds__(128) k_front_tiled(FrontParams p, FrontCoef cf
 #pragma unroll
     for (int e = 0; e < 8; ++e)
       tw[e] = tuner[(p.idx0 + (unsigned)(ib0 + e)) & 63u];
-    // (kept as a rolled loop: the unrolled FIR below already fills most of the 32 KB instruction cache)
+    // (kept as a rolled loop: the unrolled FIR below already fills most of the 32 KB instruction cache; the 16-byte
+    // load of the NEXT interior chunk is issued before the current one is converted)
+    auto interior = [&](int ib) { return ib >= i_lo && ib + 8 <= i_hi; };
+    uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
+    if (interior(ib0))
+      nxt = *reinterpret_cast<const uint4*>(row + 2 * (size_t)ib0);
 #pragma unroll 1
     for (int ib = ib0; ib < i_hi; ib += 8 * G::T)
     {
-      if (ib >= i_lo && ib + 8 <= i_hi)
+      const uint4 cur = nxt;
+      const int ibn = ib + 8 * G::T;
+      if (ibn < i_hi && interior(ibn))
+        nxt = *reinterpret_cast<const uint4*>(row + 2 * (size_t)ibn);
+      if (interior(ib))
       {
         // interior chunk (the common case): one 16-byte load, no per-sample predicates
-        const uint4 raw = *reinterpret_cast<const uint4*>(row + 2 * (size_t)ib);
+        const uint4 raw = cur;
         const unsigned wd[4] = {raw.x, raw.y, raw.z, raw.w};
         const int w0 = ib + G::ORDER - (int)vlo;
         const int q0 = w0 / G::SEG, rem = w0 - q0 * G::SEG;
@@ -894,7 +903,15 @@ void launch_bb_lanes(const LanesParams& p, cudaStream_t st)
 {
   if (p.S == 0 || p.nb == 0)
     return;
-  k_bb_lanes<<<cdiv(p.S, 32), 64, 0, st>>>(p);
+  // measurement aid: reserve extra (unused) dynamic shared memory so fewer throughput CTAs share the lanes' SMs
+  static const int reserve_kb = getenv("RFM_LANES_RESERVE_KB") ? atoi(getenv("RFM_LANES_RESERVE_KB")) : 0;
+  static bool attr = false;
+  if (reserve_kb > 0 && !attr)
+  {
+    cudaFuncSetAttribute(k_bb_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, reserve_kb * 1024);
+    attr = true;
+  }
+  k_bb_lanes<<<cdiv(p.S, 32), 64, (size_t)reserve_kb * 1024, st>>>(p);
 }
 
 
