@@ -182,6 +182,40 @@ RFM_API int rfm_freqshift_process_u8(rfm_freqshift* f, const uint8_t* iq, int sh
 RFM_API int rfm_freqshift_process_device(rfm_freqshift* f, int mode, const void* d_in, size_t in_stride, float* d_out,
                                          size_t out_stride, uint32_t n, void* cuda_stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * CRDSDownConvert (DownConvert.h:68-169, DownConvert.cpp:271-489), batched over rows: NCO_OSC mixer (the
+ * amplitude-stabilised rotating vector of DownConvert.cpp:438-442, bit-exact) followed by the planned chain of
+ * decimate-by-2 stages (half-bands HB11..HB51 of filtercoef.h:62-150, the fixed 11-tap stage, CIC3).
+ * One row per station of a wideband capture (shared u8 input) or per independent stream.
+ * n must be a multiple of 2^stages and long enough for every stage (RFM_ERR_UNSUPPORTED otherwise: the reference
+ * itself mis-filters such calls, DownConvert.cpp:519-520,544-547).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rfm_downconvert rfm_downconvert;
+/* CRDSDownConvert() + SetDataRate(in_rate, max_bw) (wfm == 0, DownConvert.cpp:327-371) or SetWfmDataRate (wfm != 0,
+ * :378-399) + SetFrequency(nco_freq[row]) (:311-320) */
+RFM_API int rfm_downconvert_create(uint32_t rows, const float* nco_freq, float in_rate, float max_bw, int wfm,
+                                   uint32_t max_len, int device, rfm_downconvert** out);
+RFM_API void rfm_downconvert_destroy(rfm_downconvert* d);
+/* the value SetDataRate / SetWfmDataRate return: in_rate / 2^stages */
+RFM_API float rfm_downconvert_output_rate(const rfm_downconvert* d);
+/* number of decimate-by-2 stages; taps[k] = length of stage k (3 = CIC3) */
+RFM_API uint32_t rfm_downconvert_stages(const rfm_downconvert* d, uint32_t* taps, uint32_t max);
+/* CRDSDownConvert::SetFrequency for every row (the carried oscillator phasors are kept) -- DownConvert.cpp:311-320 */
+RFM_API int rfm_downconvert_set_frequency(rfm_downconvert* d, const float* nco_freq);
+/* back to the freshly constructed state (m_Osc1 = 1 + 0j, empty delay lines) */
+RFM_API int rfm_downconvert_reset(rfm_downconvert* d);
+/* CRDSDownConvert::ProcessData(InLength, pInData, pOutData) -- DownConvert.cpp:412-489.  iq [rows][n][2] host (left
+ * untouched; the reference scribbles its intermediate results over pInData), out [rows][n >> stages][2] host;
+ * *n_out = the return value, n >> stages */
+RFM_API int rfm_downconvert_process_cf32(rfm_downconvert* d, const float* iq, uint32_t n, float* out, uint32_t* n_out);
+/* the same fused with cRtlSdrSource::ReadAsyncCB's u8 -> float conversion (RTL_SDR_Source.cpp:207-211); iq is one
+ * shared capture [n][2] (shared_capture != 0) or [rows][n][2] */
+RFM_API int rfm_downconvert_process_u8(rfm_downconvert* d, const uint8_t* iq, int shared_capture, uint32_t n, float* out,
+                                       uint32_t* n_out);
+/* device pointers, enqueue only; mode 0: cf32 rows, 1: one shared u8 capture, 2: u8 rows; strides in samples */
+RFM_API int rfm_downconvert_process_device(rfm_downconvert* d, int mode, const void* d_in, size_t in_stride, float* d_out,
+                                           size_t out_stride, uint32_t n, uint32_t* n_out, void* cuda_stream);
+
 /* Test hooks (no reference counterpart): evaluate one of the scalar building blocks of the kernels on the DEVICE for
  * n host operands; out2 receives two floats per element.  op: 0 rfm_sincos (sin, cos) 1 sincos fast core
  * 2 sincos generic 3 atan2f(a, b) 4 branch-free atan2f (+flag) 5 atan2f generic 6 branch-free a / b (+flag)

@@ -50,7 +50,9 @@ EXPORTED_SYMBOLS = (
     "rfm_rdssync_destroy", "rfm_rdssync_reset", "rfm_rdssync_push_bits", "rfm_rdssync_take_groups",
     "rfm_rds_check_block", "rfm_math_probe", "rfm_div_selftest", "rfm_freqshift_create",
     "rfm_freqshift_destroy", "rfm_freqshift_reset", "rfm_freqshift_process_cf32", "rfm_freqshift_process_u8",
-    "rfm_freqshift_process_device",
+    "rfm_freqshift_process_device", "rfm_downconvert_create", "rfm_downconvert_destroy", "rfm_downconvert_output_rate",
+    "rfm_downconvert_stages", "rfm_downconvert_set_frequency", "rfm_downconvert_reset", "rfm_downconvert_process_cf32",
+    "rfm_downconvert_process_u8", "rfm_downconvert_process_device",
 )
 
 
@@ -121,6 +123,19 @@ def lib():
         L.rfm_freqshift_process_u8.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_uint32, _f32p]
         L.rfm_freqshift_process_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                                    C.c_uint32, C.c_void_p]
+        L.rfm_downconvert_create.argtypes = [C.c_uint32, _f32p, C.c_float, C.c_float, C.c_int, C.c_uint32, C.c_int,
+                                             C.POINTER(C.c_void_p)]
+        L.rfm_downconvert_destroy.argtypes = [C.c_void_p]
+        L.rfm_downconvert_output_rate.restype = C.c_float
+        L.rfm_downconvert_output_rate.argtypes = [C.c_void_p]
+        L.rfm_downconvert_stages.restype = C.c_uint32
+        L.rfm_downconvert_stages.argtypes = [C.c_void_p, _u32p, C.c_uint32]
+        L.rfm_downconvert_set_frequency.argtypes = [C.c_void_p, _f32p]
+        L.rfm_downconvert_reset.argtypes = [C.c_void_p]
+        L.rfm_downconvert_process_cf32.argtypes = [C.c_void_p, _f32p, C.c_uint32, _f32p, _u32p]
+        L.rfm_downconvert_process_u8.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_uint32, _f32p, _u32p]
+        L.rfm_downconvert_process_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                                     C.c_uint32, _u32p, C.c_void_p]
         L.rfm_rds_check_block.restype = C.c_uint32
         L.rfm_rds_check_block.argtypes = [C.c_uint32, C.c_uint32, C.c_int, _u32p]
         _lib = L
@@ -362,6 +377,65 @@ class FreqShiftBatch:
         out = np.empty((self.rows, n, 2), dtype=np.float32)
         _check(lib().rfm_freqshift_process_u8(self._h, _p(iq_u8, _u8p), int(shared_capture), n, _p(out, _f32p)))
         return out
+
+    def process_device(self, mode: int, d_in_ptr: int, in_stride: int, d_out_ptr: int, out_stride: int, n: int,
+                       cuda_stream: int = 0):
+        _check(lib().rfm_freqshift_process_device(self._h, mode, C.c_void_p(d_in_ptr), in_stride, C.c_void_p(d_out_ptr),
+                                                  out_stride, n, C.c_void_p(cuda_stream)))
+
+
+class DownConvertBatch:
+    """rows x CRDSDownConvert (DownConvert.h:68-169): NCO_OSC mixer + decimate-by-2 chain, one row per station / stream."""
+
+    def __init__(self, nco_freq, in_rate: float, max_bw: float, wfm: bool = False, max_len: int = 65536, device: int = -1):
+        f = np.ascontiguousarray(np.atleast_1d(nco_freq), dtype=np.float32)
+        self.rows = f.size
+        self._h = C.c_void_p()
+        _check(lib().rfm_downconvert_create(self.rows, _p(f, _f32p), in_rate, max_bw, int(wfm), max_len, device,
+                                            C.byref(self._h)))
+        taps = np.zeros(16, dtype=np.uint32)
+        self.n_stages = int(lib().rfm_downconvert_stages(self._h, _p(taps, _u32p), 16))
+        self.stage_taps = taps[:self.n_stages].tolist()
+        self.output_rate = float(lib().rfm_downconvert_output_rate(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().rfm_downconvert_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reset(self):
+        _check(lib().rfm_downconvert_reset(self._h))
+
+    def set_frequency(self, nco_freq):
+        f = np.ascontiguousarray(np.atleast_1d(nco_freq), dtype=np.float32)
+        assert f.size == self.rows
+        _check(lib().rfm_downconvert_set_frequency(self._h, _p(f, _f32p)))
+
+    def process_cf32(self, iq: np.ndarray) -> np.ndarray:
+        iq = np.ascontiguousarray(iq, dtype=np.float32).reshape(self.rows, -1, 2)
+        n = iq.shape[1]
+        out = np.empty((self.rows, max(n >> self.n_stages, 1), 2), dtype=np.float32)
+        k = C.c_uint32(0)
+        _check(lib().rfm_downconvert_process_cf32(self._h, _p(iq, _f32p), n, _p(out, _f32p), C.byref(k)))
+        return out[:, :k.value].copy()
+
+    def process_u8(self, iq_u8: np.ndarray, shared_capture: bool) -> np.ndarray:
+        iq_u8 = np.ascontiguousarray(iq_u8, dtype=np.uint8)
+        n = iq_u8.reshape(-1, 2).shape[0] // (1 if shared_capture else self.rows)
+        out = np.empty((self.rows, max(n >> self.n_stages, 1), 2), dtype=np.float32)
+        k = C.c_uint32(0)
+        _check(lib().rfm_downconvert_process_u8(self._h, _p(iq_u8, _u8p), int(shared_capture), n, _p(out, _f32p),
+                                                C.byref(k)))
+        return out[:, :k.value].copy()
+
+    def process_device(self, mode: int, d_in_ptr: int, in_stride: int, d_out_ptr: int, out_stride: int, n: int,
+                       cuda_stream: int = 0) -> int:
+        k = C.c_uint32(0)
+        _check(lib().rfm_downconvert_process_device(self._h, mode, C.c_void_p(d_in_ptr), in_stride, C.c_void_p(d_out_ptr),
+                                                    out_stride, n, C.byref(k), C.c_void_p(cuda_stream)))
+        return int(k.value)
 
 
 def math_probe(op: int, a: np.ndarray, b: np.ndarray | None = None) -> np.ndarray:

@@ -33,11 +33,16 @@
 
 using namespace rfm;
 
+namespace rfm
+{
+// shared with the stand-alone primitives (rfm_downconvert.cu, rfm_filters.cu)
+std::atomic<uint64_t> g_launches{0};
+thread_local std::string g_err;
+void SetLastError(const std::string& m) { g_err = m; }
+} // namespace rfm
+
 namespace
 {
-thread_local std::string g_err;
-std::atomic<uint64_t> g_launches{0};
-
 int Fail(int code, const std::string& msg)
 {
   g_err = msg;

@@ -76,7 +76,11 @@ struct rfm_freqshift
 {
   unsigned rows = 0, cap = 0;
   int device = 0;
-  float *d_inc = nullptr, *d_time = nullptr, *d_ph = nullptr, *d_lut = nullptr;
+  float *d_inc = nullptr, *d_time = nullptr, *d_ph = nullptr, *d_lut = nullptr, *d_time_end = nullptr;
+  // Reset() before every block (phase-coherent blocks of a wideband capture) repeats the same phase sequence: the
+  // table computed from phase 0 is kept and the sequential k_fs_phase pass skipped when the next call is identical
+  bool at_zero = true;
+  unsigned ph0_n = 0;
   float2* d_io = nullptr;
   uint8_t* d_u8 = nullptr;
   std::string err;
@@ -107,6 +111,7 @@ int rfm_freqshift_create(uint32_t rows, const float* nco_freq, float in_rate, ui
     lut[u] = (float)(u / (255.0 / 2.0) - 1.0);
   bool ok = cudaMalloc(&f->d_inc, rows * 4) == cudaSuccess && cudaMalloc(&f->d_time, rows * 4) == cudaSuccess &&
             cudaMalloc(&f->d_ph, (size_t)rows * max_len * 4) == cudaSuccess && cudaMalloc(&f->d_lut, 1024) == cudaSuccess &&
+            cudaMalloc(&f->d_time_end, rows * 4) == cudaSuccess &&
             cudaMalloc(&f->d_io, (size_t)rows * max_len * 8) == cudaSuccess &&
             cudaMalloc(&f->d_u8, (size_t)rows * max_len * 2) == cudaSuccess;
   if (ok)
@@ -129,6 +134,7 @@ void rfm_freqshift_destroy(rfm_freqshift* f)
   if (!f)
     return;
   cudaSetDevice(f->device);
+  cudaFree(f->d_time_end);
   cudaFree(f->d_inc); cudaFree(f->d_time); cudaFree(f->d_ph); cudaFree(f->d_lut); cudaFree(f->d_io); cudaFree(f->d_u8);
   delete f;
 }
@@ -138,13 +144,26 @@ int rfm_freqshift_reset(rfm_freqshift* f) // FreqShift.cpp:18-21
   if (!f)
     return RFM_ERR_INVALID;
   cudaSetDevice(f->device);
-  return cudaMemset(f->d_time, 0, f->rows * 4) == cudaSuccess ? RFM_OK : RFM_ERR_CUDA;
+  f->at_zero = true;
+  return cudaMemsetAsync(f->d_time, 0, f->rows * 4, 0) == cudaSuccess ? RFM_OK : RFM_ERR_CUDA;
 }
 
 static int Run(rfm_freqshift* f, int mode, const void* d_in, size_t in_stride, float2* d_out, size_t out_stride,
                uint32_t n, cudaStream_t st)
 {
-  k_fs_phase<<<(f->rows + 31) / 32, 32, 0, st>>>(f->d_inc, f->d_time, f->d_ph, f->cap, n, f->rows);
+  if (f->at_zero && f->ph0_n == n)
+    cudaMemcpyAsync(f->d_time, f->d_time_end, f->rows * 4, cudaMemcpyDeviceToDevice, st); // table still valid
+  else
+  {
+    k_fs_phase<<<(f->rows + 31) / 32, 32, 0, st>>>(f->d_inc, f->d_time, f->d_ph, f->cap, n, f->rows);
+    f->ph0_n = 0;
+    if (f->at_zero)
+    {
+      cudaMemcpyAsync(f->d_time_end, f->d_time, f->rows * 4, cudaMemcpyDeviceToDevice, st);
+      f->ph0_n = n;
+    }
+  }
+  f->at_zero = false;
   dim3 grid((n + 255) / 256, f->rows);
   if (mode == 0)
     k_fs_mix<0><<<grid, 256, 0, st>>>(f->d_ph, f->cap, d_in, in_stride, d_out, out_stride, n, f->d_lut);

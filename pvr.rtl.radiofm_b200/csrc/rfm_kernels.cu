@@ -20,6 +20,7 @@
 //   k_rds_slice    [a11]        bit-clock resonator + peak slicer + differential decode
 //   k_tails                     V-buffer history carry
 #include "rfm_kernels.cuh"
+#include "rfm_dsp.cuh"
 
 #include <assert.h>
 #include <stdlib.h>
@@ -150,17 +151,6 @@ struct FrontCoef
 {
   float c[92]; // c[j], j = 0 .. order + 1 (order <= 88)
 };
-
-// float(double(u) / 127.5 - 1.0) (RTL_SDR_Source.cpp:207-211) without a table: t = u * 0x1.01p-7 - 1 is exact, the
-// second FMA adds the low part of 1/127.5 and rounds once.  Equal to the reference expression for all 256 codes
-// (tests/test_abi_host.py::test_u8_conversion_formula, and the GPU parity tests through the whole chain).
-__device__ __forceinline__ float rfm_u8_to_float(unsigned word, unsigned byte_sel)
-{
-  const float m = __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540u + byte_sel)); // 2^23 + u
-  const float u = __fsub_rn(m, 8388608.0f);
-  const float t = __fmaf_rn(u, 0x1.01p-7f, -1.0f);
-  return __fmaf_rn(u, 0x1.010102p-23f, t);
-}
 
 template <int DS>
 struct FrontGeom
@@ -1444,84 +1434,6 @@ void launch_osc(const OscParams& p, cudaStream_t st)
 // --------------------------------------------------------------------------------------------------
 constexpr unsigned kRfTile = 1024;
 constexpr unsigned kRfThreads = 128;
-
-template <int L>
-__device__ __forceinline__ float2 hb_generic(const float* h, const float2* V, unsigned k)
-{
-  const float2* x = V + 2 * k;
-  float2 acc;
-  acc.x = mulf(x[0].x, h[0]);
-  acc.y = mulf(x[0].y, h[0]);
-#pragma unroll
-  for (int j = 0; j < L; j += 2)
-  {
-    acc.x = addf(acc.x, mulf(x[j].x, h[j]));
-    acc.y = addf(acc.y, mulf(x[j].y, h[j]));
-  }
-  constexpr int c = (L - 1) / 2;
-  acc.x = addf(acc.x, mulf(x[c].x, h[c]));
-  acc.y = addf(acc.y, mulf(x[c].y, h[c]));
-  return acc;
-}
-
-__device__ __forceinline__ float2 hb_out(int kind, unsigned L, const float* h, const float2* V, unsigned k)
-{
-  float2 acc;
-  if (kind == 0)
-  {
-    switch (L) // the lengths of filtercoef.h's tables, unrolled
-    {
-      case 11: return hb_generic<11>(h, V, k);
-      case 15: return hb_generic<15>(h, V, k);
-      case 19: return hb_generic<19>(h, V, k);
-      case 23: return hb_generic<23>(h, V, k);
-      case 27: return hb_generic<27>(h, V, k);
-      case 31: return hb_generic<31>(h, V, k);
-      case 35: return hb_generic<35>(h, V, k);
-      case 39: return hb_generic<39>(h, V, k);
-      case 43: return hb_generic<43>(h, V, k);
-      case 47: return hb_generic<47>(h, V, k);
-      case 51: return hb_generic<51>(h, V, k);
-      default: break;
-    }
-    const unsigned i = 2 * k;
-    float2 x = V[i];
-    acc.x = mulf(x.x, h[0]);
-    acc.y = mulf(x.y, h[0]);
-    for (unsigned j = 0; j < L; j += 2)
-    {
-      x = V[i + j];
-      acc.x = addf(acc.x, mulf(x.x, h[j]));
-      acc.y = addf(acc.y, mulf(x.y, h[j]));
-    }
-    const unsigned c = (L - 1) / 2;
-    x = V[i + c];
-    acc.x = addf(acc.x, mulf(x.x, h[c]));
-    acc.y = addf(acc.y, mulf(x.y, h[c]));
-  }
-  else if (kind == 1)
-  {
-    const unsigned i = 2 * k;
-    const int idx[7] = {0, 2, 4, 5, 6, 8, 10};
-    float2 x = V[i];
-    acc.x = mulf(h[0], x.x);
-    acc.y = mulf(h[0], x.y);
-#pragma unroll
-    for (int t = 1; t < 7; ++t)
-    {
-      x = V[i + idx[t]];
-      acc.x = addf(acc.x, mulf(h[idx[t]], x.x));
-      acc.y = addf(acc.y, mulf(h[idx[t]], x.y));
-    }
-  }
-  else
-  {
-    const float2 xeven = V[2 * k], xodd = V[2 * k + 1], even = V[2 * k + 2], odd = V[2 * k + 3];
-    acc.x = d2f(muld(.125, addd((double)addf(odd.x, xeven.x), muld(3.0, (double)addf(xodd.x, even.x)))));
-    acc.y = d2f(muld(.125, addd((double)addf(odd.y, xeven.y), muld(3.0, (double)addf(xodd.y, even.y)))));
-  }
-  return acc;
-}
 
 __global__ void __launch_bounds__(kRfThreads) k_rds_front(RdsFrontParams p)
 {

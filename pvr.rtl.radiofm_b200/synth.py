@@ -186,3 +186,25 @@ def make_station_u8(fs: float, n: int, *, stream_id: int = 0, f_off: float | Non
                      rds_level=0.05 if rds else 0.0, rds_bits=bits, mono_tone=mono_tone)
     iq = fm_modulate_u8(mpx, fs, f_off, snr_db=snr_db, seed=1234 + stream_id)
     return iq, groups
+
+
+def make_wideband_u8(fs: float, n: int, station_freqs, *, first_stream: int = 0, rds: bool = True,
+                     amplitude: float = 0.8) -> np.ndarray:
+    """One shared wideband capture: FM stations at station_freqs[k] Hz from the LO, equal
+    power, each with the C3 multiplex of stream `first_stream + k`; the sum is scaled to `amplitude` of full scale.
+    Returns u8 [n, 2]."""
+    acc = np.zeros(n, dtype=np.complex128)
+    for k, f in enumerate(station_freqs):
+        p = stream_params(first_stream + k)
+        bits = None
+        if rds:
+            groups = rds_group_stream(p["pi"], p["ps"], int(np.ceil(n / fs * RDS_BITRATE / 104.0)) + 2)
+            bits = rds_bits_from_groups(groups)
+        mpx = mpx_signal(fs, n, left=p["left"], right=p["right"], rds_level=0.05 if rds else 0.0, rds_bits=bits)
+        phi = 2.0 * np.pi * 75000.0 / fs * np.cumsum(mpx) + 2.0 * np.pi * f * np.arange(n) / fs
+        acc += np.exp(1j * phi)
+    acc *= amplitude / max(1.0, float(np.max(np.abs(acc))))
+    out = np.empty((n, 2), dtype=np.uint8)
+    out[:, 0] = np.clip(np.rint(127.5 + 127.5 * acc.real), 0, 255).astype(np.uint8)
+    out[:, 1] = np.clip(np.rint(127.5 + 127.5 * acc.imag), 0, 255).astype(np.uint8)
+    return out

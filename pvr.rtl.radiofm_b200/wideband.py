@@ -1,0 +1,75 @@
+"""Wideband front end: S stations of ONE shared u8 capture, each mixed to baseband,
+decimated by CRDSDownConvert's SetWfmDataRate chain (7 x HB51 at 50 MS/s -> 390 625 S/s) and demodulated by a
+cFmDecoder(390625, 0, 48000, 15000, downsample = 1) -- all on the device, composed from the C-ABI primitives through
+device pointers.  Host logic only; the arithmetic lives in libradiofm_b200.so.
+
+Two mixers, both reference classes:
+  "osc"       CRDSDownConvert::SetFrequency(-f_k): the NCO_OSC rotating vector inside ProcessData (DownConvert.cpp:438-442).
+              Bit-exact needs the sequential float recurrence, one lane per station: latency-bound (~60 cycles / sample),
+              independent of the station count.
+  "freqshift" cFreqShift(-f_k, Fs) with Reset() before every phase-coherent front-end block (f_k * L / Fs integer), then
+              CRDSDownConvert at 0 Hz (whose oscillator settles into a 4-cycle).  Fully parallel; the reference's float32
+              phase costs it SNR, parity is against the reference all the same.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import DownConvertBatch, FmDecoderBatch, FreqShiftBatch
+
+
+class WidebandReceiver:
+    def __init__(self, torch, station_freqs, fs: float = 50.0e6, front_block: int = 32000, blocks_per_call: int = 64,
+                 mixer: str = "osc", max_bw: float = 100000.0, device: int = 0):
+        assert mixer in ("osc", "freqshift")
+        self.torch, self.mixer, self.fs = torch, mixer, fs
+        self.freqs = np.ascontiguousarray(station_freqs, dtype=np.float64)
+        self.S = S = self.freqs.size
+        self.front_block, self.blocks_per_call = front_block, blocks_per_call
+        self.n_call = front_block * blocks_per_call
+        dev = torch.device("cuda", device)
+        if mixer == "osc":
+            self.shift = None
+            self.dc = DownConvertBatch(-self.freqs, fs, max_bw, wfm=True, max_len=self.n_call, device=device)
+        else:
+            for f in self.freqs:
+                assert abs(f * front_block / fs - round(f * front_block / fs)) < 1e-9, "blocks must be phase-coherent"
+            self.shift = FreqShiftBatch(-self.freqs, fs, max_len=front_block, device=device)
+            self.dc = DownConvertBatch(np.zeros(S), fs, max_bw, wfm=True, max_len=self.n_call, device=device)
+            self.mixed = torch.empty((S, self.n_call, 2), dtype=torch.float32, device=dev)
+        self.n_bb = self.n_call >> self.dc.n_stages
+        self.bb = torch.empty((S, self.n_bb, 2), dtype=torch.float32, device=dev)
+        self.dec = FmDecoderBatch(self.dc.output_rate, 0.0, downsample=1, n_streams=S, max_block_len=self.n_bb,
+                                  device=device)
+        self.audio_stride = max(self.dec.max_audio_floats(self.n_bb), 2)
+        self.audio = torch.empty((S, self.audio_stride), dtype=torch.float32, device=dev)
+
+    def close(self):
+        for o in (self.shift, self.dc, self.dec):
+            if o is not None:
+                o.close()
+
+    def process_device(self, d_capture_ptr: int) -> int:
+        """One call = blocks_per_call front-end blocks of the shared capture (u8 [n_call][2] at d_capture_ptr), enqueued on
+        the default stream.  Returns the audio floats per station now in self.audio (valid after dec.wait / synchronize)."""
+        if self.mixer == "osc":
+            m = self.dc.process_device(1, d_capture_ptr, self.n_call, self.bb.data_ptr(), self.n_bb, self.n_call)
+        else:
+            for b in range(self.blocks_per_call):
+                self.shift.reset()
+                self.shift.process_device(1, d_capture_ptr + 2 * b * self.front_block, self.front_block,
+                                          self.mixed.data_ptr() + 8 * b * self.front_block, self.n_call, self.front_block)
+            m = self.dc.process_device(0, self.mixed.data_ptr(), self.n_call, self.bb.data_ptr(), self.n_bb, self.n_call)
+        assert m == self.n_bb
+        k = self.dec.process_cf32_device(self.bb.data_ptr(), self.n_bb, self.n_bb, self.audio.data_ptr(),
+                                         self.audio_stride)
+        self.dec.wait(0)
+        return k
+
+    def process_u8(self, capture_u8: np.ndarray) -> np.ndarray:
+        """Host convenience: capture [n_call, 2] uint8 -> audio [S, floats]."""
+        torch = self.torch
+        cap = torch.from_numpy(np.ascontiguousarray(capture_u8, dtype=np.uint8).reshape(self.n_call, 2)).to(self.bb.device)
+        k = self.process_device(cap.data_ptr())
+        torch.cuda.synchronize()
+        return self.audio[:, :k].cpu().numpy()

@@ -217,3 +217,35 @@ def test_port_matches_golden_primitives(port):
     lvl = L.rfo_pilot_level(h)
     L.rfo_pilot_destroy(h)
     assert bits_equal(y, g["pilot_out"]) and [l1, l2] == g["pilot_lock"].tolist() and np.float32(lvl) == g["pilot_level"]
+
+
+@pytest.mark.parametrize("in_rate,max_bw,wfm,freq,n", [
+    (4.0e6, 4800.0, False, 100000.0, 16384),      # CIC3, fixed 11-tap x4, HB15, HB23, HB47
+    (2.4e6, 100000.0, False, -57000.0, 8192),     # HB15, HB23, HB51
+    (50.0e6, 100000.0, True, -7.0e6, 32000),      # SetWfmDataRate: 7 x HB51
+    (50.0e6, 100000.0, True, 0.0, 12800),         # 0 Hz: the oscillator falls into its 4-cycle
+])
+def test_rdsdc_port_vs_ref_every_stage_kind(port, ref, in_rate, max_bw, wfm, freq, n):
+    """The C restatement of CRDSDownConvert against the compiled reference for the stage kinds and planners the decoder's
+    own RDS chain never exercises (they back the stand-alone rfm_downconvert primitive and the wideband front end)."""
+    rng = np.random.default_rng(11)
+    LP, LR = port.lib(), ref.lib()
+    hp, hr = LP.rfo_rdsdc_create(), LR.ref_rdsdc_create()
+    LP.rfo_rdsdc_set_frequency(hp, np.float32(freq))
+    LR.ref_rdsdc_set_frequency(hr, np.float32(freq))
+    if wfm:
+        rp = LP.rfo_rdsdc_set_wfm_data_rate(hp, np.float32(in_rate), np.float32(max_bw))
+        rr = LR.ref_rdsdc_set_wfm_data_rate(hr, np.float32(in_rate), np.float32(max_bw))
+    else:
+        rp = LP.rfo_rdsdc_set_data_rate(hp, np.float32(in_rate), np.float32(max_bw))
+        rr = LR.ref_rdsdc_set_data_rate(hr, np.float32(in_rate), np.float32(max_bw))
+    assert np.float32(rp) == np.float32(rr)
+    for _ in range(3):
+        x = (rng.standard_normal((n, 2)) * 0.3).astype(np.float32)
+        zp, zr = x.copy(), x.copy()
+        yp, yr = np.zeros_like(x), np.zeros_like(x)
+        kp = LP.rfo_rdsdc_process(hp, n, P(zp), P(yp))
+        kr = LR.ref_rdsdc_process(hr, n, P(zr), P(yr))
+        assert kp == kr and bits_equal(yp[:kp], yr[:kr])
+    LP.rfo_rdsdc_destroy(hp)
+    LR.ref_rdsdc_destroy(hr)
