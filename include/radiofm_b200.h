@@ -212,6 +212,13 @@ RFM_API int rfm_downconvert_process_cf32(rfm_downconvert* d, const float* iq, ui
  * shared capture [n][2] (shared_capture != 0) or [rows][n][2] */
 RFM_API int rfm_downconvert_process_u8(rfm_downconvert* d, const uint8_t* iq, int shared_capture, uint32_t n, float* out,
                                        uint32_t* n_out);
+/* Optional pre-mixer for phase-coherent blocks of a wideband capture: a cFreqShift that is Reset() every `period`
+ * samples (FreqShift.cpp:18-21) repeats the same (cos, sin) sequence, so it is a lookup table: d_table [rows][row_stride]
+ * float2 on the device, entry i = what cFreqShift::Process makes of the sample (1, 0) at position i after Reset()
+ * (rfm_freqshift_process_* on a block of ones).  Every input sample is multiplied by its entry (the four products, one
+ * subtraction, one addition of FreqShift.cpp:63-69) before CRDSDownConvert's own NCO.  The position starts at 0 when
+ * the table is set or the converter reset and advances with the samples processed.  d_table == NULL switches it off. */
+RFM_API int rfm_downconvert_set_premix(rfm_downconvert* d, const float* d_table, size_t row_stride, uint32_t period);
 /* device pointers, enqueue only; mode 0: cf32 rows, 1: one shared u8 capture, 2: u8 rows; strides in samples */
 RFM_API int rfm_downconvert_process_device(rfm_downconvert* d, int mode, const void* d_in, size_t in_stride, float* d_out,
                                            size_t out_stride, uint32_t n, uint32_t* n_out, void* cuda_stream);
@@ -220,7 +227,7 @@ RFM_API int rfm_downconvert_process_device(rfm_downconvert* d, int mode, const v
  * n host operands; out2 receives two floats per element.  op: 0 rfm_sincos (sin, cos) 1 sincos fast core
  * 2 sincos generic 3 atan2f(a, b) 4 branch-free atan2f (+flag) 5 atan2f generic 6 branch-free a / b (+flag)
  * 7 __fdiv_rn 8 / 9 branch-free demod / pilot phase wrap (+flag) 10 both exact wraps 11 RDS arctan2 approximation
- * (RDSProcess.cpp:187-217) 12 fmodf.  rfm_div_selftest: branch-free division vs __fdiv_rn over `pairs` random
+ * (RDSProcess.cpp:187-217) 12 fmodf 13 NCO_OSC gain (float form, double form).  rfm_div_selftest: branch-free division vs __fdiv_rn over `pairs` random
  * operand pairs generated on the device. */
 RFM_API int rfm_math_probe(int op, const float* a, const float* b, float* out2, uint32_t n);
 RFM_API int rfm_div_selftest(uint64_t seed, uint64_t pairs, uint64_t* mismatches, uint64_t* tested);

@@ -52,7 +52,7 @@ EXPORTED_SYMBOLS = (
     "rfm_freqshift_destroy", "rfm_freqshift_reset", "rfm_freqshift_process_cf32", "rfm_freqshift_process_u8",
     "rfm_freqshift_process_device", "rfm_downconvert_create", "rfm_downconvert_destroy", "rfm_downconvert_output_rate",
     "rfm_downconvert_stages", "rfm_downconvert_set_frequency", "rfm_downconvert_reset", "rfm_downconvert_process_cf32",
-    "rfm_downconvert_process_u8", "rfm_downconvert_process_device",
+    "rfm_downconvert_process_u8", "rfm_downconvert_process_device", "rfm_downconvert_set_premix",
 )
 
 
@@ -132,6 +132,7 @@ def lib():
         L.rfm_downconvert_stages.argtypes = [C.c_void_p, _u32p, C.c_uint32]
         L.rfm_downconvert_set_frequency.argtypes = [C.c_void_p, _f32p]
         L.rfm_downconvert_reset.argtypes = [C.c_void_p]
+        L.rfm_downconvert_set_premix.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32]
         L.rfm_downconvert_process_cf32.argtypes = [C.c_void_p, _f32p, C.c_uint32, _f32p, _u32p]
         L.rfm_downconvert_process_u8.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_uint32, _f32p, _u32p]
         L.rfm_downconvert_process_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
@@ -412,6 +413,11 @@ class DownConvertBatch:
         f = np.ascontiguousarray(np.atleast_1d(nco_freq), dtype=np.float32)
         assert f.size == self.rows
         _check(lib().rfm_downconvert_set_frequency(self._h, _p(f, _f32p)))
+
+    def set_premix(self, d_table_ptr: int, row_stride: int, period: int):
+        """Device table [rows][row_stride] float2 of a cFreqShift that is Reset() every `period` samples (0 = off)."""
+        _check(lib().rfm_downconvert_set_premix(self._h, C.c_void_p(d_table_ptr) if d_table_ptr else None, row_stride,
+                                                period))
 
     def process_cf32(self, iq: np.ndarray) -> np.ndarray:
         iq = np.ascontiguousarray(iq, dtype=np.float32).reshape(self.rows, -1, 2)

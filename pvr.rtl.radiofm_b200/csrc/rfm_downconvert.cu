@@ -69,6 +69,11 @@ struct DcParams
   float2* out;           // [rows][out_stride]
   size_t out_stride;
   unsigned chunk, warm, nchunks;
+  // optional pre-mixer: sample i of the call is first multiplied by pre[row][(pre_pos + i) mod pre_period] -- the
+  // (cos, sin) sequence of a cFreqShift that is Reset() every pre_period samples (FreqShift.cpp:55-69)
+  const float2* pre;
+  size_t pre_stride;
+  unsigned pre_period, pre_pos;
 };
 
 template <int IN>
@@ -81,7 +86,7 @@ __device__ __forceinline__ float2 dc_load(const DcParams& p, unsigned row, unsig
   return make_float2(rfm_u8_to_float(w, 0u), rfm_u8_to_float(w, 1u));
 }
 
-// DownConvert.cpp:464-465
+// DownConvert.cpp:464-465 (and FreqShift.cpp:63-69: the same four products, one subtraction, one addition)
 __device__ __forceinline__ float2 dc_mix(float2 d, float2 o)
 {
   float2 r;
@@ -90,60 +95,125 @@ __device__ __forceinline__ float2 dc_mix(float2 d, float2 o)
   return r;
 }
 
-// --------------------------------------------------------------------------------------------------
-// NCO_OSC table, DownConvert.cpp:438-442: one lane per row, sequential; coalesced stores through a shared tile.
-// --------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) k_dc_osc(const float* cosv, const float* sinv, float* osc1, float2* table,
-                                               size_t stride, unsigned n, unsigned rows)
+// input sample i of this call for `row`, pre-mixed if a table is set, times the NCO phasor
+template <int IN>
+__device__ __forceinline__ float2 dc_sample(const DcParams& p, const float2* osc, unsigned row, unsigned i)
 {
-  __shared__ float2 tile[32][33];
+  float2 d = dc_load<IN>(p, row, i);
+  if (p.pre)
+    d = dc_mix(d, p.pre[(size_t)row * p.pre_stride + (p.pre_pos + i) % p.pre_period]);
+  return dc_mix(d, osc[i]);
+}
+
+// L2 prefetch of the global operands of tile [pos, pos + tn) (issued a tile ahead: the loads then hit L2)
+template <int IN>
+__device__ __forceinline__ void dc_prefetch(const DcParams& p, const float2* osc, unsigned row, unsigned pos, unsigned tn,
+                                            unsigned tid)
+{
+  const unsigned i = tid * 16; // 16 float2 = one 128-byte line
+  if (i >= tn)
+    return;
+  if (p.osc_stride)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(osc + pos + i));
+  if (IN == 0)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const float2*>(p.in) + (size_t)row * p.in_stride + pos + i));
+  if (IN == 2 && (i & 63u) == 0)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const unsigned char*>(p.in) + 2 * ((size_t)row * p.in_stride + pos + i)));
+}
+
+// --------------------------------------------------------------------------------------------------
+// NCO_OSC table, DownConvert.cpp:438-442: one lane per row, sequential.  Dependent chain per sample: a*a -> + -> gain
+// (round-down / round-up subtraction, select, add) -> * : ~40 cycles; the rotation and the store run beside it.  Each
+// lane stores its own entries (8 bytes per sample per row: the L2 merges them into full sectors).  The gain's float
+// form is valid on [0.5, 1.69]; a 32-sample tile in which any row leaves that range is replayed with the double form.
+// --------------------------------------------------------------------------------------------------
+// rows per warp: a store instruction whose lanes hit 32 different rows costs the LSU ~64 cycles, more than the 32-cycle
+// recurrence step it accompanies; with 4 rows per warp (the other lanes idle) the stores disappear behind the chain
+constexpr unsigned kOscRows = 4;
+
+template <bool FAST>
+__device__ __forceinline__ void osc_step(float& a, float& b, float c, float s, float2* dst, bool store, bool& bad)
+{
+  const float orr = subf(mulf(a, c), mulf(b, s));
+  const float oi = addf(mulf(b, c), mulf(a, s));
+  const float q = addf(mulf(a, a), mulf(b, b));
+  float gn;
+  if (FAST)
+  {
+    gn = rfm_osc_gain_fast(q);
+    bad |= !rfm_osc_gain_domain(q);
+  }
+  else
+    gn = rfm_osc_gain(q);
+  if (store)
+    *dst = make_float2(orr, oi);
+  a = mulf(gn, orr);
+  b = mulf(gn, oi);
+}
+
+__global__ void __launch_bounds__(32) k_dc_osc(const float* cosv, const float* sinv, float* osc1, float2* table,
+                                               size_t stride, unsigned n, unsigned rows, unsigned* cyc_t0)
+{
   const unsigned lane = threadIdx.x;
-  const unsigned r0 = blockIdx.x * 32, r = r0 + lane;
-  const bool valid = r < rows;
+  const unsigned r = blockIdx.x * kOscRows + lane;
+  const bool valid = lane < kOscRows && r < rows;
   const float c = valid ? cosv[r] : 1.0f, s = valid ? sinv[r] : 0.0f;
   float a = valid ? osc1[2 * r] : 1.0f, b = valid ? osc1[2 * r + 1] : 0.0f;
-  // the last four states, h0 oldest (state before sample i - 4)
+  // the last four states, h0 oldest
   float2 h0 = make_float2(__int_as_float(0x7fc00001), 0.f), h1 = h0, h2 = h0, h3 = h0;
+  float2* row = valid ? table + (size_t)r * stride : nullptr;
   unsigned t0 = 0;
   bool cyc = false;
   for (; t0 < n && !cyc; t0 += 32)
   {
     const unsigned tn = min(32u, n - t0);
     bool per = false;
-    for (unsigned k = 0; k < tn; ++k)
+    if (tn == 32)
     {
-      const float orr = subf(mulf(a, c), mulf(b, s));
-      const float oi = addf(mulf(b, c), mulf(a, s));
-      const float gn = d2f(subd(1.95, (double)addf(mulf(a, a), mulf(b, b))));
-      tile[lane][k] = make_float2(orr, oi);
-      h0 = h1; h1 = h2; h2 = h3; h3 = make_float2(a, b);
-      a = mulf(gn, orr);
-      b = mulf(gn, oi);
-      // state after sample t0 + k equals the state four samples earlier: periodic from here on
+      const float a0 = a, b0 = b;
+      bool bad = false;
+      float2* dst = row + t0; // idle lanes: never dereferenced
+#pragma unroll
+      for (unsigned k = 0; k < 32; ++k)
+      {
+        if (k == 28) h0 = make_float2(a, b); // state before sample t0 + 28
+        if (k == 29) h1 = make_float2(a, b);
+        if (k == 30) h2 = make_float2(a, b);
+        if (k == 31) h3 = make_float2(a, b);
+        osc_step<true>(a, b, c, s, dst + k, valid, bad);
+      }
+      if (__any_sync(0xffffffffu, bad))
+      {
+        a = a0; b = b0;
+        for (unsigned k = 0; k < 32; ++k)
+        {
+          if (k == 28) h0 = make_float2(a, b);
+          if (k == 29) h1 = make_float2(a, b);
+          if (k == 30) h2 = make_float2(a, b);
+          if (k == 31) h3 = make_float2(a, b);
+          osc_step<false>(a, b, c, s, dst + k, valid, bad);
+        }
+      }
+      // the state after the tile equals the state four samples earlier: periodic from here on
       per = (__float_as_uint(a) == __float_as_uint(h0.x)) && (__float_as_uint(b) == __float_as_uint(h0.y));
     }
-    __syncwarp();
-    if (lane < tn)
-      for (unsigned q = 0; q < 32 && r0 + q < rows; ++q)
-        table[(size_t)(r0 + q) * stride + t0 + lane] = tile[q][lane];
-    __syncwarp();
-    // every row of this warp is in a short cycle (checked at a tile boundary): finish in parallel
+    else
+    {
+      bool bad = false;
+      for (unsigned k = 0; k < tn; ++k)
+        osc_step<false>(a, b, c, s, row + t0 + k, valid, bad);
+    }
+    // every row of this warp is in a short cycle (checked at a tile boundary): the rest is completed in parallel
     cyc = tn == 32 && __all_sync(0xffffffffu, per || !valid);
   }
+  if (valid)
+    cyc_t0[r] = (cyc && t0 < n) ? t0 : n; // k_dc_osc_fill completes osc[i] = osc[i - 4] for i >= t0
   if (cyc && t0 < n)
   {
-    // here: state (a, b) == h0 (the state before sample t0 - 4), so osc[i] = osc[i - 4] for i >= t0 and the state after
-    // sample n - 1 is the one m = (n - t0) mod 4 steps after h0: h0, h1, h2, h3 in turn
-    for (unsigned q = 0; q < 32 && r0 + q < rows; ++q)
-    {
-      float2* row = table + (size_t)(r0 + q) * stride;
-      const float2 v = row[t0 - 4 + (lane & 3u)];
-      for (unsigned i = t0 + lane; i < n; i += 32)
-        row[i] = v; // (i - t0) mod 4 == lane mod 4 for every i of this lane
-    }
+    // here the state (a, b) == h0, the state before sample t0 - 4: osc[i] = osc[i - 4] for i >= t0, and the state after
+    // sample n - 1 is the one (n - t0) mod 4 steps after h0: h0, h1, h2, h3 in turn
     const unsigned m = (n - t0) & 3u;
     const float2 e = m == 0 ? h0 : (m == 1 ? h1 : (m == 2 ? h2 : h3));
-    // h0 == (a, b) is the state after t0 - 1; h1, h2, h3 are the states one, two, three steps later by periodicity
     a = m == 0 ? a : e.x;
     b = m == 0 ? b : e.y;
   }
@@ -151,6 +221,25 @@ __global__ void __launch_bounds__(32) k_dc_osc(const float* cosv, const float* s
   {
     osc1[2 * r] = a;
     osc1[2 * r + 1] = b;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_dc_osc_fill(float2* table, size_t stride, unsigned n, const unsigned* cyc_t0)
+{
+  float2* row = table + (size_t)blockIdx.y * stride;
+  const unsigned t0 = cyc_t0[blockIdx.y];
+  if (t0 >= n)
+    return;
+  const unsigned i0 = t0 + (blockIdx.x * 256 + threadIdx.x) * 4; // four consecutive entries = one period
+  if (i0 >= n)
+    return;
+  const float2 v0 = row[t0 - 4], v1 = row[t0 - 3], v2 = row[t0 - 2], v3 = row[t0 - 1];
+  for (unsigned i = i0; i < n; i += gridDim.x * 1024)
+  {
+    row[i] = v0;
+    if (i + 1 < n) row[i + 1] = v1;
+    if (i + 2 < n) row[i + 2] = v2;
+    if (i + 3 < n) row[i + 3] = v3;
   }
 }
 
@@ -202,7 +291,7 @@ __global__ void __launch_bounds__(kDcThreads) k_dc_chain(DcParams p)
     const bool store = pos >= c_lo;
     const unsigned tn = min(kDcTileGeneric, (store ? c_hi : c_lo) - pos);
     for (unsigned i = tid; i < tn; i += kDcThreads)
-      B[0][p.st[0].hist + i] = dc_mix(dc_load<IN>(p, row, pos + i), osc[pos + i]);
+      B[0][p.st[0].hist + i] = dc_sample<IN>(p, osc, row, pos + i);
     __syncthreads();
     unsigned n = tn;
     for (unsigned k = 0; k < p.nst; ++k)
@@ -290,10 +379,34 @@ __device__ __forceinline__ void hb_deint(const DcTaps<L>& t, const float2* E, co
   }
 }
 
+// one stage over a tile: groups of R consecutive outputs per thread; dstO == nullptr: last stage, dstE is the output row
+// (natural order), else output o goes to the next stage's E / O by parity
+template <int L, int R>
+__device__ __forceinline__ void dc_stage(const DcTaps<L>& taps, const float2* E, const float2* O, float2* dstE, float2* dstO,
+                                         unsigned nout, unsigned tid)
+{
+  for (unsigned g = tid; g * R < nout; g += kDcThreads)
+  {
+    const unsigned o0 = g * R;
+    float2 acc[R];
+    hb_deint<L, R>(taps, E + o0, O + o0, acc);
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (o0 + r < nout)
+      {
+        const unsigned o = o0 + r;
+        if (!dstO)
+          dstE[o] = acc[r];
+        else
+          ((o & 1u) ? dstO : dstE)[o >> 1] = acc[r];
+      }
+  }
+}
+
 template <int IN, int L>
 __global__ void __launch_bounds__(kDcThreads) k_dc_chain_uniform(DcParams p, DcTaps<L> taps)
 {
-  constexpr int R = 5;
+  constexpr int R = 5;                 // largest group: sizes the slack behind each buffer
   constexpr unsigned HH = (L - 1) / 2; // history entries in each of E and O
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* vbuf = reinterpret_cast<float2*>(smem_raw);
@@ -345,30 +458,31 @@ __global__ void __launch_bounds__(kDcThreads) k_dc_chain_uniform(DcParams p, DcT
     const unsigned tn = min(kDcTileFast, (store ? c_hi : c_lo) - pos);
     // mix; V index 2 * HH + i: even i -> E[HH + i / 2], odd i -> O[HH + i / 2]
     for (unsigned i = tid; i < tn; i += kDcThreads)
-      ((i & 1u) ? O_(0) : E_(0))[HH + (i >> 1)] = dc_mix(dc_load<IN>(p, row, pos + i), osc[pos + i]);
+      ((i & 1u) ? O_(0) : E_(0))[HH + (i >> 1)] = dc_sample<IN>(p, osc, row, pos + i);
     __syncthreads();
+    // operands of the next tile on their way into L2 while this one is filtered
+    {
+      const unsigned npos = pos + tn;
+      if (npos < c_hi)
+        dc_prefetch<IN>(p, osc, row, npos, min(kDcTileFast, ((npos >= c_lo) ? c_hi : c_lo) - npos), tid);
+    }
     unsigned n = tn;
     for (unsigned k = 0; k < p.nst; ++k)
     {
       const unsigned nout = n >> 1;
       const bool last = k + 1 == p.nst;
       if (!last || store)
-        for (unsigned g = tid; g * R < nout; g += kDcThreads)
-        {
-          const unsigned o0 = g * R;
-          float2 acc[R];
-          hb_deint<L, R>(taps, E_(k) + o0, O_(k) + o0, acc);
-#pragma unroll
-          for (int r = 0; r < R; ++r)
-            if (o0 + r < nout)
-            {
-              const unsigned o = o0 + r;
-              if (last)
-                out[(pos >> p.nst) + o] = acc[r];
-              else
-                ((o & 1u) ? O_(k + 1) : E_(k + 1))[HH + (o >> 1)] = acc[r];
-            }
-        }
+      {
+        float2* dstE = last ? out + (pos >> p.nst) : E_(k + 1) + HH;
+        float2* dstO = last ? nullptr : O_(k + 1) + HH;
+        // outputs per thread: 5 while that keeps every warp busy, fewer for the short late stages (latency-bound)
+        if (nout >= 2 * kDcThreads)
+          dc_stage<L, 5>(taps, E_(k), O_(k), dstE, dstO, nout, tid);
+        else if (nout >= kDcThreads / 2)
+          dc_stage<L, 3>(taps, E_(k), O_(k), dstE, dstO, nout, tid);
+        else
+          dc_stage<L, 1>(taps, E_(k), O_(k), dstE, dstO, nout, tid);
+      }
       __syncthreads();
       n = nout;
     }
@@ -426,6 +540,10 @@ struct rfm_downconvert
   int tails_cur = 0;
   float* d_taps[kDcMaxStages] = {nullptr};
   float *d_cos = nullptr, *d_sin = nullptr, *d_osc1 = nullptr;
+  unsigned* d_cyc = nullptr;
+  const float2* pre = nullptr;
+  size_t pre_stride = 0;
+  unsigned pre_period = 0, pre_pos = 0;
   float2 *d_osc = nullptr, *d_tails[2] = {nullptr, nullptr};
   // host-pointer entry points: staging
   float2 *d_in = nullptr, *d_out = nullptr;
@@ -527,11 +645,9 @@ int Run(rfm_downconvert* d, int mode, const void* d_in, size_t in_stride, float2
                   "rfm_downconvert: n must be a multiple of 2^stages and give every stage >= 2*(taps-1) samples "
                   "(the reference mis-filters such inputs, DownConvert.cpp:519-520,544-547)");
   const unsigned orows = d->osc_shared ? 1u : d->rows;
-  k_dc_osc<<<(orows + 31) / 32, 32, 0, st>>>(d->d_cos, d->d_sin, d->d_osc1, d->d_osc, d->cap, n, orows);
-  if (d->osc_shared && d->rows > 1)
-  {
-    // every row runs the same oscillator: one table, the carried phasor is kept in row 0 (rows 1.. mirror it lazily)
-  }
+  // every row the same frequency: one table, the carried phasor lives in row 0
+  k_dc_osc<<<(orows + kOscRows - 1) / kOscRows, 32, 0, st>>>(d->d_cos, d->d_sin, d->d_osc1, d->d_osc, d->cap, n, orows, d->d_cyc);
+  k_dc_osc_fill<<<dim3(std::min(64u, (n + 1023) / 1024), orows), 256, 0, st>>>(d->d_osc, d->cap, n, d->d_cyc);
   DcParams p;
   memset(&p, 0, sizeof(p));
   p.in = d_in; p.in_stride = in_stride;
@@ -550,19 +666,33 @@ int Run(rfm_downconvert* d, int mode, const void* d_in, size_t in_stride, float2
   p.tails_out = d->d_tails[d->tails_cur ^ 1];
   p.tail_stride = d->tail_stride;
   p.out = d_out; p.out_stride = out_stride;
-  // chunking: enough CTAs to fill the machine, warm-up overhead <= 25 %
+  // chunking: the chunk count that minimises (waves of CTAs) x (chunk + warm-up) -- full waves on the 148 SMs with two
+  // resident CTAs each, warm-up overhead kept small
   const unsigned gran = 1u << d->nst;
-  unsigned nchunks = 1;
-  if (d->warm > 0 && n >= 8 * d->warm)
+  unsigned nchunks = 1, chunk = n;
   {
-    const unsigned by_work = n / (4 * d->warm);
-    const unsigned by_fill = (2 * 148 + d->rows - 1) / d->rows;
-    nchunks = std::max(1u, std::min(by_work, by_fill));
+    const unsigned slots = 2 * 148;
+    double best = 1e300;
+    const unsigned max_chunks = d->warm ? std::max(1u, n / (4 * d->warm)) : 1u;
+    for (unsigned c = 1; c <= std::min(max_chunks, 64u); ++c)
+    {
+      unsigned len = (n + c - 1) / c;
+      len = (len + gran - 1) / gran * gran;
+      const unsigned cnt = (n + len - 1) / len;
+      const unsigned waves = (cnt * d->rows + slots - 1) / slots;
+      const double cost = (double)waves * (len + (cnt > 1 ? d->warm : 0));
+      if (cost < best * 0.999)
+      {
+        best = cost;
+        nchunks = cnt;
+        chunk = len;
+      }
+    }
   }
-  unsigned chunk = (n + nchunks - 1) / nchunks;
-  chunk = (chunk + gran - 1) / gran * gran;
-  nchunks = (n + chunk - 1) / chunk;
   p.chunk = chunk; p.warm = d->warm; p.nchunks = nchunks;
+  p.pre = d->pre; p.pre_stride = d->pre_stride; p.pre_period = d->pre_period ? d->pre_period : 1; p.pre_pos = d->pre_pos;
+  if (d->pre)
+    d->pre_pos = (unsigned)(((uint64_t)d->pre_pos + n) % d->pre_period);
   if (mode == 0)
     LaunchChain<0>(d, p, st);
   else if (mode == 1)
@@ -570,7 +700,7 @@ int Run(rfm_downconvert* d, int mode, const void* d_in, size_t in_stride, float2
   else
     LaunchChain<2>(d, p, st);
   d->tails_cur ^= 1;
-  rfm::g_launches += 2;
+  rfm::g_launches += 3;
   if (n_out)
     *n_out = n >> d->nst;
   return cudaGetLastError() == cudaSuccess ? RFM_OK : DcFail(RFM_ERR_CUDA, "rfm_downconvert: kernel launch failed");
@@ -626,7 +756,7 @@ int rfm_downconvert_create(uint32_t rows, const float* nco_freq, float in_rate, 
   if (d->uniform51)
     memcpy(d->taps51.h, d->stages[0].h, 51 * sizeof(float));
   bool ok = DevAlloc(&d->d_cos, rows) == cudaSuccess && DevAlloc(&d->d_sin, rows) == cudaSuccess &&
-            DevAlloc(&d->d_osc1, 2 * (size_t)rows) == cudaSuccess &&
+            DevAlloc(&d->d_osc1, 2 * (size_t)rows) == cudaSuccess && DevAlloc(&d->d_cyc, rows) == cudaSuccess &&
             DevAlloc(&d->d_tails[0], (size_t)rows * d->tail_stride) == cudaSuccess &&
             DevAlloc(&d->d_tails[1], (size_t)rows * d->tail_stride) == cudaSuccess;
   for (unsigned k = 0; ok && k < d->nst; ++k)
@@ -654,7 +784,7 @@ void rfm_downconvert_destroy(rfm_downconvert* d)
   if (!d)
     return;
   cudaSetDevice(d->device);
-  cudaFree(d->d_cos); cudaFree(d->d_sin); cudaFree(d->d_osc1); cudaFree(d->d_osc);
+  cudaFree(d->d_cos); cudaFree(d->d_sin); cudaFree(d->d_osc1); cudaFree(d->d_osc); cudaFree(d->d_cyc);
   cudaFree(d->d_tails[0]); cudaFree(d->d_tails[1]);
   cudaFree(d->d_in); cudaFree(d->d_out); cudaFree(d->d_u8);
   for (auto* t : d->d_taps)
@@ -705,7 +835,19 @@ int rfm_downconvert_reset(rfm_downconvert* d)
   if (!d)
     return DcFail(RFM_ERR_INVALID, "rfm_downconvert_reset: null handle");
   cudaSetDevice(d->device);
+  d->pre_pos = 0;
   return ResetState(d);
+}
+
+int rfm_downconvert_set_premix(rfm_downconvert* d, const float* d_table, size_t row_stride, uint32_t period)
+{
+  if (!d || (d_table && (period == 0 || row_stride < period)))
+    return DcFail(RFM_ERR_INVALID, "rfm_downconvert_set_premix: invalid argument");
+  d->pre = reinterpret_cast<const float2*>(d_table);
+  d->pre_stride = row_stride;
+  d->pre_period = d_table ? period : 0;
+  d->pre_pos = 0;
+  return RFM_OK;
 }
 
 int rfm_downconvert_process_cf32(rfm_downconvert* d, const float* iq, uint32_t n, float* out, uint32_t* n_out)

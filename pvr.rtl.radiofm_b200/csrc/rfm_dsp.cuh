@@ -20,6 +20,27 @@ __device__ __forceinline__ float rfm_u8_to_float(unsigned word, unsigned byte_se
   return __fmaf_rn(u, 0x1.010102p-23f, t);
 }
 
+// OscGn = 1.95 - (re^2 + im^2) of the NCO_OSC rotating vector (DownConvert.cpp:441): the double literal makes it
+// float(1.95 - double(q)).  For q in [0.5, 1.69] -- the oscillator's amplitude never leaves it -- the same value comes
+// out of five dependent float additions: s + e = 1.95f - q exactly (Fast2Sum), then the low part of the constant,
+// 1.95 - 1.95f = -0x1.99999ap-25 (to float precision), joins the error term before the last rounding.  The margins to
+// the rounding boundaries (>= 0.05 * 2^-24) dwarf the 2^-48 error of that last term; checked against the double
+// expression for every one of the 14 176 749 floats of the domain on the host (tests/test_host_math.py) and on the
+// device (math probe 13).  20 cycles of dependent latency instead of 45 through the FP64 pipe, no predicates -- this
+// sits on the oscillator's critical path.
+__device__ __forceinline__ float rfm_osc_gain_exact(float q) { return d2f(subd(1.95, (double)q)); }
+__device__ __forceinline__ bool rfm_osc_gain_domain(float q) { return q >= 0.5f && q <= 1.69f; }
+__device__ __forceinline__ float rfm_osc_gain_fast(float q) // valid where rfm_osc_gain_domain(q)
+{
+  const float s = subf(1.95f, q);
+  const float e = subf(subf(1.95f, s), q);
+  return addf(s, addf(e, -0x1.99999ap-25f));
+}
+__device__ __forceinline__ float rfm_osc_gain(float q)
+{
+  return rfm_osc_gain_domain(q) ? rfm_osc_gain_fast(q) : rfm_osc_gain_exact(q);
+}
+
 // --------------------------------------------------------------------------------------------------
 // Decimate-by-2 stages over an interleaved V buffer [history | new samples]: DownConvert.cpp:516-550 (generic
 // half-band: even taps + centre, tap 0 counted twice), :589-688 (fixed 11-tap), :709-727 (CIC3).

@@ -7,6 +7,7 @@
 #include <string>
 
 #include "../../include/radiofm_b200.h"
+#include "rfm_dsp.cuh"
 #include "rfm_steps.cuh"
 
 using namespace rfm;
@@ -36,6 +37,7 @@ __global__ void k_probe(int op, const float* a, const float* b, float* out, unsi
     case 10: o0 = rfm_wrap_demod(x); o1 = rfm_wrap_pilot(x); break;
     case 11: o0 = arctan2_approx(x, y); break;
     case 12: o0 = rfm_fmodf_small(x, y); break;
+    case 13: o0 = rfm_osc_gain(x); o1 = rfm_osc_gain_exact(x); break;
     default: break;
   }
   out[2 * i] = o0;

@@ -329,6 +329,17 @@ def test_device_math_probes(rfm):
     assert bits_equal(f9[d9, 0], pil[d9])
 
 
+def test_device_osc_gain_every_float(rfm):
+    """math probe 13: the float-only NCO_OSC gain against the double expression, on the device, for every float of
+    [0.45, 1.75] (covers the fast-path domain and both fall-back edges)."""
+    lo, hi = np.float32(0.45).view(np.uint32), np.float32(1.75).view(np.uint32)
+    q = np.arange(lo, hi + 1, dtype=np.uint32).view(np.float32)
+    out = rfm.math_probe(13, q)
+    assert bits_equal(out[:, 0], out[:, 1])
+    ref = (np.float64(1.95) - q.astype(np.float64)).astype(np.float32)
+    assert bits_equal(out[:, 1], ref)
+
+
 def test_speculation_misses_and_degenerate_inputs_stay_exact(rfm, port, synth):
     """The time-parallel FM-demodulator PLL speculates on a contracting loop.  On pure noise the
     speculation misses routinely and chunks are repaired; on constant input operands hit exact zeros (the sticky-flag

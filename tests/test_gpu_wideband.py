@@ -19,13 +19,13 @@ def capture(synth):
     return synth.make_wideband_u8(FS, 2 * BPC * BLK, FREQS)
 
 
-@pytest.mark.parametrize("mixer", ["osc", "freqshift"])
+@pytest.mark.parametrize("mixer", ["osc", "freqshift", "freqshift_unfused"])
 def test_wideband_stations_bit_exact(rfm, port, capture, mixer):
     import torch
     wb_mod = importlib.import_module("radiofm_b200.wideband")
     from oracle.wideband import OracleStation
     wb = wb_mod.WidebandReceiver(torch, FREQS, FS, BLK, BPC, mixer=mixer, device=0)
-    oracles = [OracleStation(f, FS, BLK, BPC, mixer=mixer) for f in FREQS]
+    oracles = [OracleStation(f, FS, BLK, BPC, mixer=mixer.split("_")[0]) for f in FREQS]
     n_call = BPC * BLK
     peak = 0.0
     for c in range(2):

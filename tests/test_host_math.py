@@ -153,3 +153,20 @@ def test_fmod_helpers(shim):
     n = 2_000_000
     p = (rng.standard_normal(n) * 20.0).astype(np.float32)
     assert shim.cmp_fmod(_p(p), n) == 0
+
+
+def test_osc_gain_float_form_is_exact():
+    """rfm_osc_gain_fast (rfm_dsp.cuh): float(1.95 - double(q)) of the NCO_OSC oscillator (DownConvert.cpp:441) from
+    five float additions -- restated here in numpy float32 and checked on EVERY float of its domain [0.5, 1.69]."""
+    f = np.float32
+    lo, hi = f(0.5).view(np.uint32), f(1.69).view(np.uint32)
+    q = np.arange(lo, hi + 1, dtype=np.uint32).view(np.float32)
+    ref = (np.float64(1.95) - q.astype(np.float64)).astype(np.float32)
+    ch = f(1.95)
+    cl = f(np.float64(1.95) - np.float64(ch))
+    assert float(cl).hex() == "-0x1.99999a0000000p-25"
+    s = (ch - q).astype(f)
+    e = ((ch - s).astype(f) - q).astype(f)
+    r = (s + (e + cl).astype(f)).astype(f)
+    assert q.size == 14176749
+    assert np.array_equal(r.view(np.uint32), ref.view(np.uint32))
