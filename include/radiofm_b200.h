@@ -223,6 +223,72 @@ RFM_API int rfm_downconvert_set_premix(rfm_downconvert* d, const float* d_table,
 RFM_API int rfm_downconvert_process_device(rfm_downconvert* d, int mode, const void* d_in, size_t in_stride, float* d_out,
                                            size_t out_stride, uint32_t n, uint32_t* n_out, void* cuda_stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * cIirFilter (IirFilter.h:12-36, IirFilter.cpp:11-105), batched over rows (one independent biquad per row, all with
+ * the same coefficients).  type: 0 ftLP, 1 ftHP, 2 ftBP, 3 ftBR (IirFilter.h:15).  Buffers are filtered in place.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rfm_iir rfm_iir;
+RFM_API int rfm_iir_create(uint32_t rows, uint32_t max_len, int device, rfm_iir** out);
+RFM_API void rfm_iir_destroy(rfm_iir* f);
+/* cIirFilter::Init -- IirFilter.cpp:11-60.  Clears the delays; an unknown type returns RFM_ERR_INVALID (Init returns
+ * false) and keeps the previous coefficients */
+RFM_API int rfm_iir_init(rfm_iir* f, int type, float F0Freq, float FilterQ, float SampleRate);
+/* m_A1, m_A2, m_B0, m_B1, m_B2 */
+RFM_API int rfm_iir_coefficients(const rfm_iir* f, float* out5);
+/* cIirFilter::Process(RealType*, n) :78-87 / Process(ComplexType*, n) :62-76 / ProcessTwo(RealType*, RealType*, n) :89-105;
+ * host buffers [rows][n] ([rows][n][2] for complex) */
+RFM_API int rfm_iir_process_real(rfm_iir* f, float* buf, uint32_t n);
+RFM_API int rfm_iir_process_complex(rfm_iir* f, float* buf, uint32_t n);
+RFM_API int rfm_iir_process_two(rfm_iir* f, float* a, float* b, uint32_t n);
+/* device pointers, enqueue only; mode 0 real, 1 complex, 2 two buffers; stride in elements (complex: in samples) */
+RFM_API int rfm_iir_process_device(rfm_iir* f, int mode, float* d_a, float* d_b, size_t stride, uint32_t n,
+                                   void* cuda_stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * cFirFilter (FirFilter.h:17-60, FirFilter.cpp), batched over rows: Kaiser low-pass design or constant taps, the
+ * circular delay line with its rotating summation start (the sum of a given output begins at the tap the reference's
+ * m_State points at, so the rounding sequence is the reference's).  Buffers are filtered in place.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rfm_fir rfm_fir;
+RFM_API int rfm_fir_create(uint32_t rows, uint32_t max_len, int device, rfm_fir** out);
+RFM_API void rfm_fir_destroy(rfm_fir* f);
+/* cFirFilter::InitLPFilter(NumTaps, Scale, Astop, Fpass, Fstop, Fsamprate) -- FirFilter.cpp:78-148; *ntaps = its
+ * return value (the tap count, computed from the specification when NumTaps == 0) */
+RFM_API int rfm_fir_init_lp(rfm_fir* f, uint32_t NumTaps, float Scale, float Astop, float Fpass, float Fstop, float Fs,
+                            uint32_t* ntaps);
+/* cFirFilter::InitConstFir(NumTaps, const RealType* pCoef, Fsamprate) -- FirFilter.cpp:302-320 */
+RFM_API int rfm_fir_init_const(rfm_fir* f, uint32_t ntaps, const float* coef, float Fs);
+RFM_API int rfm_fir_taps(const rfm_fir* f, float* out, uint32_t max, uint32_t* n);
+/* cFirFilter::Process(RealType*, n) :360-377 / Process(ComplexType*, n) :330-350 / ProcessTwo :387-413 */
+RFM_API int rfm_fir_process_real(rfm_fir* f, float* buf, uint32_t n);
+RFM_API int rfm_fir_process_complex(rfm_fir* f, float* buf, uint32_t n);
+RFM_API int rfm_fir_process_two(rfm_fir* f, float* a, float* b, uint32_t n);
+RFM_API int rfm_fir_process_device(rfm_fir* f, int mode, float* d_a, float* d_b, size_t stride, uint32_t n,
+                                   void* cuda_stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * cRDSRxSignalProcessor (RDSProcess.h:56-110, RDSProcess.cpp:43-431), batched over rows: demodulated FM baseband in,
+ * RDS bits and groups out.  Float part on the device, block synchronisation / FEC on the host (as rfm_rdssync).
+ * n must be a multiple of 2^stages of the RDS decimation chain (RFM_ERR_UNSUPPORTED otherwise, see rfm_downconvert).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rfm_rdsproc rfm_rdsproc;
+/* cRDSRxSignalProcessor(proc, SampleRate) -- RDSProcess.cpp:43-88 */
+RFM_API int rfm_rdsproc_create(uint32_t rows, float sample_rate, uint32_t max_len, int device, rfm_rdsproc** out);
+RFM_API void rfm_rdsproc_destroy(rfm_rdsproc* r);
+/* m_ProcessRate */
+RFM_API float rfm_rdsproc_process_rate(const rfm_rdsproc* r);
+/* cRDSRxSignalProcessor::Reset -- RDSProcess.cpp:90-118 */
+RFM_API int rfm_rdsproc_reset(rfm_rdsproc* r);
+/* cRDSRxSignalProcessor::Process(const RealType* inputStream, unsigned inLength) -- RDSProcess.cpp:120-180;
+ * baseband [rows][n] host */
+RFM_API int rfm_rdsproc_process(rfm_rdsproc* r, const float* baseband, uint32_t n);
+/* device rows [rows][stride], enqueue only (bits are fetched by the take calls) */
+RFM_API int rfm_rdsproc_process_device(rfm_rdsproc* r, const float* d_bb, size_t stride, uint32_t n, void* cuda_stream);
+/* the arguments of successive ProcessNewRdsBit calls (RDSProcess.cpp:168) / the groups handed to DecodeRDS (:312,355) */
+RFM_API int rfm_rdsproc_take_bits(rfm_rdsproc* r, uint32_t row, uint8_t* bits, uint32_t max_bits, uint32_t* n_bits);
+RFM_API int rfm_rdsproc_take_groups(rfm_rdsproc* r, uint32_t row, uint16_t* groups, uint32_t max_groups,
+                                    uint32_t* n_groups);
+
 /* Test hooks (no reference counterpart): evaluate one of the scalar building blocks of the kernels on the DEVICE for
  * n host operands; out2 receives two floats per element.  op: 0 rfm_sincos (sin, cos) 1 sincos fast core
  * 2 sincos generic 3 atan2f(a, b) 4 branch-free atan2f (+flag) 5 atan2f generic 6 branch-free a / b (+flag)

@@ -53,6 +53,12 @@ EXPORTED_SYMBOLS = (
     "rfm_freqshift_process_device", "rfm_downconvert_create", "rfm_downconvert_destroy", "rfm_downconvert_output_rate",
     "rfm_downconvert_stages", "rfm_downconvert_set_frequency", "rfm_downconvert_reset", "rfm_downconvert_process_cf32",
     "rfm_downconvert_process_u8", "rfm_downconvert_process_device", "rfm_downconvert_set_premix",
+    "rfm_iir_create", "rfm_iir_destroy", "rfm_iir_init", "rfm_iir_coefficients", "rfm_iir_process_real",
+    "rfm_iir_process_complex", "rfm_iir_process_two", "rfm_iir_process_device",
+    "rfm_fir_create", "rfm_fir_destroy", "rfm_fir_init_lp", "rfm_fir_init_const", "rfm_fir_taps", "rfm_fir_process_real",
+    "rfm_fir_process_complex", "rfm_fir_process_two", "rfm_fir_process_device",
+    "rfm_rdsproc_create", "rfm_rdsproc_destroy", "rfm_rdsproc_process_rate", "rfm_rdsproc_reset", "rfm_rdsproc_process",
+    "rfm_rdsproc_process_device", "rfm_rdsproc_take_bits", "rfm_rdsproc_take_groups",
 )
 
 
@@ -137,6 +143,28 @@ def lib():
         L.rfm_downconvert_process_u8.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_uint32, _f32p, _u32p]
         L.rfm_downconvert_process_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                                      C.c_uint32, _u32p, C.c_void_p]
+        for nm in ("iir", "fir"):
+            getattr(L, f"rfm_{nm}_create").argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_void_p)]
+            getattr(L, f"rfm_{nm}_destroy").argtypes = [C.c_void_p]
+            getattr(L, f"rfm_{nm}_process_real").argtypes = [C.c_void_p, _f32p, C.c_uint32]
+            getattr(L, f"rfm_{nm}_process_complex").argtypes = [C.c_void_p, _f32p, C.c_uint32]
+            getattr(L, f"rfm_{nm}_process_two").argtypes = [C.c_void_p, _f32p, _f32p, C.c_uint32]
+            getattr(L, f"rfm_{nm}_process_device").argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
+                                                               C.c_uint32, C.c_void_p]
+        L.rfm_iir_init.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float]
+        L.rfm_iir_coefficients.argtypes = [C.c_void_p, _f32p]
+        L.rfm_fir_init_lp.argtypes = [C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _u32p]
+        L.rfm_fir_init_const.argtypes = [C.c_void_p, C.c_uint32, _f32p, C.c_float]
+        L.rfm_fir_taps.argtypes = [C.c_void_p, _f32p, C.c_uint32, _u32p]
+        L.rfm_rdsproc_create.argtypes = [C.c_uint32, C.c_float, C.c_uint32, C.c_int, C.POINTER(C.c_void_p)]
+        L.rfm_rdsproc_destroy.argtypes = [C.c_void_p]
+        L.rfm_rdsproc_process_rate.restype = C.c_float
+        L.rfm_rdsproc_process_rate.argtypes = [C.c_void_p]
+        L.rfm_rdsproc_reset.argtypes = [C.c_void_p]
+        L.rfm_rdsproc_process.argtypes = [C.c_void_p, _f32p, C.c_uint32]
+        L.rfm_rdsproc_process_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]
+        L.rfm_rdsproc_take_bits.argtypes = [C.c_void_p, C.c_uint32, _u8p, C.c_uint32, _u32p]
+        L.rfm_rdsproc_take_groups.argtypes = [C.c_void_p, C.c_uint32, _u16p, C.c_uint32, _u32p]
         L.rfm_rds_check_block.restype = C.c_uint32
         L.rfm_rds_check_block.argtypes = [C.c_uint32, C.c_uint32, C.c_int, _u32p]
         _lib = L
@@ -442,6 +470,112 @@ class DownConvertBatch:
         _check(lib().rfm_downconvert_process_device(self._h, mode, C.c_void_p(d_in_ptr), in_stride, C.c_void_p(d_out_ptr),
                                                     out_stride, n, C.byref(k), C.c_void_p(cuda_stream)))
         return int(k.value)
+
+
+class _RowFilter:
+    """Common part of IirFilterBatch / FirFilterBatch: in-place Process / ProcessTwo on host arrays [rows, n(, 2)]."""
+    _kind = ""
+
+    def __init__(self, rows: int, max_len: int = 65536, device: int = -1):
+        self.rows = rows
+        self._h = C.c_void_p()
+        _check(getattr(lib(), f"rfm_{self._kind}_create")(rows, max_len, device, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            getattr(lib(), f"rfm_{self._kind}_destroy")(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def process_real(self, x: np.ndarray) -> np.ndarray:
+        x = np.array(x, dtype=np.float32, order="C").reshape(self.rows, -1)
+        _check(getattr(lib(), f"rfm_{self._kind}_process_real")(self._h, _p(x, _f32p), x.shape[1]))
+        return x
+
+    def process_complex(self, x: np.ndarray) -> np.ndarray:
+        x = np.array(x, dtype=np.float32, order="C").reshape(self.rows, -1, 2)
+        _check(getattr(lib(), f"rfm_{self._kind}_process_complex")(self._h, _p(x, _f32p), x.shape[1]))
+        return x
+
+    def process_two(self, a: np.ndarray, b: np.ndarray):
+        a = np.array(a, dtype=np.float32, order="C").reshape(self.rows, -1)
+        b = np.array(b, dtype=np.float32, order="C").reshape(self.rows, -1)
+        _check(getattr(lib(), f"rfm_{self._kind}_process_two")(self._h, _p(a, _f32p), _p(b, _f32p), a.shape[1]))
+        return a, b
+
+
+class IirFilterBatch(_RowFilter):
+    """rows x cIirFilter (IirFilter.h:12-36).  type: 0 LP, 1 HP, 2 BP, 3 BR."""
+    _kind = "iir"
+
+    def init(self, ftype: int, f0: float, q: float, fs: float) -> bool:
+        rc = lib().rfm_iir_init(self._h, ftype, f0, q, fs)
+        if rc == -1:
+            return False            # cIirFilter::Init returns false for an unknown type
+        _check(rc)
+        return True
+
+    def coefficients(self) -> np.ndarray:
+        out = np.zeros(5, dtype=np.float32)
+        _check(lib().rfm_iir_coefficients(self._h, _p(out, _f32p)))
+        return out
+
+
+class FirFilterBatch(_RowFilter):
+    """rows x cFirFilter (FirFilter.h:17-60)."""
+    _kind = "fir"
+
+    def init_lp(self, num_taps: int, scale: float, astop: float, fpass: float, fstop: float, fs: float) -> int:
+        k = C.c_uint32(0)
+        _check(lib().rfm_fir_init_lp(self._h, num_taps, scale, astop, fpass, fstop, fs, C.byref(k)))
+        return int(k.value)
+
+    def init_const(self, coef, fs: float):
+        c = np.ascontiguousarray(coef, dtype=np.float32)
+        _check(lib().rfm_fir_init_const(self._h, c.size, _p(c, _f32p), fs))
+
+    def taps(self) -> np.ndarray:
+        out = np.zeros(128, dtype=np.float32)
+        k = C.c_uint32(0)
+        _check(lib().rfm_fir_taps(self._h, _p(out, _f32p), out.size, C.byref(k)))
+        return out[:k.value].copy()
+
+
+class RdsProcessorBatch:
+    """rows x cRDSRxSignalProcessor (RDSProcess.h:56-110): FM baseband in, RDS bits / groups out."""
+
+    def __init__(self, rows: int, sample_rate: float, max_len: int = 65536, device: int = -1):
+        self.rows = rows
+        self._h = C.c_void_p()
+        _check(lib().rfm_rdsproc_create(rows, sample_rate, max_len, device, C.byref(self._h)))
+        self.process_rate = float(lib().rfm_rdsproc_process_rate(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().rfm_rdsproc_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reset(self):
+        _check(lib().rfm_rdsproc_reset(self._h))
+
+    def process(self, baseband: np.ndarray):
+        x = np.ascontiguousarray(baseband, dtype=np.float32).reshape(self.rows, -1)
+        _check(lib().rfm_rdsproc_process(self._h, _p(x, _f32p), x.shape[1]))
+
+    def take_bits(self, row: int = 0, max_bits: int = 1 << 20) -> np.ndarray:
+        out = np.zeros(max_bits, dtype=np.uint8)
+        k = C.c_uint32(0)
+        _check(lib().rfm_rdsproc_take_bits(self._h, row, _p(out, _u8p), max_bits, C.byref(k)))
+        return out[:k.value].copy()
+
+    def take_groups(self, row: int = 0, max_groups: int = 4096) -> np.ndarray:
+        out = np.zeros((max_groups, 4), dtype=np.uint16)
+        k = C.c_uint32(0)
+        _check(lib().rfm_rdsproc_take_groups(self._h, row, _p(out, _u16p), max_groups, C.byref(k)))
+        return out[:k.value].copy()
 
 
 def math_probe(op: int, a: np.ndarray, b: np.ndarray | None = None) -> np.ndarray:

@@ -1,0 +1,50 @@
+// host/FirFilter.h -- cFirFilter with the reference's signatures (FirFilter.h:17-60) over the C ABI (rfm_fir_*): the
+// members the live chain uses -- InitLPFilter, InitConstFir (real taps), Process (real / complex, in place),
+// ProcessTwo.  InitHPFilter, GenerateHBFilter and the two-buffer Process overloads are not called anywhere on the
+// hot path and are not provided.
+#pragma once
+
+#include <stdexcept>
+#include <string>
+
+#include "../../include/radiofm_b200.h"
+#include "Definitions.h"
+
+#define MAX_NUMCOEF 75 // FirFilter.h:15
+
+class cFirFilter
+{
+public:
+  explicit cFirFilter(unsigned int max_len = 1u << 16, int cuda_device = -1)
+  {
+    if (rfm_fir_create(1, max_len, cuda_device, &m_f) != RFM_OK)
+      throw std::runtime_error(std::string("cFirFilter (B200): ") + rfm_last_error());
+  }
+  virtual ~cFirFilter() { rfm_fir_destroy(m_f); }
+  cFirFilter(const cFirFilter&) = delete;
+  cFirFilter& operator=(const cFirFilter&) = delete;
+
+  void InitConstFir(unsigned int NumTaps, const RealType* pCoef, RealType Fsamprate) // FirFilter.cpp:302-320
+  {
+    rfm_fir_init_const(m_f, NumTaps, pCoef, Fsamprate);
+  }
+  int InitLPFilter(unsigned int NumTaps, RealType Scale, RealType Astop, RealType Fpass, RealType Fstop,
+                   RealType Fsamprate) // FirFilter.cpp:78-148
+  {
+    uint32_t n = 0;
+    rfm_fir_init_lp(m_f, NumTaps, Scale, Astop, Fpass, Fstop, Fsamprate, &n);
+    return (int)n;
+  }
+  void Process(ComplexType* buffer, unsigned int length) // :330-350
+  {
+    rfm_fir_process_complex(m_f, reinterpret_cast<float*>(buffer), length);
+  }
+  void Process(RealType* buffer, unsigned int length) { rfm_fir_process_real(m_f, buffer, length); } // :360-377
+  void ProcessTwo(RealType* bufferA, RealType* bufferB, unsigned int length) // :387-413
+  {
+    rfm_fir_process_two(m_f, bufferA, bufferB, length);
+  }
+
+private:
+  rfm_fir* m_f = nullptr;
+};

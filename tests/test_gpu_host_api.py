@@ -96,3 +96,73 @@ def test_freqshift_batch_primitive(rfm, port):
         L.rfo_freqshift_process(h, y.ctypes.data_as(C.POINTER(C.c_float)), n)
         L.rfo_freqshift_destroy(h)
         assert bits_equal(got[r], y), f
+
+
+def test_primitive_classes_match_oracle(tmp_path, port):
+    """cIirFilter, cFirFilter, CRDSDownConvert and cRDSRxSignalProcessor (host/*.h) driven from C++ through the reference's
+    member signatures (tests/cpp/host_primitives_driver.cpp); every output file equals the oracle's, bit for bit."""
+    import ctypes as C
+    P = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    lib_dir = os.path.join(ROOT, "pvr.rtl.radiofm_b200")
+    exe = tmp_path / "host_primitives_driver"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", os.path.join(lib_dir, "host"),
+                           os.path.join(ROOT, "tests", "cpp", "host_primitives_driver.cpp"), "-o", str(exe),
+                           "-L", lib_dir, "-lradiofm_b200", f"-Wl,-rpath,{lib_dir}"])
+    # input: the demodulated baseband of a 1.0 MS/s station (250 kS/s, carries pilot + RDS), 8 blocks of 16384
+    fs, ds, blk = RATES["1.0M"]
+    iq, _ = station("1.0M", 8)
+    o = port.OracleFmDecoder(fs, -0.15 * fs, downsample=ds)
+    bb = []
+    for b in range(8):
+        o.process_u8(iq[b * blk:(b + 1) * blk])
+        bb.append(o.tap("baseband"))
+    x = np.concatenate(bb).astype(np.float32)
+    n, bl = x.size, 16384
+    (tmp_path / "in.f32").write_bytes(x.tobytes())
+    out = subprocess.run([str(exe), str(tmp_path / "in.f32"), str(n), str(bl), str(tmp_path / "o")],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr + out.stdout
+    rd = lambda name, dt=np.float32: np.fromfile(tmp_path / f"o_{name}", dtype=dt)
+    L = port.lib()
+    half = n // 2
+    # cIirFilter
+    h = L.rfo_iir_create()
+    L.rfo_iir_init(h, 3, 19000.0, 5.0, 48000.0)
+    a, b = x[:half].copy(), x[half:].copy()
+    L.rfo_iir_process_two(h, P(a), P(b), half)
+    assert bits_equal(rd("iir_a.f32"), a) and bits_equal(rd("iir_b.f32"), b)
+    L.rfo_iir_init(h, 2, 1187.5, 500.0, 31250.0)
+    r = x.copy()
+    L.rfo_iir_process_real(h, P(r), n)
+    L.rfo_iir_destroy(h)
+    assert bits_equal(rd("iir_r.f32"), r)
+    # cFirFilter
+    h = L.rfo_fir_create()
+    nt = L.rfo_fir_init_lp(h, 0, 1.0, 60.0, 15000.0, 21000.0, 48000.0)
+    a, b = x[:half].copy(), x[half:].copy()
+    L.rfo_fir_process_two(h, P(a), P(b), half)
+    assert f"fir_taps {nt}" in out.stdout
+    assert bits_equal(rd("fir_a.f32"), a) and bits_equal(rd("fir_b.f32"), b)
+    L.rfo_fir_init_lp(h, 0, 1.0, 40.0, 2400.0, np.float32(1.3) * np.float32(2400.0), 31250.0)
+    z = x.copy()
+    L.rfo_fir_process_complex(h, P(z), half)
+    L.rfo_fir_destroy(h)
+    assert bits_equal(rd("fir_z.f32"), z)
+    # CRDSDownConvert (block-wise, like the driver)
+    h = L.rfo_rdsdc_create()
+    rate = L.rfo_rdsdc_set_data_rate(h, 250000.0, 8000.0)
+    L.rfo_rdsdc_set_frequency(h, -57000.0)
+    zz = x.copy().reshape(-1, 2)
+    ys = []
+    for i in range(0, half - bl + 1, bl):
+        zi = zz[i:i + bl].copy()
+        y = np.zeros_like(zi)
+        k = L.rfo_rdsdc_process(h, bl, P(zi), P(y))
+        ys.append(y[:k])
+    L.rfo_rdsdc_destroy(h)
+    assert bits_equal(rd("dc.f32").reshape(-1, 2), np.concatenate(ys))
+    assert f"dc_rate {float(np.float32(rate)):.9g}" in out.stdout
+    # cRDSRxSignalProcessor: the decoder's own RDS output for this baseband
+    bits, groups = o.take_bits(), o.take_groups()
+    assert np.array_equal(rd("rds_bits.u8", np.uint8), bits) and bits.size > 400
+    assert np.array_equal(rd("rds_groups.u16", np.uint16).reshape(-1, 4), groups) and len(groups) >= 3

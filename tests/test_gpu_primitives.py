@@ -1,0 +1,130 @@
+"""Stand-alone filter primitives (rfm_iir / rfm_fir / rfm_rdsproc, include/radiofm_b200.h) against the oracle's
+restatements of cIirFilter, cFirFilter and cRDSRxSignalProcessor, bit for bit, over several calls with carried state."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import RATES, bits_equal, station
+
+pytestmark = pytest.mark.gpu
+
+_f32p = C.POINTER(C.c_float)
+
+
+def P(a):
+    return a.ctypes.data_as(_f32p)
+
+
+@pytest.mark.parametrize("ftype,f0,q,fs", [(3, 19000.0, 5.0, 48000.0), (2, 1187.5, 500.0, 31250.0),
+                                          (1, 30.0, 2.0, 48000.0), (0, 15000.0, 0.7071, 48000.0)])
+def test_iir_all_types_and_entry_points(rfm, port, ftype, f0, q, fs):
+    rng = np.random.default_rng(21)
+    L = port.lib()
+    rows = 35                       # more than one warp of rows, ragged
+    f = rfm.IirFilterBatch(rows, max_len=4096)
+    assert f.init(ftype, f0, q, fs)
+    hs = [L.rfo_iir_create() for _ in range(rows)]
+    for h in hs:
+        assert L.rfo_iir_init(h, ftype, f0, q, fs)
+    co = np.zeros(5, dtype=np.float32)
+    L.rfo_iir_coef(hs[0], P(co))
+    assert bits_equal(f.coefficients(), co)
+    for n in (1000, 37, 4096):
+        x = rng.standard_normal((rows, n)).astype(np.float32)
+        y = f.process_real(x)
+        for r, h in enumerate(hs):
+            ref = x[r].copy()
+            L.rfo_iir_process_real(h, P(ref), n)
+            assert bits_equal(y[r], ref), ("real", r, n)
+    # ProcessTwo and complex share the delay pairs a / b: continue on the same objects
+    for n in (512, 33):
+        a, b = rng.standard_normal((2, rows, n)).astype(np.float32)
+        ya, yb = f.process_two(a, b)
+        z = rng.standard_normal((rows, n, 2)).astype(np.float32)
+        yz = f.process_complex(z)
+        for r, h in enumerate(hs):
+            ra, rb, rz = a[r].copy(), b[r].copy(), z[r].copy()
+            L.rfo_iir_process_two(h, P(ra), P(rb), n)
+            L.rfo_iir_process_complex(h, P(rz), n)
+            assert bits_equal(ya[r], ra) and bits_equal(yb[r], rb) and bits_equal(yz[r], rz), (r, n)
+    assert not f.init(7, f0, q, fs)          # unknown type: Init returns false
+    for h in hs:
+        L.rfo_iir_destroy(h)
+    f.close()
+
+
+def test_fir_lowpass_and_const_taps(rfm, port):
+    rng = np.random.default_rng(22)
+    L = port.lib()
+    rows = 5
+    f = rfm.FirFilterBatch(rows, max_len=8192)
+    hs = [L.rfo_fir_create() for _ in range(rows)]
+    # the audio low-pass of the chain (FmDecode.cpp:286) and the RDS low-pass (RDSProcess.cpp:99)
+    for spec in ((0, 1.0, 60.0, 15000.0, 21000.0, 48000.0), (0, 1.0, 40.0, 2400.0, 3120.0, 31250.0)):
+        nt = f.init_lp(*spec)
+        for h in hs:
+            assert L.rfo_fir_init_lp(h, *spec) == nt
+        co = np.zeros(80, dtype=np.float32)
+        L.rfo_fir_coef(hs[0], P(co))
+        assert bits_equal(f.taps(), co[:nt])
+        for n in (1000, 29, 8192, 3):        # the summation start rotates with the running sample count
+            x = rng.standard_normal((rows, n)).astype(np.float32)
+            y = f.process_real(x)
+            z = rng.standard_normal((rows, n, 2)).astype(np.float32)
+            for r, h in enumerate(hs):
+                ref = x[r].copy()
+                L.rfo_fir_process_real(h, P(ref), n)
+                assert bits_equal(y[r], ref), ("real", spec, r, n)
+        for n in (777, 2048):
+            a, b = rng.standard_normal((2, rows, n)).astype(np.float32)
+            ya, yb = f.process_two(a, b)
+            for r, h in enumerate(hs):
+                ra, rb = a[r].copy(), b[r].copy()
+                L.rfo_fir_process_two(h, P(ra), P(rb), n)
+                assert bits_equal(ya[r], ra) and bits_equal(yb[r], rb), ("two", spec, r, n)
+        for n in (600, 75):                  # complex Process shares the delay line with ProcessTwo
+            z = rng.standard_normal((rows, n, 2)).astype(np.float32)
+            yz = f.process_complex(z)
+            for r, h in enumerate(hs):
+                rz = z[r].copy()
+                L.rfo_fir_process_complex(h, P(rz), n)
+                assert bits_equal(yz[r], rz), ("complex", spec, r, n)
+    taps = rng.standard_normal(52).astype(np.float32)
+    f.init_const(taps, 31250.0)
+    for h in hs:
+        L.rfo_fir_init_const(h, taps.size, P(taps), 31250.0)
+    for n in (2048, 100):
+        x = rng.standard_normal((rows, n)).astype(np.float32)
+        y = f.process_real(x)
+        for r, h in enumerate(hs):
+            ref = x[r].copy()
+            L.rfo_fir_process_real(h, P(ref), n)
+            assert bits_equal(y[r], ref), ("const", r, n)
+    for h in hs:
+        L.rfo_fir_destroy(h)
+    f.close()
+
+
+@pytest.mark.parametrize("rate", ["1.0M", "2.4M"])
+def test_rds_processor_from_baseband(rfm, port, rate):
+    """cRDSRxSignalProcessor on its own: fed with the demodulated baseband of the oracle decoder (its `baseband` tap is
+    exactly what FmDecode.cpp:436 passes to RDSProcess::Process), it must emit the decoder's RDS bits and groups."""
+    fs, ds, blk = RATES[rate]
+    nblk = 6
+    streams = [station(rate, nblk, stream_id=s)[0] for s in range(2)]
+    oracles = [port.OracleFmDecoder(fs, -0.15 * fs, downsample=ds) for _ in streams]
+    rp = rfm.RdsProcessorBatch(len(streams), fs / ds, max_len=blk)
+    for b in range(nblk):
+        bbs = []
+        for o, iq in zip(oracles, streams):
+            o.process_u8(iq[b * blk:(b + 1) * blk])
+            bbs.append(o.tap("baseband"))
+        rp.process(np.stack(bbs))
+    for s, o in enumerate(oracles):
+        bits = o.take_bits()
+        assert bits.size > 150
+        assert np.array_equal(rp.take_bits(s), bits)
+        groups = o.take_groups()
+        assert np.array_equal(rp.take_groups(s), groups) and (rate != "1.0M" or groups.shape[0] >= 1)
+    rp.close()
