@@ -224,6 +224,34 @@ RFM_API int rfm_downconvert_process_device(rfm_downconvert* d, int mode, const v
                                            size_t out_stride, uint32_t n, uint32_t* n_out, void* cuda_stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * cDownsampleFilter (DownConvert.h:21-60, DownConvert.cpp:58-256), batched over rows: Lanczos-windowed sinc FIR with
+ * decimation, in the two forms the chain uses -- complex input + integer factor (m_ReSampleInput, FmDecode.cpp:257-261)
+ * and real input + fractional factor (m_ReSampleMono / m_ReSampleStereo, :263-273).  Real + integer is not on the hot
+ * path and returns RFM_ERR_UNSUPPORTED; calls shorter than the filter order likewise.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rfm_downsample rfm_downsample;
+/* cDownsampleFilter(filter_order, cutoff, downsample, integer_factor) -- DownConvert.cpp:63-81 */
+RFM_API int rfm_downsample_create(uint32_t rows, uint32_t filter_order, double cutoff, double downsample,
+                                  int integer_factor, uint32_t max_len, int device, rfm_downsample** out);
+RFM_API void rfm_downsample_destroy(rfm_downsample* f);
+/* cDownsampleFilter::Reset -- DownConvert.cpp:90-96 */
+RFM_API int rfm_downsample_reset(rfm_downsample* f);
+/* m_coeff: filter_order + 2 entries (MakeLanczosCoeff, DownConvert.cpp:18-56) */
+RFM_API int rfm_downsample_coefficients(const rfm_downsample* f, float* out, uint32_t max, uint32_t* n);
+/* upper bound of the outputs of an n-sample call (size of the caller's output rows) */
+RFM_API uint32_t rfm_downsample_max_outputs(const rfm_downsample* f, uint32_t n);
+/* unsigned Process(const ComplexType*, ComplexType*, unsigned) -- DownConvert.cpp:98-154; in [rows][n][2] host,
+ * out [rows][*n_out][2] host (rows packed back to back); *n_out = the return value */
+RFM_API int rfm_downsample_process_complex(rfm_downsample* f, const float* in, float* out, uint32_t n, uint32_t* n_out);
+/* unsigned Process(const RealType*, RealType*, unsigned), fractional branch -- DownConvert.cpp:195-256 */
+RFM_API int rfm_downsample_process_real(rfm_downsample* f, const float* in, float* out, uint32_t n, uint32_t* n_out);
+/* device rows, enqueue only; strides in samples */
+RFM_API int rfm_downsample_process_complex_device(rfm_downsample* f, const float* d_in, size_t in_stride, float* d_out,
+                                                  size_t out_stride, uint32_t n, uint32_t* n_out, void* cuda_stream);
+RFM_API int rfm_downsample_process_real_device(rfm_downsample* f, const float* d_in, size_t in_stride, float* d_out,
+                                               size_t out_stride, uint32_t n, uint32_t* n_out, void* cuda_stream);
+
+/* ------------------------------------------------------------------------------------------------
  * cIirFilter (IirFilter.h:12-36, IirFilter.cpp:11-105), batched over rows (one independent biquad per row, all with
  * the same coefficients).  type: 0 ftLP, 1 ftHP, 2 ftBP, 3 ftBR (IirFilter.h:15).  Buffers are filtered in place.
  * ---------------------------------------------------------------------------------------------- */

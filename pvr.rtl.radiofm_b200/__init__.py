@@ -57,6 +57,9 @@ EXPORTED_SYMBOLS = (
     "rfm_iir_process_complex", "rfm_iir_process_two", "rfm_iir_process_device",
     "rfm_fir_create", "rfm_fir_destroy", "rfm_fir_init_lp", "rfm_fir_init_const", "rfm_fir_taps", "rfm_fir_process_real",
     "rfm_fir_process_complex", "rfm_fir_process_two", "rfm_fir_process_device",
+    "rfm_downsample_create", "rfm_downsample_destroy", "rfm_downsample_reset", "rfm_downsample_coefficients",
+    "rfm_downsample_max_outputs", "rfm_downsample_process_complex", "rfm_downsample_process_real",
+    "rfm_downsample_process_complex_device", "rfm_downsample_process_real_device",
     "rfm_rdsproc_create", "rfm_rdsproc_destroy", "rfm_rdsproc_process_rate", "rfm_rdsproc_reset", "rfm_rdsproc_process",
     "rfm_rdsproc_process_device", "rfm_rdsproc_take_bits", "rfm_rdsproc_take_groups",
 )
@@ -156,6 +159,18 @@ def lib():
         L.rfm_fir_init_lp.argtypes = [C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _u32p]
         L.rfm_fir_init_const.argtypes = [C.c_void_p, C.c_uint32, _f32p, C.c_float]
         L.rfm_fir_taps.argtypes = [C.c_void_p, _f32p, C.c_uint32, _u32p]
+        L.rfm_downsample_create.argtypes = [C.c_uint32, C.c_uint32, C.c_double, C.c_double, C.c_int, C.c_uint32, C.c_int,
+                                            C.POINTER(C.c_void_p)]
+        L.rfm_downsample_destroy.argtypes = [C.c_void_p]
+        L.rfm_downsample_reset.argtypes = [C.c_void_p]
+        L.rfm_downsample_coefficients.argtypes = [C.c_void_p, _f32p, C.c_uint32, _u32p]
+        L.rfm_downsample_max_outputs.restype = C.c_uint32
+        L.rfm_downsample_max_outputs.argtypes = [C.c_void_p, C.c_uint32]
+        L.rfm_downsample_process_complex.argtypes = [C.c_void_p, _f32p, _f32p, C.c_uint32, _u32p]
+        L.rfm_downsample_process_real.argtypes = [C.c_void_p, _f32p, _f32p, C.c_uint32, _u32p]
+        for nm in ("complex", "real"):
+            getattr(L, f"rfm_downsample_process_{nm}_device").argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                                                                          C.c_size_t, C.c_uint32, _u32p, C.c_void_p]
         L.rfm_rdsproc_create.argtypes = [C.c_uint32, C.c_float, C.c_uint32, C.c_int, C.POINTER(C.c_void_p)]
         L.rfm_rdsproc_destroy.argtypes = [C.c_void_p]
         L.rfm_rdsproc_process_rate.restype = C.c_float
@@ -540,6 +555,49 @@ class FirFilterBatch(_RowFilter):
         k = C.c_uint32(0)
         _check(lib().rfm_fir_taps(self._h, _p(out, _f32p), out.size, C.byref(k)))
         return out[:k.value].copy()
+
+
+class DownsampleFilterBatch:
+    """rows x cDownsampleFilter (DownConvert.h:21-60): complex + integer factor, or real + fractional factor."""
+
+    def __init__(self, rows: int, filter_order: int, cutoff: float, downsample: float = 1.0, integer_factor: bool = True,
+                 max_len: int = 65536, device: int = -1):
+        self.rows = rows
+        self._h = C.c_void_p()
+        _check(lib().rfm_downsample_create(rows, filter_order, cutoff, downsample, int(integer_factor), max_len, device,
+                                           C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().rfm_downsample_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reset(self):
+        _check(lib().rfm_downsample_reset(self._h))
+
+    def coefficients(self) -> np.ndarray:
+        out = np.zeros(1024, dtype=np.float32)
+        k = C.c_uint32(0)
+        _check(lib().rfm_downsample_coefficients(self._h, _p(out, _f32p), out.size, C.byref(k)))
+        return out[:k.value].copy()
+
+    def process_complex(self, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float32).reshape(self.rows, -1, 2)
+        n = x.shape[1]
+        out = np.zeros((self.rows * int(lib().rfm_downsample_max_outputs(self._h, n)), 2), dtype=np.float32)
+        k = C.c_uint32(0)
+        _check(lib().rfm_downsample_process_complex(self._h, _p(x, _f32p), _p(out, _f32p), n, C.byref(k)))
+        return out[:self.rows * k.value].reshape(self.rows, k.value, 2).copy()
+
+    def process_real(self, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float32).reshape(self.rows, -1)
+        n = x.shape[1]
+        out = np.zeros(self.rows * int(lib().rfm_downsample_max_outputs(self._h, n)), dtype=np.float32)
+        k = C.c_uint32(0)
+        _check(lib().rfm_downsample_process_real(self._h, _p(x, _f32p), _p(out, _f32p), n, C.byref(k)))
+        return out[:self.rows * k.value].reshape(self.rows, k.value).copy()
 
 
 class RdsProcessorBatch:

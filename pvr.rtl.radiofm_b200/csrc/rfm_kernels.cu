@@ -55,6 +55,8 @@ __device__ __forceinline__ float2 tuned_sample(const void* __restrict__ row, uns
     are = f.x;
     aim = f.y;
   }
+  if (!tuner) // stand-alone cDownsampleFilter (rfm_downsample): no fine tuner in front of the FIR
+    return make_float2(are, aim);
   const float2 b = tuner[(idx0 + i) & 63u];
   float2 o;
   o.x = subf(mulf(are, b.x), mulf(aim, b.y));
@@ -80,7 +82,7 @@ __global__ void __launch_bounds__(kFrontTile) k_front(FrontParams p)
   for (unsigned i = tid; i < 256; i += kFrontTile)
     s_lut[i] = p.lut[i];
   if (tid < 64)
-    s_tuner[tid] = reinterpret_cast<const float2*>(p.tuner)[tid];
+    s_tuner[tid] = p.tuner ? reinterpret_cast<const float2*>(p.tuner)[tid] : make_float2(0.f, 0.f);
   for (unsigned i = tid; i < p.order + 2; i += kFrontTile)
     s_coef[i] = p.coeff[i];
   __syncthreads();
@@ -94,7 +96,7 @@ __global__ void __launch_bounds__(kFrontTile) k_front(FrontParams p)
   for (unsigned v = tid; v < count; v += kFrontTile)
   {
     const unsigned V = vlo + v;
-    X[v] = (V < p.order) ? tail[V] : tuned_sample<U8>(row, V - p.order, p.idx0, s_lut, s_tuner);
+    X[v] = (V < p.order) ? tail[V] : tuned_sample<U8>(row, V - p.order, p.idx0, s_lut, p.tuner ? s_tuner : nullptr);
   }
   __syncthreads();
 

@@ -766,3 +766,220 @@ int rfm_rdsproc_take_groups(rfm_rdsproc* r, uint32_t row, uint16_t* groups, uint
 }
 
 } // extern "C"
+
+// ==================================================================================================
+// cDownsampleFilter (DownConvert.h:21-60, DownConvert.cpp:58-256): Lanczos-windowed sinc FIR with decimation.
+// The two forms the chain uses: complex input with an integer factor (k_front, :98-154) and real input with a
+// fractional factor (k_resample, :195-233).  The other combinations are not on the hot path: real + integer returns
+// RFM_ERR_UNSUPPORTED, complex + fractional is an endless loop in the reference (pstep == 0) and returns it too.
+// ==================================================================================================
+struct rfm_downsample
+{
+  unsigned rows = 0, cap = 0, order = 0, ds_int = 0;
+  int device = 0;
+  bool integer = true;
+  double downsample = 1.0;
+  float pstep = 1.0f, pos_frac = 0.0f;
+  unsigned pos_int = 0;
+  std::vector<float> coeff;
+  float *d_coeff = nullptr, *d_lut = nullptr, *d_v = nullptr, *d_scratch = nullptr;
+  cf32* d_tail = nullptr;
+  size_t v_stride = 0;
+  float *d_in = nullptr, *d_out = nullptr; // staging for the host entry points
+};
+
+extern "C"
+{
+
+int rfm_downsample_create(uint32_t rows, uint32_t filter_order, double cutoff, double downsample, int integer_factor,
+                          uint32_t max_len, int device, rfm_downsample** out)
+{
+  if (!out || rows == 0 || max_len == 0 || filter_order < 2 || filter_order > 512 || !(downsample >= 1.0))
+    return PFail(RFM_ERR_INVALID, "rfm_downsample_create: invalid argument");
+  *out = nullptr;
+  int rc = PickDevice(&device);
+  if (rc != RFM_OK)
+    return rc;
+  rfm_downsample* f = new rfm_downsample;
+  f->rows = rows; f->cap = max_len; f->order = filter_order; f->device = device;
+  f->integer = integer_factor != 0;
+  f->downsample = downsample;
+  f->ds_int = f->integer ? (unsigned)lrint(downsample) : 0; // DownConvert.cpp:68
+  f->pstep = (float)downsample;                             // :203 RealType pstep = m_downsample
+  f->coeff = PlanLanczos(filter_order, cutoff);             // :78 (order + 2 entries)
+  f->v_stride = ((size_t)filter_order + max_len + 15) & ~(size_t)15;
+  std::vector<float> lut(256);
+  for (int u = 0; u < 256; ++u)
+    lut[u] = (float)(u / (255.0 / 2.0) - 1.0);
+  bool ok = DevAllocZ(&f->d_coeff, f->coeff.size()) && DevAllocZ(&f->d_lut, 256) &&
+            DevAllocZ(&f->d_tail, (size_t)rows * filter_order) && DevAllocZ(&f->d_v, (size_t)rows * f->v_stride) &&
+            DevAllocZ(&f->d_scratch, (size_t)rows * (max_len + 16));
+  ok = ok && cudaMemcpy(f->d_coeff, f->coeff.data(), f->coeff.size() * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess &&
+       cudaMemcpy(f->d_lut, lut.data(), 1024, cudaMemcpyHostToDevice) == cudaSuccess;
+  if (!ok)
+  {
+    rfm_downsample_destroy(f);
+    return PFail(RFM_ERR_CUDA, "rfm_downsample_create: device allocation failed");
+  }
+  *out = f;
+  return RFM_OK;
+}
+
+void rfm_downsample_destroy(rfm_downsample* f)
+{
+  if (!f)
+    return;
+  cudaSetDevice(f->device);
+  cudaFree(f->d_coeff); cudaFree(f->d_lut); cudaFree(f->d_tail); cudaFree(f->d_v); cudaFree(f->d_scratch);
+  cudaFree(f->d_in); cudaFree(f->d_out);
+  delete f;
+}
+
+int rfm_downsample_reset(rfm_downsample* f) // DownConvert.cpp:90-96
+{
+  if (!f)
+    return PFail(RFM_ERR_INVALID, "rfm_downsample_reset: null handle");
+  cudaSetDevice(f->device);
+  f->pos_int = 0;
+  f->pos_frac = 0.0f;
+  const bool ok = cudaMemsetAsync(f->d_tail, 0, (size_t)f->rows * f->order * sizeof(cf32), 0) == cudaSuccess &&
+                  cudaMemsetAsync(f->d_v, 0, (size_t)f->rows * f->v_stride * sizeof(float), 0) == cudaSuccess;
+  return ok ? RFM_OK : PFail(RFM_ERR_CUDA, "rfm_downsample_reset: failed");
+}
+
+int rfm_downsample_coefficients(const rfm_downsample* f, float* out, uint32_t max, uint32_t* n)
+{
+  if (!f || !n)
+    return PFail(RFM_ERR_INVALID, "rfm_downsample_coefficients: invalid argument");
+  *n = (uint32_t)f->coeff.size();
+  for (size_t i = 0; out && i < f->coeff.size() && i < max; ++i)
+    out[i] = f->coeff[i];
+  return RFM_OK;
+}
+
+uint32_t rfm_downsample_max_outputs(const rfm_downsample* f, uint32_t n)
+{
+  if (!f)
+    return 0;
+  return (uint32_t)((double)n / (f->integer ? (double)f->ds_int : f->downsample)) + 2;
+}
+
+// unsigned Process(const ComplexType* in, ComplexType* out, unsigned length), DownConvert.cpp:98-154
+int rfm_downsample_process_complex_device(rfm_downsample* f, const float* d_in, size_t in_stride, float* d_out,
+                                          size_t out_stride, uint32_t n, uint32_t* n_out, void* cuda_stream)
+{
+  if (n_out)
+    *n_out = 0;
+  if (!f || !d_in || !d_out)
+    return PFail(RFM_ERR_INVALID, "rfm_downsample_process_complex_device: invalid argument");
+  if (!f->integer || f->ds_int == 0)
+    return PFail(RFM_ERR_UNSUPPORTED, "cDownsampleFilter: the complex overload needs an integer factor "
+                                      "(the reference loops forever otherwise, DownConvert.cpp:108-112)");
+  if (n == 0)
+    return RFM_OK;
+  if (n > f->cap)
+    return PFail(RFM_ERR_INVALID, "rfm_downsample: n exceeds max_len");
+  if (n < f->order)
+    return PFail(RFM_ERR_UNSUPPORTED, "rfm_downsample: calls shorter than the filter order are not supported");
+  cudaSetDevice(f->device);
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const unsigned pos = f->pos_int, ds = f->ds_int;
+  const unsigned nout = pos < n ? (n - pos + ds - 1) / ds : 0;
+  FrontParams fp;
+  memset(&fp, 0, sizeof(fp));
+  fp.in = d_in; fp.in_stride = in_stride; fp.n = n; fp.S = f->rows; fp.order = f->order; fp.ds = ds;
+  fp.p0 = pos; fp.nout = nout; fp.idx0 = 0; fp.lut = f->d_lut; fp.tuner = nullptr;
+  fp.coeff = f->d_coeff; fp.coeff_host = nullptr; // generic kernel (the tiled one has the fine tuner built in)
+  fp.tail = f->d_tail; fp.z = reinterpret_cast<cf32*>(d_out); fp.z_stride = out_stride;
+  launch_front(fp, false, st);
+  launch_front_tail(fp, false, st);
+  f->pos_int = pos + nout * ds - n; // :132
+  rfm::g_launches += 2;
+  if (n_out)
+    *n_out = nout;
+  return cudaGetLastError() == cudaSuccess ? RFM_OK : PFail(RFM_ERR_CUDA, "rfm_downsample: kernel launch failed");
+}
+
+// unsigned Process(const RealType* in, RealType* out, unsigned length), fractional branch, DownConvert.cpp:195-256
+int rfm_downsample_process_real_device(rfm_downsample* f, const float* d_in, size_t in_stride, float* d_out,
+                                       size_t out_stride, uint32_t n, uint32_t* n_out, void* cuda_stream)
+{
+  if (n_out)
+    *n_out = 0;
+  if (!f || !d_in || !d_out)
+    return PFail(RFM_ERR_INVALID, "rfm_downsample_process_real_device: invalid argument");
+  if (f->integer)
+    return PFail(RFM_ERR_UNSUPPORTED, "rfm_downsample: the real overload is built for the fractional factor the chain "
+                                      "uses (DownConvert.cpp:195-233); real + integer is not on the hot path");
+  if (n == 0)
+    return RFM_OK;
+  if (n > f->cap)
+    return PFail(RFM_ERR_INVALID, "rfm_downsample: n exceeds max_len");
+  if (n < f->order)
+    return PFail(RFM_ERR_UNSUPPORTED, "rfm_downsample: calls shorter than the filter order are not supported");
+  cudaSetDevice(f->device);
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  float pos_next = 0.0f;
+  const unsigned na = FractionalOutputs(f->pos_frac, f->pstep, n, &pos_next);
+  dim3 grid((n + 255) / 256, f->rows);
+  k_to_v<<<grid, 256, 0, st>>>(reinterpret_cast<const char*>(d_in), in_stride * 4, reinterpret_cast<char*>(f->d_v),
+                               f->v_stride * 4, f->order, n, 4);
+  ResampleParams rp;
+  memset(&rp, 0, sizeof(rp));
+  rp.bbV = f->d_v; rp.rawV = f->d_v; rp.a_stride = f->v_stride; rp.order = f->order; rp.nb = n; rp.S = f->rows;
+  rp.na = na; rp.pos_frac = f->pos_frac; rp.pstep = f->pstep; rp.coeff = f->d_coeff;
+  rp.lpM = d_out; rp.lpS = f->d_scratch; rp.lp_stride = out_stride; rp.lp_hist = 0;
+  if (out_stride > (size_t)f->cap + 16)
+    return PFail(RFM_ERR_INVALID, "rfm_downsample: out_stride exceeds max_len + 16");
+  launch_resample(rp, st);
+  TailParams tp;
+  tp.count = 0;
+  tp.d[tp.count++] = {f->d_v, f->d_v, f->v_stride * 4, f->order, n, 4, f->rows};
+  launch_tails(tp, f->rows, st);
+  f->pos_frac = pos_next;
+  rfm::g_launches += 3;
+  if (n_out)
+    *n_out = na;
+  return cudaGetLastError() == cudaSuccess ? RFM_OK : PFail(RFM_ERR_CUDA, "rfm_downsample: kernel launch failed");
+}
+
+static int DownsampleHost(rfm_downsample* f, bool cplx, const float* in, float* out, uint32_t n, uint32_t* n_out)
+{
+  if (!f || !in || !out || n > f->cap)
+    return PFail(RFM_ERR_INVALID, "rfm_downsample_process: invalid argument");
+  if (n_out)
+    *n_out = 0;
+  if (n == 0)
+    return RFM_OK;
+  cudaSetDevice(f->device);
+  const size_t cap_out = (size_t)f->cap + 16;
+  if (!f->d_in && !DevAllocZ(&f->d_in, (size_t)f->rows * f->cap * 2))
+    return PFail(RFM_ERR_CUDA, "rfm_downsample: staging allocation failed");
+  if (!f->d_out && !DevAllocZ(&f->d_out, (size_t)f->rows * cap_out * 2))
+    return PFail(RFM_ERR_CUDA, "rfm_downsample: staging allocation failed");
+  const size_t esz = cplx ? 8 : 4;
+  if (cudaMemcpy(f->d_in, in, (size_t)f->rows * n * esz, cudaMemcpyHostToDevice) != cudaSuccess)
+    return PFail(RFM_ERR_CUDA, "rfm_downsample: H2D copy failed");
+  uint32_t m = 0;
+  int rc = cplx ? rfm_downsample_process_complex_device(f, f->d_in, n, f->d_out, cap_out, n, &m, nullptr)
+                : rfm_downsample_process_real_device(f, f->d_in, n, f->d_out, cap_out, n, &m, nullptr);
+  if (rc != RFM_OK)
+    return rc;
+  // rows are compacted on the way back: out is [rows][m]
+  if (m && cudaMemcpy2D(out, (size_t)m * esz, f->d_out, cap_out * esz, (size_t)m * esz, f->rows, cudaMemcpyDeviceToHost) != cudaSuccess)
+    return PFail(RFM_ERR_CUDA, "rfm_downsample: D2H copy failed");
+  if (n_out)
+    *n_out = m;
+  return RFM_OK;
+}
+
+int rfm_downsample_process_complex(rfm_downsample* f, const float* in, float* out, uint32_t n, uint32_t* n_out)
+{
+  return DownsampleHost(f, true, in, out, n, n_out);
+}
+int rfm_downsample_process_real(rfm_downsample* f, const float* in, float* out, uint32_t n, uint32_t* n_out)
+{
+  return DownsampleHost(f, false, in, out, n, n_out);
+}
+
+} // extern "C"

@@ -1,4 +1,5 @@
-// host/DownConvert.h -- CRDSDownConvert with the reference's signatures (DownConvert.h:68-77) over the C ABI
+// host/DownConvert.h -- cDownsampleFilter (DownConvert.h:21-60) and CRDSDownConvert (DownConvert.h:68-77) with the
+// reference's signatures over the C ABI
 // (rfm_downconvert_*).  The reference object is default-constructed and configured afterwards; the device object is
 // (re)built when SetDataRate / SetWfmDataRate changes the plan, exactly when the reference rebuilds its stage list
 // (DownConvert.cpp:331,382).
@@ -9,6 +10,38 @@
 
 #include "../../include/radiofm_b200.h"
 #include "Definitions.h"
+
+// cDownsampleFilter (DownConvert.h:21-60) over rfm_downsample_*: the complex + integer and the real + fractional forms
+// (the ones cFmDecoder instantiates, FmDecode.cpp:257-273); the other combinations return 0 samples.
+class cDownsampleFilter
+{
+public:
+  cDownsampleFilter(unsigned int filter_order, double cutoff, double downsample = 1, bool integer_factor = true,
+                    unsigned int max_len = 1u << 16, int cuda_device = -1)
+  {
+    if (rfm_downsample_create(1, filter_order, cutoff, downsample, integer_factor ? 1 : 0, max_len, cuda_device, &m_f) != RFM_OK)
+      throw std::runtime_error(std::string("cDownsampleFilter (B200): ") + rfm_last_error());
+  }
+  virtual ~cDownsampleFilter() { rfm_downsample_destroy(m_f); }
+  cDownsampleFilter(const cDownsampleFilter&) = delete;
+  cDownsampleFilter& operator=(const cDownsampleFilter&) = delete;
+
+  void Reset() { rfm_downsample_reset(m_f); } // DownConvert.cpp:90-96
+  unsigned int Process(const RealType* samples_in, RealType* samples_out, unsigned int length) // :156-256
+  {
+    uint32_t n = 0;
+    return rfm_downsample_process_real(m_f, samples_in, samples_out, length, &n) == RFM_OK ? n : 0;
+  }
+  unsigned int Process(const ComplexType* samples_in, ComplexType* samples_out, unsigned int length) // :98-154
+  {
+    uint32_t n = 0;
+    return rfm_downsample_process_complex(m_f, reinterpret_cast<const float*>(samples_in),
+                                          reinterpret_cast<float*>(samples_out), length, &n) == RFM_OK ? n : 0;
+  }
+
+private:
+  rfm_downsample* m_f = nullptr;
+};
 
 class CRDSDownConvert
 {

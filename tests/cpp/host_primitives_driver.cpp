@@ -82,6 +82,22 @@ int main(int argc, char** argv)
       dump(pre + "_dc.f32", y.data(), m * 8);
       printf("dc_rate %.9g dc_out %zu\n", rate, m);
     }
+    { // cDownsampleFilter as cFmDecoder builds it at 1.0 MS/s (FmDecode.cpp:257-267): complex / 4, real -> 48 kHz
+      cDownsampleFilter in(32, 0.6 / 4, 4, true), mono(250, 15000.0 / 250000.0, 250000.0 / 48000.0, false);
+      std::vector<ComplexType> z(n / 2), y(n / 2);
+      for (unsigned i = 0; i < n / 2; ++i)
+        z[i] = ComplexType(x[2 * i], x[2 * i + 1]);
+      size_t m = 0;
+      for (unsigned i = 0; i + blk <= n / 2; i += blk)
+        m += in.Process(z.data() + i, y.data() + m, blk);
+      dump(pre + "_ds_c.f32", y.data(), m * 8);
+      std::vector<float> a(n);
+      size_t k = 0;
+      for (unsigned i = 0; i + blk <= n; i += blk)
+        k += mono.Process(x.data() + i, a.data() + k, blk);
+      dump(pre + "_ds_r.f32", a.data(), k * 4);
+      printf("ds_c %zu ds_r %zu\n", m, k);
+    }
     { // cRDSRxSignalProcessor on the real signal
       cRDSRxSignalProcessor rds(nullptr, 250000.0f);
       std::vector<uint8_t> bits;

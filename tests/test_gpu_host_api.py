@@ -162,6 +162,23 @@ def test_primitive_classes_match_oracle(tmp_path, port):
     L.rfo_rdsdc_destroy(h)
     assert bits_equal(rd("dc.f32").reshape(-1, 2), np.concatenate(ys))
     assert f"dc_rate {float(np.float32(rate)):.9g}" in out.stdout
+    # cDownsampleFilter
+    h = L.rfo_downsample_create(32, 0.6 / 4, 4.0, 1)
+    ys = []
+    for i in range(0, half - bl + 1, bl):
+        y = np.zeros((bl, 2), dtype=np.float32)
+        k = L.rfo_downsample_process_complex(h, P(zz[i:i + bl].copy()), P(y), bl)
+        ys.append(y[:k])
+    L.rfo_downsample_destroy(h)
+    assert bits_equal(rd("ds_c.f32").reshape(-1, 2), np.concatenate(ys))
+    h = L.rfo_downsample_create(250, 15000.0 / 250000.0, 250000.0 / 48000.0, 0)
+    ys = []
+    for i in range(0, n - bl + 1, bl):
+        y = np.zeros(bl, dtype=np.float32)
+        k = L.rfo_downsample_process_real(h, P(x[i:i + bl].copy()), P(y), bl)
+        ys.append(y[:k])
+    L.rfo_downsample_destroy(h)
+    assert bits_equal(rd("ds_r.f32"), np.concatenate(ys))
     # cRDSRxSignalProcessor: the decoder's own RDS output for this baseband
     bits, groups = o.take_bits(), o.take_groups()
     assert np.array_equal(rd("rds_bits.u8", np.uint8), bits) and bits.size > 400

@@ -128,3 +128,56 @@ def test_rds_processor_from_baseband(rfm, port, rate):
         groups = o.take_groups()
         assert np.array_equal(rp.take_groups(s), groups) and (rate != "1.0M" or groups.shape[0] >= 1)
     rp.close()
+
+
+def test_downsample_filter_both_live_forms(rfm, port):
+    """cDownsampleFilter as cFmDecoder builds it (FmDecode.cpp:257-273): the complex integer decimator in front of the
+    demodulator and the real fractional resampler behind it; several calls (positions and histories carried)."""
+    rng = np.random.default_rng(23)
+    L = port.lib()
+    rows = 3
+    # complex, integer: order 8 * ds, cutoff 0.6 / ds (1.0 MS/s: ds 4; 2.4 MS/s: ds 11)
+    for ds in (4, 11, 1):
+        order, cutoff = 8 * ds, 0.6 / ds
+        f = rfm.DownsampleFilterBatch(rows, order, cutoff, ds, True, max_len=8192)
+        hs = [L.rfo_downsample_create(order, cutoff, float(ds), 1) for _ in range(rows)]
+        co = np.zeros(1024, dtype=np.float32)
+        k = L.rfo_downsample_coeff(hs[0], P(co))
+        assert bits_equal(f.coefficients(), co[:k])
+        for n in (8192, 1000, 4097, 8192):
+            x = rng.standard_normal((rows, n, 2)).astype(np.float32)
+            y = f.process_complex(x)
+            for r, h in enumerate(hs):
+                ref = np.zeros((n, 2), dtype=np.float32)
+                m = L.rfo_downsample_process_complex(h, P(x[r].copy()), P(ref), n)
+                assert y.shape[1] == m and bits_equal(y[r], ref[:m]), ("complex", ds, r, n)
+        f.reset()
+        for h in hs:
+            L.rfo_downsample_reset(h)
+        x = rng.standard_normal((rows, 2048, 2)).astype(np.float32)
+        y = f.process_complex(x)
+        for r, h in enumerate(hs):
+            ref = np.zeros((2048, 2), dtype=np.float32)
+            m = L.rfo_downsample_process_complex(h, P(x[r].copy()), P(ref), 2048)
+            assert bits_equal(y[r], ref[:m]), ("complex after Reset", ds, r)
+            L.rfo_downsample_destroy(h)
+        f.close()
+    # real, fractional: order int(Fb / 1000), cutoff 0.75 * 48000 / Fb ... as FmDecode.cpp:263-267
+    for fb in (250000.0, 218181.8125):
+        order = int(fb / 1000.0)
+        ratio = fb / 48000.0
+        cutoff = 15000.0 / fb
+        f = rfm.DownsampleFilterBatch(rows, order, cutoff, ratio, False, max_len=16384)
+        hs = [L.rfo_downsample_create(order, cutoff, ratio, 0) for _ in range(rows)]
+        for n in (16384, 5952, 1000, 16384):
+            x = rng.standard_normal((rows, n)).astype(np.float32)
+            y = f.process_real(x)
+            for r, h in enumerate(hs):
+                ref = np.zeros(n, dtype=np.float32)
+                m = L.rfo_downsample_process_real(h, P(x[r].copy()), P(ref), n)
+                assert y.shape[1] == m and bits_equal(y[r], ref[:m]), ("real", fb, r, n)
+        for h in hs:
+            L.rfo_downsample_destroy(h)
+        with pytest.raises(rfm.RadioFmError):
+            f.process_complex(np.zeros((rows, 4096, 2), dtype=np.float32))
+        f.close()
