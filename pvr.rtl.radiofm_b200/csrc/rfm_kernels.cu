@@ -1407,7 +1407,7 @@ __global__ void k_osc(OscParams p)
   {
     const float orr = subf(mulf(o1r, p.cosv), mulf(o1i, p.sinv));
     const float oi = addf(mulf(o1i, p.cosv), mulf(o1r, p.sinv));
-    const float gn = d2f(subd(1.95, (double)addf(mulf(o1r, o1r), mulf(o1i, o1i))));
+    const float gn = rfm_osc_gain(addf(mulf(o1r, o1r), mulf(o1i, o1i))); // == float(1.95 - double(q)), rfm_dsp.cuh
     o1r = mulf(gn, orr);
     o1i = mulf(gn, oi);
     out[i] = make_float2(orr, oi);
