@@ -95,8 +95,18 @@ struct Group
 {
   unsigned s0 = 0, S = 0;
   ProfSlot prof[kMaxProfKinds];
-  cudaStream_t sF = nullptr, sA = nullptr, sB = nullptr, sR = nullptr; // front / lanes / audio branch / RDS branch
-  cudaEvent_t ev_rds[3] = {nullptr, nullptr, nullptr};  // RDS branch of the block finished (mod 3)
+  // front / lanes / resamplers / audio tail (LP, deemphasis, notch, matrix, D2H) / RDS front / RDS PLL + slicer
+  cudaStream_t sF = nullptr, sA = nullptr, sB = nullptr, sC = nullptr, sR = nullptr, sP = nullptr;
+  cudaStream_t* AllStreams(cudaStream_t (&v)[6]) const
+  {
+    v[0] = sF; v[1] = sA; v[2] = sB; v[3] = sC; v[4] = sR; v[5] = sP;
+    return v;
+  }
+  cudaEvent_t ev_rds[3] = {nullptr, nullptr, nullptr};  // RDS front of the block finished (mod 3): bbV / oscV released
+  cudaEvent_t ev_res[2] = {nullptr, nullptr};   // resamplers of the block with this parity finished: lpS / lpM [parity] written
+  cudaEvent_t ev_aud[2] = {nullptr, nullptr};   // audio tail ... finished (its stereo-flag slot may be rewritten)
+  cudaEvent_t ev_carry[2] = {nullptr, nullptr}; // LP history carried out of lpS / lpM [parity ^ 1]: they may be overwritten
+  cudaEvent_t ev_pll[2] = {nullptr, nullptr};   // RDS PLL + slicer ... finished: rlp_out[parity] may be overwritten
   cudaEvent_t ev_front[2] = {nullptr, nullptr}; // front end of the block with this parity finished
   cudaEvent_t ev_demod[2] = {nullptr, nullptr}; // demodulator done: z[parity] may be overwritten
   cudaEvent_t ev_lanes[2] = {nullptr, nullptr}; // PLL lanes ...
@@ -105,12 +115,12 @@ struct Group
   DevBuf<float> incr[2];       // NCO increments, demodulator (stage F) -> lanes (stage A), by parity
   DevBuf<float2> dm_start, dm_end; // speculative demodulator chunk states
   DevBuf<float> bbV[3], rawV[3]; // lanes -> stage B hand-over: three deep, so stage B of block k has two lane periods
-  DevBuf<cf32> rlpV, rlp_out;   // rlpV: decimator output of the last block (stage tap); rlp_out: RDS LP output
+  DevBuf<cf32> rlpV, rlp_out[2]; // rlpV: decimator output of the last block (stage tap); rlp_out: RDS LP output, by parity
   DevBuf<cf32> rds_tails;       // fused RDS front: per-stream histories of every stage + LP delay line
   DevBuf<float> mfV, mf_out;
   DevBuf<uint8_t> bits;
   DevBuf<unsigned> bit_count;
-  DevBuf<float> lpS, lpM, fS, fM;
+  DevBuf<float> lpS[2], lpM[2], fS, fM; // resampler outputs ([history | block], by parity); audio LP outputs
   DevBuf<float> state;
   DevBuf<uint8_t> in_stage;  // host-API staging of the input block
   DevBuf<float> audio_stage; // host-API staging of the audio block
@@ -174,7 +184,9 @@ void FreeDecoder(rfm_decoder* d)
   cudaSetDevice(d->device);
   for (auto& g : d->groups)
   {
-    for (cudaStream_t st : {g.sF, g.sA, g.sB, g.sR})
+    cudaStream_t all[6];
+    g.AllStreams(all);
+    for (cudaStream_t st : all)
       if (st)
         cudaStreamSynchronize(st);
     g.tail.Free(); g.z[0].Free(); g.z[1].Free(); g.incr[0].Free(); g.incr[1].Free(); g.dm_start.Free(); g.dm_end.Free();
@@ -183,15 +195,17 @@ void FreeDecoder(rfm_decoder* d)
       g.bbV[b].Free();
       g.rawV[b].Free();
     }
-    g.rlpV.Free(); g.rlp_out.Free(); g.rds_tails.Free(); g.mfV.Free(); g.mf_out.Free(); g.bits.Free(); g.bit_count.Free();
-    g.lpS.Free(); g.lpM.Free(); g.fS.Free(); g.fM.Free(); g.state.Free(); g.in_stage.Free(); g.audio_stage.Free();
+    g.rlpV.Free(); g.rlp_out[0].Free(); g.rlp_out[1].Free(); g.rds_tails.Free(); g.mfV.Free(); g.mf_out.Free(); g.bits.Free(); g.bit_count.Free();
+    g.lpS[0].Free(); g.lpS[1].Free(); g.lpM[0].Free(); g.lpM[1].Free(); g.fS.Free(); g.fM.Free(); g.state.Free(); g.in_stage.Free(); g.audio_stage.Free();
     ProfFree(g.prof);
-    for (cudaEvent_t e : {g.ev_demod[0], g.ev_demod[1], g.ev_front[0], g.ev_front[1], g.ev_lanes[0], g.ev_lanes[1], g.ev_rest[0], g.ev_rest[1], g.ev_rest[2], g.ev_rds[0], g.ev_rds[1], g.ev_rds[2]})
+    for (cudaEvent_t e : {g.ev_demod[0], g.ev_demod[1], g.ev_front[0], g.ev_front[1], g.ev_lanes[0], g.ev_lanes[1], g.ev_rest[0], g.ev_rest[1], g.ev_rest[2], g.ev_rds[0], g.ev_rds[1], g.ev_rds[2],
+                          g.ev_res[0], g.ev_res[1], g.ev_aud[0], g.ev_aud[1], g.ev_pll[0], g.ev_pll[1], g.ev_carry[0], g.ev_carry[1]})
       if (e)
         cudaEventDestroy(e);
     if (g.sF == g.sA)
-      g.sF = g.sB = g.sR = nullptr; // RFM_DEBUG_SERIAL aliasing
-    for (cudaStream_t st : {g.sF, g.sA, g.sB, g.sR})
+      g.sF = g.sB = g.sC = g.sR = g.sP = nullptr; // RFM_DEBUG_SERIAL aliasing
+    g.AllStreams(all);
+    for (cudaStream_t st : all)
       if (st)
         cudaStreamDestroy(st);
   }
@@ -334,12 +348,10 @@ cudaError_t ResetGroupState(rfm_decoder* d, Group& g, bool initial)
   if (e != cudaSuccess)
     return e;
   // InitLPFilter / InitConstFir clear the delay lines (FirFilter.cpp:138-144,313-319)
-  // the LP delay line is the last segment of every stream's tail row
+  // the LP delay line is the head of every stream's rlpV row
   {
-    const unsigned nst = (unsigned)d->plan.rds_stages.size();
     const unsigned lp_hist = (unsigned)d->plan.rlp_coef.size() - 1;
-    e = cudaMemset2D(g.rds_tails.p + d->rds_tail_off[nst], (size_t)d->rds_tail_stride * sizeof(cf32), 0,
-                     (size_t)lp_hist * sizeof(cf32), S);
+    e = cudaMemset2D(g.rlpV.p, (size_t)d->rlp_stride * sizeof(cf32), 0, (size_t)lp_hist * sizeof(cf32), S);
     if (e != cudaSuccess)
       return e;
   }
@@ -353,7 +365,7 @@ int DrainBits(rfm_decoder* d)
     return RFM_OK;
   for (auto& g : d->groups)
   {
-    RFM_CUDA(cudaStreamSynchronize(g.sB));
+    RFM_CUDA(cudaStreamSynchronize(g.sP)); // the slicer's stream
     d->h_counts.resize(g.S);
     RFM_CUDA(cudaMemcpy(d->h_counts.data(), g.bit_count.p, g.S * sizeof(unsigned), cudaMemcpyDeviceToHost));
     unsigned mx = 0;
@@ -495,27 +507,45 @@ void EnqueueStageA(rfm_decoder* d, Group& g, const BlockGeom& bg, unsigned par, 
   g_launches += 2;
 }
 
-// Stage B of one block for one group (stream sB): audio branch, RDS branch, history carry of its own buffers.
-void EnqueueStageB(rfm_decoder* d, Group& g, const BlockGeom& bg, unsigned par, float* d_audio, size_t audio_stride)
+// Stage B of one block for one group, four streams:
+//   sB  resamplers (bbV / rawV [par3] -> lpS / lpM [par])           sC  audio LP, deemphasis, notch, matrix (-> audio)
+//   sR  RDS front (bbV [par3], oscV [par3] -> rlp_out [par])        sP  Costas loop, matched filter, slicer (-> bits)
+// The lane kernels (k_rds_pll, k_audio_tail, k_rds_slice) are latency-bound and stretch when they share the SMs with
+// the FIR kernels; on their own streams they overlap the FIR kernels of the NEXT block instead of delaying them.
+void EnqueueStageB(rfm_decoder* d, Group& g, const BlockGeom& bg, unsigned par, unsigned par3, float* d_audio,
+                   size_t audio_stride)
 {
   const DecoderPlan& p = d->plan;
-  cudaStream_t st = g.sB;
   const unsigned S = g.S;
   const unsigned a_hist = p.a_order;
   const unsigned lp_taps = (unsigned)p.lp_coef.size(), rlp_taps = (unsigned)p.rlp_coef.size();
   const unsigned mf_taps = (unsigned)p.mf_coef.size();
   const unsigned nst = (unsigned)p.rds_stages.size();
 
-  // ---- audio branch
+  // ---- sB: fractional resamplers
+  cudaStream_t st = g.sB;
   ResampleParams rp;
-  rp.bbV = g.bbV[par].p; rp.rawV = g.rawV[par].p; rp.a_stride = d->a_stride; rp.order = p.a_order; rp.nb = bg.nb;
-  rp.S = S; rp.na = bg.na; rp.pos_frac = d->a_pos; rp.pstep = p.a_pstep; rp.coeff = d->d_a_coeff.p; rp.lpS = g.lpS.p;
-  rp.lpM = g.lpM.p; rp.lp_stride = d->lp_stride; rp.lp_hist = lp_taps - 1;
-  rp.kk = d->res_kk[par].p; rp.meta = d->res_meta[par].p; rp.lp = d->res_lp;
+  rp.bbV = g.bbV[par3].p; rp.rawV = g.rawV[par3].p; rp.a_stride = d->a_stride; rp.order = p.a_order; rp.nb = bg.nb;
+  rp.S = S; rp.na = bg.na; rp.pos_frac = d->a_pos; rp.pstep = p.a_pstep; rp.coeff = d->d_a_coeff.p;
+  rp.lpS = g.lpS[par].p; rp.lpM = g.lpM[par].p; rp.lp_stride = d->lp_stride; rp.lp_hist = lp_taps - 1;
+  rp.kk = d->res_kk[par3].p; rp.meta = d->res_meta[par3].p; rp.lp = d->res_lp;
   RFM_PROF(g.prof, "k_resample", st, launch_resample_tiled(rp, st));
+  cudaEventRecord(g.ev_res[par], st);
+  ++g_launches;
 
+  // ---- sC: audio tail.  History of the LP input rows: last lp_taps-1 samples of the previous block (other parity)
+  st = g.sC;
+  cudaStreamWaitEvent(st, g.ev_res[par], 0);
+  {
+    TailParams tpa;
+    tpa.count = 2;
+    tpa.d[0] = {g.lpS[par ^ 1u].p, g.lpS[par].p, d->lp_stride * sizeof(float), lp_taps - 1, d->last_na, 4, S};
+    tpa.d[1] = {g.lpM[par ^ 1u].p, g.lpM[par].p, d->lp_stride * sizeof(float), lp_taps - 1, d->last_na, 4, S};
+    RFM_PROF(g.prof, "k_tails", st, launch_tails(tpa, S, st));
+    cudaEventRecord(g.ev_carry[par], st);
+  }
   RotFirParams f29;
-  f29.inA = g.lpS.p; f29.inB = g.lpM.p; f29.in_stride = d->lp_stride; f29.outA = g.fS.p; f29.outB = g.fM.p;
+  f29.inA = g.lpS[par].p; f29.inB = g.lpM[par].p; f29.in_stride = d->lp_stride; f29.outA = g.fS.p; f29.outB = g.fM.p;
   f29.out_stride = d->na_max; f29.out_off = 0; f29.n = bg.na; f29.S = S; f29.taps = lp_taps; f29.g0 = d->lp_g;
   f29.coef = d->d_lp_coef.p; f29.cplx = 0;
   RFM_PROF(g.prof, "k_rotfir_lp29", st, launch_rotfir(f29, st));
@@ -523,23 +553,16 @@ void EnqueueStageB(rfm_decoder* d, Group& g, const BlockGeom& bg, unsigned par, 
   AudioTailParams at;
   at.inS = g.fS.p; at.inM = g.fM.p; at.in_stride = d->na_max; at.na = bg.na; at.S = S; at.state = g.state.p;
   at.de_alpha = p.de_alpha; at.notch = {p.notch.A1, p.notch.A2, p.notch.B0, p.notch.B1, p.notch.B2};
-  at.audio = d_audio; at.audio_stride = audio_stride; at.parity = par;
+  at.audio = d_audio; at.audio_stride = audio_stride; at.parity = par3;
   RFM_PROF(g.prof, "k_audio_tail", st, launch_audio_tail(at, st));
-  {
-    TailParams tpa;
-    tpa.count = 2;
-    tpa.d[0] = {g.lpS.p, g.lpS.p, d->lp_stride * sizeof(float), lp_taps - 1, bg.na, 4, S};
-    tpa.d[1] = {g.lpM.p, g.lpM.p, d->lp_stride * sizeof(float), lp_taps - 1, bg.na, 4, S};
-    RFM_PROF(g.prof, "k_tails", st, launch_tails(tpa, S, st));
-  }
-  g_launches += 4;
+  g_launches += 3;
 
-  // ---- RDS branch, on its own stream (its PLL / slicer lane kernels are latency-bound and overlap the audio FIRs)
+  // ---- sR: RDS front (mix, decimate-by-2 chain, LP)
   st = g.sR;
   RdsFrontParams rf;
   memset(&rf, 0, sizeof(rf));
-  rf.bbV = g.bbV[par].p; rf.a_stride = d->a_stride; rf.a_hist = a_hist;
-  rf.osc = d->oscV[par].p + d->osc_hist; rf.nb = bg.nb; rf.S = S; rf.nst = nst;
+  rf.bbV = g.bbV[par3].p; rf.a_stride = d->a_stride; rf.a_hist = a_hist;
+  rf.osc = d->oscV[par3].p + d->osc_hist; rf.nb = bg.nb; rf.S = S; rf.nst = nst;
   for (unsigned k = 0; k < nst; ++k)
   {
     const HalfBandStage& hs = p.rds_stages[k];
@@ -552,12 +575,30 @@ void EnqueueStageB(rfm_decoder* d, Group& g, const BlockGeom& bg, unsigned par, 
   rf.tail_off[nst] = d->rds_tail_off[nst];
   rf.lp_coef = d->d_rlp_coef.p; rf.lp_n = rlp_taps; rf.g0 = d->rlp_g;
   rf.tails = g.rds_tails.p; rf.tail_stride = d->rds_tail_stride;
-  rf.out = g.rlp_out.p; rf.dec_out = g.rlpV.p; rf.out_stride = d->nr_stride;
+  rf.out = nullptr; rf.dec_out = nullptr; rf.out_stride = d->nr_stride;
+  rf.lp_v = g.rlpV.p; rf.lp_v_stride = d->rlp_stride; // decimator output -> [LP history | block] rows
   RFM_PROF(g.prof, "k_rds_front", st, launch_rds_front(rf, st));
-  ++g_launches;
+  {
+    // the 2.4 kHz LP (RDSProcess.cpp:128), lane = stream form, then its history carry
+    RotFirParams flp;
+    flp.inA = reinterpret_cast<const float*>(g.rlpV.p); flp.inB = nullptr; flp.in_stride = d->rlp_stride;
+    flp.outA = reinterpret_cast<float*>(g.rlp_out[par].p); flp.outB = nullptr; flp.out_stride = d->nr_stride;
+    flp.out_off = 0; flp.n = bg.nr; flp.S = S; flp.taps = rlp_taps; flp.g0 = d->rlp_g; flp.coef = d->d_rlp_coef.p;
+    flp.cplx = 1;
+    RFM_PROF(g.prof, "k_rotfir_rdslp", st, launch_rotfir(flp, st));
+    TailParams tpl;
+    tpl.count = 1;
+    tpl.d[0] = {g.rlpV.p, g.rlpV.p, d->rlp_stride * sizeof(cf32), rlp_taps - 1, bg.nr, 8, S};
+    RFM_PROF(g.prof, "k_tails", st, launch_tails(tpl, S, st));
+  }
+  cudaEventRecord(g.ev_rds[par3], st);
+  g_launches += 3;
 
+  // ---- sP: Costas loop, matched filter, bit clock + slicer
+  st = g.sP;
+  cudaStreamWaitEvent(st, g.ev_rds[par3], 0);
   RdsPllParams pp;
-  pp.in = g.rlp_out.p; pp.in_stride = d->nr_stride; pp.nr = bg.nr; pp.S = S; pp.state = g.state.p;
+  pp.in = g.rlp_out[par].p; pp.in_stride = d->nr_stride; pp.nr = bg.nr; pp.S = S; pp.state = g.state.p;
   pp.lo = p.rpll_lo; pp.hi = p.rpll_hi; pp.alpha = p.rpll_alpha; pp.beta = p.rpll_beta;
   pp.out = g.mfV.p; pp.out_stride = d->mf_stride; pp.out_off = mf_taps - 1;
   RFM_PROF(g.prof, "k_rds_pll", st, launch_rds_pll(pp, st));
@@ -573,17 +614,13 @@ void EnqueueStageB(rfm_decoder* d, Group& g, const BlockGeom& bg, unsigned par, 
   sp.sync = {p.rsync.A1, p.rsync.A2, p.rsync.B0, p.rsync.B1, p.rsync.B2};
   sp.bits = g.bits.p; sp.bits_cap = d->bits_cap; sp.bit_count = g.bit_count.p;
   RFM_PROF(g.prof, "k_rds_slice", st, launch_rds_slice(sp, st));
-  g_launches += 4;
+  g_launches += 3;
 
-  // ---- in-place history carry of the stage-B buffers
+  // in-place history carry of the matched filter's input rows
   TailParams tp;
   tp.count = 0;
-  auto add = [&](void* base, size_t stride_elems, unsigned hist, unsigned n, unsigned elem) {
-    if (hist == 0)
-      return;
-    tp.d[tp.count++] = {base, base, stride_elems * elem, hist, n, elem, S};
-  };
-  add(g.mfV.p, d->mf_stride, mf_taps - 1, bg.nr, 4);
+  if (mf_taps > 1)
+    tp.d[tp.count++] = {g.mfV.p, g.mfV.p, d->mf_stride * sizeof(float), mf_taps - 1, bg.nr, 4, S};
   RFM_PROF(g.prof, "k_tails", st, launch_tails(tp, S, st));
   ++g_launches;
 }
@@ -689,6 +726,7 @@ int ProcessDevice(rfm_decoder* d, const void* d_in, size_t in_stride, bool u8, u
     // ---- stage A
     RFM_CUDA(cudaStreamWaitEvent(g.sA, g.ev_front[par], 0));
     RFM_CUDA(cudaStreamWaitEvent(g.sA, g.ev_rest[par3], 0)); // stage B of block k-3 has released bbV / rawV [par3]
+    RFM_CUDA(cudaStreamWaitEvent(g.sA, g.ev_aud[par], 0));    // ... and its audio tail (k-2 implies k-3) the stereo-flag slot
     if (!DebugSkip("lanes"))
       EnqueueStageA(d, g, bg, par, par3);
     RFM_CUDA(cudaEventRecord(g.ev_lanes[par], g.sA));
@@ -698,18 +736,23 @@ int ProcessDevice(rfm_decoder* d, const void* d_in, size_t in_stride, bool u8, u
       RFM_CUDA(cudaStreamWaitEvent(st, g.ev_lanes[par], 0));
       RFM_CUDA(cudaStreamWaitEvent(st, d->ev_osc[par3], 0));
     }
+    // lpS / lpM [par]: the audio tail of block k-2 has read them and block k-1 has carried its history out of them
+    // (both on sC, in that order)
+    RFM_CUDA(cudaStreamWaitEvent(g.sB, g.ev_carry[par ^ 1u], 0));
+    RFM_CUDA(cudaStreamWaitEvent(g.sR, g.ev_pll[par], 0)); // RDS PLL of block k-2 has released rlp_out [par]
     if (!DebugSkip("rest"))
-      EnqueueStageB(d, g, bg, par3, audio_dev, audio_stride_dev);
-    RFM_CUDA(cudaEventRecord(g.ev_rds[par3], g.sR));
-    RFM_CUDA(cudaStreamWaitEvent(g.sB, g.ev_rds[par3], 0)); // ev_rest (recorded on sB) covers both branches
+      EnqueueStageB(d, g, bg, par, par3, audio_dev, audio_stride_dev);
+    RFM_CUDA(cudaStreamWaitEvent(g.sB, g.ev_rds[par3], 0)); // ev_rest: both readers of bbV / rawV / oscV [par3] are done
+    RFM_CUDA(cudaEventRecord(g.ev_rest[par3], g.sB));
+    RFM_CUDA(cudaEventRecord(g.ev_pll[par], g.sP));
     if (host_staged)
     {
-      ProfScope ps_(d, g.prof, "copy_d2h", g.sB);
+      ProfScope ps_(d, g.prof, "copy_d2h", g.sC);
       RFM_CUDA(cudaMemcpy2DAsync(audio_g, audio_stride * sizeof(float), g.audio_stage.p,
                                  (size_t)d->audio_cap * sizeof(float), (size_t)2 * bg.na * sizeof(float), g.S,
-                                 cudaMemcpyDeviceToHost, g.sB));
+                                 cudaMemcpyDeviceToHost, g.sC));
     }
-    RFM_CUDA(cudaEventRecord(g.ev_rest[par3], g.sB));
+    RFM_CUDA(cudaEventRecord(g.ev_aud[par], g.sC));
   }
   RFM_CUDA(cudaGetLastError());
 
@@ -728,7 +771,8 @@ int ProcessDevice(rfm_decoder* d, const void* d_in, size_t in_stride, bool u8, u
     *n_audio_floats = 2 * bg.na;
   if (host_staged && host_sync)
     for (auto& g : d->groups)
-      RFM_CUDA(cudaStreamSynchronize(g.sB)); // the last stage: everything before it has completed too
+      RFM_CUDA(cudaStreamSynchronize(g.sC)); // the audio is on the host (the RDS branch may still be running: the
+                                             // rds_take_* entry points synchronise it)
   return RFM_OK;
 }
 
@@ -747,9 +791,13 @@ int SyncAll(rfm_decoder* d)
 {
   RFM_CUDA(cudaSetDevice(d->device));
   for (auto& g : d->groups)
-    for (cudaStream_t st : {g.sF, g.sA, g.sB, g.sR})
+  {
+    cudaStream_t all[6];
+    g.AllStreams(all);
+    for (cudaStream_t st : all)
       if (st)
         RFM_CUDA(cudaStreamSynchronize(st));
+  }
   RFM_CUDA(cudaStreamSynchronize(d->s_osc));
   return RFM_OK;
 }
@@ -913,6 +961,7 @@ int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out)
       const char* flow = getenv("RFM_DEBUG_FLOW");
       const int mode = flow ? atoi(flow) : 0;
       int pA = prio_hi, pF = std::min(prio_lo, prio_hi + 1), pB = prio_lo;
+      int pL = getenv("RFM_DEBUG_LANEPRIO") ? atoi(getenv("RFM_DEBUG_LANEPRIO")) + prio_hi : prio_hi; // small lane kernels of stage B
       if (mode == 1) { pF = prio_lo; }
       if (mode == 2) { pF = prio_lo; pB = std::min(prio_lo, prio_hi + 1); }
       if (mode == 3) { pA = prio_lo; pF = prio_lo; pB = prio_hi; }
@@ -920,10 +969,12 @@ int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out)
       RFM_TRY(cudaStreamCreateWithPriority(&g.sF, cudaStreamNonBlocking, pF));
       RFM_TRY(cudaStreamCreateWithPriority(&g.sB, cudaStreamNonBlocking, pB));
       RFM_TRY(cudaStreamCreateWithPriority(&g.sR, cudaStreamNonBlocking, pB));
+      RFM_TRY(cudaStreamCreateWithPriority(&g.sC, cudaStreamNonBlocking, pL));
+      RFM_TRY(cudaStreamCreateWithPriority(&g.sP, cudaStreamNonBlocking, pL));
       if (getenv("RFM_DEBUG_SERIAL"))
       { // measurement aid: every stage on ONE stream, so per-kernel event times are isolated durations
-        cudaStreamDestroy(g.sF); cudaStreamDestroy(g.sB); cudaStreamDestroy(g.sR);
-        g.sF = g.sB = g.sR = g.sA;
+        cudaStreamDestroy(g.sF); cudaStreamDestroy(g.sB); cudaStreamDestroy(g.sR); cudaStreamDestroy(g.sC); cudaStreamDestroy(g.sP);
+        g.sF = g.sB = g.sR = g.sC = g.sP = g.sA;
       }
     }
     for (int b = 0; b < 2; ++b)
@@ -931,6 +982,13 @@ int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out)
       RFM_TRY(cudaEventCreateWithFlags(&g.ev_front[b], cudaEventDisableTiming));
       RFM_TRY(cudaEventCreateWithFlags(&g.ev_demod[b], cudaEventDisableTiming));
       RFM_TRY(cudaEventCreateWithFlags(&g.ev_lanes[b], cudaEventDisableTiming));
+      RFM_TRY(cudaEventCreateWithFlags(&g.ev_res[b], cudaEventDisableTiming));
+      RFM_TRY(cudaEventCreateWithFlags(&g.ev_aud[b], cudaEventDisableTiming));
+      RFM_TRY(cudaEventCreateWithFlags(&g.ev_carry[b], cudaEventDisableTiming));
+      RFM_TRY(cudaEventCreateWithFlags(&g.ev_pll[b], cudaEventDisableTiming));
+      RFM_TRY(g.rlp_out[b].Alloc(S * d->nr_stride));
+      RFM_TRY(g.lpS[b].Alloc(S * d->lp_stride));
+      RFM_TRY(g.lpM[b].Alloc(S * d->lp_stride));
     }
     RFM_TRY(g.tail.Alloc(S * p.in_order));
     RFM_TRY(g.z[0].Alloc(S * d->z_stride));
@@ -947,15 +1005,12 @@ int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out)
       RFM_TRY(cudaEventCreateWithFlags(&g.ev_rds[b], cudaEventDisableTiming));
     }
 
-    RFM_TRY(g.rlpV.Alloc(S * d->nr_stride));
+    RFM_TRY(g.rlpV.Alloc(S * d->rlp_stride));
     RFM_TRY(g.rds_tails.Alloc(S * d->rds_tail_stride));
-    RFM_TRY(g.rlp_out.Alloc(S * d->nr_stride));
     RFM_TRY(g.mfV.Alloc(S * d->mf_stride));
     RFM_TRY(g.mf_out.Alloc(S * d->nr_stride));
     RFM_TRY(g.bits.Alloc(S * d->bits_cap));
     RFM_TRY(g.bit_count.Alloc(S));
-    RFM_TRY(g.lpS.Alloc(S * d->lp_stride));
-    RFM_TRY(g.lpM.Alloc(S * d->lp_stride));
     RFM_TRY(g.fS.Alloc(S * d->na_max));
     RFM_TRY(g.fM.Alloc(S * d->na_max));
     RFM_TRY(g.state.Alloc(S * SF_COUNT));
@@ -1077,11 +1132,15 @@ int rfm_decoder_wait(rfm_decoder* d, void* cuda_stream)
   RFM_CUDA(cudaSetDevice(d->device));
   cudaStream_t user = static_cast<cudaStream_t>(cuda_stream);
   for (auto& g : d->groups)
-    for (cudaStream_t st : {g.sF, g.sA, g.sB, g.sR})
+  {
+    cudaStream_t all[6];
+    g.AllStreams(all);
+    for (cudaStream_t st : all)
     {
       RFM_CUDA(cudaEventRecord(d->ev_join, st));
       RFM_CUDA(cudaStreamWaitEvent(user, d->ev_join, 0));
     }
+  }
   return RFM_OK;
 }
 
@@ -1149,9 +1208,12 @@ int rfm_decoder_get_status(rfm_decoder* d, uint32_t stream, rfm_stream_status* o
   unsigned ls = 0;
   Group* g = FindGroup(d, stream, &ls);
   RFM_CUDA(cudaSetDevice(d->device));
-  RFM_CUDA(cudaStreamSynchronize(g->sF));
-  RFM_CUDA(cudaStreamSynchronize(g->sA));
-  RFM_CUDA(cudaStreamSynchronize(g->sB));
+  {
+    cudaStream_t all[6];
+    g->AllStreams(all);
+    for (cudaStream_t st : all)
+      RFM_CUDA(cudaStreamSynchronize(st));
+  }
   float v[SF_COUNT];
   RFM_CUDA(cudaMemcpy2D(v, sizeof(float), g->state.p + ls, (size_t)g->S * sizeof(float), sizeof(float), SF_COUNT,
                         cudaMemcpyDeviceToHost));
@@ -1314,12 +1376,12 @@ int rfm_decoder_tap(rfm_decoder* d, const char* name, uint32_t stream, float* ou
   if (nm == "demod_in") { src = g->z[lastpar].p + (size_t)ls * d->z_stride; cnt = 2 * (size_t)d->last_nb; }
   else if (nm == "baseband") { src = g->bbV[lastpar3].p + (size_t)ls * d->a_stride + p.a_order; cnt = d->last_nb; }
   else if (nm == "rawstereo") { src = g->rawV[lastpar3].p + (size_t)ls * d->a_stride + p.a_order; cnt = d->last_nb; }
-  else if (nm == "mono_rs") { src = g->lpM.p + (size_t)ls * d->lp_stride + p.lp_coef.size() - 1; cnt = d->last_na; }
-  else if (nm == "stereo_rs") { src = g->lpS.p + (size_t)ls * d->lp_stride + p.lp_coef.size() - 1; cnt = d->last_na; }
+  else if (nm == "mono_rs") { src = g->lpM[(d->block_index + 1) & 1u].p + (size_t)ls * d->lp_stride + p.lp_coef.size() - 1; cnt = d->last_na; }
+  else if (nm == "stereo_rs") { src = g->lpS[(d->block_index + 1) & 1u].p + (size_t)ls * d->lp_stride + p.lp_coef.size() - 1; cnt = d->last_na; }
   else if (nm == "lp_stereo") { src = g->fS.p + (size_t)ls * d->na_max; cnt = d->last_na; }
   else if (nm == "lp_mono") { src = g->fM.p + (size_t)ls * d->na_max; cnt = d->last_na; }
-  else if (nm == "rds_dec") { src = g->rlpV.p + (size_t)ls * d->nr_stride; cnt = 2 * (size_t)d->last_nr; }
-  else if (nm == "rds_lp") { src = g->rlp_out.p + (size_t)ls * d->nr_stride; cnt = 2 * (size_t)d->last_nr; }
+  else if (nm == "rds_dec") { src = g->rlpV.p + (size_t)ls * d->rlp_stride + p.rlp_coef.size() - 1; cnt = 2 * (size_t)d->last_nr; }
+  else if (nm == "rds_lp") { src = g->rlp_out[(d->block_index + 1) & 1u].p + (size_t)ls * d->nr_stride; cnt = 2 * (size_t)d->last_nr; }
   else if (nm == "rds_pll") { src = g->mfV.p + (size_t)ls * d->mf_stride + p.mf_coef.size() - 1; cnt = d->last_nr; }
   else if (nm == "rds_mf") { src = g->mf_out.p + (size_t)ls * d->nr_stride; cnt = d->last_nr; }
   else

@@ -1288,10 +1288,226 @@ __global__ void __launch_bounds__(kFirTile) k_rotfir(RotFirParams p)
   }
 }
 
+// --------------------------------------------------------------------------------------------------
+// Lane = stream form of the same filter.  All streams of a decoder are in lock step, so the rotation
+// k0 = (g0 + i) mod N of output i is the same for the 32 streams of a warp: taps become warp-uniform (one broadcast
+// LDS), no per-lane modulo, and four consecutive outputs i .. i+3 whose rotations k0 .. k0+3 do not wrap share their
+// samples.  Output i + r walks taps k0+r .. N-1 and then 0 .. k0+r-1 (the reference's buffer order), i.e. samples
+//   phase 1:  V[N-1 + i - k0 - m],  m = 0 .. N-1-k0-r     tap k0 + r + m
+//   phase 2:  V[N-1 + i + r - k],   k = 0 .. k0+r-1       tap k
+// so the four outputs read the same sample at the same phase-1 step m, output r just stops r steps earlier, and in
+// phase 2 output r starts r samples later: both phases are a common main loop (one sample LDS + one new tap per
+// step, 4 x (mul, add) per channel) plus a 3-step triangle.  Every output receives exactly the reference's
+// products in the reference's order (FirFilter.cpp:330-413) -- no zero padding, nothing reassociated.
+// A CTA covers 32 streams x `cyc` whole rotation cycles (N outputs each, cut in G = g0 + i space so that groups of
+// four never straddle a wrap); leftovers (N mod 4 outputs per cycle, block edges) take the one-output path.
+// --------------------------------------------------------------------------------------------------
+constexpr unsigned kRlWarps = 4;
+
+template <int MODE> // 0 real, 1 real pair, 2 complex
+__global__ void __launch_bounds__(32 * kRlWarps) k_rotfir_lanes(RotFirParams p, unsigned cyc, unsigned pitch)
+{
+  extern __shared__ __align__(16) float rl_smem[];
+  float* s_h = rl_smem;                                  // [N + 4]
+  float* X = rl_smem + ((p.taps + 4 + 3) & ~3u);         // MODE 0: [32][pitch]; 1: [2][32][pitch]; 2: float2 [32][pitch]
+  const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const int N = (int)p.taps;
+  const unsigned s0 = blockIdx.y * 32;
+  const unsigned rows = min(32u, p.S - s0);
+  // tile = cycles [blockIdx.x * cyc, +cyc) counted from the cycle that holds output 0
+  const int ia_raw = (int)(blockIdx.x * cyc) * N - (int)(p.g0 % (unsigned)N);
+  const int ia = max(ia_raw, 0), ib = min(ia_raw + (int)cyc * N, (int)p.n);
+  if (ia >= ib)
+    return;
+  for (int i = tid; i < N + 4; i += 32 * kRlWarps)
+    s_h[i] = i < N ? p.coef[i] : 0.0f;
+  const int wlen = ib - ia + N - 1; // V[ia .. ia + wlen)
+  for (unsigned r = warp; r < rows; r += kRlWarps)
+  {
+    if (MODE == 2)
+    {
+      const float2* src = reinterpret_cast<const float2*>(p.inA) + (size_t)(s0 + r) * p.in_stride + ia;
+      float2* dst = reinterpret_cast<float2*>(X) + (size_t)r * pitch;
+      for (int c = lane; c < wlen; c += 32)
+        dst[c] = src[c];
+    }
+    else
+    {
+      const float* src = p.inA + (size_t)(s0 + r) * p.in_stride + ia;
+      float* dst = X + (size_t)r * pitch;
+      for (int c = lane; c < wlen; c += 32)
+        dst[c] = src[c];
+      if (MODE == 1)
+      {
+        const float* srcb = p.inB + (size_t)(s0 + r) * p.in_stride + ia;
+        float* dstb = X + (size_t)(32 + r) * pitch;
+        for (int c = lane; c < wlen; c += 32)
+          dstb[c] = srcb[c];
+      }
+    }
+  }
+  __syncthreads();
+  if (lane >= rows)
+    return;
+  const float* xa = X + (size_t)lane * pitch;
+  const float* xb = X + (size_t)(32 + lane) * pitch;
+  const float2* xc = reinterpret_cast<const float2*>(X) + (size_t)lane * pitch;
+  auto ld = [&](int col) -> float2 {
+    if (MODE == 2)
+      return xc[col];
+    if (MODE == 1)
+      return make_float2(xa[col], xb[col]);
+    return make_float2(xa[col], 0.0f);
+  };
+  constexpr bool TWO = MODE != 0;
+  const int gpc = (N + 3) / 4;
+  const int total = (int)cyc * gpc;
+  for (int gi = warp; gi < total; gi += kRlWarps)
+  {
+    const int cy = gi / gpc;
+    const int k0 = (gi - cy * gpc) * 4;
+    const int R = min(4, N - k0);
+    const int i0 = ia_raw + cy * N + k0; // output index of r = 0
+    if (R == 4 && i0 >= ia && i0 + 3 < ib)
+    {
+      const int col0 = i0 - ia + N - 1; // column of V[N-1 + i0]
+      float2 a0, a1, a2, a3;
+      float w0 = s_h[k0], w1 = s_h[k0 + 1], w2 = s_h[k0 + 2], w3 = s_h[k0 + 3];
+      const int M1 = N - k0 - 3;
+      int col = col0 - k0;
+      {
+        const float2 x = ld(col);
+        a0.x = mulf(w0, x.x); a1.x = mulf(w1, x.x); a2.x = mulf(w2, x.x); a3.x = mulf(w3, x.x);
+        if (TWO) { a0.y = mulf(w0, x.y); a1.y = mulf(w1, x.y); a2.y = mulf(w2, x.y); a3.y = mulf(w3, x.y); }
+      }
+#define RL_STEP4(x)                                                                                           \
+  a0.x = addf(a0.x, mulf(w0, (x).x)); a1.x = addf(a1.x, mulf(w1, (x).x));                                     \
+  a2.x = addf(a2.x, mulf(w2, (x).x)); a3.x = addf(a3.x, mulf(w3, (x).x));                                     \
+  if (TWO) { a0.y = addf(a0.y, mulf(w0, (x).y)); a1.y = addf(a1.y, mulf(w1, (x).y));                          \
+             a2.y = addf(a2.y, mulf(w2, (x).y)); a3.y = addf(a3.y, mulf(w3, (x).y)); }
+#pragma unroll 4
+      for (int m = 1; m < M1; ++m)
+      {
+        w0 = w1; w1 = w2; w2 = w3; w3 = s_h[k0 + m + 3];
+        const float2 x = ld(col - m);
+        RL_STEP4(x)
+      }
+      col -= M1;
+      { // phase-1 triangle: taps (N-3, N-2, N-1), (N-2, N-1), (N-1) = (w1, w2, w3), (w2, w3), (w3)
+        float2 x = ld(col);
+        a0.x = addf(a0.x, mulf(w1, x.x)); a1.x = addf(a1.x, mulf(w2, x.x)); a2.x = addf(a2.x, mulf(w3, x.x));
+        if (TWO) { a0.y = addf(a0.y, mulf(w1, x.y)); a1.y = addf(a1.y, mulf(w2, x.y)); a2.y = addf(a2.y, mulf(w3, x.y)); }
+        x = ld(col - 1);
+        a0.x = addf(a0.x, mulf(w2, x.x)); a1.x = addf(a1.x, mulf(w3, x.x));
+        if (TWO) { a0.y = addf(a0.y, mulf(w2, x.y)); a1.y = addf(a1.y, mulf(w3, x.y)); }
+        x = ld(col - 2);
+        a0.x = addf(a0.x, mulf(w3, x.x));
+        if (TWO) { a0.y = addf(a0.y, mulf(w3, x.y)); }
+      }
+      w0 = s_h[0]; w1 = s_h[1]; w2 = s_h[2]; w3 = s_h[3];
+      { // phase-2 triangle: samples V[N-1 + i0 + 3], + 2, + 1
+        float2 x = ld(col0 + 3);
+        a3.x = addf(a3.x, mulf(w0, x.x));
+        if (TWO) { a3.y = addf(a3.y, mulf(w0, x.y)); }
+        x = ld(col0 + 2);
+        a2.x = addf(a2.x, mulf(w0, x.x)); a3.x = addf(a3.x, mulf(w1, x.x));
+        if (TWO) { a2.y = addf(a2.y, mulf(w0, x.y)); a3.y = addf(a3.y, mulf(w1, x.y)); }
+        x = ld(col0 + 1);
+        a1.x = addf(a1.x, mulf(w0, x.x)); a2.x = addf(a2.x, mulf(w1, x.x)); a3.x = addf(a3.x, mulf(w2, x.x));
+        if (TWO) { a1.y = addf(a1.y, mulf(w0, x.y)); a2.y = addf(a2.y, mulf(w1, x.y)); a3.y = addf(a3.y, mulf(w2, x.y)); }
+      }
+#pragma unroll 4
+      for (int u = 0; u < k0; ++u)
+      {
+        const float2 x = ld(col0 - u);
+        RL_STEP4(x)
+        w0 = w1; w1 = w2; w2 = w3; w3 = s_h[u + 4];
+      }
+#undef RL_STEP4
+      const size_t o = (size_t)(s0 + lane) * p.out_stride + p.out_off + (unsigned)i0;
+      if (MODE == 2)
+      {
+        float2* out = reinterpret_cast<float2*>(p.outA) + o;
+        out[0] = a0; out[1] = a1; out[2] = a2; out[3] = a3;
+      }
+      else
+      {
+        p.outA[o] = a0.x; p.outA[o + 1] = a1.x; p.outA[o + 2] = a2.x; p.outA[o + 3] = a3.x;
+        if (MODE == 1)
+        {
+          p.outB[o] = a0.y; p.outB[o + 1] = a1.y; p.outB[o + 2] = a2.y; p.outB[o + 3] = a3.y;
+        }
+      }
+      continue;
+    }
+    for (int r = 0; r < R; ++r)
+    {
+      const int i = i0 + r;
+      if (i < ia || i >= ib)
+        continue;
+      const int kr = k0 + r;
+      const int colx = i - ia + N - 1;
+      float2 x = ld(colx - kr);
+      float c = s_h[kr];
+      float2 a;
+      a.x = mulf(c, x.x);
+      a.y = TWO ? mulf(c, x.y) : 0.0f;
+      int k = kr;
+      for (int j = 1; j < N; ++j)
+      {
+        k = (k + 1 == N) ? 0 : k + 1;
+        x = ld(colx - k);
+        c = s_h[k];
+        a.x = addf(a.x, mulf(c, x.x));
+        if (TWO)
+          a.y = addf(a.y, mulf(c, x.y));
+      }
+      const size_t o = (size_t)(s0 + lane) * p.out_stride + p.out_off + (unsigned)i;
+      if (MODE == 2)
+        reinterpret_cast<float2*>(p.outA)[o] = a;
+      else
+      {
+        p.outA[o] = a.x;
+        if (MODE == 1)
+          p.outB[o] = a.y;
+      }
+    }
+  }
+}
+
+template <int MODE>
+static void launch_rotfir_lanes(const RotFirParams& p, cudaStream_t st)
+{
+  const unsigned N = p.taps;
+  const unsigned cyc = std::max(1u, (128u + N / 2) / N); // ~128 outputs per CTA
+  const unsigned pitch = (cyc * N + N - 1) | 1u;        // odd: lanes (rows) hit distinct banks
+  const size_t smem = (((N + 4 + 3) & ~3u) + (size_t)(MODE == 0 ? 1 : 2) * 32 * pitch) * sizeof(float);
+  static size_t attr = 0;
+  if (smem > attr)
+  {
+    cudaFuncSetAttribute(k_rotfir_lanes<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = smem;
+  }
+  const unsigned cycles = (p.g0 % N + p.n + N - 1) / N;
+  dim3 grid(cdiv(cycles, cyc), cdiv(p.S, 32));
+  k_rotfir_lanes<MODE><<<grid, 32 * kRlWarps, smem, st>>>(p, cyc, pitch);
+}
+
 void launch_rotfir(const RotFirParams& p, cudaStream_t st)
 {
   if (p.n == 0 || p.S == 0)
     return;
+  static const bool old_form = getenv("RFM_ROTFIR_OLD") != nullptr; // measurement aid
+  if (p.taps >= 8 && !old_form)
+  {
+    if (p.cplx)
+      launch_rotfir_lanes<2>(p, st);
+    else if (p.inB)
+      launch_rotfir_lanes<1>(p, st);
+    else
+      launch_rotfir_lanes<0>(p, st);
+    return;
+  }
   dim3 grid(cdiv(p.n, kFirOut), p.S);
   if (p.cplx)
     k_rotfir<2><<<grid, kFirTile, 0, st>>>(p);
@@ -1472,8 +1688,11 @@ __global__ void __launch_bounds__(kRfThreads) k_rds_front(RdsFrontParams p)
   for (unsigned i = tid; i < p.lp_n; i += kRfThreads)
     s_lp[i] = p.lp_coef[i];
   // histories from the previous block
+  const bool ext_lp = p.lp_v != nullptr;           // the LP runs as its own kernel on lp_v
+  const unsigned nbuf = ext_lp ? p.nst : p.nst + 1; // V buffers with a carried history
+  float2* lpv = ext_lp ? reinterpret_cast<float2*>(p.lp_v) + (size_t)blockIdx.x * p.lp_v_stride + (p.lp_n - 1) : nullptr;
   float2* tails = reinterpret_cast<float2*>(p.tails) + (size_t)s * p.tail_stride;
-  for (unsigned k = 0; k <= p.nst; ++k)
+  for (unsigned k = 0; k < nbuf; ++k)
   {
     const unsigned hist = (k < p.nst) ? p.st[k].hist : p.lp_n - 1;
     for (unsigned i = tid; i < hist; i += kRfThreads)
@@ -1506,10 +1725,14 @@ __global__ void __launch_bounds__(kRfThreads) k_rds_front(RdsFrontParams p)
       const unsigned nout = n >> 1;
       const unsigned ohist = (k + 1 < p.nst) ? p.st[k + 1].hist : N - 1;
       const bool last = (k + 1 == p.nst) && p.dec_out != nullptr;
+      const bool to_lpv = (k + 1 == p.nst) && ext_lp;
       for (unsigned o = tid; o < nout; o += kRfThreads)
       {
         const float2 v = hb_out(p.st[k].kind, p.st[k].len, s_h + hoff[k], B[k], o);
-        B[k + 1][ohist + o] = v;
+        if (to_lpv)
+          lpv[out_base + o] = v;
+        else
+          B[k + 1][ohist + o] = v;
         if (last) // decimator output (cRDSRxSignalProcessor's m_RdsRaw before the LP), kept for the stage taps
           reinterpret_cast<float2*>(p.dec_out)[(size_t)s * p.out_stride + out_base + o] = v;
       }
@@ -1517,7 +1740,7 @@ __global__ void __launch_bounds__(kRfThreads) k_rds_front(RdsFrontParams p)
       n = nout;
     }
     // LP with cFirFilter's rotating summation start: y[g] = sum_j h[k_j] x[g - k_j], k_j = (g + j) mod N
-    for (unsigned i = tid; i < n; i += kRfThreads)
+    for (unsigned i = tid; i < n && !ext_lp; i += kRfThreads)
     {
       unsigned k = (p.g0 + out_base + i) % N;
       const float2* x = B[p.nst] + (N - 1) + i;
@@ -1540,7 +1763,7 @@ __global__ void __launch_bounds__(kRfThreads) k_rds_front(RdsFrontParams p)
     // carry the histories: last `hist` entries of [hist | n_k] to the front
     {
       unsigned nk = tn;
-      for (unsigned k = 0; k <= p.nst; ++k)
+      for (unsigned k = 0; k < nbuf; ++k)
       {
         const unsigned hist = (k < p.nst) ? p.st[k].hist : N - 1;
         float2 v0 = make_float2(0.f, 0.f);
@@ -1554,7 +1777,7 @@ __global__ void __launch_bounds__(kRfThreads) k_rds_front(RdsFrontParams p)
     }
     __syncthreads();
   }
-  for (unsigned k = 0; k <= p.nst; ++k)
+  for (unsigned k = 0; k < nbuf; ++k)
   {
     const unsigned hist = (k < p.nst) ? p.st[k].hist : p.lp_n - 1;
     for (unsigned i = tid; i < hist; i += kRfThreads)
