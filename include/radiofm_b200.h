@@ -119,6 +119,11 @@ RFM_API int rfm_decoder_rds_take_groups(rfm_decoder* d, uint32_t stream, uint16_
                                         uint32_t max_groups, uint32_t* n_groups);
 RFM_API int rfm_decoder_rds_take_bits(rfm_decoder* d, uint32_t stream, uint8_t* bits, uint32_t max_bits,
                                       uint32_t* n_bits);
+/* The UECP byte stream the add-on publishes on its RDS PID: every decoded group of the stream goes through the
+ * stream's own group decoder (cRDSGroupDecoder::DecodeRDS, RDSGroupDecoder.cpp:166-272, see rfm_rdsgroup below) the
+ * moment the block synchroniser delivers it, the frames are framed as cRadioReceiver::AddUECPDataFrame does
+ * (RadioReceiver.cpp:387-414).  Independent of rfm_decoder_rds_take_groups: both see every group once. */
+RFM_API int rfm_decoder_rds_take_uecp(rfm_decoder* d, uint32_t stream, uint8_t* out, uint32_t cap, uint32_t* n_bytes);
 
 typedef struct rfm_stream_status
 {
@@ -337,6 +342,36 @@ RFM_API int rfm_rdssync_push_bits(rfm_rdssync* s, const uint8_t* bits, uint32_t 
 RFM_API int rfm_rdssync_take_groups(rfm_rdssync* s, uint16_t* groups, uint32_t max_groups, uint32_t* n_groups);
 /* cRDSRxSignalProcessor::CheckBlock, RDSProcess.cpp:377-431 */
 RFM_API uint32_t rfm_rds_check_block(uint32_t word26, uint32_t offset_syndrome, int use_fec, uint32_t* corrected);
+
+/* ------------------------------------------------------------------------------------------------
+ * RDS groups -> UECP frames (host integer code): cRDSGroupDecoder(cRadioReceiver*), Reset(), DecodeRDS(uint16_t*)
+ * (RDSGroupDecoder.h:24-31, RDSGroupDecoder.cpp:136-1001 with the reference's default build macros).
+ * The callbacks are the three calls the reference makes on its cRadioReceiver from inside DecodeRDS
+ * (RadioReceiver.h:77,80,115); any of them may be NULL:
+ *   add_uecp_frame    NULL: frames collect inside the object in the transport framing of
+ *                     cRadioReceiver::AddUECPDataFrame (0xFE, byte stuffing, 0xFF) -> rfm_rdsgroup_take_uecp
+ *   set_channel_name  NULL: every name is accepted (RadioReceiver.cpp:600-612 without a settings dialog) and kept
+ *                     -> rfm_rdsgroup_channel_name
+ *   is_setting_active NULL: never active
+ * Members the reference leaves uninitialised (m_PTY, m_DI_Finished, m_RadioText_ABFlag, m_PTYN_ABFlag,
+ * m_UECPDataFrameSeqCnt) start at zero here; its function-static PS buffer is per object.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rfm_rdsgroup rfm_rdsgroup;
+typedef struct rfm_rdsgroup_callbacks
+{
+  void* user;
+  int (*add_uecp_frame)(void* user, const uint8_t* frame, uint32_t len);
+  int (*set_channel_name)(void* user, const char* name8); /* nonzero: accepted */
+  int (*is_setting_active)(void* user);
+} rfm_rdsgroup_callbacks;
+RFM_API int rfm_rdsgroup_create(const rfm_rdsgroup_callbacks* cb /* may be NULL */, rfm_rdsgroup** out);
+RFM_API void rfm_rdsgroup_destroy(rfm_rdsgroup* g);
+RFM_API void rfm_rdsgroup_reset(rfm_rdsgroup* g);
+RFM_API int rfm_rdsgroup_decode(rfm_rdsgroup* g, const uint16_t* blocks /* [n_groups][4] */, uint32_t n_groups);
+RFM_API int rfm_rdsgroup_take_uecp(rfm_rdsgroup* g, uint8_t* out, uint32_t cap, uint32_t* n_bytes);
+RFM_API int rfm_rdsgroup_channel_name(const rfm_rdsgroup* g, char out[9]);
+/* cRadioReceiver::AddUECPDataFrame's framing alone; returns the framed length (written only when it fits cap) */
+RFM_API uint32_t rfm_uecp_stuff_frame(const uint8_t* frame, uint32_t len, uint8_t* out, uint32_t cap);
 
 #ifdef __cplusplus
 }

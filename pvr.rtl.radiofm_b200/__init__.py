@@ -17,7 +17,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libradiofm_b200.so")
+LIB_PATH = os.environ.get("RFM_LIB_PATH") or os.path.join(_HERE, "libradiofm_b200.so")  # override: tuning experiments
 
 RFM_OK = 0
 _u8p = C.POINTER(C.c_uint8)
@@ -44,7 +44,9 @@ EXPORTED_SYMBOLS = (
     "rfm_decoder_destroy", "rfm_decoder_reset", "rfm_decoder_max_audio_floats", "rfm_decoder_process_u8",
     "rfm_decoder_process_cf32", "rfm_decoder_submit_u8", "rfm_decoder_process_u8_device", "rfm_decoder_process_cf32_device", "rfm_decoder_wait",
     "rfm_decoder_synchronize", "rfm_decoder_demod_repairs",
-    "rfm_decoder_rds_take_groups", "rfm_decoder_rds_take_bits", "rfm_decoder_get_status",
+    "rfm_decoder_rds_take_groups", "rfm_decoder_rds_take_bits", "rfm_decoder_rds_take_uecp", "rfm_decoder_get_status",
+    "rfm_rdsgroup_create", "rfm_rdsgroup_destroy", "rfm_rdsgroup_reset", "rfm_rdsgroup_decode", "rfm_rdsgroup_take_uecp",
+    "rfm_rdsgroup_channel_name", "rfm_uecp_stuff_frame",
     "rfm_decoder_constants", "rfm_decoder_table", "rfm_plan_constants", "rfm_plan_table", "rfm_decoder_set_profiling",
     "rfm_decoder_profile_read", "rfm_decoder_tap", "rfm_rdssync_create",
     "rfm_rdssync_destroy", "rfm_rdssync_reset", "rfm_rdssync_push_bits", "rfm_rdssync_take_groups",
@@ -63,6 +65,17 @@ EXPORTED_SYMBOLS = (
     "rfm_rdsproc_create", "rfm_rdsproc_destroy", "rfm_rdsproc_process_rate", "rfm_rdsproc_reset", "rfm_rdsproc_process",
     "rfm_rdsproc_process_device", "rfm_rdsproc_take_bits", "rfm_rdsproc_take_groups",
 )
+
+
+_ADD_FRAME_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint8), C.c_uint32)
+_SET_NAME_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_char_p)
+_SETTING_CB = C.CFUNCTYPE(C.c_int, C.c_void_p)
+
+
+class RdsGroupCallbacks(C.Structure):
+    """rfm_rdsgroup_callbacks (include/radiofm_b200.h)."""
+    _fields_ = [("user", C.c_void_p), ("add_uecp_frame", _ADD_FRAME_CB), ("set_channel_name", _SET_NAME_CB),
+                ("is_setting_active", _SETTING_CB)]
 
 
 class RadioFmError(RuntimeError):
@@ -108,6 +121,15 @@ def lib():
         L.rfm_decoder_synchronize.argtypes = [C.c_void_p]
         L.rfm_decoder_demod_repairs.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.rfm_decoder_rds_take_groups.argtypes = [C.c_void_p, C.c_uint32, _u16p, C.c_uint32, _u32p]
+        L.rfm_decoder_rds_take_uecp.argtypes = [C.c_void_p, C.c_uint32, _u8p, C.c_uint32, _u32p]
+        L.rfm_rdsgroup_create.argtypes = [C.POINTER(RdsGroupCallbacks), C.POINTER(C.c_void_p)]
+        L.rfm_rdsgroup_destroy.argtypes = [C.c_void_p]
+        L.rfm_rdsgroup_reset.argtypes = [C.c_void_p]
+        L.rfm_rdsgroup_decode.argtypes = [C.c_void_p, _u16p, C.c_uint32]
+        L.rfm_rdsgroup_take_uecp.argtypes = [C.c_void_p, _u8p, C.c_uint32, _u32p]
+        L.rfm_rdsgroup_channel_name.argtypes = [C.c_void_p, C.c_char_p]
+        L.rfm_uecp_stuff_frame.restype = C.c_uint32
+        L.rfm_uecp_stuff_frame.argtypes = [_u8p, C.c_uint32, _u8p, C.c_uint32]
         L.rfm_decoder_rds_take_bits.argtypes = [C.c_void_p, C.c_uint32, _u8p, C.c_uint32, _u32p]
         L.rfm_decoder_get_status.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(RfmStreamStatus)]
         L.rfm_decoder_constants.argtypes = [C.c_void_p, _f64p, C.c_uint32]
@@ -305,6 +327,13 @@ class FmDecoderBatch:
         _check(lib().rfm_decoder_synchronize(self._h))
 
     # ---- RDS / telemetry ----
+    def take_uecp(self, stream: int = 0, cap: int = 1 << 16) -> bytes:
+        """UECP byte stream of the stream's group decoder (cRDSGroupDecoder + AddUECPDataFrame framing)."""
+        out = np.zeros(cap, dtype=np.uint8)
+        k = C.c_uint32(0)
+        _check(lib().rfm_decoder_rds_take_uecp(self._h, stream, _p(out, _u8p), cap, C.byref(k)))
+        return out[:k.value].tobytes()
+
     def take_groups(self, stream: int = 0, max_groups: int = 4096) -> np.ndarray:
         out = np.zeros((max_groups, 4), dtype=np.uint16)
         k = C.c_uint32(0)
@@ -389,6 +418,59 @@ class RdsBlockSync:
         k = C.c_uint32(0)
         _check(lib().rfm_rdssync_take_groups(self._h, _p(out, _u16p), max_groups, C.byref(k)))
         return out[:k.value].copy()
+
+
+class RdsGroupDecoder:
+    """cRDSGroupDecoder (RDSGroupDecoder.cpp:136-1001) on the host: RDS groups -> UECP frames.
+
+    Without callbacks the frames collect in the transport framing of cRadioReceiver::AddUECPDataFrame
+    (take_uecp).  With `on_frame(bytes)`, `on_name(bytes) -> bool`, `setting_active() -> bool` they are the three
+    calls the reference makes on its cRadioReceiver."""
+
+    def __init__(self, on_frame=None, on_name=None, setting_active=None):
+        self._h = C.c_void_p()
+        self._cb = RdsGroupCallbacks()
+        if on_frame is not None:
+            self._cb.add_uecp_frame = _ADD_FRAME_CB(lambda u, f, n: int(bool(on_frame(bytes(f[:n])) or True)))
+        if on_name is not None:
+            self._cb.set_channel_name = _SET_NAME_CB(lambda u, s: int(bool(on_name(s))))
+        if setting_active is not None:
+            self._cb.is_setting_active = _SETTING_CB(lambda u: int(bool(setting_active())))
+        have = on_frame is not None or on_name is not None or setting_active is not None
+        _check(lib().rfm_rdsgroup_create(C.byref(self._cb) if have else None, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().rfm_rdsgroup_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reset(self):
+        lib().rfm_rdsgroup_reset(self._h)
+
+    def decode(self, groups: np.ndarray):
+        g = np.ascontiguousarray(groups, dtype=np.uint16).reshape(-1, 4)
+        _check(lib().rfm_rdsgroup_decode(self._h, _p(g, _u16p), g.shape[0]))
+
+    def take_uecp(self, cap: int = 1 << 16) -> bytes:
+        out = np.zeros(cap, dtype=np.uint8)
+        k = C.c_uint32(0)
+        _check(lib().rfm_rdsgroup_take_uecp(self._h, _p(out, _u8p), cap, C.byref(k)))
+        return out[:k.value].tobytes()
+
+    def channel_name(self) -> bytes:
+        buf = C.create_string_buffer(9)
+        _check(lib().rfm_rdsgroup_channel_name(self._h, buf))
+        return buf.raw[:8]
+
+
+def uecp_stuff_frame(frame: bytes) -> bytes:
+    """cRadioReceiver::AddUECPDataFrame's framing (RadioReceiver.cpp:387-414)."""
+    src = np.frombuffer(frame, dtype=np.uint8)
+    out = np.zeros(2 * len(frame) + 2, dtype=np.uint8)
+    n = lib().rfm_uecp_stuff_frame(_p(src, _u8p) if len(frame) else None, len(frame), _p(out, _u8p), out.size)
+    return out[:n].tobytes()
 
 
 class FreqShiftBatch:

@@ -29,6 +29,7 @@
 #include "../../include/radiofm_b200.h"
 #include "rfm_kernels.cuh"
 #include "rfm_plan.h"
+#include "rfm_rdsgroup.h"
 #include "rfm_rdssync.h"
 
 using namespace rfm;
@@ -167,6 +168,7 @@ struct rfm_decoder
   unsigned last_hb_n[kMaxDecStages + 1] = {0};
   // host RDS state
   std::vector<RdsBlockSync> sync;
+  std::vector<RdsGroupDecoder> uecp; // per stream: groups -> UECP byte stream (never reset by cFmDecoder::Reset either)
   std::vector<std::vector<uint8_t>> host_bits;
   std::vector<uint8_t> h_bits;
   std::vector<unsigned> h_counts;
@@ -388,8 +390,13 @@ int DrainBits(rfm_decoder* d)
           hb.erase(hb.begin(), hb.begin() + std::min(hb.size(), hb.size() + cnt - kMaxKeptBits));
         hb.insert(hb.end(), b, b + cnt);
         auto& sy = d->sync[g.s0 + s];
+        const size_t had = sy.Groups().size();
         for (unsigned i = 0; i < cnt; ++i)
           sy.PushBit(b[i]);
+        // RDSProcess.cpp:312,355: every decoded group goes straight to the group decoder
+        auto& ud = d->uecp[g.s0 + s];
+        for (size_t w = had; w + 4 <= sy.Groups().size(); w += 4)
+          ud.Decode(sy.Groups().data() + w);
       }
     };
     const unsigned nthreads = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), std::max(1u, g.S / 64));
@@ -1018,6 +1025,7 @@ int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out)
   }
   (void)esz_max;
   d->sync.resize(d->S);
+  d->uecp.resize(d->S);
   d->host_bits.resize(d->S);
   RFM_TRY(cudaDeviceSynchronize());
 #undef RFM_TRY
@@ -1180,6 +1188,24 @@ int rfm_decoder_rds_take_groups(rfm_decoder* d, uint32_t stream, uint16_t* group
     memcpy(groups, g.data(), (size_t)n * 4 * sizeof(uint16_t));
   g.erase(g.begin(), g.begin() + (size_t)n * 4);
   *n_groups = n;
+  return RFM_OK;
+}
+
+int rfm_decoder_rds_take_uecp(rfm_decoder* d, uint32_t stream, uint8_t* out, uint32_t cap, uint32_t* n_bytes)
+{
+  if (!d || stream >= d->S || !n_bytes)
+    return Fail(RFM_ERR_INVALID, "bad argument");
+  int rc = SyncAll(d);
+  if (rc == RFM_OK)
+    rc = DrainBits(d);
+  if (rc != RFM_OK)
+    return rc;
+  auto& p = d->uecp[stream].Pending();
+  const uint32_t n = (uint32_t)std::min<size_t>(p.size(), out ? cap : 0);
+  if (n)
+    memcpy(out, p.data(), n);
+  p.erase(p.begin(), p.begin() + n);
+  *n_bytes = n;
   return RFM_OK;
 }
 

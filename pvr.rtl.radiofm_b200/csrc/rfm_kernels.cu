@@ -519,7 +519,10 @@ void launch_if_level(const FrontParams& p, float* state, bool u8, cudaStream_t s
 // anywhere else -- in practice never on a tuned station, routinely on pure noise -- the chunk is recomputed
 // sequentially from the exact state.  The result is always exactly the reference's sequential recurrence.
 // --------------------------------------------------------------------------------------------------
-constexpr unsigned kDemodChunk = 192; // multiples of the 32-sample tile
+#ifndef RFM_DEMOD_CHUNK
+#define RFM_DEMOD_CHUNK 192
+#endif
+constexpr unsigned kDemodChunk = RFM_DEMOD_CHUNK; // multiples of the 32-sample tile
 
 __global__ void __launch_bounds__(32) k_demod_spec(DemodSpecParams p)
 {

@@ -113,6 +113,31 @@ def test_golden_rds_fixture(rfm):
     assert np.array_equal(d.take_groups(), g["groups"]) and np.array_equal(d.take_bits(), g["bits"])
 
 
+def test_uecp_stream_of_the_batched_decoder(rfm):
+    """SURVEY.md 8f N1 end to end: IQ -> ... -> groups -> per-stream cRDSGroupDecoder -> framed UECP bytes
+    (rfm_decoder_rds_take_uecp), against the golden groups of the reference chain pushed through the oracle's
+    restatement of the group decoder (itself pinned to the compiled reference in tests/test_uecp.py)."""
+    from oracle import uecp_port
+    g = np.load(os.path.join(GOLDEN, "rds_1.0M.npz"))
+    fs, ds, blk, nblk = float(g["fs"]), int(g["ds"]), int(g["blk"]), int(g["nblk"])
+    iq, _ = station("1.0M", nblk)
+    d = rfm.FmDecoderBatch(fs, -0.15 * fs, downsample=ds, n_streams=2, max_block_len=blk)
+    half = nblk // 2
+    got = [b"", b""]
+    for b in range(nblk):
+        d.process_u8(np.stack([iq[b * blk:(b + 1) * blk]] * 2))
+        if b == half:                     # draining in the middle must not lose or repeat a group
+            got[0] += d.take_uecp(0)
+            d.take_groups(0)
+    for s in range(2):
+        got[s] += d.take_uecp(s)
+    o = uecp_port.OracleGroupDecoder()
+    want = b"".join(uecp_port.stuff_frame(f) for f in o.decode(g["groups"]))
+    assert len(g["groups"]) > 8 and len(want) > 40
+    assert got[0] == want and got[1] == want
+    assert d.take_uecp(0) == b""
+
+
 def test_mono_tone_snr(rfm, port):
     """BASELINE config 0: 1 s of 1.0 MS/s, 1 kHz mono tone; SNR within 0.1 dB of the reference chain."""
     fs, ds, blk = RATES["1.0M"]
