@@ -315,12 +315,14 @@ def run_b200(args):
     torch.cuda.synchronize()
     dt = max_over_ranks(time.perf_counter() - t0)
     barrier()
-    e2e = {"value": world * S * BLK * K / dt / 1e6, "unit": "MS/s", "h2d_bytes_per_step": S * BLK * 2,
-           "d2h_bytes_per_step": S * int(kout.value) * 4, "ms_per_step": dt / K * 1e3,
-           "api": "rfm_decoder_process_u8 (pinned host IQ in, host audio out) + rfm_decoder_rds_take_groups"}
+    e2e_sync = {"value": world * S * BLK * K / dt / 1e6, "unit": "MS/s", "ms_per_step": dt / K * 1e3,
+                "api": "rfm_decoder_process_u8 (blocking: returns with the block's audio on the host) + rfm_decoder_rds_take_groups"}
 
-    # the same with asynchronous submission (rfm_decoder_submit_u8 + rfm_decoder_synchronize): two host input / output
-    # buffers alternate, so the H2D copy of block k+1 overlaps the kernels of block k
+    # the streaming form of the same public API (rfm_decoder_submit_u8 + rfm_decoder_synchronize): what a producer that
+    # has the next block ready uses.  Two pinned host input / output buffers alternate, so the H2D copy of block k+1
+    # overlaps the kernels and the D2H of block k.  This is the headline e2e figure; every step still moves its
+    # inputs host -> device and its audio device -> host inside the timed region, and the RDS groups of every stream
+    # are drained to the host before the clock stops.
     h_audio2 = torch.empty((2, S, stride), dtype=torch.float32).pin_memory()
 
     def submit_host(i):
@@ -329,7 +331,8 @@ def run_b200(args):
         if rc != 0:
             raise RuntimeError(lib.rfm_last_error().decode())
 
-    submit_host(0)
+    for i in range(max(1, W // 2)):
+        submit_host(i)
     dec.synchronize()
     barrier()
     t0 = time.perf_counter()
@@ -339,8 +342,11 @@ def run_b200(args):
     groups = dec.take_groups(0)
     dt = max_over_ranks(time.perf_counter() - t0)
     barrier()
-    e2e["async"] = {"value": world * S * BLK * K / dt / 1e6, "unit": "MS/s", "ms_per_step": dt / K * 1e3,
-                    "api": "rfm_decoder_submit_u8 x K + rfm_decoder_synchronize + rfm_decoder_rds_take_groups"}
+    e2e = {"value": world * S * BLK * K / dt / 1e6, "unit": "MS/s", "h2d_bytes_per_step": S * BLK * 2,
+           "d2h_bytes_per_step": S * int(kout.value) * 4, "ms_per_step": dt / K * 1e3,
+           "api": "rfm_decoder_submit_u8 x K + rfm_decoder_synchronize + rfm_decoder_rds_take_groups (pinned host IQ "
+                  "in, host audio out)",
+           "blocking": e2e_sync}
 
     cpu = cpu_baseline_leg() if (rank == 0 and world == 1 and not args.no_cpu) else None
     if rank == 0:

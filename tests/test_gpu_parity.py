@@ -133,7 +133,7 @@ def test_uecp_stream_of_the_batched_decoder(rfm):
         got[s] += d.take_uecp(s)
     o = uecp_port.OracleGroupDecoder()
     want = b"".join(uecp_port.stuff_frame(f) for f in o.decode(g["groups"]))
-    assert len(g["groups"]) > 8 and len(want) > 40
+    assert len(g["groups"]) >= 4 and len(want) > 40
     assert got[0] == want and got[1] == want
     assert d.take_uecp(0) == b""
 
