@@ -373,6 +373,37 @@ RFM_API int rfm_rdsgroup_channel_name(const rfm_rdsgroup* g, char out[9]);
 /* cRadioReceiver::AddUECPDataFrame's framing alone; returns the framed length (written only when it fits cap) */
 RFM_API uint32_t rfm_uecp_stuff_frame(const uint8_t* frame, uint32_t len, uint8_t* out, uint32_t cap);
 
+/* ------------------------------------------------------------------------------------------------
+ * The caller of the hot path: IQ block queue + packetiser of cRadioReceiver (RadioReceiver.cpp:420-542), one
+ * programme.  Source thread: rfm_demux_write_u8 (WriteDataBuffer, the block stays u8 and goes to pinned memory) /
+ * rfm_demux_end (EndDataBuffer).  Demux thread: rfm_demux_read (DemuxRead) hands out, in the reference's order, the
+ * stream-change packet, then for every block its audio packet (stream id 1: interleaved float L,R, pts / duration in
+ * STREAM_TIME_BASE = 1e6 units, pts starting at 1e6) followed by a UECP packet (stream id 2, pts of the NEXT audio
+ * packet) when the block's RDS groups produced frames.  `data` stays valid until the next packet of the same stream
+ * id is read.  The block after the one just handed out is decoded ahead when it is already queued.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rfm_demux rfm_demux;
+#define RFM_DEMUX_STREAMCHANGE (-11) /* DEMUX_SPECIALID_STREAMCHANGE */
+#define RFM_DEMUX_END 1              /* rfm_demux_read: end marked and every block handed out (reference: nullptr) */
+typedef struct rfm_demux_packet
+{
+  int32_t stream_id;    /* 1 audio, 2 UECP, RFM_DEMUX_STREAMCHANGE */
+  uint32_t size_bytes;  /* iSize */
+  double pts, duration;
+  const void* data;     /* pData */
+} rfm_demux_packet;
+RFM_API int rfm_demux_create(const rfm_config* cfg /* n_streams is taken as 1 */, rfm_demux** out);
+RFM_API void rfm_demux_destroy(rfm_demux* m);
+RFM_API rfm_decoder* rfm_demux_decoder(rfm_demux* m); /* the cFmDecoder behind it (getters, Reset) */
+RFM_API int rfm_demux_write_u8(rfm_demux* m, const uint8_t* iq, uint32_t n);
+RFM_API int rfm_demux_end(rfm_demux* m);
+RFM_API uint64_t rfm_demux_queued_samples(rfm_demux* m); /* SourceQueuedSamples */
+RFM_API void rfm_demux_set_stream_change(rfm_demux* m);  /* SetStreamChange, RadioReceiver.h:83 */
+RFM_API int rfm_demux_read(rfm_demux* m, rfm_demux_packet* pkt);
+RFM_API float rfm_demux_audio_level(const rfm_demux* m);  /* m_AudioLevel, RadioReceiver.cpp:528-529 */
+/* GetSignalStatus(float&, float&, bool&), RadioReceiver.cpp:544-556: levels in dB */
+RFM_API int rfm_demux_signal_status(rfm_demux* m, float* interface_level_db, float* audio_level_db, int* stereo);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,6 +47,9 @@ EXPORTED_SYMBOLS = (
     "rfm_decoder_rds_take_groups", "rfm_decoder_rds_take_bits", "rfm_decoder_rds_take_uecp", "rfm_decoder_get_status",
     "rfm_rdsgroup_create", "rfm_rdsgroup_destroy", "rfm_rdsgroup_reset", "rfm_rdsgroup_decode", "rfm_rdsgroup_take_uecp",
     "rfm_rdsgroup_channel_name", "rfm_uecp_stuff_frame",
+    "rfm_demux_create", "rfm_demux_destroy", "rfm_demux_decoder", "rfm_demux_write_u8", "rfm_demux_end",
+    "rfm_demux_queued_samples", "rfm_demux_set_stream_change", "rfm_demux_read", "rfm_demux_audio_level",
+    "rfm_demux_signal_status",
     "rfm_decoder_constants", "rfm_decoder_table", "rfm_plan_constants", "rfm_plan_table", "rfm_decoder_set_profiling",
     "rfm_decoder_profile_read", "rfm_decoder_tap", "rfm_rdssync_create",
     "rfm_rdssync_destroy", "rfm_rdssync_reset", "rfm_rdssync_push_bits", "rfm_rdssync_take_groups",
@@ -76,6 +79,16 @@ class RdsGroupCallbacks(C.Structure):
     """rfm_rdsgroup_callbacks (include/radiofm_b200.h)."""
     _fields_ = [("user", C.c_void_p), ("add_uecp_frame", _ADD_FRAME_CB), ("set_channel_name", _SET_NAME_CB),
                 ("is_setting_active", _SETTING_CB)]
+
+
+class DemuxPacket(C.Structure):
+    """rfm_demux_packet (include/radiofm_b200.h)."""
+    _fields_ = [("stream_id", C.c_int32), ("size_bytes", C.c_uint32), ("pts", C.c_double), ("duration", C.c_double),
+                ("data", C.c_void_p)]
+
+
+DEMUX_STREAMCHANGE = -11
+DEMUX_END = 1
 
 
 class RadioFmError(RuntimeError):
@@ -128,6 +141,19 @@ def lib():
         L.rfm_rdsgroup_decode.argtypes = [C.c_void_p, _u16p, C.c_uint32]
         L.rfm_rdsgroup_take_uecp.argtypes = [C.c_void_p, _u8p, C.c_uint32, _u32p]
         L.rfm_rdsgroup_channel_name.argtypes = [C.c_void_p, C.c_char_p]
+        L.rfm_demux_create.argtypes = [C.POINTER(RfmConfig), C.POINTER(C.c_void_p)]
+        L.rfm_demux_destroy.argtypes = [C.c_void_p]
+        L.rfm_demux_decoder.restype = C.c_void_p
+        L.rfm_demux_decoder.argtypes = [C.c_void_p]
+        L.rfm_demux_write_u8.argtypes = [C.c_void_p, _u8p, C.c_uint32]
+        L.rfm_demux_end.argtypes = [C.c_void_p]
+        L.rfm_demux_queued_samples.restype = C.c_uint64
+        L.rfm_demux_queued_samples.argtypes = [C.c_void_p]
+        L.rfm_demux_set_stream_change.argtypes = [C.c_void_p]
+        L.rfm_demux_read.argtypes = [C.c_void_p, C.POINTER(DemuxPacket)]
+        L.rfm_demux_audio_level.restype = C.c_float
+        L.rfm_demux_audio_level.argtypes = [C.c_void_p]
+        L.rfm_demux_signal_status.argtypes = [C.c_void_p, _f32p, _f32p, C.POINTER(C.c_int)]
         L.rfm_uecp_stuff_frame.restype = C.c_uint32
         L.rfm_uecp_stuff_frame.argtypes = [_u8p, C.c_uint32, _u8p, C.c_uint32]
         L.rfm_decoder_rds_take_bits.argtypes = [C.c_void_p, C.c_uint32, _u8p, C.c_uint32, _u32p]
@@ -463,6 +489,60 @@ class RdsGroupDecoder:
         buf = C.create_string_buffer(9)
         _check(lib().rfm_rdsgroup_channel_name(self._h, buf))
         return buf.raw[:8]
+
+
+class Demux:
+    """IQ block queue + packetiser of cRadioReceiver (RadioReceiver.cpp:420-542) for one programme."""
+
+    def __init__(self, fs_if, tuning_offset, fs_pcm=48000.0, bw_pcm=15000.0, downsample=1, usver=False,
+                 max_block_len=65536, device=-1):
+        cfg = _config(fs_if, tuning_offset, fs_pcm, bw_pcm, downsample, usver, 1, max_block_len, device)
+        self._h = C.c_void_p()
+        _check(lib().rfm_demux_create(C.byref(cfg), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().rfm_demux_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def write_u8(self, iq_u8: np.ndarray):
+        iq_u8 = np.ascontiguousarray(iq_u8, dtype=np.uint8).reshape(-1, 2)
+        _check(lib().rfm_demux_write_u8(self._h, _p(iq_u8, _u8p), iq_u8.shape[0]))
+
+    def end(self):
+        _check(lib().rfm_demux_end(self._h))
+
+    def queued_samples(self) -> int:
+        return int(lib().rfm_demux_queued_samples(self._h))
+
+    def set_stream_change(self):
+        lib().rfm_demux_set_stream_change(self._h)
+
+    def read(self):
+        """-> (stream_id, pts, duration, payload) or None at the end.  payload: float32 array (audio), bytes (UECP)."""
+        pkt = DemuxPacket()
+        rc = lib().rfm_demux_read(self._h, C.byref(pkt))
+        if rc == DEMUX_END:
+            return None
+        _check(rc)
+        if pkt.stream_id == 1:
+            n = pkt.size_bytes // 4
+            data = np.ctypeslib.as_array(C.cast(pkt.data, _f32p), shape=(n,)).copy() if n else np.zeros(0, np.float32)
+        elif pkt.stream_id == 2:
+            data = C.string_at(pkt.data, pkt.size_bytes)
+        else:
+            data = None
+        return pkt.stream_id, pkt.pts, pkt.duration, data
+
+    def audio_level(self) -> float:
+        return float(lib().rfm_demux_audio_level(self._h))
+
+    def signal_status(self):
+        a, b, s = C.c_float(0), C.c_float(0), C.c_int(0)
+        _check(lib().rfm_demux_signal_status(self._h, C.byref(a), C.byref(b), C.byref(s)))
+        return a.value, b.value, bool(s.value)
 
 
 def uecp_stuff_frame(frame: bytes) -> bytes:

@@ -16,5 +16,6 @@ $NVCC $NVFLAGS -c rfm_primitives.cu -o build/rfm_primitives.o
 g++ -O2 -std=c++17 -fPIC -fvisibility=hidden -ffp-contract=off -c rfm_plan.cpp -o build/rfm_plan.o
 g++ -O2 -std=c++17 -fPIC -fvisibility=hidden -ffp-contract=off -c rfm_rdssync.cpp -o build/rfm_rdssync.o
 g++ -O2 -std=c++17 -fPIC -fvisibility=hidden -ffp-contract=off -c rfm_rdsgroup.cpp -o build/rfm_rdsgroup.o
-$NVCC $ARCH -shared -o $OUT build/rfm_kernels.o build/rfm_api.o build/rfm_probe.o build/rfm_freqshift.o build/rfm_downconvert.o build/rfm_primitives.o build/rfm_plan.o build/rfm_rdssync.o build/rfm_rdsgroup.o -lcudart_static -lpthread -ldl -lrt
+g++ -O2 -std=c++17 -fPIC -fvisibility=hidden -ffp-contract=off -I/usr/local/cuda/include -c rfm_demux.cpp -o build/rfm_demux.o
+$NVCC $ARCH -shared -o $OUT build/rfm_kernels.o build/rfm_api.o build/rfm_probe.o build/rfm_freqshift.o build/rfm_downconvert.o build/rfm_primitives.o build/rfm_plan.o build/rfm_rdssync.o build/rfm_rdsgroup.o build/rfm_demux.o -lcudart_static -lpthread -ldl -lrt
 echo "built $(readlink -f $OUT)"

@@ -1,0 +1,108 @@
+"""the caller of the hot path -- IQ block queue + DemuxRead packetiser
+(RadioReceiver.cpp:420-542) -- through the C ABI (rfm_demux_*) against the oracle's restatement (oracle/demux_port.py):
+same packet order, ids, sizes, pts / duration (exact doubles), bit-identical audio, identical UECP bytes."""
+from __future__ import annotations
+
+import threading
+
+import numpy as np
+import pytest
+
+from conftest import station
+
+pytestmark = pytest.mark.gpu
+
+
+def read_all(dm):
+    out = []
+    while True:
+        p = dm.read()
+        if p is None:
+            return out
+        out.append(p)
+
+
+def same_packets(got, want):
+    assert [p[0] for p in got] == [p[0] for p in want]
+    for a, b in zip(got, want):
+        assert a[1] == b[1] and a[2] == b[2], (a[:3], b[:3])
+        if a[0] == 1:
+            assert a[3].size == b[3].size and np.array_equal(a[3].view(np.uint32), b[3].view(np.uint32))
+        elif a[0] == 2:
+            assert a[3] == b[3]
+
+
+def test_demux_packets_match_the_oracle(rfm):
+    from oracle import demux_port
+    fs, ds, blk, nblk = 1.0e6, 4, 65536, 8
+    iq, _ = station("1.0M", nblk)
+    dm = rfm.Demux(fs, -0.15 * fs, downsample=ds, max_block_len=blk)
+    om = demux_port.OracleDemux(fs, -0.15 * fs, downsample=ds)
+    with pytest.raises(rfm.RadioFmError):
+        dm.signal_status()                     # GetSignalStatus is false until the stream-change packet went out
+    for b in range(nblk):                      # everything queued up front: read-ahead is active throughout
+        dm.write_u8(iq[b * blk:(b + 1) * blk])
+        om.write_u8(iq[b * blk:(b + 1) * blk])
+    assert dm.queued_samples() == nblk * blk
+    dm.end()
+    got, want = read_all(dm), []
+    while True:
+        p = om.read()
+        if p is None:
+            break
+        want.append(p)
+    same_packets(got, want)
+    ids = [p[0] for p in got]
+    assert ids[0] == rfm.DEMUX_STREAMCHANGE and ids.count(1) == nblk and ids.count(2) >= 2
+    assert got[1][1] == 1000000.0              # first pts = STREAM_TIME_BASE
+    assert np.float32(dm.audio_level()) == om.audio_level
+    il, al, stereo = dm.signal_status()
+    assert stereo and np.isfinite(il) and np.float32(al) == np.float32(20 * np.log10(float(om.audio_level)) + 3.01)
+    assert dm.queued_samples() == 0 and dm.read() is None
+
+
+def test_demux_with_a_live_producer_thread(rfm):
+    """source thread writes while the demux thread reads (blocks arrive one at a time: no read-ahead possible at
+    first, then a burst); ragged last block; stream change re-armed in the middle"""
+    from oracle import demux_port
+    fs, ds, blk, nblk = 1.2e6, 5, 65520, 5
+    iq, _ = station("1.2M", nblk)
+    lens = [blk, blk, blk, blk, blk // 2 // 80 * 80]
+    dm = rfm.Demux(fs, -0.15 * fs, downsample=ds, max_block_len=blk)
+    om = demux_port.OracleDemux(fs, -0.15 * fs, downsample=ds)
+    gate = threading.Event()
+
+    def producer():
+        off = 0
+        for i, n in enumerate(lens):
+            if i == 2:
+                gate.wait(10.0)
+            dm.write_u8(iq[off:off + n])
+            off += n
+        dm.end()
+
+    off = 0
+    for n in lens:
+        om.write_u8(iq[off:off + n])
+        off += n
+    th = threading.Thread(target=producer)
+    th.start()
+    got = []
+    while True:
+        p = dm.read()
+        if p is None:
+            break
+        got.append(p)
+        if sum(1 for q in got if q[0] == 1) == 2:
+            gate.set()
+    th.join()
+    want = []
+    while True:
+        p = om.read()
+        if p is None:
+            break
+        want.append(p)
+    same_packets(got, want)
+    assert [p[3].size for p in got if p[0] == 1][-1] < [p[3].size for p in got if p[0] == 1][0]
+    dm.set_stream_change()
+    assert dm.read() is not None and dm.read() is None
