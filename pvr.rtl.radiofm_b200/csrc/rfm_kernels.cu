@@ -520,7 +520,7 @@ void launch_if_level(const FrontParams& p, float* state, bool u8, cudaStream_t s
 // sequentially from the exact state.  The result is always exactly the reference's sequential recurrence.
 // --------------------------------------------------------------------------------------------------
 #ifndef RFM_DEMOD_CHUNK
-#define RFM_DEMOD_CHUNK 192
+#define RFM_DEMOD_CHUNK 384
 #endif
 constexpr unsigned kDemodChunk = RFM_DEMOD_CHUNK; // multiples of the 32-sample tile
 
