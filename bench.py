@@ -38,11 +38,11 @@ METRIC = "demodulated complex MS/s per GPU (stereo+RDS) at 1/2/4/8 B200; % of HB
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at the C4 workload (4096 streams, one 65472-sample block),
 # from one `ncu --set full` capture per kernel: profiles/r01_ncu_top_kernels.txt
 NCU_TRAFFIC_BYTES = {
-    "k_bb_lanes": 98.313984e6 + 139.291648e6,
-    "k_front": 539.271424e6 + 175.535104e6,
-    "k_demod_spec": 275.005696e6 + 69.869824e6,
-    "k_resample": 204.2816e6 + 33.52192e6,
-    "k_rds_front": 103.283968e6 + 33.89312e6,
+    "k_bb_lanes": 98.327808e6 + 137.724672e6,
+    "k_front": 539.337728e6 + 174.3936e6,
+    "k_demod_spec": 242.277632e6 + 67.041792e6,
+    "k_resample": 204.107264e6 + 32.296448e6,
+    "k_rds_front": 101.139968e6 + 12.347392e6,
 }
 
 
