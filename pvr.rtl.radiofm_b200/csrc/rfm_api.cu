@@ -170,8 +170,8 @@ struct rfm_decoder
   std::vector<RdsBlockSync> sync;
   std::vector<RdsGroupDecoder> uecp; // per stream: groups -> UECP byte stream (never reset by cFmDecoder::Reset either)
   std::vector<std::vector<uint8_t>> host_bits;
-  std::vector<uint8_t> h_bits;
-  std::vector<unsigned> h_counts;
+  uint8_t* h_drain = nullptr; // pinned staging of the drained bit counts + bits of every stream
+  size_t h_drain_cap = 0;
 };
 
 namespace
@@ -228,6 +228,8 @@ void FreeDecoder(rfm_decoder* d)
       cudaEventDestroy(e);
   if (d->s_osc)
     cudaStreamDestroy(d->s_osc);
+  if (d->h_drain)
+    cudaFreeHost(d->h_drain);
   delete d;
 }
 
@@ -360,57 +362,71 @@ cudaError_t ResetGroupState(rfm_decoder* d, Group& g, bool initial)
   return cudaMemset(g.mfV.p, 0, g.mfV.n * sizeof(float));
 }
 
-// Bring undrained slicer bits to the host and run the block-sync state machines on them.
+// Bring undrained slicer bits to the host and run the block-sync state machines on them.  All groups at once: the
+// copies of every group are in flight together (pinned staging, each on the group's slicer stream), then ONE fan-out
+// over the host cores covers all streams.
 int DrainBits(rfm_decoder* d)
 {
   if (d->pending_bits_bound == 0)
     return RFM_OK;
+  const unsigned width = std::min(d->pending_bits_bound, d->bits_cap); // no stream can hold more undrained bits
+  const size_t need = (size_t)d->S * (d->bits_cap + sizeof(unsigned)); // allocated once, at its largest
+  if (d->h_drain_cap < need)
+  {
+    if (d->h_drain)
+      cudaFreeHost(d->h_drain);
+    d->h_drain = nullptr;
+    d->h_drain_cap = 0;
+    RFM_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&d->h_drain), need, cudaHostAllocDefault));
+    d->h_drain_cap = need;
+  }
+  unsigned* h_counts = reinterpret_cast<unsigned*>(d->h_drain);
+  uint8_t* h_bits = d->h_drain + (size_t)d->S * sizeof(unsigned);
   for (auto& g : d->groups)
   {
-    RFM_CUDA(cudaStreamSynchronize(g.sP)); // the slicer's stream
-    d->h_counts.resize(g.S);
-    RFM_CUDA(cudaMemcpy(d->h_counts.data(), g.bit_count.p, g.S * sizeof(unsigned), cudaMemcpyDeviceToHost));
-    unsigned mx = 0;
-    for (unsigned c : d->h_counts)
-      mx = std::max(mx, c);
-    if (mx > d->bits_cap)
+    RFM_CUDA(cudaMemcpyAsync(h_counts + g.s0, g.bit_count.p, g.S * sizeof(unsigned), cudaMemcpyDeviceToHost, g.sP));
+    RFM_CUDA(cudaMemcpy2DAsync(h_bits + (size_t)g.s0 * width, width, g.bits.p, d->bits_cap, width, g.S,
+                               cudaMemcpyDeviceToHost, g.sP));
+    RFM_CUDA(cudaMemsetAsync(g.bit_count.p, 0, g.S * sizeof(unsigned), g.sP));
+  }
+  for (auto& g : d->groups)
+    RFM_CUDA(cudaStreamSynchronize(g.sP));
+  for (unsigned s = 0; s < d->S; ++s)
+    if (h_counts[s] > width)
       return Fail(RFM_ERR_OVERFLOW, "RDS bit buffer overflow (internal drain bound violated)");
-    if (mx == 0)
-      continue;
-    d->h_bits.resize((size_t)g.S * mx);
-    RFM_CUDA(cudaMemcpy2D(d->h_bits.data(), mx, g.bits.p, d->bits_cap, mx, g.S, cudaMemcpyDeviceToHost));
-    // host block sync / FEC (RDSProcess.cpp:272-431): streams are independent -> spread over the host cores
-    auto work = [&](unsigned lo, unsigned hi) {
-      for (unsigned s = lo; s < hi; ++s)
-      {
-        const uint8_t* b = d->h_bits.data() + (size_t)s * mx;
-        const unsigned cnt = d->h_counts[s];
-        auto& hb = d->host_bits[g.s0 + s];
-        if (hb.size() + cnt > kMaxKeptBits) // raw bits are kept for rfm_decoder_rds_take_bits, bounded
-          hb.erase(hb.begin(), hb.begin() + std::min(hb.size(), hb.size() + cnt - kMaxKeptBits));
-        hb.insert(hb.end(), b, b + cnt);
-        auto& sy = d->sync[g.s0 + s];
-        const size_t had = sy.Groups().size();
-        for (unsigned i = 0; i < cnt; ++i)
-          sy.PushBit(b[i]);
-        // RDSProcess.cpp:312,355: every decoded group goes straight to the group decoder
-        auto& ud = d->uecp[g.s0 + s];
-        for (size_t w = had; w + 4 <= sy.Groups().size(); w += 4)
-          ud.Decode(sy.Groups().data() + w);
-      }
-    };
-    const unsigned nthreads = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), std::max(1u, g.S / 64));
-    if (nthreads <= 1)
-      work(0, g.S);
-    else
+  // host block sync / FEC (RDSProcess.cpp:272-431) and group decoder: streams are independent
+  auto work = [&](unsigned lo, unsigned hi) {
+    for (unsigned s = lo; s < hi; ++s)
     {
-      std::vector<std::thread> pool;
-      for (unsigned t = 0; t < nthreads; ++t)
-        pool.emplace_back(work, (unsigned)((uint64_t)g.S * t / nthreads), (unsigned)((uint64_t)g.S * (t + 1) / nthreads));
-      for (auto& th : pool)
-        th.join();
+      const uint8_t* b = h_bits + (size_t)s * width;
+      const unsigned cnt = h_counts[s];
+      if (cnt == 0)
+        continue;
+      auto& hb = d->host_bits[s];
+      if (hb.size() + cnt > kMaxKeptBits) // raw bits are kept for rfm_decoder_rds_take_bits, bounded
+        hb.erase(hb.begin(), hb.begin() + std::min(hb.size(), hb.size() + cnt - kMaxKeptBits));
+      hb.insert(hb.end(), b, b + cnt);
+      auto& sy = d->sync[s];
+      const size_t had = sy.Groups().size();
+      for (unsigned i = 0; i < cnt; ++i)
+        sy.PushBit(b[i]);
+      // RDSProcess.cpp:312,355: every decoded group goes straight to the group decoder
+      auto& ud = d->uecp[s];
+      for (size_t w = had; w + 4 <= sy.Groups().size(); w += 4)
+        ud.Decode(sy.Groups().data() + w);
     }
-    RFM_CUDA(cudaMemset(g.bit_count.p, 0, g.S * sizeof(unsigned)));
+  };
+  const unsigned nthreads = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), std::max(1u, d->S / 64));
+  if (nthreads <= 1)
+    work(0, d->S);
+  else
+  {
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < nthreads; ++t)
+      pool.emplace_back(work, (unsigned)((uint64_t)d->S * t / nthreads), (unsigned)((uint64_t)d->S * (t + 1) / nthreads));
+    work(0, (unsigned)((uint64_t)d->S / nthreads));
+    for (auto& th : pool)
+      th.join();
   }
   d->pending_bits_bound = 0;
   return RFM_OK;

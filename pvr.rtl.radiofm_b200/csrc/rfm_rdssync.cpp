@@ -14,15 +14,38 @@ const uint32_t kParity[16] = {0x2DC, 0x16E, 0x0B7, 0x287, 0x39F, 0x313, 0x355, 0
 const uint32_t kCrcPoly = 0x5B9; // x^10+x^8+x^7+x^5+x^4+x^3+1
 const int kBitsPerBlock = 26;
 const int kBlockErrorLimit = 0;  // BLOCK_ERROR_LIMIT, RDSProcess.h:31
+
+// The syndrome is linear in the 26 received bits: bits 25..16 map to themselves (identity part of the check matrix),
+// bit 15-i to kParity[i].  One table per byte of the word turns the reference's 16-step loop (RDSProcess.cpp:386-396)
+// into four lookups -- the bit-sync search evaluates it for every incoming bit of every stream.
+struct SyndromeTables
+{
+  uint16_t t[4][256];
+  SyndromeTables()
+  {
+    for (int k = 0; k < 4; ++k)
+      for (int v = 0; v < 256; ++v)
+      {
+        uint32_t syn = 0;
+        for (int b = 0; b < 8; ++b)
+        {
+          const int j = 8 * k + b; // bit position in the 26-bit word
+          if (!((v >> b) & 1) || j > 25)
+            continue;
+          syn ^= (j >= 16) ? (1u << (j - 16)) : kParity[15 - j];
+        }
+        t[k][v] = (uint16_t)syn;
+      }
+  }
+};
+const SyndromeTables kSyn;
 } // namespace
 
 uint32_t RdsCheckBlock(uint32_t* in_bits, uint32_t offset_syndrome, bool use_fec)
 {
-  uint32_t block = *in_bits & 0x3FFFFFF;
-  uint32_t syn = block >> 16; // identity part of the check matrix
-  for (int i = 0; i < 16; ++i, block <<= 1)
-    if (block & 0x8000)
-      syn ^= kParity[i];
+  const uint32_t block = *in_bits & 0x3FFFFFF;
+  uint32_t syn = (uint32_t)(kSyn.t[0][block & 0xff] ^ kSyn.t[1][(block >> 8) & 0xff] ^ kSyn.t[2][(block >> 16) & 0xff] ^
+                            kSyn.t[3][block >> 24]);
   syn ^= offset_syndrome;
   if (syn != 0 && use_fec)
   {
