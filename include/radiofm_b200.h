@@ -401,6 +401,14 @@ RFM_API uint64_t rfm_demux_queued_samples(rfm_demux* m); /* SourceQueuedSamples 
 RFM_API void rfm_demux_set_stream_change(rfm_demux* m);  /* SetStreamChange, RadioReceiver.h:83 */
 RFM_API int rfm_demux_read(rfm_demux* m, rfm_demux_packet* pkt);
 RFM_API float rfm_demux_audio_level(const rfm_demux* m);  /* m_AudioLevel, RadioReceiver.cpp:528-529 */
+/* The source side of cRtlSdrSource without librtlsdr: its block-length rule (clamp to 4096 .. 2^20,
+ * multiple of 4096; RTL_SDR_Source.cpp:124-126) and its async read callback (RTL_SDR_Source.cpp:196-213) with the
+ * signature of rtlsdr_read_async_cb_t -- pass it to rtlsdr_read_async with ctx = the rfm_demux and
+ * buf_len = 2 * block length.  Buffers of any other length are dropped and counted, as the reference drops them. */
+RFM_API uint32_t rfm_source_block_length(uint32_t requested);
+RFM_API int rfm_demux_set_source_block_length(rfm_demux* m, uint32_t requested);
+RFM_API void rfm_demux_source_cb(unsigned char* buf, uint32_t len, void* ctx);
+RFM_API uint64_t rfm_demux_short_reads(rfm_demux* m);
 /* GetSignalStatus(float&, float&, bool&), RadioReceiver.cpp:544-556: levels in dB */
 RFM_API int rfm_demux_signal_status(rfm_demux* m, float* interface_level_db, float* audio_level_db, int* stereo);
 

@@ -49,7 +49,8 @@ EXPORTED_SYMBOLS = (
     "rfm_rdsgroup_channel_name", "rfm_uecp_stuff_frame",
     "rfm_demux_create", "rfm_demux_destroy", "rfm_demux_decoder", "rfm_demux_write_u8", "rfm_demux_end",
     "rfm_demux_queued_samples", "rfm_demux_set_stream_change", "rfm_demux_read", "rfm_demux_audio_level",
-    "rfm_demux_signal_status",
+    "rfm_demux_signal_status", "rfm_source_block_length", "rfm_demux_set_source_block_length", "rfm_demux_source_cb",
+    "rfm_demux_short_reads",
     "rfm_decoder_constants", "rfm_decoder_table", "rfm_plan_constants", "rfm_plan_table", "rfm_decoder_set_profiling",
     "rfm_decoder_profile_read", "rfm_decoder_tap", "rfm_rdssync_create",
     "rfm_rdssync_destroy", "rfm_rdssync_reset", "rfm_rdssync_push_bits", "rfm_rdssync_take_groups",
@@ -154,6 +155,13 @@ def lib():
         L.rfm_demux_audio_level.restype = C.c_float
         L.rfm_demux_audio_level.argtypes = [C.c_void_p]
         L.rfm_demux_signal_status.argtypes = [C.c_void_p, _f32p, _f32p, C.POINTER(C.c_int)]
+        L.rfm_source_block_length.restype = C.c_uint32
+        L.rfm_source_block_length.argtypes = [C.c_uint32]
+        L.rfm_demux_set_source_block_length.argtypes = [C.c_void_p, C.c_uint32]
+        L.rfm_demux_source_cb.restype = None
+        L.rfm_demux_source_cb.argtypes = [_u8p, C.c_uint32, C.c_void_p]
+        L.rfm_demux_short_reads.restype = C.c_uint64
+        L.rfm_demux_short_reads.argtypes = [C.c_void_p]
         L.rfm_uecp_stuff_frame.restype = C.c_uint32
         L.rfm_uecp_stuff_frame.argtypes = [_u8p, C.c_uint32, _u8p, C.c_uint32]
         L.rfm_decoder_rds_take_bits.argtypes = [C.c_void_p, C.c_uint32, _u8p, C.c_uint32, _u32p]
@@ -510,6 +518,17 @@ class Demux:
     def write_u8(self, iq_u8: np.ndarray):
         iq_u8 = np.ascontiguousarray(iq_u8, dtype=np.uint8).reshape(-1, 2)
         _check(lib().rfm_demux_write_u8(self._h, _p(iq_u8, _u8p), iq_u8.shape[0]))
+
+    def set_source_block_length(self, requested: int):
+        _check(lib().rfm_demux_set_source_block_length(self._h, requested))
+
+    def source_cb(self, buf: np.ndarray):
+        """what librtlsdr's reader thread would call (cRtlSdrSource::ReadAsyncCB)"""
+        buf = np.ascontiguousarray(buf, dtype=np.uint8).reshape(-1)
+        lib().rfm_demux_source_cb(_p(buf, _u8p), buf.size, self._h)
+
+    def short_reads(self) -> int:
+        return int(lib().rfm_demux_short_reads(self._h))
 
     def end(self):
         _check(lib().rfm_demux_end(self._h))

@@ -58,6 +58,8 @@ struct rfm_demux
   PinnedBlock flying;
   uint32_t flying_floats = 0;
   uint64_t blocks_done = 0;
+  uint32_t source_block = 0;   // cRtlSdrSource::m_BlockLength for rfm_demux_source_cb
+  uint64_t short_reads = 0;
 };
 
 namespace
@@ -287,6 +289,49 @@ int rfm_demux_read(rfm_demux* m, rfm_demux_packet* pkt)
     // (this packet's audio buffer is the OTHER one: it stays valid until the next audio packet is read)
   }
   return RFM_OK;
+}
+
+/* cRtlSdrSource::Configure's block-length rule, RTL_SDR_Source.cpp:124-126 */
+uint32_t rfm_source_block_length(uint32_t requested)
+{
+  uint32_t n = requested < 4096u ? 4096u : (requested > 1024u * 1024u ? 1024u * 1024u : requested);
+  return n - n % 4096u;
+}
+
+int rfm_demux_set_source_block_length(rfm_demux* m, uint32_t requested)
+{
+  if (!m)
+    return RFM_ERR_INVALID;
+  const uint32_t n = rfm_source_block_length(requested);
+  if (n > m->cfg.max_block_len)
+    return RFM_ERR_INVALID;
+  m->source_block = n;
+  return RFM_OK;
+}
+
+/* cRtlSdrSource::ReadAsyncCB, RTL_SDR_Source.cpp:196-213: the signature of rtlsdr_read_async_cb_t with ctx = the
+ * rfm_demux.  A buffer that is not exactly one block is dropped ("short read, samples lost"); a good one is queued as
+ * it is -- the u8 -> float conversion of :207-211 happens on the device. */
+void rfm_demux_source_cb(unsigned char* buf, uint32_t len, void* ctx)
+{
+  rfm_demux* m = static_cast<rfm_demux*>(ctx);
+  if (!m || !buf)
+    return;
+  if (m->source_block == 0 || len != 2 * m->source_block)
+  {
+    std::lock_guard<std::mutex> lock(m->mu);
+    m->short_reads += 1;
+    return;
+  }
+  rfm_demux_write_u8(m, buf, m->source_block);
+}
+
+uint64_t rfm_demux_short_reads(rfm_demux* m)
+{
+  if (!m)
+    return 0;
+  std::lock_guard<std::mutex> lock(m->mu);
+  return m->short_reads;
 }
 
 float rfm_demux_audio_level(const rfm_demux* m) { return m ? m->audio_level : 0.0f; }

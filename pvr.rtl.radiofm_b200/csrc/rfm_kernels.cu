@@ -1708,20 +1708,48 @@ __global__ void __launch_bounds__(kRfThreads) k_rds_front(RdsFrontParams p)
   float2* out = reinterpret_cast<float2*>(p.out) + (size_t)s * p.out_stride;
   const unsigned N = p.lp_n;
   unsigned out_base = 0; // LP outputs produced so far in this block
+  // the baseband / oscillator samples of the NEXT tile travel to shared memory (cp.async) while the stages of the
+  // current one run: the tile loads were this kernel's largest stall
+  float* s_bbst;
+  float2* s_oscst;
+  {
+    unsigned off = 0, n = kRfTile;
+    for (unsigned k = 0; k <= p.nst; ++k)
+    {
+      off += ((k < p.nst) ? p.st[k].hist : p.lp_n - 1) + n;
+      n >>= 1;
+    }
+    s_oscst = vbuf + off;
+    s_bbst = reinterpret_cast<float*>(s_oscst + kRfTile);
+  }
+  auto stage_tile = [&](unsigned t0n) {
+    const unsigned tnn = min(kRfTile, p.nb - t0n);
+    for (unsigned i = tid; i < tnn; i += kRfThreads)
+    {
+      cp_async_4(&s_bbst[i], &bb[t0n + i]);
+      cp_async_8(&s_oscst[i], &osc[t0n + i]);
+    }
+    cp_async_commit();
+  };
+  stage_tile(0);
   for (unsigned t0 = 0; t0 < p.nb; t0 += kRfTile)
   {
     const unsigned tn = min(kRfTile, p.nb - t0);
+    cp_async_wait<0>();
+    __syncthreads();
     // mix: real baseband x NCO phasor, imaginary input exactly +0 (RDSProcess.cpp:122-123)
     for (unsigned i = tid; i < tn; i += kRfThreads)
     {
-      const float b = bb[t0 + i];
-      const float2 o = osc[t0 + i];
+      const float b = s_bbst[i];
+      const float2 o = s_oscst[i];
       float2 r;
       r.x = subf(mulf(b, o.x), mulf(0.0f, o.y));
       r.y = addf(mulf(b, o.y), mulf(0.0f, o.x));
       B[0][p.st[0].hist + i] = r;
     }
     __syncthreads();
+    if (t0 + kRfTile < p.nb)
+      stage_tile(t0 + kRfTile);
     unsigned n = tn;
     for (unsigned k = 0; k < p.nst; ++k)
     {
@@ -1803,7 +1831,7 @@ void launch_rds_front(const RdsFrontParams& p, cudaStream_t st)
     f2 += ((k < p.nst) ? p.st[k].hist : p.lp_n - 1) + n;
     n >>= 1;
   }
-  const size_t smem = floats * sizeof(float) + f2 * sizeof(float2);
+  const size_t smem = floats * sizeof(float) + f2 * sizeof(float2) + kRfTile * (sizeof(float2) + sizeof(float)); // + tile staging
   static size_t attr = 0;
   if (smem > attr)
   {

@@ -106,3 +106,30 @@ def test_demux_with_a_live_producer_thread(rfm):
     assert [p[3].size for p in got if p[0] == 1][-1] < [p[3].size for p in got if p[0] == 1][0]
     dm.set_stream_change()
     assert dm.read() is not None and dm.read() is None
+
+
+def test_source_callback_block_rule_and_short_reads(rfm):
+    """cRtlSdrSource without librtlsdr: block-length rule, async-read callback, short reads dropped"""
+    from oracle import demux_port
+    L = rfm.lib()
+    assert [L.rfm_source_block_length(v) for v in (0, 4095, 4096, 65536, 70000, 1 << 21)] == [4096, 4096, 4096, 65536, 69632, 1 << 20]
+    fs, ds, blk, nblk = 1.0e6, 4, 65536, 3
+    iq, _ = station("1.0M", nblk)
+    dm = rfm.Demux(fs, -0.15 * fs, downsample=ds, max_block_len=blk)
+    om = demux_port.OracleDemux(fs, -0.15 * fs, downsample=ds)
+    dm.source_cb(iq[:blk])                     # no block length configured yet: dropped
+    dm.set_source_block_length(blk + 100)      # 65636 -> 65536
+    for b in range(nblk):
+        dm.source_cb(iq[b * blk:(b + 1) * blk])
+        if b == 0:
+            dm.source_cb(iq[:blk // 2])        # short read: samples lost, nothing queued
+        om.write_u8(iq[b * blk:(b + 1) * blk])
+    dm.end()
+    assert dm.short_reads() == 2 and dm.queued_samples() == nblk * blk
+    want = []
+    while True:
+        p = om.read()
+        if p is None:
+            break
+        want.append(p)
+    same_packets(read_all(dm), want)
