@@ -758,6 +758,8 @@ struct LanesSmem
   float win[2][32][kLT + 1];   // NCO increments from the demodulator
   float ring[2][32][kLT + 1];  // baseband, warp 0 -> warp 1
   float rawt[32][kLT + 1];
+  double kd[13];               // sincos constants / pilot constants, re-read ONCE per block with volatile loads
+  float kf[8];
 };
 
 __global__ void __launch_bounds__(64) k_bb_lanes(LanesParams p)
@@ -822,6 +824,24 @@ __global__ void __launch_bounds__(64) k_bb_lanes(LanesParams p)
   {
     // ---------------- consumer: pilot PLL, demux multiply ----------------
     PilotState pl = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 1000.0f};
+    // loop constants through shared memory and volatile loads: held in registers for the whole block (rfm_math.cuh)
+    if (lane < 13)
+      sm.kd[lane] = kSinCosDev[lane];
+    if (lane == 0)
+    {
+      sm.kf[0] = p.pilot.minfreq; sm.kf[1] = p.pilot.maxfreq; sm.kf[2] = p.pilot.b0; sm.kf[3] = p.pilot.a1;
+      sm.kf[4] = p.pilot.a2; sm.kf[5] = p.pilot.lb0; sm.kf[6] = p.pilot.lb1;
+    }
+    __syncwarp();
+    SinCosRegs sca;
+#pragma unroll
+    for (int i = 0; i < 13; ++i)
+      sca.k[i] = *reinterpret_cast<volatile double*>(&sm.kd[i]);
+    PilotConstDev pk = p.pilot;
+    {
+      volatile float* kf = sm.kf;
+      pk.minfreq = kf[0]; pk.maxfreq = kf[1]; pk.b0 = kf[2]; pk.a1 = kf[3]; pk.a2 = kf[4]; pk.lb0 = kf[5]; pk.lb1 = kf[6];
+    }
     if (valid)
     {
       pl.phase = st[SF_PILOT_PHASE * S + s];
@@ -843,10 +863,11 @@ __global__ void __launch_bounds__(64) k_bb_lanes(LanesParams p)
       bool bad = false;
       if (valid)
       {
+#pragma unroll 2
         for (unsigned k = 0; k < tn; ++k)
         {
           const float bb = sm.ring[b][lane][k];
-          const float p38 = pilot_step_fast(pl, bb, p.pilot, bad);
+          const float p38 = pilot_step_fast(pl, bb, pk, sca, bad);
           sm.rawt[lane][k] = mulf(p38, mulf(2.0f, bb)); // FmDecode.cpp:455-456
         }
       }

@@ -113,11 +113,11 @@ RFM_HD float pilot_step(PilotState& st, float x, const PilotConstDev& k)
   return out;
 }
 
-RFM_HD float pilot_step_fast(PilotState& st, float x, const PilotConstDev& k, bool& bad)
+RFM_HD float pilot_step_fast(PilotState& st, float x, const PilotConstDev& k, const SinCosRegs& sca, bool& bad)
 {
   float ps, pc;
   bad = bad | (!(absf(st.phase) < 16.0f));
-  rfm_sincos_core(st.phase, &ps, &pc);
+  rfm_sincos_core_a(st.phase, sca, &ps, &pc);
   const float out = mulf(mulf(2.0f, ps), pc);
   float pi = mulf(ps, x);
   float pq = mulf(pc, x);
@@ -128,7 +128,7 @@ RFM_HD float pilot_step_fast(PilotState& st, float x, const PilotConstDev& k, bo
   st.q2 = st.q1;
   st.q1 = pq;
   const bool use_div = pi > absf(pq);
-  bad = bad | (use_div & rfm_div_unsafe(pq, pi));
+  bad = bad | (use_div & rfm_div_unsafe_below(pq, pi));
   const float ediv = rfm_div_fast(pq, pi);
   const float esat = (pq > 0.0f) ? 1.0f : -1.0f;
   const float err = use_div ? ediv : esat;

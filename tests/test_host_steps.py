@@ -35,7 +35,7 @@ unsigned run_pilot(const float* x, unsigned n, const float* k8, float freq0, flo
   for (unsigned i = 0; i < n; ++i) {
     out[i] = pilot_step(a, x[i], k);
     bool bad = false; PilotState save = b;
-    float o = pilot_step_fast(b, x[i], k, bad);
+    float o = pilot_step_fast(b, x[i], k, rfm_sincos_regs(), bad);
     if (bad) { ++flagged; b = save; o = pilot_step(b, x[i], k); }
     out_fast[i] = o;
   }

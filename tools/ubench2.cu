@@ -30,7 +30,7 @@ template <bool FAST, bool DC = true> __global__ void k_pilot(const float* bbin, 
     for (int r = 0; r < 32; ++r) { zs[r][threadIdx.x] = bbin[r * N + t0 + threadIdx.x]; zs[r][threadIdx.x + 32] = bbin[r * N + t0 + 32 + threadIdx.x]; }
     __syncwarp();
     long long a = clock64();
-    for (int i = 0; i < 64; ++i) { if (FAST) { bool bad = false; float dcv = DC ? demod_output(zs[threadIdx.x][i], dc, 0.57f) : zs[threadIdx.x][i]; acc += pilot_step_fast(st, dcv, k, bad); acc += bad ? 1.f : 0.f; } else acc += pilot_step(st, zs[threadIdx.x][i], k); }
+    for (int i = 0; i < 64; ++i) { if (FAST) { bool bad = false; float dcv = DC ? demod_output(zs[threadIdx.x][i], dc, 0.57f) : zs[threadIdx.x][i]; acc += pilot_step_fast(st, dcv, k, rfm_sincos_regs(), bad); acc += bad ? 1.f : 0.f; } else acc += pilot_step(st, zs[threadIdx.x][i], k); }
     total += clock64() - a;
     __syncwarp();
   }
