@@ -29,6 +29,7 @@
 
 #include "../../include/radiofm_b200.h"
 #include "rfm_dsp.cuh"
+#include "rfm_kernels.cuh"
 #include "rfm_math.cuh"
 #include "rfm_plan.h"
 
@@ -602,12 +603,7 @@ void LaunchChain(rfm_downconvert* d, const DcParams& p, cudaStream_t st)
       smem += 2 * (size_t)(25 + n / 2 + 5) * sizeof(float2);
       n >>= 1;
     }
-    static size_t attr = 0;
-    if (smem > attr)
-    {
-      cudaFuncSetAttribute(k_dc_chain_uniform<IN, 51>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      attr = smem;
-    }
+    EnsureDynSmem(k_dc_chain_uniform<IN, 51>, smem);
     k_dc_chain_uniform<IN, 51><<<grid, kDcThreads, smem, st>>>(p, d->taps51);
   }
   else
@@ -621,12 +617,7 @@ void LaunchChain(rfm_downconvert* d, const DcParams& p, cudaStream_t st)
       n >>= 1;
     }
     const size_t smem = floats * sizeof(float) + f2 * sizeof(float2);
-    static size_t attr = 0;
-    if (smem > attr)
-    {
-      cudaFuncSetAttribute(k_dc_chain<IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      attr = smem;
-    }
+    EnsureDynSmem(k_dc_chain<IN>, smem);
     k_dc_chain<IN><<<grid, kDcThreads, smem, st>>>(p);
   }
 }

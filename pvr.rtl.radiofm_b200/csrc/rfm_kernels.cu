@@ -26,10 +26,29 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 namespace rfm
 {
 
 static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
+
+void EnsureDynSmemImpl(const void* func, size_t smem)
+{
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, size_t> set;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& cur = set[std::make_pair(dev, func)];
+  if (smem > cur)
+  {
+    cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cur = smem;
+  }
+}
 
 // ==================================================================================================
 // front end
@@ -326,12 +345,7 @@ static void launch_front_tiled(const FrontParams& p, const FrontCoef& cf, cudaSt
 {
   using G = FrontGeom<DS>;
   const size_t smem = (size_t)G::WP * sizeof(float2);
-  static bool attr_done = false; // per instantiation
-  if (!attr_done)
-  {
-    cudaFuncSetAttribute(k_front_tiled<U8, DS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_done = true;
-  }
+  EnsureDynSmem(k_front_tiled<U8, DS>, smem);
   dim3 grid(cdiv(p.nout, G::OB), p.S);
   k_front_tiled<U8, DS><<<grid, G::T, smem, st>>>(p, cf);
 }
@@ -367,12 +381,12 @@ void launch_front(const FrontParams& p, bool u8, cudaStream_t st)
   dim3 grid(cdiv(p.nout, kFrontTile), p.S);
   if (u8)
   {
-    cudaFuncSetAttribute(k_front<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    EnsureDynSmem(k_front<true>, smem);
     k_front<true><<<grid, kFrontTile, smem, st>>>(p);
   }
   else
   {
-    cudaFuncSetAttribute(k_front<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    EnsureDynSmem(k_front<false>, smem);
     k_front<false><<<grid, kFrontTile, smem, st>>>(p);
   }
 }
@@ -921,12 +935,8 @@ void launch_bb_lanes(const LanesParams& p, cudaStream_t st)
     return;
   // measurement aid: reserve extra (unused) dynamic shared memory so fewer throughput CTAs share the lanes' SMs
   static const int reserve_kb = getenv("RFM_LANES_RESERVE_KB") ? atoi(getenv("RFM_LANES_RESERVE_KB")) : 0;
-  static bool attr = false;
-  if (reserve_kb > 0 && !attr)
-  {
-    cudaFuncSetAttribute(k_bb_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, reserve_kb * 1024);
-    attr = true;
-  }
+  if (reserve_kb > 0)
+    EnsureDynSmem(k_bb_lanes, (size_t)reserve_kb * 1024);
   k_bb_lanes<<<cdiv(p.S, 32), 64, (size_t)reserve_kb * 1024, st>>>(p);
 }
 
@@ -998,7 +1008,7 @@ void launch_resample(const ResampleParams& p, cudaStream_t st)
     return;
   const unsigned max_span = (unsigned)((float)kResTile * p.pstep) + p.order + 8;
   const size_t smem = (size_t)(p.order + 2 + 2 * max_span) * sizeof(float);
-  cudaFuncSetAttribute(k_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  EnsureDynSmem(k_resample, smem);
   dim3 grid(cdiv(p.na, kResTile), p.S);
   k_resample<<<grid, kResTile, smem, st>>>(p, max_span);
 }
@@ -1188,12 +1198,7 @@ __global__ void __launch_bounds__(kResThreads) k_resample_tiled(ResampleParams p
 template <int GB, int NCH>
 static void launch_resample_tiled_gb(const ResampleParams& p, unsigned pitch, size_t smem, cudaStream_t st)
 {
-  static size_t attr = 0;
-  if (smem > attr)
-  {
-    cudaFuncSetAttribute(k_resample_tiled<GB, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr = smem;
-  }
+  EnsureDynSmem(k_resample_tiled<GB, NCH>, smem);
   dim3 grid(cdiv((p.na + 3) / 4, GB), cdiv(p.S, 32), NCH == 2 ? 1 : 2);
   k_resample_tiled<GB, NCH><<<grid, kResThreads, smem, st>>>(p, pitch);
 }
@@ -1506,12 +1511,7 @@ static void launch_rotfir_lanes(const RotFirParams& p, cudaStream_t st)
   const unsigned cyc = std::max(1u, (128u + N / 2) / N); // ~128 outputs per CTA
   const unsigned pitch = (cyc * N + N - 1) | 1u;        // odd: lanes (rows) hit distinct banks
   const size_t smem = (((N + 4 + 3) & ~3u) + (size_t)(MODE == 0 ? 1 : 2) * 32 * pitch) * sizeof(float);
-  static size_t attr = 0;
-  if (smem > attr)
-  {
-    cudaFuncSetAttribute(k_rotfir_lanes<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr = smem;
-  }
+  EnsureDynSmem(k_rotfir_lanes<MODE>, smem);
   const unsigned cycles = (p.g0 % N + p.n + N - 1) / N;
   dim3 grid(cdiv(cycles, cyc), cdiv(p.S, 32));
   k_rotfir_lanes<MODE><<<grid, 32 * kRlWarps, smem, st>>>(p, cyc, pitch);
@@ -1853,12 +1853,7 @@ void launch_rds_front(const RdsFrontParams& p, cudaStream_t st)
     n >>= 1;
   }
   const size_t smem = floats * sizeof(float) + f2 * sizeof(float2) + kRfTile * (sizeof(float2) + sizeof(float)); // + tile staging
-  static size_t attr = 0;
-  if (smem > attr)
-  {
-    cudaFuncSetAttribute(k_rds_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr = smem;
-  }
+  EnsureDynSmem(k_rds_front, smem);
   k_rds_front<<<p.S, kRfThreads, smem, st>>>(p);
 }
 

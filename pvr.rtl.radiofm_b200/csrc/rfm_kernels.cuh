@@ -20,6 +20,17 @@
 namespace rfm
 {
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device, per-function setting: remember the largest value set
+// for every (device, function) pair, so that decoders on several devices of one process (and several host threads)
+// all get it.  Cheap enough for every launch (one cudaGetDevice + a map lookup under a mutex).
+void EnsureDynSmemImpl(const void* func, size_t smem);
+template <typename F>
+inline void EnsureDynSmem(F* func, size_t smem)
+{
+  EnsureDynSmemImpl(reinterpret_cast<const void*>(func), smem);
+}
+
+
 constexpr unsigned kMaxFirTapsDev = 80; // >= cFirFilter MAX_NUMCOEF (75)
 
 // ---- per-stream scalar state, SoA: state[field * S + stream] --------------------------------------

@@ -138,6 +138,24 @@ def test_uecp_stream_of_the_batched_decoder(rfm):
     assert d.take_uecp(0) == b""
 
 
+def test_two_devices_in_one_process(rfm, port):
+    """per-device kernel attributes (dynamic shared memory limits) and state: a decoder on cuda:1 next to one on cuda:0"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    fs, ds, blk = RATES["2.4M"]
+    iq, _ = station("2.4M", 2)
+    outs = []
+    for dev in (1, 0, 1):
+        d = rfm.FmDecoderBatch(fs, -0.15 * fs, downsample=ds, max_block_len=blk, device=dev)
+        outs.append([d.process_u8(iq[None, b * blk:(b + 1) * blk])[0] for b in range(2)])
+        d.close()
+    o = port.OracleFmDecoder(fs, -0.15 * fs, downsample=ds)
+    want = [o.process_u8(iq[b * blk:(b + 1) * blk]) for b in range(2)]
+    for got in outs:
+        assert all(bits_equal(a, w) for a, w in zip(got, want))
+
+
 def test_mono_tone_snr(rfm, port):
     """BASELINE config 0: 1 s of 1.0 MS/s, 1 kHz mono tone; SNR within 0.1 dB of the reference chain."""
     fs, ds, blk = RATES["1.0M"]
