@@ -106,6 +106,65 @@ def test_fir_lowpass_and_const_taps(rfm, port):
     f.close()
 
 
+@pytest.mark.parametrize("ntaps,rows", [(8, 1), (9, 33), (10, 3), (11, 70), (29, 33), (44, 2), (50, 65), (75, 31), (74, 4), (73, 5), (5, 3)])
+def test_fir_tap_count_sweep(rfm, port, ntaps, rows):
+    """the lane = stream rotating FIR (groups of four outputs, rotation cycles of `ntaps` outputs, one-output path for
+    the N mod 4 leftovers and the block edges) for every residue of N mod 4, row counts that leave partial warps, and
+    call lengths around the cycle length; 5 taps takes the thread-per-output form.  InitConstFir only sets the real
+    path's taps (FirFilter.cpp:302-320), so this sweep is the real Process."""
+    rng = np.random.default_rng(100 + ntaps)
+    L = port.lib()
+    f = rfm.FirFilterBatch(rows, max_len=4096)
+    hs = [L.rfo_fir_create() for _ in range(rows)]
+    taps = rng.standard_normal(ntaps).astype(np.float32)
+    f.init_const(taps, 48000.0)
+    for h in hs:
+        L.rfo_fir_init_const(h, taps.size, P(taps), 48000.0)
+    for n in (1, ntaps - 1, ntaps, ntaps + 1, 4 * ntaps + 3, 1000, 2, 4096):
+        x = rng.standard_normal((rows, n)).astype(np.float32)
+        y = f.process_real(x)
+        for r, h in enumerate(hs):
+            ref = x[r].copy()
+            L.rfo_fir_process_real(h, P(ref), n)
+            assert bits_equal(y[r], ref), ("real", ntaps, r, n)
+    for h in hs:
+        L.rfo_fir_destroy(h)
+    f.close()
+
+
+@pytest.mark.parametrize("spec,rows", [((0, 1.0, 60.0, 15000.0, 21000.0, 48000.0), 33), ((0, 1.0, 40.0, 2400.0, 3120.0, 31250.0), 70),
+                                       ((0, 2.0, 50.0, 5000.0, 9000.0, 48000.0), 3), ((0, 1.0, 30.0, 1000.0, 6000.0, 48000.0), 65),
+                                       ((0, 0.5, 45.0, 3000.0, 5500.0, 48000.0), 1)])
+def test_fir_two_channel_and_complex_interleaved(rfm, port, spec, rows):
+    """ProcessTwo and the complex Process interleaved (they share one delay line and the rotation index,
+    FirFilter.cpp:330-413), short and long calls, for several Kaiser designs (different tap counts).  The real
+    Process is not mixed in: it has its own delay line but the SAME rotation index, so in the reference a real call
+    after complex calls finds stale slots in its line -- a use the chain never makes and the library does not
+    reproduce."""
+    rng = np.random.default_rng(int(spec[3]))
+    L = port.lib()
+    f = rfm.FirFilterBatch(rows, max_len=4096)
+    hs = [L.rfo_fir_create() for _ in range(rows)]
+    nt = f.init_lp(*spec)
+    for h in hs:
+        assert L.rfo_fir_init_lp(h, *spec) == nt
+    for n in (1, nt - 1, nt + 1, 4 * nt + 3, 1000, 2, 4096):
+        a, b = rng.standard_normal((2, rows, n)).astype(np.float32)
+        ya, yb = f.process_two(a, b)
+        z = rng.standard_normal((rows, n, 2)).astype(np.float32)
+        yz = f.process_complex(z)
+        for r, h in enumerate(hs):
+            ra, rb = a[r].copy(), b[r].copy()
+            L.rfo_fir_process_two(h, P(ra), P(rb), n)
+            rz = z[r].copy()
+            L.rfo_fir_process_complex(h, P(rz), n)
+            assert bits_equal(ya[r], ra) and bits_equal(yb[r], rb), ("two", nt, r, n)
+            assert bits_equal(yz[r], rz), ("complex", nt, r, n)
+    for h in hs:
+        L.rfo_fir_destroy(h)
+    f.close()
+
+
 @pytest.mark.parametrize("rate", ["1.0M", "2.4M"])
 def test_rds_processor_from_baseband(rfm, port, rate):
     """cRDSRxSignalProcessor on its own: fed with the demodulated baseband of the oracle decoder (its `baseband` tap is
