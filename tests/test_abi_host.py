@@ -80,6 +80,28 @@ def test_rds_check_block_kat(rfm):
         assert rfm.rds_check_block(w, osyn, bool(fec)) == (syn, fixed)
 
 
+def test_rds_syndrome_tables_against_the_bit_loop(rfm):
+    """the table-driven syndrome (four byte lookups) against the reference's 16-step loop (RDSProcess.cpp:386-396)
+    restated here, on random 26-bit words and every single-bit word"""
+    parity = [0x2DC, 0x16E, 0x0B7, 0x287, 0x39F, 0x313, 0x355, 0x376, 0x1BB, 0x201, 0x3DC, 0x1EE, 0x0F7, 0x2A7, 0x38F, 0x31B]
+
+    def loop(word, osyn):
+        block = word & 0x3FFFFFF
+        syn = block >> 16
+        for i in range(16):
+            if block & 0x8000:
+                syn ^= parity[i]
+            block <<= 1
+        return syn ^ osyn
+
+    rng = np.random.default_rng(7)
+    words = [1 << b for b in range(26)] + rng.integers(0, 1 << 26, 4000).tolist() + [0, (1 << 26) - 1, (1 << 32) - 1]
+    for w in words:
+        for osyn in (0x3D8, 0x258, 0x3CC):
+            assert rfm.rds_check_block(int(w), osyn, False)[0] == loop(int(w), osyn)
+    assert rfm.lib().rfm_source_block_length(70000) == 69632      # cRtlSdrSource's rule is host-only arithmetic
+
+
 def test_rds_block_sync_matches_oracle(rfm, port, synth):
     rng = np.random.default_rng(3)
     groups = synth.rds_group_stream(0x1234, "ABCDEFGH", 40, radiotext="hello b200")
