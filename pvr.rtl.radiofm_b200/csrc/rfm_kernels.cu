@@ -776,6 +776,7 @@ struct LanesSmem
   float kf[8];
 };
 
+template <bool FAKE_SINCOS> // true: RFM_DEBUG_FAKE_SINCOS timing experiment (wrong results)
 __global__ void __launch_bounds__(64) k_bb_lanes(LanesParams p)
 {
   __shared__ LanesSmem sm;
@@ -881,7 +882,7 @@ __global__ void __launch_bounds__(64) k_bb_lanes(LanesParams p)
         for (unsigned k = 0; k < tn; ++k)
         {
           const float bb = sm.ring[b][lane][k];
-          const float p38 = pilot_step_fast(pl, bb, pk, sca, bad);
+          const float p38 = pilot_step_fast<FAKE_SINCOS>(pl, bb, pk, sca, bad);
           sm.rawt[lane][k] = mulf(p38, mulf(2.0f, bb)); // FmDecode.cpp:455-456
         }
       }
@@ -935,9 +936,16 @@ void launch_bb_lanes(const LanesParams& p, cudaStream_t st)
     return;
   // measurement aid: reserve extra (unused) dynamic shared memory so fewer throughput CTAs share the lanes' SMs
   static const int reserve_kb = getenv("RFM_LANES_RESERVE_KB") ? atoi(getenv("RFM_LANES_RESERVE_KB")) : 0;
+  static const bool fake = getenv("RFM_DEBUG_FAKE_SINCOS") && atoi(getenv("RFM_DEBUG_FAKE_SINCOS")) != 0;
   if (reserve_kb > 0)
-    EnsureDynSmem(k_bb_lanes, (size_t)reserve_kb * 1024);
-  k_bb_lanes<<<cdiv(p.S, 32), 64, (size_t)reserve_kb * 1024, st>>>(p);
+  {
+    EnsureDynSmem(k_bb_lanes<false>, (size_t)reserve_kb * 1024);
+    EnsureDynSmem(k_bb_lanes<true>, (size_t)reserve_kb * 1024);
+  }
+  if (fake)
+    k_bb_lanes<true><<<cdiv(p.S, 32), 64, (size_t)reserve_kb * 1024, st>>>(p);
+  else
+    k_bb_lanes<false><<<cdiv(p.S, 32), 64, (size_t)reserve_kb * 1024, st>>>(p);
 }
 
 

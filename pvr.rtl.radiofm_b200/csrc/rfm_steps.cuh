@@ -113,11 +113,19 @@ RFM_HD float pilot_step(PilotState& st, float x, const PilotConstDev& k)
   return out;
 }
 
+// FAKE_SINCOS: timing experiment only (RFM_DEBUG_FAKE_SINCOS: what would a shorter pilot chain buy?) -- the hardware's
+// approximate sincos, results are NOT the reference's
+template <bool FAKE_SINCOS = false>
 RFM_HD float pilot_step_fast(PilotState& st, float x, const PilotConstDev& k, const SinCosRegs& sca, bool& bad)
 {
   float ps, pc;
   bad = bad | (!(absf(st.phase) < 16.0f));
-  rfm_sincos_core_a(st.phase, sca, &ps, &pc);
+#if defined(__CUDA_ARCH__)
+  if (FAKE_SINCOS)
+    __sincosf(st.phase, &ps, &pc);
+  else
+#endif
+    rfm_sincos_core_a(st.phase, sca, &ps, &pc);
   const float out = mulf(mulf(2.0f, ps), pc);
   float pi = mulf(ps, x);
   float pq = mulf(pc, x);
