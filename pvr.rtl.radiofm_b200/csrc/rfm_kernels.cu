@@ -1365,19 +1365,22 @@ __global__ void __launch_bounds__(32 * kRlWarps) k_rotfir_lanes(RotFirParams p, 
     {
       const float2* src = reinterpret_cast<const float2*>(p.inA) + (size_t)(s0 + r) * p.in_stride + ia;
       float2* dst = reinterpret_cast<float2*>(X) + (size_t)r * pitch;
-      for (int c = lane; c < wlen; c += 32)
+#pragma unroll 4
+      for (int c = lane; c < wlen; c += 32) // (unrolled: four loads in flight per lane, the tile load is latency-bound)
         dst[c] = src[c];
     }
     else
     {
       const float* src = p.inA + (size_t)(s0 + r) * p.in_stride + ia;
       float* dst = X + (size_t)r * pitch;
+#pragma unroll 4
       for (int c = lane; c < wlen; c += 32)
         dst[c] = src[c];
       if (MODE == 1)
       {
         const float* srcb = p.inB + (size_t)(s0 + r) * p.in_stride + ia;
         float* dstb = X + (size_t)(32 + r) * pitch;
+#pragma unroll 4
         for (int c = lane; c < wlen; c += 32)
           dstb[c] = srcb[c];
       }
