@@ -1693,33 +1693,42 @@ __global__ void __launch_bounds__(kRfThreads) k_rds_front(RdsFrontParams p)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // layout: taps of every stage, LP taps, then the V buffers of stage 0 .. nst-1 and of the LP
   float* s_h = reinterpret_cast<float*>(smem_raw);
-  unsigned hoff[kRfMaxStages + 1];
-  unsigned acc_f = 0;
-  for (unsigned k = 0; k < p.nst; ++k)
+  // per-stage descriptors in SHARED memory: the stage loops index them with a run-time k, and as local arrays they
+  // lived on the stack (88 bytes of local memory, a long-scoreboard stall per access: 26 % of this kernel's stalls)
+  __shared__ unsigned s_hoff[kRfMaxStages + 1], s_boff[kRfMaxStages + 1], s_len[kRfMaxStages], s_hist[kRfMaxStages + 1],
+      s_kind[kRfMaxStages], s_lpoff[2];
+  if (threadIdx.x == 0)
   {
-    hoff[k] = acc_f;
-    acc_f += (p.st[k].len + 1u) & ~1u;
-  }
-  hoff[p.nst] = acc_f;
-  float* s_lp = s_h + acc_f;
-  acc_f += (p.lp_n + 1u) & ~1u;
-  float2* vbuf = reinterpret_cast<float2*>(s_h + acc_f);
-  float2* B[kRfMaxStages + 1];
-  {
-    unsigned off = 0, n = kRfTile;
+    unsigned acc = 0, off = 0, n = kRfTile;
+    for (unsigned k = 0; k < p.nst; ++k)
+    {
+      s_hoff[k] = acc;
+      acc += (p.st[k].len + 1u) & ~1u;
+      s_len[k] = p.st[k].len;
+      s_hist[k] = p.st[k].hist;
+      s_kind[k] = (unsigned)p.st[k].kind;
+    }
+    s_hoff[p.nst] = acc;
+    s_hist[p.nst] = p.lp_n - 1;
+    s_lpoff[0] = acc;
+    acc += (p.lp_n + 1u) & ~1u;
+    s_lpoff[1] = acc;
     for (unsigned k = 0; k <= p.nst; ++k)
     {
-      B[k] = vbuf + off;
-      const unsigned hist = (k < p.nst) ? p.st[k].hist : p.lp_n - 1;
-      off += hist + n;
+      s_boff[k] = off;
+      off += s_hist[k] + n;
       n >>= 1;
     }
   }
+  __syncthreads();
+  float* s_lp = s_h + s_lpoff[0];
+  float2* vbuf = reinterpret_cast<float2*>(s_h + s_lpoff[1]);
+#define RFM_B(k) (vbuf + s_boff[k])
   const unsigned tid = threadIdx.x;
   const unsigned s = blockIdx.x;
   for (unsigned k = 0; k < p.nst; ++k)
-    for (unsigned i = tid; i < p.st[k].len; i += kRfThreads)
-      s_h[hoff[k] + i] = p.st[k].h ? p.st[k].h[i] : 0.0f;
+    for (unsigned i = tid; i < s_len[k]; i += kRfThreads)
+      s_h[s_hoff[k] + i] = p.st[k].h ? p.st[k].h[i] : 0.0f;
   for (unsigned i = tid; i < p.lp_n; i += kRfThreads)
     s_lp[i] = p.lp_coef[i];
   // histories from the previous block
@@ -1729,9 +1738,9 @@ __global__ void __launch_bounds__(kRfThreads) k_rds_front(RdsFrontParams p)
   float2* tails = reinterpret_cast<float2*>(p.tails) + (size_t)s * p.tail_stride;
   for (unsigned k = 0; k < nbuf; ++k)
   {
-    const unsigned hist = (k < p.nst) ? p.st[k].hist : p.lp_n - 1;
+    const unsigned hist = s_hist[k];
     for (unsigned i = tid; i < hist; i += kRfThreads)
-      B[k][i] = tails[p.tail_off[k] + i];
+      RFM_B(k)[i] = tails[p.tail_off[k] + i];
   }
   __syncthreads();
 
@@ -1745,13 +1754,8 @@ __global__ void __launch_bounds__(kRfThreads) k_rds_front(RdsFrontParams p)
   float* s_bbst;
   float2* s_oscst;
   {
-    unsigned off = 0, n = kRfTile;
-    for (unsigned k = 0; k <= p.nst; ++k)
-    {
-      off += ((k < p.nst) ? p.st[k].hist : p.lp_n - 1) + n;
-      n >>= 1;
-    }
-    s_oscst = vbuf + off;
+    unsigned n = kRfTile >> p.nst;
+    s_oscst = vbuf + s_boff[p.nst] + s_hist[p.nst] + n;
     s_bbst = reinterpret_cast<float*>(s_oscst + kRfTile);
   }
   auto stage_tile = [&](unsigned t0n) {
@@ -1777,7 +1781,7 @@ __global__ void __launch_bounds__(kRfThreads) k_rds_front(RdsFrontParams p)
       float2 r;
       r.x = subf(mulf(b, o.x), mulf(0.0f, o.y));
       r.y = addf(mulf(b, o.y), mulf(0.0f, o.x));
-      B[0][p.st[0].hist + i] = r;
+      RFM_B(0)[s_hist[0] + i] = r;
     }
     __syncthreads();
     if (t0 + kRfTile < p.nb)
@@ -1786,16 +1790,20 @@ __global__ void __launch_bounds__(kRfThreads) k_rds_front(RdsFrontParams p)
     for (unsigned k = 0; k < p.nst; ++k)
     {
       const unsigned nout = n >> 1;
-      const unsigned ohist = (k + 1 < p.nst) ? p.st[k + 1].hist : N - 1;
+      const unsigned ohist = s_hist[k + 1];
+      const unsigned kind = s_kind[k], len = s_len[k];
+      const float* hk = s_h + s_hoff[k];
+      const float2* bin = RFM_B(k);
+      float2* bout = RFM_B(k + 1);
       const bool last = (k + 1 == p.nst) && p.dec_out != nullptr;
       const bool to_lpv = (k + 1 == p.nst) && ext_lp;
       for (unsigned o = tid; o < nout; o += kRfThreads)
       {
-        const float2 v = hb_out(p.st[k].kind, p.st[k].len, s_h + hoff[k], B[k], o);
+        const float2 v = hb_out((int)kind, len, hk, bin, o);
         if (to_lpv)
           lpv[out_base + o] = v;
         else
-          B[k + 1][ohist + o] = v;
+          bout[ohist + o] = v;
         if (last) // decimator output (cRDSRxSignalProcessor's m_RdsRaw before the LP), kept for the stage taps
           reinterpret_cast<float2*>(p.dec_out)[(size_t)s * p.out_stride + out_base + o] = v;
       }
@@ -1806,7 +1814,7 @@ __global__ void __launch_bounds__(kRfThreads) k_rds_front(RdsFrontParams p)
     for (unsigned i = tid; i < n && !ext_lp; i += kRfThreads)
     {
       unsigned k = (p.g0 + out_base + i) % N;
-      const float2* x = B[p.nst] + (N - 1) + i;
+      const float2* x = RFM_B(p.nst) + (N - 1) + i;
       float2 v = x[-(int)k];
       float ar = mulf(s_lp[k], v.x), ai = mulf(s_lp[k], v.y);
       // uniform trip count (the start tap differs per lane): wrap with a compare / select, no modulo
@@ -1828,13 +1836,14 @@ __global__ void __launch_bounds__(kRfThreads) k_rds_front(RdsFrontParams p)
       unsigned nk = tn;
       for (unsigned k = 0; k < nbuf; ++k)
       {
-        const unsigned hist = (k < p.nst) ? p.st[k].hist : N - 1;
+        const unsigned hist = s_hist[k];
+        float2* bk = RFM_B(k);
         float2 v0 = make_float2(0.f, 0.f);
         if (tid < hist)
-          v0 = B[k][nk + tid];
+          v0 = bk[nk + tid];
         __syncthreads();
         if (tid < hist)
-          B[k][tid] = v0;
+          bk[tid] = v0;
         nk >>= 1;
       }
     }
@@ -1842,11 +1851,12 @@ __global__ void __launch_bounds__(kRfThreads) k_rds_front(RdsFrontParams p)
   }
   for (unsigned k = 0; k < nbuf; ++k)
   {
-    const unsigned hist = (k < p.nst) ? p.st[k].hist : p.lp_n - 1;
+    const unsigned hist = s_hist[k];
     for (unsigned i = tid; i < hist; i += kRfThreads)
-      tails[p.tail_off[k] + i] = B[k][i];
+      tails[p.tail_off[k] + i] = RFM_B(k)[i];
   }
 }
+#undef RFM_B
 
 void launch_rds_front(const RdsFrontParams& p, cudaStream_t st)
 {
