@@ -1359,30 +1359,56 @@ __global__ void __launch_bounds__(32 * kRlWarps) k_rotfir_lanes(RotFirParams p, 
   for (int i = tid; i < N + 4; i += 32 * kRlWarps)
     s_h[i] = i < N ? p.coef[i] : 0.0f;
   const int wlen = ib - ia + N - 1; // V[ia .. ia + wlen)
-  for (unsigned r = warp; r < rows; r += kRlWarps)
+  // stage the window: a warp owns rows warp, warp + 4, ... (8 of them) and loads the same column of ALL its rows before
+  // storing any (eight independent loads in flight per lane: the tile load is latency-bound, 28 % of the kernel's
+  // stalls when the rows went one after the other)
   {
-    if (MODE == 2)
+    constexpr int RW = 32 / kRlWarps;
+    for (int c = lane; c < wlen; c += 32)
     {
-      const float2* src = reinterpret_cast<const float2*>(p.inA) + (size_t)(s0 + r) * p.in_stride + ia;
-      float2* dst = reinterpret_cast<float2*>(X) + (size_t)r * pitch;
-#pragma unroll 4
-      for (int c = lane; c < wlen; c += 32) // (unrolled: four loads in flight per lane, the tile load is latency-bound)
-        dst[c] = src[c];
-    }
-    else
-    {
-      const float* src = p.inA + (size_t)(s0 + r) * p.in_stride + ia;
-      float* dst = X + (size_t)r * pitch;
-#pragma unroll 4
-      for (int c = lane; c < wlen; c += 32)
-        dst[c] = src[c];
-      if (MODE == 1)
+      if (MODE == 2)
       {
-        const float* srcb = p.inB + (size_t)(s0 + r) * p.in_stride + ia;
-        float* dstb = X + (size_t)(32 + r) * pitch;
-#pragma unroll 4
-        for (int c = lane; c < wlen; c += 32)
-          dstb[c] = srcb[c];
+        float2 v[RW];
+#pragma unroll
+        for (int j = 0; j < RW; ++j)
+        {
+          const unsigned r = warp + kRlWarps * j;
+          if (r < rows)
+            v[j] = (reinterpret_cast<const float2*>(p.inA) + (size_t)(s0 + r) * p.in_stride + ia)[c];
+        }
+#pragma unroll
+        for (int j = 0; j < RW; ++j)
+        {
+          const unsigned r = warp + kRlWarps * j;
+          if (r < rows)
+            (reinterpret_cast<float2*>(X) + (size_t)r * pitch)[c] = v[j];
+        }
+      }
+      else
+      {
+        float va[RW], vb[RW];
+#pragma unroll
+        for (int j = 0; j < RW; ++j)
+        {
+          const unsigned r = warp + kRlWarps * j;
+          if (r < rows)
+          {
+            va[j] = (p.inA + (size_t)(s0 + r) * p.in_stride + ia)[c];
+            if (MODE == 1)
+              vb[j] = (p.inB + (size_t)(s0 + r) * p.in_stride + ia)[c];
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < RW; ++j)
+        {
+          const unsigned r = warp + kRlWarps * j;
+          if (r < rows)
+          {
+            (X + (size_t)r * pitch)[c] = va[j];
+            if (MODE == 1)
+              (X + (size_t)(32 + r) * pitch)[c] = vb[j];
+          }
+        }
       }
     }
   }
