@@ -411,22 +411,13 @@ __global__ void __launch_bounds__(kDcThreads) k_dc_chain_uniform(DcParams p, DcT
   constexpr unsigned HH = (L - 1) / 2; // history entries in each of E and O
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* vbuf = reinterpret_cast<float2*>(smem_raw);
-  // offsets, not pointers: keeps every access an LDS / STS (a pointer array would decay to generic loads)
-  unsigned eo[kDcMaxStages + 1], oo[kDcMaxStages + 1];
-  {
-    unsigned off = 0, n = kDcTileFast;
-    for (unsigned k = 0; k < p.nst; ++k)
-    {
-      eo[k] = off;
-      off += HH + n / 2 + R; // + R: the last, partial group of outputs may read (never use) a few entries past the end
-      oo[k] = off;
-      off += HH + n / 2 + R;
-      n >>= 1;
-    }
-    eo[p.nst] = oo[p.nst] = 0;
-  }
-#define E_(k) (vbuf + eo[k])
-#define O_(k) (vbuf + oo[k])
+  // buffer offsets in closed form (every stage has the same history, the tile halves from stage to stage): arrays
+  // indexed with the run-time stage number would live in local memory
+  //   E(k) starts at sum_{j<k} 2 (HH + (T >> j) / 2 + R) = 2 k (HH + R) + 2 T - (T >> (k - 1)),  O(k) follows E(k)
+  auto eo = [&](unsigned k) { return 2u * k * (HH + R) + (k ? 2u * kDcTileFast - (kDcTileFast >> (k - 1)) : 0u); };
+  auto oo = [&](unsigned k) { return eo(k) + HH + (kDcTileFast >> (k + 1)) + R; };
+#define E_(k) (vbuf + eo(k))
+#define O_(k) (vbuf + oo(k))
   const unsigned tid = threadIdx.x;
   const unsigned c = blockIdx.x, row = blockIdx.y;
   const unsigned c_lo = c * p.chunk;
