@@ -231,8 +231,9 @@ RFM_API int rfm_downconvert_process_device(rfm_downconvert* d, int mode, const v
 /* ------------------------------------------------------------------------------------------------
  * cDownsampleFilter (DownConvert.h:21-60, DownConvert.cpp:58-256), batched over rows: Lanczos-windowed sinc FIR with
  * decimation, in the two forms the chain uses -- complex input + integer factor (m_ReSampleInput, FmDecode.cpp:257-261)
- * and real input + fractional factor (m_ReSampleMono / m_ReSampleStereo, :263-273).  Real + integer is not on the hot
- * path and returns RFM_ERR_UNSUPPORTED; calls shorter than the filter order likewise.
+ * and real input + fractional factor (m_ReSampleMono / m_ReSampleStereo, :263-273) -- plus real input + integer
+ * factor (DownConvert.cpp:164-192; no caller in the reference).  Complex + fractional (an endless loop in the
+ * reference) and calls shorter than the filter order return RFM_ERR_UNSUPPORTED.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct rfm_downsample rfm_downsample;
 /* cDownsampleFilter(filter_order, cutoff, downsample, integer_factor) -- DownConvert.cpp:63-81 */
@@ -248,7 +249,8 @@ RFM_API uint32_t rfm_downsample_max_outputs(const rfm_downsample* f, uint32_t n)
 /* unsigned Process(const ComplexType*, ComplexType*, unsigned) -- DownConvert.cpp:98-154; in [rows][n][2] host,
  * out [rows][*n_out][2] host (rows packed back to back); *n_out = the return value */
 RFM_API int rfm_downsample_process_complex(rfm_downsample* f, const float* in, float* out, uint32_t n, uint32_t* n_out);
-/* unsigned Process(const RealType*, RealType*, unsigned), fractional branch -- DownConvert.cpp:195-256 */
+/* unsigned Process(const RealType*, RealType*, unsigned) -- DownConvert.cpp:156-256 (integer branch :164-192,
+ * fractional branch :195-233, whichever the object was created with) */
 RFM_API int rfm_downsample_process_real(rfm_downsample* f, const float* in, float* out, uint32_t n, uint32_t* n_out);
 /* device rows, enqueue only; strides in samples */
 RFM_API int rfm_downsample_process_complex_device(rfm_downsample* f, const float* d_in, size_t in_stride, float* d_out,

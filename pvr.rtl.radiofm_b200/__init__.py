@@ -739,7 +739,7 @@ class FirFilterBatch(_RowFilter):
 
 
 class DownsampleFilterBatch:
-    """rows x cDownsampleFilter (DownConvert.h:21-60): complex + integer factor, or real + fractional factor."""
+    """rows x cDownsampleFilter (DownConvert.h:21-60): complex + integer factor, real + fractional or integer factor."""
 
     def __init__(self, rows: int, filter_order: int, cutoff: float, downsample: float = 1.0, integer_factor: bool = True,
                  max_len: int = 65536, device: int = -1):

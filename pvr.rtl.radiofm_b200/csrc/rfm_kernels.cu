@@ -1545,7 +1545,8 @@ template <int MODE>
 static void launch_rotfir_lanes(const RotFirParams& p, cudaStream_t st)
 {
   const unsigned N = p.taps;
-  const unsigned cyc = std::max(1u, (128u + N / 2) / N); // ~128 outputs per CTA
+  static const unsigned target = getenv("RFM_ROTFIR_OUT") ? (unsigned)atoi(getenv("RFM_ROTFIR_OUT")) : 128u; // measurement aid
+  const unsigned cyc = std::max(1u, (target + N / 2) / N); // ~128 outputs per CTA
   const unsigned pitch = (cyc * N + N - 1) | 1u;        // odd: lanes (rows) hit distinct banks
   const size_t smem = (((N + 4 + 3) & ~3u) + (size_t)(MODE == 0 ? 1 : 2) * 32 * pitch) * sizeof(float);
   EnsureDynSmem(k_rotfir_lanes<MODE>, smem);

@@ -770,9 +770,33 @@ int rfm_rdsproc_take_groups(rfm_rdsproc* r, uint32_t row, uint16_t* groups, uint
 // ==================================================================================================
 // cDownsampleFilter (DownConvert.h:21-60, DownConvert.cpp:58-256): Lanczos-windowed sinc FIR with decimation.
 // The two forms the chain uses: complex input with an integer factor (k_front, :98-154) and real input with a
-// fractional factor (k_resample, :195-233).  The other combinations are not on the hot path: real + integer returns
-// RFM_ERR_UNSUPPORTED, complex + fractional is an endless loop in the reference (pstep == 0) and returns it too.
+// fractional factor (k_resample, :195-233).  Real + integer (:164-192, no caller in the reference) is a plain
+// thread-per-output kernel below; complex + fractional is an endless loop in the reference (pstep == 0) and returns
+// RFM_ERR_UNSUPPORTED.
 // ==================================================================================================
+
+// Real input, integer factor: y[i] = sum_{j = 1 .. order} x[p - j] c[j], p = pos + i ds, ascending j, every product and
+// sum rounded on its own (DownConvert.cpp:172-190; both of its loops are this sum over V = [history(order) | block],
+// x[p - j] = V[order + p - j]).  Thread per output, taps in shared memory; not on the hot path, so no window staging.
+__global__ void __launch_bounds__(128) k_downsample_real_int(const float* __restrict__ v, size_t v_stride,
+                                                             const float* __restrict__ coeff, unsigned order, unsigned ds,
+                                                             unsigned pos, unsigned nout, float* __restrict__ out,
+                                                             size_t out_stride)
+{
+  extern __shared__ float s_c[]; // c[0 .. order]
+  for (unsigned j = threadIdx.x; j <= order; j += 128)
+    s_c[j] = coeff[j];
+  __syncthreads();
+  const unsigned i = blockIdx.x * 128 + threadIdx.x;
+  if (i >= nout)
+    return;
+  const float* x = v + (size_t)blockIdx.y * v_stride + order + pos + (size_t)i * ds;
+  float y = 0.0f;
+  for (unsigned j = 1; j <= order; ++j)
+    y = addf(y, mulf(x[-(int)j], s_c[j]));
+  out[(size_t)blockIdx.y * out_stride + i] = y;
+}
+
 struct rfm_downsample
 {
   unsigned rows = 0, cap = 0, order = 0, ds_int = 0;
@@ -908,9 +932,6 @@ int rfm_downsample_process_real_device(rfm_downsample* f, const float* d_in, siz
     *n_out = 0;
   if (!f || !d_in || !d_out)
     return PFail(RFM_ERR_INVALID, "rfm_downsample_process_real_device: invalid argument");
-  if (f->integer)
-    return PFail(RFM_ERR_UNSUPPORTED, "rfm_downsample: the real overload is built for the fractional factor the chain "
-                                      "uses (DownConvert.cpp:195-233); real + integer is not on the hot path");
   if (n == 0)
     return RFM_OK;
   if (n > f->cap)
@@ -919,6 +940,30 @@ int rfm_downsample_process_real_device(rfm_downsample* f, const float* d_in, siz
     return PFail(RFM_ERR_UNSUPPORTED, "rfm_downsample: calls shorter than the filter order are not supported");
   cudaSetDevice(f->device);
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  if (f->integer) // DownConvert.cpp:164-192
+  {
+    if (f->ds_int == 0)
+      return PFail(RFM_ERR_INVALID, "rfm_downsample: integer factor of 0");
+    const unsigned pos = f->pos_int, ds = f->ds_int;
+    const unsigned nout = pos < n ? (n - pos + ds - 1) / ds : 0;
+    if (nout > out_stride)
+      return PFail(RFM_ERR_INVALID, "rfm_downsample: out_stride is shorter than the output");
+    dim3 grid((n + 255) / 256, f->rows);
+    k_to_v<<<grid, 256, 0, st>>>(reinterpret_cast<const char*>(d_in), in_stride * 4, reinterpret_cast<char*>(f->d_v),
+                                 f->v_stride * 4, f->order, n, 4);
+    if (nout)
+      k_downsample_real_int<<<dim3((nout + 127) / 128, f->rows), 128, (f->order + 1) * sizeof(float), st>>>(
+          f->d_v, f->v_stride, f->d_coeff, f->order, ds, pos, nout, d_out, out_stride);
+    TailParams tp;
+    tp.count = 0;
+    tp.d[tp.count++] = {f->d_v, f->d_v, f->v_stride * 4, f->order, n, 4, f->rows};
+    launch_tails(tp, f->rows, st);
+    f->pos_int = pos + nout * ds - n; // :192
+    rfm::g_launches += 3;
+    if (n_out)
+      *n_out = nout;
+    return cudaGetLastError() == cudaSuccess ? RFM_OK : PFail(RFM_ERR_CUDA, "rfm_downsample: kernel launch failed");
+  }
   float pos_next = 0.0f;
   const unsigned na = FractionalOutputs(f->pos_frac, f->pstep, n, &pos_next);
   dim3 grid((n + 255) / 256, f->rows);

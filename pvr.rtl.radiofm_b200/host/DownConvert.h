@@ -12,7 +12,8 @@
 #include "Definitions.h"
 
 // cDownsampleFilter (DownConvert.h:21-60) over rfm_downsample_*: the complex + integer and the real + fractional forms
-// (the ones cFmDecoder instantiates, FmDecode.cpp:257-273); the other combinations return 0 samples.
+// (the ones cFmDecoder instantiates, FmDecode.cpp:257-273) and real + integer; complex + fractional (an endless loop in
+// the reference) returns 0 samples.
 class cDownsampleFilter
 {
 public:

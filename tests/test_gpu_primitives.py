@@ -240,3 +240,28 @@ def test_downsample_filter_both_live_forms(rfm, port):
         with pytest.raises(rfm.RadioFmError):
             f.process_complex(np.zeros((rows, 4096, 2), dtype=np.float32))
         f.close()
+
+
+def test_downsample_filter_real_integer(rfm, port):
+    """cDownsampleFilter real input + integer factor (DownConvert.cpp:164-192; no caller in the reference, provided for
+    users of the class): call lengths that leave every residue of the output position, Reset in between."""
+    rng = np.random.default_rng(29)
+    L = port.lib()
+    rows = 3
+    for order, ds, cutoff in ((32, 4, 0.15), (40, 5, 0.12), (24, 1, 0.4), (130, 7, 0.07)):
+        f = rfm.DownsampleFilterBatch(rows, order, cutoff, ds, True, max_len=8192)
+        hs = [L.rfo_downsample_create(order, cutoff, float(ds), 1) for _ in range(rows)]
+        for rep in range(2):
+            for n in (8192, 1001, 4097, 130, 8191):
+                x = rng.standard_normal((rows, n)).astype(np.float32)
+                y = f.process_real(x)
+                for r, h in enumerate(hs):
+                    ref = np.zeros(n, dtype=np.float32)
+                    m = L.rfo_downsample_process_real(h, P(x[r].copy()), P(ref), n)
+                    assert y.shape[1] == m and bits_equal(y[r], ref[:m]), ("real integer", order, ds, rep, r, n)
+            f.reset()
+            for h in hs:
+                L.rfo_downsample_reset(h)
+        for h in hs:
+            L.rfo_downsample_destroy(h)
+        f.close()

@@ -175,6 +175,14 @@ def test_port_matches_golden_primitives(port):
     k2 = L.rfo_downsample_process_real(h, P(r[1700:]), P(y[k1:]), 1300)
     L.rfo_downsample_destroy(h)
     assert [k1, k2] == g["ds_frac_split"].tolist() and bits_equal(y[:k1 + k2], g["ds_frac_out"])
+    # integer (real), the last call shorter than the filter order
+    h = L.rfo_downsample_create(40, 0.12, 5.0, 1)
+    y = np.zeros(3000, dtype=np.float32)
+    k1 = L.rfo_downsample_process_real(h, P(r), P(y), 1501)
+    k2 = L.rfo_downsample_process_real(h, P(r[1501:]), P(y[k1:]), 1478)
+    k3 = L.rfo_downsample_process_real(h, P(r[2979:]), P(y[k1 + k2:]), 21)
+    L.rfo_downsample_destroy(h)
+    assert [k1, k2, k3] == g["ds_rint_split"].tolist() and bits_equal(y[:k1 + k2 + k3], g["ds_rint_out"])
     # CRDSDownConvert
     h = L.rfo_rdsdc_create()
     L.rfo_rdsdc_set_frequency(h, -57000.0)
