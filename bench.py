@@ -45,6 +45,11 @@ NCU_TRAFFIC_BYTES = {
     "k_rds_front": 101.139968e6 + 12.347392e6,
 }
 
+# warp instructions of one step (one block of 4096 streams through every kernel of the chain), ncu
+# smsp__inst_executed.sum summed over the step's launches (profiles/r01_ncu_top_kernels.txt)
+NCU_WARP_INSTR_PER_STEP = 1.35e9
+SCHEDULERS = 148 * 4
+
 
 def load_peaks():
     try:
@@ -287,6 +292,15 @@ def run_b200(args):
                 "timed_pass": "second pass of the same K steps with per-kernel CUDA events (the metric pass carries none)",
                 "ms_per_step_with_events": (ms_prof / K) if ms_prof else None,
                 "kernel_ms_per_step": {k: round(v[0] / K, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
+    if S == STREAMS_PER_GPU and clk.get("sm_mhz"):
+        # the bound that actually binds beside the pilot recurrence: warp-instruction issue slots (SURVEY.md 8d asks for
+        # the FP32 figure alongside the HBM one); every FP32 operation of the bit-exact chain is its own instruction
+        issue_peak = SCHEDULERS * float(clk["sm_mhz"]) * 1e6
+        roofline["issue"] = {"warp_instructions_per_step": NCU_WARP_INSTR_PER_STEP, "schedulers": SCHEDULERS,
+                             "achieved_per_s": NCU_WARP_INSTR_PER_STEP / (ms / K * 1e-3), "peak_per_s": issue_peak,
+                             "frac": NCU_WARP_INSTR_PER_STEP / (ms / K * 1e-3) / issue_peak,
+                             "source": "ncu smsp__inst_executed.sum over the step's kernels (profiles/), one issue slot "
+                                       "per scheduler per cycle at the sampled SM clock"}
 
     # ---- e2e: host buffers through the public host-pointer entry point (its own decoder: stream groups overlap
     # the H2D copy of one group with the kernels / D2H of the others)
