@@ -280,7 +280,7 @@ RFM_API int rfm_iir_process_device(rfm_iir* f, int mode, float* d_a, float* d_b,
                                    void* cuda_stream);
 
 /* ------------------------------------------------------------------------------------------------
- * cFirFilter (FirFilter.h:17-60, FirFilter.cpp), batched over rows: Kaiser low-pass design or constant taps, the
+ * cFirFilter (FirFilter.h:17-60, FirFilter.cpp), batched over rows: Kaiser low-/high-pass design or constant taps, the
  * circular delay line with its rotating summation start (the sum of a given output begins at the tap the reference's
  * m_State points at, so the rounding sequence is the reference's).  Buffers are filtered in place.
  * ---------------------------------------------------------------------------------------------- */
@@ -291,6 +291,13 @@ RFM_API void rfm_fir_destroy(rfm_fir* f);
  * return value (the tap count, computed from the specification when NumTaps == 0) */
 RFM_API int rfm_fir_init_lp(rfm_fir* f, uint32_t NumTaps, float Scale, float Astop, float Fpass, float Fstop, float Fs,
                             uint32_t* ntaps);
+/* cFirFilter::InitHPFilter(NumTaps, Scale, Astop, Fpass, Fstop, Fsamprate) -- FirFilter.cpp:195-264 (no caller in the
+ * reference; odd tap count, at most 73 unless forced) */
+RFM_API int rfm_fir_init_hp(rfm_fir* f, uint32_t NumTaps, float Scale, float Astop, float Fpass, float Fstop, float Fs,
+                            uint32_t* ntaps);
+/* the Kaiser designs alone, host only (no device): kind 0 = InitLPFilter's taps, 1 = InitHPFilter's; *n = tap count */
+RFM_API int rfm_fir_design(int kind, uint32_t NumTaps, float Scale, float Astop, float Fpass, float Fstop, float Fs,
+                           float* out, uint32_t max, uint32_t* n);
 /* cFirFilter::InitConstFir(NumTaps, const RealType* pCoef, Fsamprate) -- FirFilter.cpp:302-320 */
 RFM_API int rfm_fir_init_const(rfm_fir* f, uint32_t ntaps, const float* coef, float Fs);
 RFM_API int rfm_fir_taps(const rfm_fir* f, float* out, uint32_t max, uint32_t* n);

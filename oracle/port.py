@@ -93,6 +93,8 @@ def lib():
         L.rfo_fir_create.restype = C.c_void_p
         L.rfo_fir_init_lp.restype = C.c_int
         L.rfo_fir_init_lp.argtypes = [C.c_void_p, C.c_uint] + [C.c_float] * 5
+        L.rfo_fir_init_hp.restype = C.c_int
+        L.rfo_fir_init_hp.argtypes = [C.c_void_p, C.c_uint] + [C.c_float] * 5
         L.rfo_fir_init_const.argtypes = [C.c_void_p, C.c_uint, _f32p, C.c_float]
         L.rfo_fir_coef.restype = C.c_uint
         L.rfo_fir_coef.argtypes = [C.c_void_p, _f32p]

@@ -332,6 +332,35 @@ static int fir_init_lp(rfo_fir* f, unsigned NumTaps, float Scale, float Astop, f
   return (int)f->ntaps;
 }
 
+static int fir_init_hp(rfo_fir* f, unsigned NumTaps, float Scale, float Astop, float Fpass, float Fstop, float Fs)
+{                                                                   /* :195-264 */
+  float Beta;
+  f->fs = Fs;
+  float normFpass = Fpass / Fs, normFstop = Fstop / Fs;
+  float normFcut = (float)((normFstop + normFpass) / 2.0);
+  if (Astop < 20.96f) Beta = 0;
+  else if (Astop >= 50.0f) Beta = .1102f * (Astop - 8.71f);
+  else Beta = .5842f * powf((Astop - 20.96f), 0.4f) + .07886f * (Astop - 20.96f);
+  f->ntaps = (unsigned)((Astop - 8.0f) / (2.285f * K_2PI * (normFpass - normFstop)) + 1);
+  if (f->ntaps > (MAX_NUMCOEF - 1)) f->ntaps = MAX_NUMCOEF - 1;
+  if (f->ntaps < 3) f->ntaps = 3;
+  f->ntaps |= 1;
+  if (NumTaps) f->ntaps = NumTaps;
+  float izb = izero(Beta);
+  float fCenter = .5f * (float)(f->ntaps - 1);
+  for (unsigned n = 0; n < f->ntaps; n++) {
+    float x = (float)((float)n - (float)(f->ntaps - 1) / 2.0);
+    float c;
+    if ((float)n == fCenter) c = (float)(1.0 - 2.0 * normFcut);
+    else c = (float)(sinf((float)(K_PI * x)) / (K_PI * x) - sinf((float)(K_2PI * x * normFcut)) / (K_PI * x));
+    x = ((float)n - ((float)f->ntaps - 1.0f) / 2.0f) / (((float)f->ntaps - 1.0f) / 2.0f);
+    f->coef[n] = Scale * c * izero(Beta * sqrtf(1 - (x * x))) / izb;
+  }
+  for (unsigned n = 0; n < f->ntaps; ++n) { f->icoef[n] = f->coef[n]; f->qcoef[n] = f->coef[n]; }
+  fir_clear(f);
+  return (int)f->ntaps;
+}
+
 static void fir_init_const(rfo_fir* f, unsigned NumTaps, const float* coef, float Fs)
 {                                                                   /* :302-320 (m_Coef only) */
   f->fs = Fs;
@@ -1305,6 +1334,8 @@ rfo_fir* rfo_fir_create(void) { rfo_fir* f = (rfo_fir*)malloc(sizeof(*f)); fir_c
 void rfo_fir_destroy(rfo_fir* f) { free(f); }
 int rfo_fir_init_lp(rfo_fir* f, unsigned taps, float scale, float astop, float fpass, float fstop, float fs)
 { return fir_init_lp(f, taps, scale, astop, fpass, fstop, fs); }
+int rfo_fir_init_hp(rfo_fir* f, unsigned taps, float scale, float astop, float fpass, float fstop, float fs)
+{ return fir_init_hp(f, taps, scale, astop, fpass, fstop, fs); }
 void rfo_fir_init_const(rfo_fir* f, unsigned taps, const float* coef, float fs)
 {
   fir_init_const(f, taps, coef, fs);

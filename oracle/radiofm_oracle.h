@@ -77,6 +77,7 @@ typedef struct rfo_fir rfo_fir;                /* cFirFilter, FirFilter.cpp */
 rfo_fir* rfo_fir_create(void);
 void rfo_fir_destroy(rfo_fir* f);
 int rfo_fir_init_lp(rfo_fir* f, unsigned taps, float scale, float astop, float fpass, float fstop, float fs);
+int rfo_fir_init_hp(rfo_fir* f, unsigned taps, float scale, float astop, float fpass, float fstop, float fs); /* :195-264 */
 void rfo_fir_init_const(rfo_fir* f, unsigned taps, const float* coef, float fs);
 unsigned rfo_fir_coef(const rfo_fir* f, float* out);
 void rfo_fir_process_real(rfo_fir* f, float* buf, unsigned n);

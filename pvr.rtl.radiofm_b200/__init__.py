@@ -61,7 +61,7 @@ EXPORTED_SYMBOLS = (
     "rfm_downconvert_process_u8", "rfm_downconvert_process_device", "rfm_downconvert_set_premix",
     "rfm_iir_create", "rfm_iir_destroy", "rfm_iir_init", "rfm_iir_coefficients", "rfm_iir_process_real",
     "rfm_iir_process_complex", "rfm_iir_process_two", "rfm_iir_process_device",
-    "rfm_fir_create", "rfm_fir_destroy", "rfm_fir_init_lp", "rfm_fir_init_const", "rfm_fir_taps", "rfm_fir_process_real",
+    "rfm_fir_create", "rfm_fir_destroy", "rfm_fir_init_lp", "rfm_fir_init_hp", "rfm_fir_design", "rfm_fir_init_const", "rfm_fir_taps", "rfm_fir_process_real",
     "rfm_fir_process_complex", "rfm_fir_process_two", "rfm_fir_process_device",
     "rfm_downsample_create", "rfm_downsample_destroy", "rfm_downsample_reset", "rfm_downsample_coefficients",
     "rfm_downsample_max_outputs", "rfm_downsample_process_complex", "rfm_downsample_process_real",
@@ -213,6 +213,9 @@ def lib():
         L.rfm_iir_init.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float]
         L.rfm_iir_coefficients.argtypes = [C.c_void_p, _f32p]
         L.rfm_fir_init_lp.argtypes = [C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _u32p]
+        L.rfm_fir_init_hp.argtypes = L.rfm_fir_init_lp.argtypes
+        L.rfm_fir_design.argtypes = [C.c_int, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _f32p,
+                                     C.c_uint32, _u32p]
         L.rfm_fir_init_const.argtypes = [C.c_void_p, C.c_uint32, _f32p, C.c_float]
         L.rfm_fir_taps.argtypes = [C.c_void_p, _f32p, C.c_uint32, _u32p]
         L.rfm_downsample_create.argtypes = [C.c_uint32, C.c_uint32, C.c_double, C.c_double, C.c_int, C.c_uint32, C.c_int,
@@ -718,6 +721,15 @@ class IirFilterBatch(_RowFilter):
         return out
 
 
+def fir_design(kind: str, num_taps: int, scale: float, astop: float, fpass: float, fstop: float, fs: float) -> np.ndarray:
+    """Taps of cFirFilter::InitLPFilter (kind "lp", FirFilter.cpp:78-148) / InitHPFilter ("hp", :195-264); host only."""
+    out = np.zeros(128, dtype=np.float32)
+    k = C.c_uint32(0)
+    _check(lib().rfm_fir_design({"lp": 0, "hp": 1}[kind], num_taps, scale, astop, fpass, fstop, fs, _p(out, _f32p),
+                                out.size, C.byref(k)))
+    return out[:k.value].copy()
+
+
 class FirFilterBatch(_RowFilter):
     """rows x cFirFilter (FirFilter.h:17-60)."""
     _kind = "fir"
@@ -725,6 +737,12 @@ class FirFilterBatch(_RowFilter):
     def init_lp(self, num_taps: int, scale: float, astop: float, fpass: float, fstop: float, fs: float) -> int:
         k = C.c_uint32(0)
         _check(lib().rfm_fir_init_lp(self._h, num_taps, scale, astop, fpass, fstop, fs, C.byref(k)))
+        return int(k.value)
+
+    def init_hp(self, num_taps: int, scale: float, astop: float, fpass: float, fstop: float, fs: float) -> int:
+        """cFirFilter::InitHPFilter (FirFilter.cpp:195-264)."""
+        k = C.c_uint32(0)
+        _check(lib().rfm_fir_init_hp(self._h, num_taps, scale, astop, fpass, fstop, fs, C.byref(k)))
         return int(k.value)
 
     def init_const(self, coef, fs: float):

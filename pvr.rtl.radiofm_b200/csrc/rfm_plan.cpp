@@ -129,6 +129,45 @@ std::vector<float> PlanKaiserLP(unsigned NumTaps, float Scale, float Astop, floa
   return coef;
 }
 
+// cFirFilter::InitHPFilter, FirFilter.cpp:195-264 (RealType = float; the double sub-expressions are the reference's:
+// its literals 2.0 / 1.0 and K_PI are doubles, Beta's are floats here -- unlike InitLPFilter)
+std::vector<float> PlanKaiserHP(unsigned NumTaps, float Scale, float Astop, float Fpass, float Fstop, float Fs)
+{
+  float Beta;
+  const float normFpass = Fpass / Fs;
+  const float normFstop = Fstop / Fs;
+  const float normFcut = (float)((normFstop + normFpass) / 2.0);
+  if (Astop < 20.96f)
+    Beta = 0;
+  else if (Astop >= 50.0f)
+    Beta = .1102f * (Astop - 8.71f);
+  else
+    Beta = .5842f * powf((Astop - 20.96f), 0.4f) + .07886f * (Astop - 20.96f);
+  unsigned taps = (unsigned)((Astop - 8.0f) / (2.285f * K_2PI * (normFpass - normFstop)) + 1);
+  if (taps > kMaxFirTaps - 1)
+    taps = kMaxFirTaps - 1;
+  if (taps < 3)
+    taps = 3;
+  taps |= 1;
+  if (NumTaps)
+    taps = NumTaps;
+  std::vector<float> coef(taps);
+  const float izb = Izero(Beta);
+  const float fCenter = .5f * (float)(taps - 1);
+  for (unsigned n = 0; n < taps; n++)
+  {
+    float x = (float)((float)n - (float)(taps - 1) / 2.0);
+    float c;
+    if ((float)n == fCenter)
+      c = (float)(1.0 - 2.0 * normFcut);
+    else
+      c = (float)(sinf((float)(K_PI * x)) / (K_PI * x) - sinf((float)(K_2PI * x * normFcut)) / (K_PI * x));
+    x = ((float)n - ((float)taps - 1.0f) / 2.0f) / (((float)taps - 1.0f) / 2.0f);
+    coef[n] = Scale * c * Izero(Beta * sqrtf(1 - (x * x))) / izb;
+  }
+  return coef;
+}
+
 float PlanDecimationChain(float InRate, float MaxBW, bool wfm, std::vector<HalfBandStage>* st)
 {
   st->clear();

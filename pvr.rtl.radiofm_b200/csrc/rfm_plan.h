@@ -27,6 +27,7 @@ std::vector<float> PlanLanczos(unsigned order, double cutoff);
 
 // cFirFilter::InitLPFilter, FirFilter.cpp:78-148.  Returns the taps.
 std::vector<float> PlanKaiserLP(unsigned NumTaps, float Scale, float Astop, float Fpass, float Fstop, float Fs);
+std::vector<float> PlanKaiserHP(unsigned NumTaps, float Scale, float Astop, float Fpass, float Fstop, float Fs); // FirFilter.cpp:195-264
 
 struct HalfBandStage
 {

@@ -370,6 +370,33 @@ int rfm_fir_init_lp(rfm_fir* f, uint32_t NumTaps, float Scale, float Astop, floa
   return FirInstall(f, taps);
 }
 
+// cFirFilter::InitHPFilter, FirFilter.cpp:195-264
+int rfm_fir_init_hp(rfm_fir* f, uint32_t NumTaps, float Scale, float Astop, float Fpass, float Fstop, float Fs,
+                    uint32_t* ntaps)
+{
+  if (!f)
+    return PFail(RFM_ERR_INVALID, "rfm_fir_init_hp: null handle");
+  cudaSetDevice(f->device);
+  const std::vector<float> taps = PlanKaiserHP(NumTaps, Scale, Astop, Fpass, Fstop, Fs);
+  if (ntaps)
+    *ntaps = (uint32_t)taps.size();
+  return FirInstall(f, taps);
+}
+
+// the two Kaiser designs on their own (host only, no device): kind 0 = InitLPFilter, 1 = InitHPFilter
+int rfm_fir_design(int kind, uint32_t NumTaps, float Scale, float Astop, float Fpass, float Fstop, float Fs, float* out,
+                   uint32_t max, uint32_t* n)
+{
+  if (!n || kind < 0 || kind > 1 || NumTaps > kMaxFirTaps)
+    return PFail(RFM_ERR_INVALID, "rfm_fir_design: invalid argument");
+  const std::vector<float> taps = kind == 0 ? PlanKaiserLP(NumTaps, Scale, Astop, Fpass, Fstop, Fs)
+                                            : PlanKaiserHP(NumTaps, Scale, Astop, Fpass, Fstop, Fs);
+  *n = (uint32_t)taps.size();
+  for (size_t i = 0; out && i < taps.size() && i < max; ++i)
+    out[i] = taps[i];
+  return RFM_OK;
+}
+
 // cFirFilter::InitConstFir(NumTaps, const RealType*, Fsamprate), FirFilter.cpp:302-320
 int rfm_fir_init_const(rfm_fir* f, uint32_t ntaps, const float* coef, float Fs)
 {

@@ -1,7 +1,7 @@
 // host/FirFilter.h -- cFirFilter with the reference's signatures (FirFilter.h:17-60) over the C ABI (rfm_fir_*): the
 // members the live chain uses -- InitLPFilter, InitConstFir (real taps), Process (real / complex, in place),
-// ProcessTwo.  InitHPFilter, GenerateHBFilter and the two-buffer Process overloads are not called anywhere on the
-// hot path and are not provided.
+// ProcessTwo -- plus InitHPFilter.  GenerateHBFilter and the two-buffer Process overloads are not called anywhere on
+// the hot path and are not provided.
 #pragma once
 
 #include <stdexcept>
@@ -33,6 +33,13 @@ public:
   {
     uint32_t n = 0;
     rfm_fir_init_lp(m_f, NumTaps, Scale, Astop, Fpass, Fstop, Fsamprate, &n);
+    return (int)n;
+  }
+  int InitHPFilter(unsigned int NumTaps, RealType Scale, RealType Astop, RealType Fpass, RealType Fstop,
+                   RealType Fsamprate) // FirFilter.cpp:195-264
+  {
+    uint32_t n = 0;
+    rfm_fir_init_hp(m_f, NumTaps, Scale, Astop, Fpass, Fstop, Fsamprate, &n);
     return (int)n;
   }
   void Process(ComplexType* buffer, unsigned int length) // :330-350

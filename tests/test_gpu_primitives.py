@@ -61,10 +61,12 @@ def test_fir_lowpass_and_const_taps(rfm, port):
     f = rfm.FirFilterBatch(rows, max_len=8192)
     hs = [L.rfo_fir_create() for _ in range(rows)]
     # the audio low-pass of the chain (FmDecode.cpp:286) and the RDS low-pass (RDSProcess.cpp:99)
-    for spec in ((0, 1.0, 60.0, 15000.0, 21000.0, 48000.0), (0, 1.0, 40.0, 2400.0, 3120.0, 31250.0)):
-        nt = f.init_lp(*spec)
+    # ... and a high-pass design (InitHPFilter, FirFilter.cpp:195-264: no caller in the reference)
+    for kind, spec in (("lp", (0, 1.0, 60.0, 15000.0, 21000.0, 48000.0)), ("lp", (0, 1.0, 40.0, 2400.0, 3120.0, 31250.0)),
+                       ("hp", (0, 1.0, 50.0, 6000.0, 3000.0, 48000.0))):
+        nt = getattr(f, "init_" + kind)(*spec)
         for h in hs:
-            assert L.rfo_fir_init_lp(h, *spec) == nt
+            assert getattr(L, "rfo_fir_init_" + kind)(h, *spec) == nt
         co = np.zeros(80, dtype=np.float32)
         L.rfo_fir_coef(hs[0], P(co))
         assert bits_equal(f.taps(), co[:nt])

@@ -149,6 +149,29 @@ def test_port_matches_golden_rds_block_kat(port):
         assert f(w, osyn, fec, C.byref(c)) == syn and c.value == fixed
 
 
+def test_fir_designs_match_golden(port):
+    """cFirFilter::InitLPFilter / InitHPFilter taps (FirFilter.cpp:78-148, 195-264) of the C restatement and of the
+    library's host-only planner entry point against the compiled reference's (three Kaiser-beta ranges, forced and
+    clamped tap counts)."""
+    from conftest import load_package
+    rfm = load_package()
+    g = np.load(os.path.join(GOLDEN, "kat_primitives.npz"))
+    L = port.lib()
+    off = 0
+    for row, nt in zip(g["fir_design_specs"], g["fir_design_lens"].tolist()):
+        kind, spec = int(row[0]), (int(row[1]),) + tuple(float(np.float32(v)) for v in row[2:])
+        want = g["fir_design_taps"][off:off + nt]
+        off += nt
+        h = L.rfo_fir_create()
+        assert (L.rfo_fir_init_hp if kind else L.rfo_fir_init_lp)(h, *spec) == nt, (kind, spec)
+        co = np.zeros(160, dtype=np.float32)
+        L.rfo_fir_coef(h, P(co))
+        L.rfo_fir_destroy(h)
+        assert bits_equal(co[:nt], want), ("port", kind, spec)
+        assert bits_equal(rfm.fir_design("hp" if kind else "lp", *spec), want), ("library", kind, spec)
+    assert off == g["fir_design_taps"].size
+
+
 def test_port_matches_golden_primitives(port):
     g = np.load(os.path.join(GOLDEN, "kat_primitives.npz"))
     L = port.lib()
