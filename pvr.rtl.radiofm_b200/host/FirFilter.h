@@ -1,9 +1,11 @@
 // host/FirFilter.h -- cFirFilter with the reference's signatures (FirFilter.h:17-60) over the C ABI (rfm_fir_*): the
 // members the live chain uses -- InitLPFilter, InitConstFir (real taps), Process (real / complex, in place),
-// ProcessTwo -- plus InitHPFilter.  GenerateHBFilter and the two-buffer Process overloads are not called anywhere on
-// the hot path and are not provided.
+// ProcessTwo -- plus InitHPFilter and the complex two-buffer Process.  GenerateHBFilter, the I/Q form of InitConstFir
+// and Process(RealType*, ComplexType*) (whose sum is an assignment in the reference, FirFilter.cpp:466-468) are not
+// called anywhere on the hot path and are not provided.
 #pragma once
 
+#include <cstring>
 #include <stdexcept>
 #include <string>
 
@@ -47,6 +49,13 @@ public:
     rfm_fir_process_complex(m_f, reinterpret_cast<float*>(buffer), length);
   }
   void Process(RealType* buffer, unsigned int length) { rfm_fir_process_real(m_f, buffer, length); } // :360-377
+  // :421-445 -- the in-place complex form writing to a second buffer (InBuf is left untouched)
+  void Process(ComplexType* InBuf, ComplexType* OutBuf, unsigned int length)
+  {
+    if (OutBuf != InBuf)
+      std::memcpy(static_cast<void*>(OutBuf), InBuf, (size_t)length * sizeof(ComplexType));
+    Process(OutBuf, length);
+  }
   void ProcessTwo(RealType* bufferA, RealType* bufferB, unsigned int length) // :387-413
   {
     rfm_fir_process_two(m_f, bufferA, bufferB, length);

@@ -67,6 +67,16 @@ int main(int argc, char** argv)
       for (unsigned i = 0; i + blk <= n / 2; i += blk)
         rlp.Process(z.data() + i, blk);
       dump(pre + "_fir_z.f32", z.data(), z.size() * 8);
+      // the two-buffer complex form (FirFilter.cpp:421-445) and a high-pass design (:195-264)
+      cFirFilter hp;
+      const int nh = hp.InitHPFilter(0, 1.0f, 50.0f, 6000.0f, 3000.0f, 48000.0f);
+      std::vector<ComplexType> zi(n / 2), zo(n / 2);
+      for (unsigned i = 0; i < n / 2; ++i)
+        zi[i] = ComplexType(x[2 * i], x[2 * i + 1]);
+      for (unsigned i = 0; i + blk <= n / 2; i += blk)
+        hp.Process(zi.data() + i, zo.data() + i, blk);
+      dump(pre + "_fir_hp.f32", zo.data(), zo.size() * 8);
+      printf("fir_hp_taps %d\n", nh);
       printf("fir_taps %d\n", nt);
     }
     { // CRDSDownConvert as cRDSRxSignalProcessor sets it up (RDSProcess.cpp:46-48)

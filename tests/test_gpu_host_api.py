@@ -146,8 +146,12 @@ def test_primitive_classes_match_oracle(tmp_path, port):
     L.rfo_fir_init_lp(h, 0, 1.0, 40.0, 2400.0, np.float32(1.3) * np.float32(2400.0), 31250.0)
     z = x.copy()
     L.rfo_fir_process_complex(h, P(z), half)
-    L.rfo_fir_destroy(h)
     assert bits_equal(rd("fir_z.f32"), z)
+    nh = L.rfo_fir_init_hp(h, 0, 1.0, 50.0, 6000.0, 3000.0, 48000.0)   # InitHPFilter + the two-buffer complex Process
+    z = x.copy()
+    L.rfo_fir_process_complex(h, P(z), half)
+    L.rfo_fir_destroy(h)
+    assert f"fir_hp_taps {nh}" in out.stdout and bits_equal(rd("fir_hp.f32"), z)
     # CRDSDownConvert (block-wise, like the driver)
     h = L.rfo_rdsdc_create()
     rate = L.rfo_rdsdc_set_data_rate(h, 250000.0, 8000.0)
