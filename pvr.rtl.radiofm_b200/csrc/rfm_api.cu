@@ -13,6 +13,7 @@
 // the throughput-bound FIR kernels.  Everything handed from one stage to the next (decimated IQ, baseband / L-R
 // rows, stereo flag) is double-buffered by block parity; the NCO-oscillator table of the RDS mixer (identical for
 // all streams) is produced ahead on its own stream.
+#include <cuda.h> // declarations only: the green-context entry points are looked up at run time (libcuda is not linked)
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -128,8 +129,18 @@ struct Group
 };
 } // namespace
 
+// Experimental SM partition (RFM_LANES_SMS=N, N a multiple of 8): the stream of the latency-bound lanes kernel lives in
+// a green context of N SMs, every other stream in a green context of the remaining SMs, so the pilot recurrence does
+// not wait for issue slots behind the FIR kernels.  Placement only: kernels and results unchanged.
+struct SmPartition
+{
+  CUgreenCtx lanes = nullptr, rest = nullptr;
+  unsigned lanes_sms = 0, rest_sms = 0;
+};
+
 struct rfm_decoder
 {
+  SmPartition part;
   rfm_config cfg;
   DecoderPlan plan;
   int device = 0;
@@ -176,6 +187,82 @@ struct rfm_decoder
 
 namespace
 {
+
+template <typename F>
+bool DriverEntry(const char* name, F* fn)
+{
+  void* f = nullptr;
+  cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+  if (cudaGetDriverEntryPoint(name, &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !f)
+  {
+    cudaGetLastError();
+    return false;
+  }
+  *fn = reinterpret_cast<F>(f);
+  return true;
+}
+
+// false (with a reason) when the driver cannot do it: the caller then stays on ordinary streams
+bool MakeSmPartition(int device, unsigned lanes_sms, SmPartition* out, std::string* why)
+{
+  decltype(&cuDeviceGet) p_get = nullptr;
+  decltype(&cuDeviceGetDevResource) p_res = nullptr;
+  decltype(&cuDevSmResourceSplitByCount) p_split = nullptr;
+  decltype(&cuDevResourceGenerateDesc) p_desc = nullptr;
+  decltype(&cuGreenCtxCreate) p_create = nullptr;
+  if (!DriverEntry("cuDeviceGet", &p_get) || !DriverEntry("cuDeviceGetDevResource", &p_res) ||
+      !DriverEntry("cuDevSmResourceSplitByCount", &p_split) || !DriverEntry("cuDevResourceGenerateDesc", &p_desc) ||
+      !DriverEntry("cuGreenCtxCreate", &p_create))
+  {
+    *why = "green-context entry points not available in this driver";
+    return false;
+  }
+  CUdevice dev;
+  CUdevResource all, part, rest;
+  unsigned groups = 1;
+  CUdevResourceDesc d_part, d_rest;
+  CUresult rc;
+  if ((rc = p_get(&dev, device)) != CUDA_SUCCESS || (rc = p_res(dev, &all, CU_DEV_RESOURCE_TYPE_SM)) != CUDA_SUCCESS ||
+      (rc = p_split(&part, &groups, &all, &rest, 0, lanes_sms)) != CUDA_SUCCESS || groups != 1 ||
+      (rc = p_desc(&d_part, &part, 1)) != CUDA_SUCCESS || (rc = p_desc(&d_rest, &rest, 1)) != CUDA_SUCCESS ||
+      (rc = p_create(&out->lanes, d_part, dev, CU_GREEN_CTX_DEFAULT_STREAM)) != CUDA_SUCCESS ||
+      (rc = p_create(&out->rest, d_rest, dev, CU_GREEN_CTX_DEFAULT_STREAM)) != CUDA_SUCCESS)
+  {
+    *why = "SM partition failed, CUresult " + std::to_string((int)rc);
+    return false;
+  }
+  out->lanes_sms = part.sm.smCount;
+  out->rest_sms = rest.sm.smCount;
+  return true;
+}
+
+// a stream of priority `prio`: in the given green context when the decoder is partitioned, an ordinary one otherwise
+cudaError_t MakeStream(CUgreenCtx ctx, cudaStream_t* st, int prio)
+{
+  if (!ctx)
+    return cudaStreamCreateWithPriority(st, cudaStreamNonBlocking, prio);
+  decltype(&cuGreenCtxStreamCreate) p_stream = nullptr;
+  if (!DriverEntry("cuGreenCtxStreamCreate", &p_stream))
+    return cudaErrorNotSupported;
+  CUstream cs = nullptr;
+  if (p_stream(&cs, ctx, CU_STREAM_NON_BLOCKING, prio) != CUDA_SUCCESS)
+    return cudaErrorUnknown;
+  *st = cs;
+  return cudaSuccess;
+}
+
+void FreeSmPartition(SmPartition* p)
+{
+  decltype(&cuGreenCtxDestroy) p_destroy = nullptr;
+  if ((p->lanes || p->rest) && DriverEntry("cuGreenCtxDestroy", &p_destroy))
+  {
+    if (p->lanes)
+      p_destroy(p->lanes);
+    if (p->rest)
+      p_destroy(p->rest);
+  }
+  p->lanes = p->rest = nullptr;
+}
 
 void ProfFree(ProfSlot* slots);
 
@@ -230,6 +317,7 @@ void FreeDecoder(rfm_decoder* d)
     cudaStreamDestroy(d->s_osc);
   if (d->h_drain)
     cudaFreeHost(d->h_drain);
+  FreeSmPartition(&d->part);
   delete d;
 }
 
@@ -957,7 +1045,23 @@ int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out)
     const float one[2] = {1.0f, 0.0f}; // m_Osc1 initial unit vector, DownConvert.cpp:283-284
     RFM_TRY(Upload(d->osc1, one, 2));
   }
-  RFM_TRY(cudaStreamCreateWithFlags(&d->s_osc, cudaStreamNonBlocking));
+  if (const char* e = getenv("RFM_LANES_SMS"))
+  {
+    std::string why;
+    const unsigned n = (unsigned)atoi(e);
+    if (n >= 8 && !MakeSmPartition(d->device, n, &d->part, &why))
+    {
+      FreeSmPartition(&d->part);
+      fprintf(stderr, "radiofm_b200: RFM_LANES_SMS=%u ignored (%s)\n", n, why.c_str());
+    }
+    else if (n >= 8 && getenv("RFM_DEBUG_TIMELINE"))
+      fprintf(stderr, "radiofm_b200: lanes on %u SMs, everything else on %u\n", d->part.lanes_sms, d->part.rest_sms);
+  }
+  {
+    int lo = 0, hi = 0;
+    RFM_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    RFM_TRY(MakeStream(d->part.lanes, &d->s_osc, lo));
+  }
   RFM_TRY(cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming));
   for (int b = 0; b < 3; ++b)
     RFM_TRY(cudaEventCreateWithFlags(&d->ev_osc[b], cudaEventDisableTiming));
@@ -988,12 +1092,12 @@ int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out)
       if (mode == 1) { pF = prio_lo; }
       if (mode == 2) { pF = prio_lo; pB = std::min(prio_lo, prio_hi + 1); }
       if (mode == 3) { pA = prio_lo; pF = prio_lo; pB = prio_hi; }
-      RFM_TRY(cudaStreamCreateWithPriority(&g.sA, cudaStreamNonBlocking, pA));
-      RFM_TRY(cudaStreamCreateWithPriority(&g.sF, cudaStreamNonBlocking, pF));
-      RFM_TRY(cudaStreamCreateWithPriority(&g.sB, cudaStreamNonBlocking, pB));
-      RFM_TRY(cudaStreamCreateWithPriority(&g.sR, cudaStreamNonBlocking, pB));
-      RFM_TRY(cudaStreamCreateWithPriority(&g.sC, cudaStreamNonBlocking, pL));
-      RFM_TRY(cudaStreamCreateWithPriority(&g.sP, cudaStreamNonBlocking, pL));
+      RFM_TRY(MakeStream(d->part.lanes, &g.sA, pA));
+      RFM_TRY(MakeStream(d->part.rest, &g.sF, pF));
+      RFM_TRY(MakeStream(d->part.rest, &g.sB, pB));
+      RFM_TRY(MakeStream(d->part.rest, &g.sR, pB));
+      RFM_TRY(MakeStream(d->part.rest, &g.sC, pL));
+      RFM_TRY(MakeStream(d->part.rest, &g.sP, pL));
       if (getenv("RFM_DEBUG_SERIAL"))
       { // measurement aid: every stage on ONE stream, so per-kernel event times are isolated durations
         cudaStreamDestroy(g.sF); cudaStreamDestroy(g.sB); cudaStreamDestroy(g.sR); cudaStreamDestroy(g.sC); cudaStreamDestroy(g.sP);

@@ -781,7 +781,7 @@ __global__ void __launch_bounds__(64) k_bb_lanes(LanesParams p)
 {
   __shared__ LanesSmem sm;
   const unsigned lane = threadIdx.x & 31u;
-  const unsigned role = threadIdx.x >> 5;
+  const unsigned role = (threadIdx.x >> 5) ^ (p.role_swap & blockIdx.x & 1u);
   const unsigned s0 = blockIdx.x * 32;
   const unsigned s = s0 + lane;
   const bool valid = s < p.S;
@@ -930,10 +930,27 @@ __global__ void __launch_bounds__(64) k_bb_lanes(LanesParams p)
   }
 }
 
-void launch_bb_lanes(const LanesParams& p, cudaStream_t st)
+void launch_bb_lanes(const LanesParams& p_in, cudaStream_t st)
 {
-  if (p.S == 0 || p.nb == 0)
+  if (p_in.S == 0 || p_in.nb == 0)
     return;
+  static const unsigned swap = getenv("RFM_LANES_SWAP") ? (unsigned)atoi(getenv("RFM_LANES_SWAP")) & 1u : 0u;
+  LanesParams p = p_in;
+  p.role_swap = swap;
+  // experiment (with RFM_LANES_SMS): ask for the largest shared-memory carve-out so that 8 lanes CTAs fit on one SM
+  static const bool carve = getenv("RFM_LANES_CARVEOUT") && atoi(getenv("RFM_LANES_CARVEOUT")) != 0;
+  if (carve)
+  {
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !done[dev])
+    {
+      cudaFuncSetAttribute(k_bb_lanes<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      cudaFuncSetAttribute(k_bb_lanes<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      done[dev] = true;
+    }
+  }
   // measurement aid: reserve extra (unused) dynamic shared memory so fewer throughput CTAs share the lanes' SMs
   static const int reserve_kb = getenv("RFM_LANES_RESERVE_KB") ? atoi(getenv("RFM_LANES_RESERVE_KB")) : 0;
   static const bool fake = getenv("RFM_DEBUG_FAKE_SINCOS") && atoi(getenv("RFM_DEBUG_FAKE_SINCOS")) != 0;

@@ -129,6 +129,7 @@ struct LanesParams
   size_t a_stride;
   unsigned a_hist;
   unsigned parity;         // selects SF_STEREO / SF_STEREO1
+  unsigned role_swap;      // set by launch_bb_lanes: odd CTAs run the pilot PLL on warp 0 (RFM_LANES_SWAP, experiment)
 };
 void launch_bb_lanes(const LanesParams& p, cudaStream_t st);
 
