@@ -461,6 +461,12 @@ __device__ __forceinline__ void tile_store(T* base, size_t stride, unsigned s0, 
 // named barriers (producer / consumer hand-off between the two warps of k_bb_lanes)
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+// the same with the barrier id as an immediate: with register ids ptxas reserves all 16 named barriers for the CTA
+// (EIATTR_NUM_BARRIERS = 16), and four such CTAs exhaust an SM's barriers
+template <int ID>
+__device__ __forceinline__ void bar_sync_imm() { asm volatile("bar.sync %0, 64;" ::"n"(ID) : "memory"); }
+template <int ID>
+__device__ __forceinline__ void bar_arrive_imm() { asm volatile("bar.arrive %0, 64;" ::"n"(ID) : "memory"); }
 
 // --------------------------------------------------------------------------------------------------
 // IF level meter: RMSLevelApprox over the first ceil(n/64) tuned samples, FmDecode.cpp:427,505-519
@@ -776,7 +782,9 @@ struct LanesSmem
   float kf[8];
 };
 
-template <bool FAKE_SINCOS> // true: RFM_DEBUG_FAKE_SINCOS timing experiment (wrong results)
+// FAKE_SINCOS: RFM_DEBUG_FAKE_SINCOS timing experiment (wrong results).  IMMBAR: RFM_LANES_IMMBAR experiment, barrier
+// ids as immediates (5 named barriers per CTA instead of 16; same hand-off)
+template <bool FAKE_SINCOS, bool IMMBAR = false>
 __global__ void __launch_bounds__(64) k_bb_lanes(LanesParams p)
 {
   __shared__ LanesSmem sm;
@@ -789,6 +797,30 @@ __global__ void __launch_bounds__(64) k_bb_lanes(LanesParams p)
   float* st = p.state;
   const unsigned ntiles = (p.nb + kLT - 1) / kLT;
   enum { BAR_FULL = 1, BAR_EMPTY = 3 };
+  auto sync_bar = [](int base, unsigned b) {
+    if (!IMMBAR)
+      bar_sync(base + (int)b, 64);
+    else if (base == BAR_FULL)
+    {
+      if (b) bar_sync_imm<BAR_FULL + 1>(); else bar_sync_imm<BAR_FULL>();
+    }
+    else
+    {
+      if (b) bar_sync_imm<BAR_EMPTY + 1>(); else bar_sync_imm<BAR_EMPTY>();
+    }
+  };
+  auto arrive_bar = [](int base, unsigned b) {
+    if (!IMMBAR)
+      bar_arrive(base + (int)b, 64);
+    else if (base == BAR_FULL)
+    {
+      if (b) bar_arrive_imm<BAR_FULL + 1>(); else bar_arrive_imm<BAR_FULL>();
+    }
+    else
+    {
+      if (b) bar_arrive_imm<BAR_EMPTY + 1>(); else bar_arrive_imm<BAR_EMPTY>();
+    }
+  };
 
   if (role == 0)
   {
@@ -808,7 +840,7 @@ __global__ void __launch_bounds__(64) k_bb_lanes(LanesParams p)
       cp_async_wait<1>();
       __syncwarp();
       if (t >= 2)
-        bar_sync(BAR_EMPTY + b, 64);
+        sync_bar(BAR_EMPTY, b);
       if (valid)
       {
         for (unsigned k = 0; k < tn; ++k)
@@ -820,7 +852,7 @@ __global__ void __launch_bounds__(64) k_bb_lanes(LanesParams p)
         }
       }
       __threadfence_block();
-      bar_arrive(BAR_FULL + b, 64);
+      arrive_bar(BAR_FULL, b);
       __syncwarp();
       tile_store(p.bbV + p.a_hist, p.a_stride, s0, S, t0, p.nb, lane, sm.ring[b]);
       __syncwarp();
@@ -872,7 +904,7 @@ __global__ void __launch_bounds__(64) k_bb_lanes(LanesParams p)
     {
       const unsigned b = t & 1u, t0 = t * kLT;
       const unsigned tn = min(kLT, p.nb - t0);
-      bar_sync(BAR_FULL + b, 64);
+      sync_bar(BAR_FULL, b);
       // branch-free fast path; if any lane raised the sticky flag the tile is replayed with the exact routines
       const PilotState pl_start = pl;
       bool bad = false;
@@ -900,7 +932,7 @@ __global__ void __launch_bounds__(64) k_bb_lanes(LanesParams p)
         }
       }
       if (t + 2 < ntiles)
-        bar_arrive(BAR_EMPTY + b, 64);
+        arrive_bar(BAR_EMPTY, b);
       __syncwarp();
       tile_store(p.rawV + p.a_hist, p.a_stride, s0, S, t0, p.nb, lane, sm.rawt);
       __syncwarp();
@@ -959,8 +991,11 @@ void launch_bb_lanes(const LanesParams& p_in, cudaStream_t st)
     EnsureDynSmem(k_bb_lanes<false>, (size_t)reserve_kb * 1024);
     EnsureDynSmem(k_bb_lanes<true>, (size_t)reserve_kb * 1024);
   }
+  static const bool immbar = getenv("RFM_LANES_IMMBAR") && atoi(getenv("RFM_LANES_IMMBAR")) != 0;
   if (fake)
     k_bb_lanes<true><<<cdiv(p.S, 32), 64, (size_t)reserve_kb * 1024, st>>>(p);
+  else if (immbar)
+    k_bb_lanes<false, true><<<cdiv(p.S, 32), 64, (size_t)reserve_kb * 1024, st>>>(p);
   else
     k_bb_lanes<false><<<cdiv(p.S, 32), 64, (size_t)reserve_kb * 1024, st>>>(p);
 }
