@@ -805,6 +805,8 @@ int rfm_rdsproc_take_groups(rfm_rdsproc* r, uint32_t row, uint16_t* groups, uint
 // Real input, integer factor: y[i] = sum_{j = 1 .. order} x[p - j] c[j], p = pos + i ds, ascending j, every product and
 // sum rounded on its own (DownConvert.cpp:172-190; both of its loops are this sum over V = [history(order) | block],
 // x[p - j] = V[order + p - j]).  Thread per output, taps in shared memory; not on the hot path, so no window staging.
+namespace
+{
 __global__ void __launch_bounds__(128) k_downsample_real_int(const float* __restrict__ v, size_t v_stride,
                                                              const float* __restrict__ coeff, unsigned order, unsigned ds,
                                                              unsigned pos, unsigned nout, float* __restrict__ out,
@@ -823,6 +825,7 @@ __global__ void __launch_bounds__(128) k_downsample_real_int(const float* __rest
     y = addf(y, mulf(x[-(int)j], s_c[j]));
   out[(size_t)blockIdx.y * out_stride + i] = y;
 }
+} // namespace
 
 struct rfm_downsample
 {

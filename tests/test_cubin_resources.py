@@ -1,0 +1,74 @@
+"""Static checks on the compiled sm_100a objects (no GPU needed): the hot kernels of the chain keep their state in
+registers (no stack frame, no local memory), and the register counts stay inside the occupancy the launch geometry
+assumes.  Skipped when the objects or cuobjdump are not there (build() makes them)."""
+import glob
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "pvr.rtl.radiofm_b200", "csrc", "build")
+CUOBJDUMP = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+
+# kernel-name fragment -> (max registers per thread, note)
+HOT = {
+    "k_front_tiledILb1ELi11E": (64, "128 threads, 4 outputs per thread: >= 8 CTAs per SM"),
+    "k_front_tiledILb1ELi4E": (64, ""),
+    "k_front_tiledILb1ELi5E": (64, ""),
+    "k_bb_lanesILb0ELb0E": (128, "64 threads; pilot state + 13 double constants in registers"),
+    "k_bb_lanesILb0ELb1E": (128, "immediate-barrier variant"),
+    "k_demod_spec": (96, "32-thread CTAs, ~17 per SM"),
+    "k_resample_tiledILi16ELi2E": (96, ""),
+    "k_rotfir_lanesILi0E": (64, ""),
+    "k_rotfir_lanesILi1E": (64, ""),
+    "k_rotfir_lanesILi2E": (64, ""),
+    "k_rds_front": (64, ""),
+    "k_rds_pll": (96, ""),
+    "k_rds_slice": (96, ""),
+    "k_audio_tail": (128, ""),
+    "k_dc_chain_uniform": (64, "512 threads, two CTAs per SM"),
+    "k_dc_oscE": (64, ""),
+}
+
+
+def _usage():
+    objs = sorted(glob.glob(os.path.join(BUILD, "*.o")))
+    if not objs or not os.path.exists(CUOBJDUMP):
+        pytest.skip("no compiled objects / cuobjdump (run __graft_entry__.build())")
+    out = {}
+    for o in objs:
+        r = subprocess.run([CUOBJDUMP, "--dump-resource-usage", o], capture_output=True, text=True)
+        if r.returncode != 0:
+            continue  # host-only object
+        assert "sm_100a" in r.stdout, o
+        name = None
+        for line in r.stdout.splitlines():
+            m = re.match(r"\s*Function\s+(\S+):", line)
+            if m:
+                name = m.group(1)
+                continue
+            m = re.search(r"REG:(\d+)\s+STACK:(\d+)\s+SHARED:(\d+)\s+LOCAL:(\d+)", line)
+            if m and name:
+                out[name] = tuple(int(v) for v in m.groups())
+    return out
+
+
+def test_hot_kernels_have_no_stack_or_local_memory():
+    usage = _usage()
+    for frag, (max_regs, _) in HOT.items():
+        hits = {n: u for n, u in usage.items() if frag in n}
+        assert hits, f"kernel {frag} not found in the compiled objects"
+        for n, (regs, stack, _shared, local) in hits.items():
+            assert stack == 0 and local == 0, (n, stack, local)
+            assert regs <= max_regs, (n, regs, max_regs)
+
+
+def test_every_kernel_is_sm_100a_and_fits_shared_memory():
+    usage = _usage()
+    assert len(usage) >= 40
+    for n, (regs, _stack, shared, local) in usage.items():
+        assert regs <= 128 and local == 0, (n, regs, local)
+        assert shared <= 48 * 1024, (n, shared)  # static part; the dynamic part is opted in per launch (EnsureDynSmem)
