@@ -1057,10 +1057,14 @@ int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out)
     else if (n >= 8 && getenv("RFM_DEBUG_TIMELINE"))
       fprintf(stderr, "radiofm_b200: lanes on %u SMs, everything else on %u\n", d->part.lanes_sms, d->part.rest_sms);
   }
+  // which streams live in the lanes partition: letters of RFM_LANES_STREAMS among A (lanes), O (oscillator / resampler
+  // tables), P (RDS PLL, matched filter, slicer), C (audio tail), R (RDS front), B (resamplers), F (front end)
+  const char* in_lanes = getenv("RFM_LANES_STREAMS") ? getenv("RFM_LANES_STREAMS") : "AO";
+  auto ctx_of = [&](char which) { return strchr(in_lanes, which) ? d->part.lanes : d->part.rest; };
   {
     int lo = 0, hi = 0;
     RFM_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    RFM_TRY(MakeStream(d->part.lanes, &d->s_osc, lo));
+    RFM_TRY(MakeStream(ctx_of('O'), &d->s_osc, lo));
   }
   RFM_TRY(cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming));
   for (int b = 0; b < 3; ++b)
@@ -1092,12 +1096,12 @@ int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out)
       if (mode == 1) { pF = prio_lo; }
       if (mode == 2) { pF = prio_lo; pB = std::min(prio_lo, prio_hi + 1); }
       if (mode == 3) { pA = prio_lo; pF = prio_lo; pB = prio_hi; }
-      RFM_TRY(MakeStream(d->part.lanes, &g.sA, pA));
-      RFM_TRY(MakeStream(d->part.rest, &g.sF, pF));
-      RFM_TRY(MakeStream(d->part.rest, &g.sB, pB));
-      RFM_TRY(MakeStream(d->part.rest, &g.sR, pB));
-      RFM_TRY(MakeStream(d->part.rest, &g.sC, pL));
-      RFM_TRY(MakeStream(d->part.rest, &g.sP, pL));
+      RFM_TRY(MakeStream(ctx_of('A'), &g.sA, pA));
+      RFM_TRY(MakeStream(ctx_of('F'), &g.sF, pF));
+      RFM_TRY(MakeStream(ctx_of('B'), &g.sB, pB));
+      RFM_TRY(MakeStream(ctx_of('R'), &g.sR, pB));
+      RFM_TRY(MakeStream(ctx_of('C'), &g.sC, pL));
+      RFM_TRY(MakeStream(ctx_of('P'), &g.sP, pL));
       if (getenv("RFM_DEBUG_SERIAL"))
       { // measurement aid: every stage on ONE stream, so per-kernel event times are isolated durations
         cudaStreamDestroy(g.sF); cudaStreamDestroy(g.sB); cudaStreamDestroy(g.sR); cudaStreamDestroy(g.sC); cudaStreamDestroy(g.sP);
