@@ -151,3 +151,15 @@ def test_u8_conversion_formula(rfm):
     v = (u * a_lo + t).astype(np.float32)                                   # exact in float64, rounded once
     assert bits_equal(v, rfm.plan_table(6, 1e6, 0.0))
     assert bits_equal(v, (np.arange(256) / (255.0 / 2.0) - 1.0).astype(np.float32))
+
+
+def test_source_block_length_rule(rfm):
+    """cRtlSdrSource's block-length rule (RTL_SDR_Source.cpp:124-126): clamp to 4096 .. 2^20, then down to a multiple
+    of 4096 -- host only; cRadioReceiver asks for 65536 (default_block_length)."""
+    L = rfm.lib()
+    L.rfm_source_block_length.restype = C.c_uint32
+    L.rfm_source_block_length.argtypes = [C.c_uint32]
+    for req, want in ((0, 4096), (1, 4096), (4095, 4096), (4096, 4096), (4097, 4096), (8191, 4096), (8192, 8192),
+                      (65536, 65536), (65537, 65536), (100000, 98304), (1 << 20, 1 << 20), ((1 << 20) + 1, 1 << 20),
+                      (0xFFFFFFFF, 1 << 20)):
+        assert L.rfm_source_block_length(req) == want, (req, want)
