@@ -19,3 +19,11 @@ for n in 8 16 24 32; do run $n 1 AO; done
 run 16 1 AOP
 run 16 1 AOPC
 run 8 1 AOPC
+# What the co-resident pilot warps contend for (one capture each; read with `ncu -i ... --page raw --csv`, look at
+# smsp__inst_executed_pipe_fp64 / _xu, smsp__issue_active, launch__occupancy_limit_*, smsp__warp_issue_stalled_*):
+if [ "${WITH_NCU:-0}" = 1 ]; then
+  for n in 0 16 32; do
+    RFM_LANES_SMS=$n RFM_LANES_IMMBAR=1 ncu --set full --clock-control none --import-source on -k regex:k_bb_lanes -s 6 -c 1 \
+      -f -o gpurun_out/lanes_sms$n python bench.py --no-e2e --no-cpu --no-prof --steps 4 --warmup 3 > /dev/null 2>&1
+  done
+fi
