@@ -2,7 +2,7 @@
 // the drop-in host classes (pvr.rtl.radiofm_b200/host/*.h) are one-line forwards:
 //
 //   rfm_iir      cIirFilter            (IirFilter.h:12-36, IirFilter.cpp:11-105): RBJ biquad LP/HP/BP/BR, DF-II
-//   rfm_fir      cFirFilter            (FirFilter.h:17-60, FirFilter.cpp:78-148,273-413): Kaiser LP design / constant taps,
+//   rfm_fir      cFirFilter            (FirFilter.h:17-60, FirFilter.cpp:78-148,195-264,273-413): Kaiser LP / HP design / constant taps,
 //                                      circular delay line with its rotating summation start
 //   rfm_rdsproc  cRDSRxSignalProcessor (RDSProcess.h:56-110, RDSProcess.cpp:43-180): 57 kHz mix, decimation, LP, Costas
 //                                      loop, matched filter, bit clock / slicer on the device; block sync + FEC on the
