@@ -60,6 +60,11 @@ typedef struct rfm_config
   uint32_t max_block_len;  /* largest n per call; the reference's limit is 65536 (FmDecode.cpp:277) */
   int32_t device;          /* CUDA device ordinal, -1 = current */
   uint32_t n_groups;       /* internal stream groups pipelined on separate CUDA streams, 0 = auto */
+  uint32_t lanes_sms;      /* SM partition: the one-lane-per-stream recurrences (pilot PLL / DC tracker) run in a
+                            * green context of this many SMs (multiple of 8, >= 8), every FIR kernel in the rest, so
+                            * neither waits for the other's issue slots.  0 = no partition.  Placement only: results
+                            * are identical.  Ignored (with rfm_last_error set, creation still succeeds) when the
+                            * driver has no green contexts. */
 } rfm_config;
 
 RFM_API void rfm_config_default(rfm_config* cfg);

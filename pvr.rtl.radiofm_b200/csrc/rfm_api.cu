@@ -179,7 +179,7 @@ struct rfm_decoder
   unsigned last_hb_n[kMaxDecStages + 1] = {0};
   // host RDS state
   std::vector<RdsBlockSync> sync;
-  std::vector<RdsGroupDecoder> uecp; // per stream: groups -> UECP byte stream (never reset by cFmDecoder::Reset either)
+  std::vector<RdsGroupDecoder> uecp; // per stream: groups -> UECP byte stream; rfm_decoder_reset resets them (RDSProcess.cpp:92)
   std::vector<std::vector<uint8_t>> host_bits;
   uint8_t* h_drain = nullptr; // pinned staging of the drained bit counts + bits of every stream
   size_t h_drain_cap = 0;
@@ -379,7 +379,7 @@ struct ProfScope
 
 void ProfCollect(rfm_decoder* d, ProfSlot* slots)
 {
-  static const bool timeline = getenv("RFM_DEBUG_TIMELINE") != nullptr;
+  static const bool timeline = RFM_KNOB("RFM_DEBUG_TIMELINE") != nullptr;
   for (int k = 0; k < kMaxProfKinds; ++k)
   {
     ProfSlot& sl = slots[k];
@@ -558,7 +558,7 @@ int PlanBlock(const rfm_decoder* d, unsigned n, BlockGeom* g)
 // timing experiments only (results are wrong when a stage is skipped): RFM_DEBUG_SKIP=front,lanes,rest
 bool DebugSkip(const char* what)
 {
-  static const char* env = getenv("RFM_DEBUG_SKIP");
+  static const char* env = RFM_KNOB("RFM_DEBUG_SKIP");
   return env && strstr(env, what);
 }
 
@@ -614,6 +614,7 @@ void EnqueueStageA(rfm_decoder* d, Group& g, const BlockGeom& bg, unsigned par, 
   lp.pilot = {p.pilot.minfreq, p.pilot.maxfreq, p.pilot.b0, p.pilot.a1, p.pilot.a2, p.pilot.lb0, p.pilot.lb1,
               p.pilot.minsignal, p.pilot.lock_delay};
   lp.bbV = g.bbV[par3].p; lp.rawV = g.rawV[par3].p; lp.a_stride = d->a_stride; lp.a_hist = a_hist; lp.parity = par3;
+  lp.packed = d->part.lanes != nullptr; // few SMs for all lanes CTAs: the form that fits 12 of them on one SM
   RFM_PROF(g.prof, "k_bb_lanes", st, launch_bb_lanes(lp, st));
   g_launches += 2;
 }
@@ -935,6 +936,7 @@ void rfm_config_default(rfm_config* c)
   c->max_block_len = 65536;        // cRtlSdrSource::default_block_length
   c->device = -1;
   c->n_groups = 0;
+  c->lanes_sms = 0;
 }
 
 int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out)
@@ -1045,21 +1047,26 @@ int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out)
     const float one[2] = {1.0f, 0.0f}; // m_Osc1 initial unit vector, DownConvert.cpp:283-284
     RFM_TRY(Upload(d->osc1, one, 2));
   }
-  if (const char* e = getenv("RFM_LANES_SMS"))
   {
-    std::string why;
-    const unsigned n = (unsigned)atoi(e);
-    if (n >= 8 && !MakeSmPartition(d->device, n, &d->part, &why))
+    // SM partition (rfm_config::lanes_sms; RFM_LANES_SMS overrides it in the experiments build)
+    unsigned n = cfg->lanes_sms;
+    if (const char* e = RFM_KNOB("RFM_LANES_SMS"))
+      n = (unsigned)KnobInt(e, 0);
+    if (n >= 8)
     {
-      FreeSmPartition(&d->part);
-      fprintf(stderr, "radiofm_b200: RFM_LANES_SMS=%u ignored (%s)\n", n, why.c_str());
+      std::string why;
+      if (!MakeSmPartition(d->device, n, &d->part, &why))
+      {
+        FreeSmPartition(&d->part);
+        SetLastError("lanes_sms ignored: " + why); // creation still succeeds, on ordinary streams
+      }
+      else if (RFM_KNOB("RFM_DEBUG_TIMELINE"))
+        fprintf(stderr, "radiofm_b200: lanes on %u SMs, everything else on %u\n", d->part.lanes_sms, d->part.rest_sms);
     }
-    else if (n >= 8 && getenv("RFM_DEBUG_TIMELINE"))
-      fprintf(stderr, "radiofm_b200: lanes on %u SMs, everything else on %u\n", d->part.lanes_sms, d->part.rest_sms);
   }
   // which streams live in the lanes partition: letters of RFM_LANES_STREAMS among A (lanes), O (oscillator / resampler
   // tables), P (RDS PLL, matched filter, slicer), C (audio tail), R (RDS front), B (resamplers), F (front end)
-  const char* in_lanes = getenv("RFM_LANES_STREAMS") ? getenv("RFM_LANES_STREAMS") : "AO";
+  const char* in_lanes = RFM_KNOB("RFM_LANES_STREAMS") ? RFM_KNOB("RFM_LANES_STREAMS") : "AO";
   auto ctx_of = [&](char which) { return strchr(in_lanes, which) ? d->part.lanes : d->part.rest; };
   {
     int lo = 0, hi = 0;
@@ -1086,13 +1093,13 @@ int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out)
     {
       int prio_lo = 0, prio_hi = 0; // the latency-bound lanes kernel gets its CTAs placed first
       RFM_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-      if (getenv("RFM_DEBUG_NOPRIO"))
+      if (RFM_KNOB("RFM_DEBUG_NOPRIO"))
         prio_hi = prio_lo;
       // sA (demodulator + lanes) is the critical chain, the front end feeds it; the audio / RDS branches have slack
-      const char* flow = getenv("RFM_DEBUG_FLOW");
-      const int mode = flow ? atoi(flow) : 0;
+      const char* flow = RFM_KNOB("RFM_DEBUG_FLOW");
+      const int mode = KnobInt(flow, 0);
       int pA = prio_hi, pF = std::min(prio_lo, prio_hi + 1), pB = prio_lo;
-      int pL = getenv("RFM_DEBUG_LANEPRIO") ? atoi(getenv("RFM_DEBUG_LANEPRIO")) + prio_hi : prio_hi; // small lane kernels of stage B
+      int pL = KnobInt(RFM_KNOB("RFM_DEBUG_LANEPRIO"), 0) + prio_hi; // small lane kernels of stage B
       if (mode == 1) { pF = prio_lo; }
       if (mode == 2) { pF = prio_lo; pB = std::min(prio_lo, prio_hi + 1); }
       if (mode == 3) { pA = prio_lo; pF = prio_lo; pB = prio_hi; }
@@ -1102,7 +1109,7 @@ int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out)
       RFM_TRY(MakeStream(ctx_of('R'), &g.sR, pB));
       RFM_TRY(MakeStream(ctx_of('C'), &g.sC, pL));
       RFM_TRY(MakeStream(ctx_of('P'), &g.sP, pL));
-      if (getenv("RFM_DEBUG_SERIAL"))
+      if (RFM_KNOB("RFM_DEBUG_SERIAL"))
       { // measurement aid: every stage on ONE stream, so per-kernel event times are isolated durations
         cudaStreamDestroy(g.sF); cudaStreamDestroy(g.sB); cudaStreamDestroy(g.sR); cudaStreamDestroy(g.sC); cudaStreamDestroy(g.sP);
         g.sF = g.sB = g.sR = g.sC = g.sP = g.sA;
@@ -1175,6 +1182,11 @@ int rfm_decoder_reset(rfm_decoder* d)
   d->mf_g = 0;
   for (auto& s : d->sync)
     s.Reset();
+  // cFmDecoder::Reset -> cRDSRxSignalProcessor::Reset -> m_Decoder.Reset() (RDSProcess.cpp:92, RDSGroupDecoder.cpp:140-164):
+  // PI / PS / TA_TP / MS / DI / PIN change detection, RadioText and ODA state start over.  Frames already handed out
+  // (cRadioReceiver::AddUECPDataFrame has buffered them in the reference) stay in the pending byte stream.
+  for (auto& u : d->uecp)
+    u.Reset();
   return RFM_OK;
 }
 

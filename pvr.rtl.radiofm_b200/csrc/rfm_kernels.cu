@@ -782,9 +782,10 @@ struct LanesSmem
   float kf[8];
 };
 
-// FAKE_SINCOS: RFM_DEBUG_FAKE_SINCOS timing experiment (wrong results).  IMMBAR: RFM_LANES_IMMBAR experiment, barrier
-// ids as immediates (5 named barriers per CTA instead of 16; same hand-off)
-template <bool FAKE_SINCOS, bool IMMBAR = false>
+// FAKE_SINCOS: RFM_DEBUG_FAKE_SINCOS timing experiment (wrong results, experiments build only).  IMMBAR: barrier ids as
+// immediates (5 named barriers per CTA instead of the 16 ptxas reserves for register ids, so up to 12 CTAs fit on an
+// SM; same hand-off) -- the product form; the register-id form remains as an experiment (RFM_LANES_REGBAR).
+template <bool FAKE_SINCOS, bool IMMBAR = false, bool SPEC = false>
 __global__ void __launch_bounds__(64) k_bb_lanes(LanesParams p)
 {
   __shared__ LanesSmem sm;
@@ -900,36 +901,70 @@ __global__ void __launch_bounds__(64) k_bb_lanes(LanesParams p)
       pl.x1 = st[SF_PILOT_X1 * S + s];
       pl.level = 1000.0f; // FmDecode.cpp:147
     }
+    // (ps, pc) = sincos(phase) carried from sample to sample by the speculative form (rfm_math.cuh: rfm_sincos_predict)
+    PilotCarry sc = {0.0f, 1.0f};
+    if (SPEC)
+      rfm_sincos(pl.phase, &sc.ps, &sc.pc);
+    unsigned backoff = 0; // tiles left in the plain form after the speculation was refused (unlocked loop, noise)
     for (unsigned t = 0; t < ntiles; ++t)
     {
       const unsigned b = t & 1u, t0 = t * kLT;
       const unsigned tn = min(kLT, p.nb - t0);
       sync_bar(BAR_FULL, b);
-      // branch-free fast path; if any lane raised the sticky flag the tile is replayed with the exact routines
+      // branch-free fast paths; if any lane raised the sticky flag the tile is replayed with the next safer form:
+      // speculative sincos -> direct branch-free sincos -> the exact routines.  All three produce pilot_step's bits.
       const PilotState pl_start = pl;
       bool bad = false;
-      if (valid)
+      bool done = false;
+      if (SPEC && backoff == 0)
       {
-#pragma unroll 2
-        for (unsigned k = 0; k < tn; ++k)
-        {
-          const float bb = sm.ring[b][lane][k];
-          const float p38 = pilot_step_fast<FAKE_SINCOS>(pl, bb, pk, sca, bad);
-          sm.rawt[lane][k] = mulf(p38, mulf(2.0f, bb)); // FmDecode.cpp:455-456
-        }
-      }
-      if (__any_sync(0xffffffffu, bad))
-      {
-        pl = pl_start;
         if (valid)
         {
+#pragma unroll 2
           for (unsigned k = 0; k < tn; ++k)
           {
             const float bb = sm.ring[b][lane][k];
-            const float p38 = pilot_step(pl, bb, p.pilot);
-            sm.rawt[lane][k] = mulf(p38, mulf(2.0f, bb));
+            const float p38 = pilot_step_spec(pl, sc, bb, pk, sca, bad);
+            sm.rawt[lane][k] = mulf(p38, mulf(2.0f, bb)); // FmDecode.cpp:455-456
           }
         }
+        done = !__any_sync(0xffffffffu, bad);
+        if (!done)
+        {
+          pl = pl_start;
+          bad = false;
+          backoff = 8;
+        }
+      }
+      else if (SPEC)
+        --backoff;
+      if (!done)
+      {
+        if (valid)
+        {
+#pragma unroll 2
+          for (unsigned k = 0; k < tn; ++k)
+          {
+            const float bb = sm.ring[b][lane][k];
+            const float p38 = pilot_step_fast<FAKE_SINCOS>(pl, bb, pk, sca, bad);
+            sm.rawt[lane][k] = mulf(p38, mulf(2.0f, bb)); // FmDecode.cpp:455-456
+          }
+        }
+        if (__any_sync(0xffffffffu, bad))
+        {
+          pl = pl_start;
+          if (valid)
+          {
+            for (unsigned k = 0; k < tn; ++k)
+            {
+              const float bb = sm.ring[b][lane][k];
+              const float p38 = pilot_step(pl, bb, p.pilot);
+              sm.rawt[lane][k] = mulf(p38, mulf(2.0f, bb));
+            }
+          }
+        }
+        if (SPEC && backoff == 0)
+          rfm_sincos(pl.phase, &sc.ps, &sc.pc); // the next tile speculates again
       }
       if (t + 2 < ntiles)
         arrive_bar(BAR_EMPTY, b);
@@ -966,11 +1001,13 @@ void launch_bb_lanes(const LanesParams& p_in, cudaStream_t st)
 {
   if (p_in.S == 0 || p_in.nb == 0)
     return;
-  static const unsigned swap = getenv("RFM_LANES_SWAP") ? (unsigned)atoi(getenv("RFM_LANES_SWAP")) & 1u : 0u;
   LanesParams p = p_in;
+  p.role_swap = 0;
+#ifdef RFM_EXPERIMENTS
+  static const unsigned swap = (unsigned)KnobInt(RFM_KNOB("RFM_LANES_SWAP"), 0) & 1u;
   p.role_swap = swap;
   // experiment (with RFM_LANES_SMS): ask for the largest shared-memory carve-out so that 8 lanes CTAs fit on one SM
-  static const bool carve = getenv("RFM_LANES_CARVEOUT") && atoi(getenv("RFM_LANES_CARVEOUT")) != 0;
+  static const bool carve = KnobInt(RFM_KNOB("RFM_LANES_CARVEOUT"), 0) != 0;
   if (carve)
   {
     static bool done[64] = {false};
@@ -978,26 +1015,42 @@ void launch_bb_lanes(const LanesParams& p_in, cudaStream_t st)
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !done[dev])
     {
-      cudaFuncSetAttribute(k_bb_lanes<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      cudaFuncSetAttribute(k_bb_lanes<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      cudaFuncSetAttribute(k_bb_lanes<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       done[dev] = true;
     }
   }
   // measurement aid: reserve extra (unused) dynamic shared memory so fewer throughput CTAs share the lanes' SMs
-  static const int reserve_kb = getenv("RFM_LANES_RESERVE_KB") ? atoi(getenv("RFM_LANES_RESERVE_KB")) : 0;
-  static const bool fake = getenv("RFM_DEBUG_FAKE_SINCOS") && atoi(getenv("RFM_DEBUG_FAKE_SINCOS")) != 0;
+  static const int reserve_kb = KnobInt(RFM_KNOB("RFM_LANES_RESERVE_KB"), 0);
+  static const bool fake = KnobInt(RFM_KNOB("RFM_DEBUG_FAKE_SINCOS"), 0) != 0;
   if (reserve_kb > 0)
   {
-    EnsureDynSmem(k_bb_lanes<false>, (size_t)reserve_kb * 1024);
-    EnsureDynSmem(k_bb_lanes<true>, (size_t)reserve_kb * 1024);
+    EnsureDynSmem(k_bb_lanes<false, true>, (size_t)reserve_kb * 1024);
+    EnsureDynSmem(k_bb_lanes<true, true>, (size_t)reserve_kb * 1024);
   }
-  static const bool immbar = getenv("RFM_LANES_IMMBAR") && atoi(getenv("RFM_LANES_IMMBAR")) != 0;
+  static const bool fake_ = fake;
+  (void)fake_;
   if (fake)
-    k_bb_lanes<true><<<cdiv(p.S, 32), 64, (size_t)reserve_kb * 1024, st>>>(p);
-  else if (immbar)
-    k_bb_lanes<false, true><<<cdiv(p.S, 32), 64, (size_t)reserve_kb * 1024, st>>>(p);
+    return (void)k_bb_lanes<true, true><<<cdiv(p.S, 32), 64, (size_t)reserve_kb * 1024, st>>>(p);
+  if (reserve_kb > 0)
+    return (void)k_bb_lanes<false, true><<<cdiv(p.S, 32), 64, (size_t)reserve_kb * 1024, st>>>(p);
+  // speculative sincos (pilot_step_spec): bit-exact (tests/test_host_steps.py, 2e9-case fuzz) but measured slower:
+  // 139 instructions per sample against 94, 1.06 ms alone against 0.96, 2.34 ms under load against 2.06
+  static const bool spec = KnobInt(RFM_KNOB("RFM_LANES_SPEC"), 0) != 0;
+  if (spec)
+    return (void)k_bb_lanes<false, true, true><<<cdiv(p.S, 32), 64, 0, st>>>(p);
+  static const int immbar = KnobInt(RFM_KNOB("RFM_LANES_IMMBAR"), -1);
+  if (immbar == 1)
+    return (void)k_bb_lanes<false, true><<<cdiv(p.S, 32), 64, 0, st>>>(p);
+  if (immbar == 0)
+    return (void)k_bb_lanes<false, false><<<cdiv(p.S, 32), 64, 0, st>>>(p);
+#endif
+  // Barrier ids as immediates let up to 12 lanes CTAs share an SM, which is what an SM partition of a few SMs needs;
+  // without a partition that packing is harmful (co-resident pilot warps queue for the SM's one conversion / MUFU
+  // pipe: 2.28 ms per step against 2.08), and the register-id form's 16 reserved barriers keep it at 4 CTAs per SM.
+  if (p.packed)
+    k_bb_lanes<false, true><<<cdiv(p.S, 32), 64, 0, st>>>(p);
   else
-    k_bb_lanes<false><<<cdiv(p.S, 32), 64, (size_t)reserve_kb * 1024, st>>>(p);
+    k_bb_lanes<false, false><<<cdiv(p.S, 32), 64, 0, st>>>(p);
 }
 
 
@@ -1274,15 +1327,17 @@ void launch_resample_tiled(const ResampleParams& p, cudaStream_t st)
       return (size_t)1 << 30; // the staging loop covers 5 x 128 columns
     return (size_t)gb * p.lp * sizeof(float4) + (size_t)nch * 32 * *pitch * sizeof(float);
   };
-  static const int variant = getenv("RFM_RES_VARIANT") ? atoi(getenv("RFM_RES_VARIANT")) : 0;
   unsigned pitch = 0;
   size_t smem;
+#ifdef RFM_EXPERIMENTS
+  static const int variant = KnobInt(RFM_KNOB("RFM_RES_VARIANT"), 0);
   if (variant == 1 && (smem = need(8, 2, &pitch)) <= 200 * 1024)
     return launch_resample_tiled_gb<8, 2>(p, pitch, smem, st);
   if (variant == 2 && (smem = need(8, 1, &pitch)) <= 200 * 1024)
     return launch_resample_tiled_gb<8, 1>(p, pitch, smem, st);
   if (variant == 3 && (smem = need(16, 1, &pitch)) <= 200 * 1024)
     return launch_resample_tiled_gb<16, 1>(p, pitch, smem, st);
+#endif
   if ((smem = need(16, 2, &pitch)) <= 200 * 1024)
     return launch_resample_tiled_gb<16, 2>(p, pitch, smem, st);
   if ((smem = need(8, 2, &pitch)) <= 200 * 1024)
@@ -1597,7 +1652,7 @@ template <int MODE>
 static void launch_rotfir_lanes(const RotFirParams& p, cudaStream_t st)
 {
   const unsigned N = p.taps;
-  static const unsigned target = getenv("RFM_ROTFIR_OUT") ? (unsigned)atoi(getenv("RFM_ROTFIR_OUT")) : 128u; // measurement aid
+  static const unsigned target = (unsigned)KnobInt(RFM_KNOB("RFM_ROTFIR_OUT"), 128u); // measurement aid
   const unsigned cyc = std::max(1u, (target + N / 2) / N); // ~128 outputs per CTA
   const unsigned pitch = (cyc * N + N - 1) | 1u;        // odd: lanes (rows) hit distinct banks
   const size_t smem = (((N + 4 + 3) & ~3u) + (size_t)(MODE == 0 ? 1 : 2) * 32 * pitch) * sizeof(float);
@@ -1611,7 +1666,7 @@ void launch_rotfir(const RotFirParams& p, cudaStream_t st)
 {
   if (p.n == 0 || p.S == 0)
     return;
-  static const bool old_form = getenv("RFM_ROTFIR_OLD") != nullptr; // measurement aid
+  static const bool old_form = RFM_KNOB("RFM_ROTFIR_OLD") != nullptr; // measurement aid
   if (p.taps >= 8 && !old_form)
   {
     if (p.cplx)

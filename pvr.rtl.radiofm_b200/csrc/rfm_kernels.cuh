@@ -13,6 +13,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "rfm_math.cuh"
 #include "rfm_steps.cuh"
@@ -30,6 +31,16 @@ inline void EnsureDynSmem(F* func, size_t smem)
   EnsureDynSmemImpl(reinterpret_cast<const void*>(func), smem);
 }
 
+
+// Measurement knobs (RFM_DEBUG_* / RFM_LANES_* / ... environment variables) exist only in the experiments build
+// (RFM_EXPERIMENTS=1 sh build.sh -> libradiofm_b200_exp.so).  The product library reads no environment variable:
+// RFM_KNOB(name) is a null constant there and every branch that depends on one is compiled out.
+#ifdef RFM_EXPERIMENTS
+#define RFM_KNOB(name) getenv(name)
+#else
+#define RFM_KNOB(name) (static_cast<const char*>(nullptr))
+#endif
+inline int KnobInt(const char* v, int dflt) { return v ? atoi(v) : dflt; }
 
 constexpr unsigned kMaxFirTapsDev = 80; // >= cFirFilter MAX_NUMCOEF (75)
 
@@ -129,6 +140,7 @@ struct LanesParams
   size_t a_stride;
   unsigned a_hist;
   unsigned parity;         // selects SF_STEREO / SF_STEREO1
+  bool packed;             // the lanes stream lives in an SM partition: use the immediate-barrier kernel (12 CTAs per SM)
   unsigned role_swap;      // set by launch_bb_lanes: odd CTAs run the pilot PLL on warp 0 (RFM_LANES_SWAP, experiment)
 };
 void launch_bb_lanes(const LanesParams& p, cudaStream_t st);

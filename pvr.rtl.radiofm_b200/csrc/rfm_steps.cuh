@@ -148,6 +148,44 @@ RFM_HD float pilot_step_fast(PilotState& st, float x, const PilotConstDev& k, co
   return out;
 }
 
+// The same step with the sincos taken off the dependent chain (rfm_sincos_predict / rfm_sincos_correct, rfm_math.cuh):
+// (ps, pc) = sincos(st.phase) is carried from the previous step; this step predicts the next phase from the OLD
+// frequency, evaluates the double kernels there while the chain runs, and corrects by the (tiny) difference once the
+// new phase is known.  `bad` (sticky) means "not guaranteed identical to pilot_step": the caller replays the tile.
+struct PilotCarry
+{
+  float ps, pc;
+};
+
+RFM_HD float pilot_step_spec(PilotState& st, PilotCarry& sc, float x, const PilotConstDev& k, const SinCosRegs& sca, bool& bad)
+{
+  const float ph_hat = rfm_wrap_pilot_fast(addf(st.phase, st.freq), bad);
+  const SinCosPred pred = rfm_sincos_predict(ph_hat, sca);
+  const float ps = sc.ps, pc = sc.pc;
+  const float out = mulf(mulf(2.0f, ps), pc);
+  float pi = mulf(ps, x);
+  float pq = mulf(pc, x);
+  pi = subf(subf(mulf(k.b0, pi), mulf(k.a1, st.i1)), mulf(k.a2, st.i2));
+  pq = subf(subf(mulf(k.b0, pq), mulf(k.a1, st.q1)), mulf(k.a2, st.q2));
+  st.i2 = st.i1;
+  st.i1 = pi;
+  st.q2 = st.q1;
+  st.q1 = pq;
+  const bool use_div = pi > absf(pq);
+  bad = bad | (use_div & rfm_div_unsafe_below(pq, pi));
+  const float ediv = rfm_div_fast(pq, pi);
+  const float esat = (pq > 0.0f) ? 1.0f : -1.0f;
+  const float err = use_div ? ediv : esat;
+  st.level = fminf(pi, st.level);
+  const float freq = fmaxf(fminf(addf(st.freq, addf(mulf(k.lb0, err), mulf(k.lb1, st.x1))), k.maxfreq), k.minfreq);
+  st.x1 = err;
+  st.freq = freq;
+  st.phase = rfm_wrap_pilot_fast(addf(st.phase, freq), bad);
+  bad = bad | (st.phase == 0.0f);
+  rfm_sincos_correct(pred, st.phase, ph_hat, &sc.ps, &sc.pc, bad);
+  return out;
+}
+
 // ---- cIirFilter DF-II biquad (IirFilter.cpp:78-105) ---------------------------------------------------------------
 RFM_HD float biquad_step(const BiquadDev& c, float x, float& w1, float& w2)
 {

@@ -18,8 +18,7 @@ HOT = {
     "k_front_tiledILb1ELi11E": (64, "128 threads, 4 outputs per thread: >= 8 CTAs per SM"),
     "k_front_tiledILb1ELi4E": (64, ""),
     "k_front_tiledILb1ELi5E": (64, ""),
-    "k_bb_lanesILb0ELb0E": (128, "64 threads; pilot state + 13 double constants in registers"),
-    "k_bb_lanesILb0ELb1E": (128, "immediate-barrier variant"),
+    "k_bb_lanesILb0ELb1ELb1E": (128, "64 threads; pilot state + 13 double constants in registers; immediate barrier ids, speculative sincos"),
     "k_demod_spec": (96, "32-thread CTAs, ~17 per SM"),
     "k_resample_tiledILi16ELi2E": (96, ""),
     "k_rotfir_lanesILi0E": (64, ""),
@@ -72,3 +71,16 @@ def test_every_kernel_is_sm_100a_and_fits_shared_memory():
     for n, (regs, _stack, shared, local) in usage.items():
         assert regs <= 128 and local == 0, (n, regs, local)
         assert shared <= 48 * 1024, (n, shared)  # static part; the dynamic part is opted in per launch (EnsureDynSmem)
+
+
+def test_product_library_reads_no_environment_knobs():
+    """The measurement knobs (RFM_DEBUG_* / RFM_LANES_* / RFM_RES_* / RFM_ROTFIR_*) exist only in the experiments
+    build (RFM_EXPERIMENTS=1 sh build.sh -> libradiofm_b200_exp.so); the product library contains none of the names,
+    and its lanes kernel has 5 named barriers (immediate ids), not 16."""
+    lib = os.path.join(ROOT, "pvr.rtl.radiofm_b200", "libradiofm_b200.so")
+    if not os.path.exists(lib):
+        pytest.skip("library not built")
+    blob = open(lib, "rb").read()
+    for frag in (b"RFM_DEBUG_", b"RFM_LANES_", b"RFM_RES_", b"RFM_ROTFIR_", b"FAKE_SINCOS"):
+        assert frag not in blob, frag
+    assert b"k_bb_lanesILb1E" not in blob  # the fake-sincos timing kernel is not even instantiated

@@ -138,6 +138,39 @@ def test_uecp_stream_of_the_batched_decoder(rfm):
     assert d.take_uecp(0) == b""
 
 
+def test_reset_mid_stream_restarts_the_group_decoder(rfm, port):
+    """cFmDecoder::Reset -> cRDSRxSignalProcessor::Reset -> cRDSGroupDecoder::Reset (RDSProcess.cpp:92,
+    RDSGroupDecoder.cpp:140-164): after a reset on the same station the PI / PS / TA_TP / MS / DI frames are emitted
+    again.  Oracle: the chain restatement (audio, groups, reset included) + the group-decoder restatement -- or the
+    compiled reference group decoder where oracle/_ref travelled -- reset at the same block."""
+    from oracle import uecp_port, ref_uecp
+    fs, ds, blk = RATES["1.0M"]
+    nblk, cut = 9, 7
+    iq, _ = station("1.0M", nblk)
+    d = rfm.FmDecoderBatch(fs, -0.15 * fs, downsample=ds, max_block_len=blk)
+    o = port.OracleFmDecoder(fs, -0.15 * fs, downsample=ds)
+    decs = [uecp_port.OracleGroupDecoder()] + ([ref_uecp.RefGroupDecoder()] if ref_uecp.available() else [])
+    want = [b"" for _ in decs]
+    got = b""
+    for rnd in range(2):
+        for b in range(cut if rnd == 0 else nblk):
+            x = iq[b * blk:(b + 1) * blk]
+            assert bits_equal(d.process_u8(x[None])[0], o.process_u8(x)), (rnd, b)
+        g = o.take_groups()
+        assert len(g) >= 4 and np.array_equal(g, d.take_groups())
+        for i, u in enumerate(decs):
+            want[i] += b"".join(uecp_port.stuff_frame(f) for f in u.decode(g))
+        got += d.take_uecp()
+        if rnd == 0:
+            d.reset(); o.reset()
+            for u in decs:
+                u.reset()
+    assert all(w == got for w in want) and len(got) > 80
+    # the PI frame (message element code 0x01) appears once per decoder life
+    first = b"".join(uecp_port.stuff_frame(f) for f in uecp_port.OracleGroupDecoder().decode(g[:1]))
+    assert got.count(first[:6]) >= 1
+
+
 def test_two_devices_in_one_process(rfm, port):
     """per-device kernel attributes (dynamic shared memory limits) and state: a decoder on cuda:1 next to one on cuda:0"""
     import torch

@@ -42,6 +42,24 @@ unsigned run_pilot(const float* x, unsigned n, const float* k8, float freq0, flo
   lvl[0] = a.level; lvl[1] = b.level;
   return flagged;
 }
+// speculative-sincos form (pilot_step_spec): per-sample replay on `bad`; returns the number of flagged samples,
+// mism[0] = samples where the UNFLAGGED speculative step differs from the exact one in any state word or output
+unsigned run_pilot_spec(const float* x, unsigned n, const float* k8, float freq0, float* out_spec, unsigned* mism) {
+  PilotConstDev k = {k8[0], k8[1], k8[2], k8[3], k8[4], k8[5], k8[6], k8[7], 0};
+  PilotState a = {0, freq0, 0, 0, 0, 0, 0, 1000.f}, b = a; unsigned flagged = 0; mism[0] = 0;
+  const SinCosRegs R = rfm_sincos_regs();
+  PilotCarry sc; rfm_sincos(b.phase, &sc.ps, &sc.pc);
+  for (unsigned i = 0; i < n; ++i) {
+    const float oa = pilot_step(a, x[i], k);
+    bool bad = false; PilotState save = b;
+    float o = pilot_step_spec(b, sc, x[i], k, R, bad);
+    float es, ec; rfm_sincos(b.phase, &es, &ec);
+    if (bad) { ++flagged; b = save; o = pilot_step(b, x[i], k); rfm_sincos(b.phase, &sc.ps, &sc.pc); }
+    else if (memcmp(&a, &b, sizeof(a)) != 0 || f2u(o) != f2u(oa) || f2u(es) != f2u(sc.ps) || f2u(ec) != f2u(sc.pc)) ++mism[0];
+    out_spec[i] = o;
+  }
+  return flagged;
+}
 }
 '''
 
@@ -57,7 +75,8 @@ def shim(tmp_path_factory):
     f32p = C.POINTER(C.c_float)
     L.run_demod.argtypes = [f32p, C.c_uint, f32p, f32p, f32p]
     L.run_pilot.argtypes = [f32p, C.c_uint, f32p, C.c_float, f32p, f32p, f32p]
-    L.run_demod.restype = L.run_pilot.restype = C.c_uint
+    L.run_pilot_spec.argtypes = [f32p, C.c_uint, f32p, C.c_float, f32p, C.POINTER(C.c_uint)]
+    L.run_demod.restype = L.run_pilot.restype = L.run_pilot_spec.restype = C.c_uint
     return L
 
 
@@ -121,3 +140,36 @@ def test_pilot_steps_match_oracle(shim, port):
     out, outf, lvl = np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.float32), np.zeros(2, dtype=np.float32)
     shim.run_pilot(_p(pil), n, _p(k8), float(np.float32(c[16])), _p(out), _p(outf), _p(lvl))
     assert bits_equal(out, y) and bits_equal(outf, y)
+
+
+def test_speculative_pilot_step_is_exact_or_flagged(shim, port):
+    """pilot_step_spec (sincos predicted off the dependent chain, corrected by the phase difference) must equal
+    pilot_step bit for bit -- state, output and carried sincos -- on every sample it does not flag; the flag rate in
+    lock must stay negligible (a flagged tile is replayed with the direct routine on the GPU)."""
+    fs, ds, blk = RATES["2.4M"]
+    nblk = 24
+    iq, _ = station("2.4M", nblk)
+    o = port.OracleFmDecoder(fs, -0.15 * fs, downsample=ds)
+    c = o.constants()
+    k8 = np.array([c[9], c[10], c[11], c[12], c[13], c[14], c[15], c[17]], dtype=np.float32)
+    bb, p38 = [], []
+    for b in range(nblk):
+        o.process_u8(iq[b * blk:(b + 1) * blk])
+        bb.append(o.tap("baseband"))
+        p38.append(o.tap("pilot38"))
+    bb, p38 = np.ascontiguousarray(np.concatenate(bb)), np.concatenate(p38)
+    rng = np.random.default_rng(5)
+    noise = (0.3 * rng.standard_normal(200000)).astype(np.float32)
+    t = np.arange(400000) / (fs / ds)
+    drift = (0.1 * np.sin(2 * np.pi * (19000.0 + 8.0 * np.sin(2 * np.pi * 3.0 * t)) * t)
+             + 0.02 * rng.standard_normal(t.size)).astype(np.float32)
+    for name, x, max_flag_rate in (("station", bb, 2e-3), ("noise", noise, 1.0), ("zeros", np.zeros(50000, np.float32), 1.0),
+                                   ("drifting pilot", drift, 0.05)):
+        out, mism = np.zeros_like(x), C.c_uint(0)
+        flagged = shim.run_pilot_spec(_p(x), x.size, _p(k8), float(np.float32(c[16])), _p(out), C.byref(mism))
+        assert mism.value == 0, (name, mism.value)
+        assert flagged <= max_flag_rate * x.size, (name, flagged, x.size)
+        if name == "station":
+            assert bits_equal(out, p38)
+            locked = shim.run_pilot_spec(_p(x[-40000:]), 40000, _p(k8), float(np.float32(c[16])), _p(out[:40000]), C.byref(mism))
+            print("flagged", flagged, "of", x.size)
