@@ -18,7 +18,8 @@ HOT = {
     "k_front_tiledILb1ELi11E": (64, "128 threads, 4 outputs per thread: >= 8 CTAs per SM"),
     "k_front_tiledILb1ELi4E": (64, ""),
     "k_front_tiledILb1ELi5E": (64, ""),
-    "k_bb_lanesILb0ELb1ELb1E": (128, "64 threads; pilot state + 13 double constants in registers; immediate barrier ids, speculative sincos"),
+    "k_bb_lanesILb0ELb0ELb0E": (128, "64 threads; pilot state + 13 double constants in registers"),
+    "k_bb_lanesILb0ELb1ELb0E": (128, "immediate-barrier form (SM partition: up to 12 CTAs per SM)"),
     "k_demod_spec": (96, "32-thread CTAs, ~17 per SM"),
     "k_resample_tiledILi16ELi2E": (96, ""),
     "k_rotfir_lanesILi0E": (64, ""),
