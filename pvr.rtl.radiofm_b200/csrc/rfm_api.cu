@@ -106,7 +106,7 @@ struct Group
   }
   cudaEvent_t ev_rds[3] = {nullptr, nullptr, nullptr};  // RDS front of the block finished (mod 3): bbV / oscV released
   cudaEvent_t ev_res[2] = {nullptr, nullptr};   // resamplers of the block with this parity finished: lpS / lpM [parity] written
-  cudaEvent_t ev_aud[2] = {nullptr, nullptr};   // audio tail ... finished (its stereo-flag slot may be rewritten)
+  cudaEvent_t ev_aud[3] = {nullptr, nullptr, nullptr}; // audio tail ... finished (its stereo-flag slot, by block index mod 3, may be rewritten)
   cudaEvent_t ev_carry[2] = {nullptr, nullptr}; // LP history carried out of lpS / lpM [parity ^ 1]: they may be overwritten
   cudaEvent_t ev_pll[2] = {nullptr, nullptr};   // RDS PLL + slicer ... finished: rlp_out[parity] may be overwritten
   cudaEvent_t ev_front[2] = {nullptr, nullptr}; // front end of the block with this parity finished
@@ -288,7 +288,7 @@ void FreeDecoder(rfm_decoder* d)
     g.lpS[0].Free(); g.lpS[1].Free(); g.lpM[0].Free(); g.lpM[1].Free(); g.fS.Free(); g.fM.Free(); g.state.Free(); g.in_stage.Free(); g.audio_stage.Free();
     ProfFree(g.prof);
     for (cudaEvent_t e : {g.ev_demod[0], g.ev_demod[1], g.ev_front[0], g.ev_front[1], g.ev_lanes[0], g.ev_lanes[1], g.ev_rest[0], g.ev_rest[1], g.ev_rest[2], g.ev_rds[0], g.ev_rds[1], g.ev_rds[2],
-                          g.ev_res[0], g.ev_res[1], g.ev_aud[0], g.ev_aud[1], g.ev_pll[0], g.ev_pll[1], g.ev_carry[0], g.ev_carry[1]})
+                          g.ev_res[0], g.ev_res[1], g.ev_aud[0], g.ev_aud[1], g.ev_aud[2], g.ev_pll[0], g.ev_pll[1], g.ev_carry[0], g.ev_carry[1]})
       if (e)
         cudaEventDestroy(e);
     if (g.sF == g.sA)
@@ -574,6 +574,7 @@ void EnqueueStageF(rfm_decoder* d, Group& g, const void* d_in, size_t in_stride,
   fp.in = d_in; fp.in_stride = in_stride; fp.n = bg.n; fp.S = S; fp.order = p.in_order; fp.ds = p.downsample;
   fp.p0 = d->in_pos; fp.nout = bg.nb; fp.idx0 = d->tuner_idx; fp.lut = d->d_lut.p; fp.tuner = d->d_tuner.p;
   fp.coeff = d->d_in_coeff.p; fp.coeff_host = p.in_coeff.data(); fp.tail = g.tail.p; fp.z = g.z[par].p; fp.z_stride = d->z_stride;
+  fp.sm_count = d->part.rest ? d->part.rest_sms : 0;
   RFM_PROF(g.prof, "k_if_level", st, launch_if_level(fp, g.state.p, u8, st));
   RFM_PROF(g.prof, "k_front", st, launch_front(fp, u8, st));
   RFM_PROF(g.prof, "k_front_tail", st, launch_front_tail(fp, u8, st));
@@ -682,6 +683,7 @@ void EnqueueStageB(rfm_decoder* d, Group& g, const BlockGeom& bg, unsigned par, 
     rf.st[k].len = (unsigned)hs.len;
     rf.st[k].hist = StageHist(hs);
     rf.st[k].h = hs.h ? d->d_hb[k].p : nullptr;
+    rf.st[k].h_host = hs.h;
     rf.tail_off[k] = d->rds_tail_off[k];
   }
   rf.tail_off[nst] = d->rds_tail_off[nst];
@@ -838,7 +840,9 @@ int ProcessDevice(rfm_decoder* d, const void* d_in, size_t in_stride, bool u8, u
     // ---- stage A
     RFM_CUDA(cudaStreamWaitEvent(g.sA, g.ev_front[par], 0));
     RFM_CUDA(cudaStreamWaitEvent(g.sA, g.ev_rest[par3], 0)); // stage B of block k-3 has released bbV / rawV [par3]
-    RFM_CUDA(cudaStreamWaitEvent(g.sA, g.ev_aud[par], 0));    // ... and its audio tail (k-2 implies k-3) the stereo-flag slot
+    RFM_CUDA(cudaStreamWaitEvent(g.sA, g.ev_aud[par3], 0));   // ... and its audio tail the stereo-flag slot (k mod 3).  Waiting
+                                                              // for block k-2's instead made lanes(k) -> resamplers(k) -> audio
+                                                              // tail(k) -> lanes(k+2) a two-step cycle that bound the step
     if (!DebugSkip("lanes"))
       EnqueueStageA(d, g, bg, par, par3);
     RFM_CUDA(cudaEventRecord(g.ev_lanes[par], g.sA));
@@ -864,7 +868,7 @@ int ProcessDevice(rfm_decoder* d, const void* d_in, size_t in_stride, bool u8, u
                                  (size_t)d->audio_cap * sizeof(float), (size_t)2 * bg.na * sizeof(float), g.S,
                                  cudaMemcpyDeviceToHost, g.sC));
     }
-    RFM_CUDA(cudaEventRecord(g.ev_aud[par], g.sC));
+    RFM_CUDA(cudaEventRecord(g.ev_aud[par3], g.sC));
   }
   RFM_CUDA(cudaGetLastError());
 
@@ -985,7 +989,7 @@ int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out)
   d->na_max = (unsigned)(d->nb_max / p.a_ratio) + 4;
   d->nr_max = d->nb_max; // generous: halved per stage below
   d->z_stride = AlignUp(d->nb_max, 16);
-  d->a_stride = AlignUp(p.a_order + d->nb_max, 32);
+  d->a_stride = AlignUp(p.a_order + d->nb_max + 4, 32); // + 4: the resampler's 16-byte tile copies may end past the block
   d->lp_stride = AlignUp((unsigned)p.lp_coef.size() - 1 + d->na_max, 32);
   unsigned m = d->nb_max;
   for (size_t k = 0; k < p.rds_stages.size(); ++k)
@@ -1035,7 +1039,8 @@ int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out)
       RFM_TRY(d->d_hb[k].Alloc(4));
   }
   RFM_TRY(d->d_repairs.Alloc(1));
-  d->res_lp = p.a_order + 1 + 3 * ((unsigned)p.a_ratio + 1) + 4;
+  // time steps per group of 4 outputs: one window + 3 output spacings, + the alignment of both ends to 4 samples
+  d->res_lp = AlignUp(p.a_order + 1 + 3 * ((unsigned)p.a_ratio + 1) + 4 + 6, 4);
   for (int b = 0; b < 3; ++b)
   {
     RFM_TRY(d->res_kk[b].Alloc((size_t)(d->na_max / 4 + 2) * d->res_lp * 4));
@@ -1121,7 +1126,6 @@ int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out)
       RFM_TRY(cudaEventCreateWithFlags(&g.ev_demod[b], cudaEventDisableTiming));
       RFM_TRY(cudaEventCreateWithFlags(&g.ev_lanes[b], cudaEventDisableTiming));
       RFM_TRY(cudaEventCreateWithFlags(&g.ev_res[b], cudaEventDisableTiming));
-      RFM_TRY(cudaEventCreateWithFlags(&g.ev_aud[b], cudaEventDisableTiming));
       RFM_TRY(cudaEventCreateWithFlags(&g.ev_carry[b], cudaEventDisableTiming));
       RFM_TRY(cudaEventCreateWithFlags(&g.ev_pll[b], cudaEventDisableTiming));
       RFM_TRY(g.rlp_out[b].Alloc(S * d->nr_stride));
@@ -1141,6 +1145,7 @@ int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out)
       RFM_TRY(g.rawV[b].Alloc(S * d->a_stride));
       RFM_TRY(cudaEventCreateWithFlags(&g.ev_rest[b], cudaEventDisableTiming));
       RFM_TRY(cudaEventCreateWithFlags(&g.ev_rds[b], cudaEventDisableTiming));
+      RFM_TRY(cudaEventCreateWithFlags(&g.ev_aud[b], cudaEventDisableTiming));
     }
 
     RFM_TRY(g.rlpV.Alloc(S * d->rlp_stride));

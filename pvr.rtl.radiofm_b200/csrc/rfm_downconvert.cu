@@ -340,46 +340,6 @@ __global__ void __launch_bounds__(kDcThreads) k_dc_chain(DcParams p)
 // registers (7 LDS.64 per output instead of 27; lane stride 5 float2 = 10 banks: conflict-free), taps are constant-bank
 // operands.  Same products, same summation order as hb_generic.
 // --------------------------------------------------------------------------------------------------
-template <int L>
-struct DcTaps
-{
-  float h[L];
-};
-
-template <int L, int R>
-__device__ __forceinline__ void hb_deint(const DcTaps<L>& t, const float2* E, const float2* O, float2 (&acc)[R])
-{
-  constexpr int NE = (L + 1) / 2; // even taps 0, 2, .., L - 1
-  constexpr int C = (L - 1) / 2;  // centre tap (odd index)
-#pragma unroll
-  for (int m = 0; m < NE + R - 1; ++m)
-  {
-    const float2 v = E[m];
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-    {
-      const int j = m - r;
-      if (j == 0)
-      {
-        acc[r].x = mulf(v.x, t.h[0]);                 // DownConvert.cpp:528-529
-        acc[r].y = mulf(v.y, t.h[0]);
-      }
-      if (j >= 0 && j < NE)
-      {
-        acc[r].x = addf(acc[r].x, mulf(v.x, t.h[2 * j])); // :533-534 (j = 0 again: tap 0 is counted twice)
-        acc[r].y = addf(acc[r].y, mulf(v.y, t.h[2 * j]));
-      }
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < R; ++r)
-  {
-    const float2 v = O[r + (C - 1) / 2];
-    acc[r].x = addf(acc[r].x, mulf(v.x, t.h[C]));       // :537-540
-    acc[r].y = addf(acc[r].y, mulf(v.y, t.h[C]));
-  }
-}
-
 // one stage over a tile: groups of R consecutive outputs per thread; dstO == nullptr: last stage, dstE is the output row
 // (natural order), else output o goes to the next stage's E / O by parity
 template <int L, int R>

@@ -123,4 +123,51 @@ __device__ __forceinline__ float2 hb_out(int kind, unsigned L, const float* h, c
   return acc;
 }
 
+// --------------------------------------------------------------------------------------------------
+// The generic half-band over DE-INTERLEAVED V buffers -- E[m] = V[2m], O[m] = V[2m+1] -- so that output
+// o = sum_j h[2j] E[o + j] + h[c] O[o + (c-1)/2] reads consecutive entries: a thread makes R consecutive outputs from
+// (L+1)/2 + R - 1 even and R odd samples held in registers, the taps are constant-bank operands (kernel parameters).
+// Same products, same summation order as hb_generic (DownConvert.cpp:528-540).  Used by the wideband chain
+// (rfm_downconvert.cu) and by the RDS front (rfm_kernels.cu).
+// --------------------------------------------------------------------------------------------------
+template <int L>
+struct DcTaps
+{
+  float h[L];
+};
+
+template <int L, int R>
+__device__ __forceinline__ void hb_deint(const DcTaps<L>& t, const float2* E, const float2* O, float2 (&acc)[R])
+{
+  constexpr int NE = (L + 1) / 2; // even taps 0, 2, .., L - 1
+  constexpr int C = (L - 1) / 2;  // centre tap (odd index)
+#pragma unroll
+  for (int m = 0; m < NE + R - 1; ++m)
+  {
+    const float2 v = E[m];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+    {
+      const int j = m - r;
+      if (j == 0)
+      {
+        acc[r].x = mulf(v.x, t.h[0]);                 // DownConvert.cpp:528-529
+        acc[r].y = mulf(v.y, t.h[0]);
+      }
+      if (j >= 0 && j < NE)
+      {
+        acc[r].x = addf(acc[r].x, mulf(v.x, t.h[2 * j])); // :533-534 (j = 0 again: tap 0 is counted twice)
+        acc[r].y = addf(acc[r].y, mulf(v.y, t.h[2 * j]));
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+  {
+    const float2 v = O[r + (C - 1) / 2];
+    acc[r].x = addf(acc[r].x, mulf(v.x, t.h[C]));       // :537-540
+    acc[r].y = addf(acc[r].y, mulf(v.y, t.h[C]));
+  }
+}
+
 } // namespace rfm

@@ -19,6 +19,8 @@
 //   k_rds_pll      [a9]         Costas loop, one lane per stream
 //   k_rds_slice    [a11]        bit-clock resonator + peak slicer + differential decode
 //   k_tails                     V-buffer history carry
+#include <cuda.h> // CUtensorMap (declarations only: the encoder is looked up at run time, libcuda is not linked)
+
 #include "rfm_kernels.cuh"
 #include "rfm_dsp.cuh"
 
@@ -26,6 +28,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <utility>
@@ -340,6 +343,231 @@ __global__ void __launch_bounds__(128) k_front_tiled(FrontParams p, FrontCoef cf
   }
 }
 
+// --------------------------------------------------------------------------------------------------
+// TMA form of the same kernel for u8 input and ds = 1, 5, 11 (390 625 S/s, 1.2 and 2.4 MS/s).
+//   * the raw u8 window -- ((384-1) ds + order) IQ pairs plus alignment -- is fetched by the TMA unit: one elected
+//     thread issues cp.async.bulk.tensor.2d over a tensor map of the caller's [S][n] rows (8-byte elements = 4 IQ
+//     pairs, boxes of 256 elements = 2 KB) and the CTA waits on an mbarrier.  Out-of-range coordinates (before the
+//     row: the history part comes from the tail buffer; behind it) are zero-filled by the hardware: no edge paths,
+//     no per-sample predicates, no address arithmetic in the conversion loop;
+//   * the raw bytes land at the END of the window buffer they are expanded into; every thread pulls its 16-byte
+//     chunks into registers, one barrier retires the raw region, then u8 -> float -> fine tuner -> window as before;
+//   * R = 3 outputs per thread: the thread stride R ds float2 = 6 ds words is 2 (mod 4) banks for odd ds, so the
+//     64-bit window loads of a half warp are conflict-free WITHOUT the padding slot of the R = 4 kernel -- and with
+//     it goes the carry logic of the staging stores (4 of its 24 instructions per sample).  Six CTAs per SM.
+// Same taps, same products, same ascending-j summation per output (DownConvert.cpp:112-129).
+// --------------------------------------------------------------------------------------------------
+template <int DS>
+struct FrontGeom3
+{
+  static constexpr int R = 3, T = 128, ORDER = 8 * DS, OB = T * R, SEG = R * DS;
+  static constexpr int W = (OB - 1) * DS + ORDER;          // window samples
+  static constexpr int WIN = ORDER + DS * (R - 1);         // samples one thread touches
+  static constexpr int RAW_ELEMS = (W + 3 + 3) / 4 + 1;    // 8-byte elements that cover any alignment of the window
+  static constexpr int BOXES = (RAW_ELEMS + 255) / 256;    // 2 KB boxes
+  static constexpr int NPAIR = (BOXES * 512 + T - 1) / T;  // IQ pairs of pairs (32-bit words) per thread
+  static constexpr int XBYTES = (W + 1) * 8;               // + 1: the window is shifted by one slot when vlo is odd
+  // the raw window has its own region behind the float window: it is refilled (next tile) while this one is filtered
+  static constexpr int RAW_OFF = (XBYTES + 127) / 128 * 128;
+  static constexpr int SMEM = RAW_OFF + BOXES * 2048;
+  static_assert(RAW_OFF >= ORDER * 8 && RAW_OFF % 128 == 0, "raw region must not overlap the history part of the window");
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+template <int DS>
+__global__ void __launch_bounds__(128) k_front_tma(FrontParams p, FrontCoef cf, const __grid_constant__ CUtensorMap tmap,
+                                                   unsigned tiles_per_row, unsigned total_tiles)
+{
+  using G = FrontGeom3<DS>;
+  extern __shared__ __align__(128) unsigned char smem_front_tma[];
+  __shared__ __align__(8) unsigned long long mbar;
+  float2* X = reinterpret_cast<float2*>(smem_front_tma);
+  const unsigned char* raw = smem_front_tma + G::RAW_OFF;
+
+  const unsigned tid = threadIdx.x;
+  const float2* tuner = reinterpret_cast<const float2*>(p.tuner);
+  // persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the TMA fetch of the NEXT tile's raw window is in
+  // flight while this tile is converted and filtered
+  auto issue = [&](unsigned tile) {
+    const unsigned s = tile / tiles_per_row, bx = tile - s * tiles_per_row;
+    const int c0 = ((int)(p.p0 + bx * G::OB * DS) - G::ORDER) >> 2; // first 8-byte element (floor; negative at a row's start)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(G::BOXES * 2048) : "memory");
+#pragma unroll
+    for (int b = 0; b < G::BOXES; ++b)
+      asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                   ::"r"(smem_u32(raw + b * 2048)), "l"(reinterpret_cast<unsigned long long>(&tmap)), "r"(smem_u32(&mbar)),
+                   "r"(c0 + 256 * b), "r"((int)s)
+                   : "memory");
+  };
+  if (tid == 0)
+  {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (blockIdx.x < total_tiles)
+      issue(blockIdx.x);
+  }
+  __syncthreads();
+  unsigned phase = 0;
+  for (unsigned tile = blockIdx.x; tile < total_tiles; tile += gridDim.x)
+  {
+    const unsigned s = tile / tiles_per_row, bx = tile - s * tiles_per_row;
+    const unsigned o0 = bx * G::OB;
+    const unsigned nt = min((unsigned)G::OB, p.nout - o0);
+    // V = tail(order) ++ block(n); this tile needs V[vlo .. vlo + count)
+    const int vlo = (int)(p.p0 + o0 * DS);
+    const int count = (int)(nt - 1) * DS + G::ORDER;
+    const int i_lo = max(0, vlo - G::ORDER);                       // block samples [i_lo, i_hi) -> w = i + order - vlo
+    const int i_hi = min((int)p.n, vlo + count - G::ORDER);
+    const int c0 = (vlo - G::ORDER) >> 2;
+    // A thread converts the IQ pairs 2 m, 2 m + 1 (counted from the raw window's first pair), m = tid + 128 j: one
+    // 32-bit load, one 16-byte store per pair -- consecutive lanes touch consecutive words / quads of shared memory, so
+    // neither side has bank conflicts (8 consecutive pairs per lane made the window stores collide 8-way: 120 M
+    // conflict wavefronts per launch).  Its pairs are 256 samples apart: the two fine-tuner phasors never change.
+    const int ib0 = 4 * c0 + 2 * (int)tid;
+    const float2 tw0 = tuner[(p.idx0 + (unsigned)ib0) & 63u], tw1 = tuner[(p.idx0 + (unsigned)(ib0 + 1)) & 63u];
+    // window slot of sample i: i + order - vlo (+ 1 when vlo is odd, so that even i lands on a 16-byte boundary)
+    float2* Xs = X + (vlo & 1);
+    {
+      unsigned done = 0;
+      while (!done)
+        asm volatile("{ .reg .pred q; mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2; selp.u32 %0, 1, 0, q; }"
+                     : "=r"(done) : "r"(smem_u32(&mbar)), "r"(phase) : "memory");
+      phase ^= 1u;
+    }
+    __syncthreads(); // every thread has left the previous tile's FIR: X may be rewritten
+    // ---- window: history part (first tile of a row only)
+    if (vlo < G::ORDER)
+    {
+      const float2* tail = reinterpret_cast<const float2*>(p.tail) + (size_t)s * G::ORDER;
+      for (int V = vlo + (int)tid; V < G::ORDER && V - vlo < count; V += G::T)
+        Xs[V - vlo] = tail[V];
+    }
+    const unsigned* raw32 = reinterpret_cast<const unsigned*>(raw) + tid;
+    auto tuned_pair = [&](int j) {
+      const unsigned word = raw32[G::T * j];
+      const float are0 = rfm_u8_to_float(word, 0u), aim0 = rfm_u8_to_float(word, 1u);
+      const float are1 = rfm_u8_to_float(word, 2u), aim1 = rfm_u8_to_float(word, 3u);
+      float4 o;
+      o.x = subf(mulf(are0, tw0.x), mulf(aim0, tw0.y));   // FmDecode.cpp:66-82
+      o.y = addf(mulf(are0, tw0.y), mulf(aim0, tw0.x));
+      o.z = subf(mulf(are1, tw1.x), mulf(aim1, tw1.y));
+      o.w = addf(mulf(are1, tw1.y), mulf(aim1, tw1.x));
+      return o;
+    };
+    float2* xw = Xs + (ib0 + G::ORDER - vlo); // slot of this thread's pair j = 0; pair j is 2 T slots further
+    {
+      // pairs that lie completely inside [i_lo, i_hi): no predicates (sample index of pair j: ib0 + 256 j)
+      const int jA = max(0, (i_lo - ib0 + 2 * G::T - 1) >> 8);
+      const int jB = (i_hi - 2 - ib0) >= 0 ? ((i_hi - 2 - ib0) >> 8) + 1 : 0;
+      static_assert(2 * G::T == 256, "pair stride");
+#pragma unroll 4
+      for (int j = jA; j < jB; ++j)
+        *reinterpret_cast<float4*>(xw + 2 * G::T * j) = tuned_pair(j);
+      // the (at most two) pairs of a window that straddle its ends
+      const int dl = i_lo - 1 - ib0, dh = i_hi - 1 - ib0;
+      if (dl >= 0 && (dl & 255) == 0 && i_lo < i_hi)
+      {
+        const float4 o = tuned_pair(dl >> 8);
+        xw[2 * G::T * (dl >> 8) + 1] = make_float2(o.z, o.w);
+      }
+      if (dh >= 0 && (dh & 255) == 0 && i_hi - 1 >= i_lo)
+      {
+        const float4 o = tuned_pair(dh >> 8);
+        xw[2 * G::T * (dh >> 8)] = make_float2(o.x, o.y);
+      }
+    }
+    __syncthreads();
+    // the raw window has gone through the conversion: its region may be refilled.  The next tile's fetch overlaps the
+    // FIR below.
+    if (tid == 0 && tile + gridDim.x < total_tiles)
+    {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy reads before the async-proxy writes
+      issue(tile + gridDim.x);
+    }
+
+    // ---- FIR: outputs tid*R .. tid*R + R-1; thread window w = SEG*tid + (WIN-1) - u, u = 0 .. WIN-1 (newest first)
+    if (tid * G::R < nt)
+    {
+      float2 acc[G::R];
+#pragma unroll
+      for (int i = 0; i < G::R; ++i)
+        acc[i] = make_float2(0.0f, 0.0f);
+      const float2* xt = Xs + tid * G::SEG;
+#pragma unroll
+      for (int u = 0; u < G::WIN; ++u)
+      {
+        const float2 v = xt[G::WIN - 1 - u];
+#pragma unroll
+        for (int i = 0; i < G::R; ++i)
+        {
+          const int j = u + 1 - DS * (G::R - 1 - i); // tap of output i that meets this sample
+          if (j >= 1 && j <= G::ORDER)
+          {
+            acc[i].x = addf(acc[i].x, mulf(v.x, cf.c[j]));
+            acc[i].y = addf(acc[i].y, mulf(v.y, cf.c[j]));
+          }
+        }
+      }
+      float2* zo = reinterpret_cast<float2*>(p.z) + (size_t)s * p.z_stride + o0 + tid * G::R;
+#pragma unroll
+      for (int i = 0; i < G::R; ++i)
+        if (tid * G::R + i < nt)
+          zo[i] = acc[i];
+    }
+  }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libcuda is not linked)
+static bool EncodeFrontMap(const FrontParams& p, CUtensorMap* map)
+{
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+    {
+      cudaGetLastError();
+      f = nullptr;
+    }
+    return reinterpret_cast<EncodeFn>(f);
+  }();
+  if (!fn)
+    return false;
+  const cuuint64_t dims[2] = {p.n / 4, p.S};                      // 8-byte elements = 4 IQ pairs
+  const cuuint64_t strides[1] = {(cuuint64_t)p.in_stride * 2};    // bytes between rows
+  const cuuint32_t box[2] = {256, 1};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<void*>(p.in), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int DS>
+static bool launch_front_tma(const FrontParams& p, const FrontCoef& cf, cudaStream_t st)
+{
+  using G = FrontGeom3<DS>;
+  CUtensorMap map;
+  if (!EncodeFrontMap(p, &map))
+    return false;
+  EnsureDynSmem(k_front_tma<DS>, G::SMEM);
+  const unsigned tpr = cdiv(p.nout, G::OB), total = tpr * p.S;
+  // persistent: one wave of resident CTAs (as many as fit on the device), each walks total / grid tiles
+  int dev = 0, sms = 0, occ = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (p.sm_count) // the launching stream lives in an SM partition
+    sms = (int)p.sm_count;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_front_tma<DS>, G::T, G::SMEM) != cudaSuccess)
+    occ = 1;
+  const unsigned grid = std::min<unsigned>(total, (unsigned)(std::max(sms, 1) * std::max(occ, 1)));
+  k_front_tma<DS><<<grid, G::T, G::SMEM, st>>>(p, cf, map, tpr, total);
+  return true;
+}
+
 template <bool U8, int DS>
 static void launch_front_tiled(const FrontParams& p, const FrontCoef& cf, cudaStream_t st)
 {
@@ -361,6 +589,14 @@ void launch_front(const FrontParams& p, bool u8, cudaStream_t st)
     FrontCoef cf;
     memset(&cf, 0, sizeof(cf));
     memcpy(cf.c, p.coeff_host, (p.order + 2) * sizeof(float));
+    // TMA form: u8 rows that a tensor map can describe (16-byte aligned base and row pitch, whole 8-byte elements)
+    if (u8 && p.tuner && (p.ds == 1 || p.ds == 5 || p.ds == 11) && p.n % 4 == 0 && p.n >= 4 &&
+        (reinterpret_cast<uintptr_t>(p.in) & 15u) == 0 && (p.in_stride * 2) % 16 == 0)
+    {
+      const bool ok = p.ds == 11 ? launch_front_tma<11>(p, cf, st) : p.ds == 5 ? launch_front_tma<5>(p, cf, st) : launch_front_tma<1>(p, cf, st);
+      if (ok)
+        return;
+    }
 #define RFM_FT(DS)                                    \
   if (u8)                                             \
     launch_front_tiled<true, DS>(p, cf, st);          \
@@ -1130,13 +1366,16 @@ void launch_resample(const ResampleParams& p, cudaStream_t st)
 // Tiled form.  The output positions pf = p + i * pstep and with them the interpolated taps
 // k[i][j] = c[j] (1 - k1_i) + c[j+1] k1_i are the same for EVERY stream of the decoder (lock-step), so they are
 // formed once per block by k_res_taps (DownConvert.cpp:203-224, same float operations) and shared:
-//   * outputs are handled in groups of 4 consecutive ones; a group's taps are stored against a common time axis
-//     (zero outside an output's own window: adding +-0 leaves the running sum unchanged), 4 taps per time step
-//     as one float4;
-//   * k_resample_tiled: lane = stream (32 streams per CTA, rows staged transposed into shared memory with an odd
-//     pitch), a warp walks one group from the newest sample down -- every output receives its taps in ascending j,
-//     the reference's order (DownConvert.cpp:210-222) -- with one broadcast LDS.128 (4 taps) + 2 LDS (mono / L-R
-//     sample) per 16 individually rounded multiply / add operations.
+//   * outputs are handled in groups of 4 consecutive ones; a group's taps are stored against a common time axis that
+//     starts at a multiple of 4 samples and is a multiple of 4 long (zero outside an output's own window: adding +-0
+//     leaves a running sum that started at +0 unchanged), 4 taps per time step as one float4;
+//   * k_resample_tiled: lane = stream, warp = group.  The [32 streams][span] input tiles of both channels and the
+//     groups' taps travel to shared memory with 16-byte cp.async copies (no registers, no per-element stores); rows
+//     keep a 16-byte aligned pitch of 4 * odd floats, so a lane's LDS.128 of four consecutive samples is
+//     conflict-free across the 8 lanes of a quarter warp.  A warp walks its group from the newest sample down --
+//     every output receives its taps in ascending j, the reference's order (DownConvert.cpp:210-222) -- with
+//     6 LDS.128 (4 tap vectors, 4 mono + 4 L-R samples) per 64 individually rounded multiply / add operations;
+//   * the tile (GB groups) is sized so that two CTAs fit on an SM: one stages while the other computes.
 // --------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_res_taps(ResTapsParams p)
 {
@@ -1158,9 +1397,9 @@ __global__ void __launch_bounds__(128) k_res_taps(ResTapsParams p)
   unsigned cnt = 0;
   for (unsigned r = 0; r < 4; ++r)
     cnt += s_pi[r] >= 0;
-  const int vlo = s_pi[0];                       // V index (history included) of the oldest sample of output 0
+  const int vlo = s_pi[0] & ~3;                  // V index (history included) of the oldest sample of output 0, aligned down
   const int vhi = (int)p.order + s_pi[cnt - 1];  // newest sample of the last valid output
-  const int L = vhi - vlo + 1;
+  const int L = (vhi - vlo + 1 + 3) & ~3;
   if (threadIdx.x == 0)
   {
     p.meta[2 * g] = vlo;
@@ -1174,7 +1413,7 @@ __global__ void __launch_bounds__(128) k_res_taps(ResTapsParams p)
     {
       const int j = (int)p.order + s_pi[r] - (vlo + tt); // tap of output r that meets V = vlo + tt
       v[r] = 0.0f;
-      if (s_pi[r] >= 0 && j >= 0 && j <= (int)p.order && tt < L)
+      if (s_pi[r] >= 0 && j >= 0 && j <= (int)p.order)
         v[r] = addf(mulf(p.coeff[j], s_k0[r]), mulf(p.coeff[j + 1], s_k1[r]));
     }
     kk[tt] = make_float4(v[0], v[1], v[2], v[3]);
@@ -1188,17 +1427,17 @@ void launch_res_taps(const ResTapsParams& p, cudaStream_t st)
   k_res_taps<<<cdiv(p.na, 4), 128, 0, st>>>(p);
 }
 
-constexpr unsigned kResThreads = 256;
-constexpr unsigned kResWarps = kResThreads / 32;
+__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem)
+{
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
 
-// NCH = 2: one CTA makes both channels (mono and L-R share the taps: one broadcast LDS.128 per 16 multiply / add);
-// NCH = 1: blockIdx.z selects the channel (half the shared-memory tile per CTA).
-template <int GB, int NCH> // groups of 4 outputs per CTA
-__global__ void __launch_bounds__(kResThreads) k_resample_tiled(ResampleParams p, unsigned pitch)
+template <int GB> // groups of 4 outputs per CTA == warps per CTA
+__global__ void __launch_bounds__(32 * GB) k_resample_tiled(ResampleParams p, unsigned pitch)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* KK = reinterpret_cast<float4*>(smem_raw);                 // [GB][lp]
-  float* X = reinterpret_cast<float*>(KK + (size_t)GB * p.lp);      // [NCH][32][pitch]
+  float* X = reinterpret_cast<float*>(KK + (size_t)GB * p.lp);      // [2][32][pitch]
   __shared__ int s_meta[2 * GB];
 
   const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -1207,143 +1446,112 @@ __global__ void __launch_bounds__(kResThreads) k_resample_tiled(ResampleParams p
   const unsigned gn = min((unsigned)GB, ngroups - g0);
   const unsigned s0 = blockIdx.y * 32;
   const unsigned rows = min(32u, p.S - s0);
-  const float* src[2] = {(NCH == 2 || blockIdx.z == 0) ? p.bbV : p.rawV, p.rawV};
-  float* dst[2] = {(NCH == 2 || blockIdx.z == 0) ? p.lpM : p.lpS, p.lpS};
   if (tid < 2 * gn)
     s_meta[tid] = p.meta[2 * g0 + tid];
   __syncthreads();
-  const int v0 = s_meta[0];
-  const int span = s_meta[2 * (gn - 1)] + s_meta[2 * (gn - 1) + 1] - v0; // V range of the CTA
+  const int v0 = s_meta[0];                                                  // multiple of 4
+  const int nq = (s_meta[2 * (gn - 1)] + s_meta[2 * (gn - 1) + 1] - v0) >> 2; // 16-byte columns of the CTA's V range
   {
     const float4* ksrc = reinterpret_cast<const float4*>(p.kk) + (size_t)g0 * p.lp;
-    for (unsigned i = tid; i < gn * p.lp; i += kResThreads)
-      KK[i] = ksrc[i];
+    for (unsigned i = tid; i < gn * p.lp; i += 32 * GB)
+      cp_async_16(&KK[i], &ksrc[i]);
   }
-  // input rows, transposed into X[row][col] (odd pitch): warp w stages rows w, w + kResWarps, ...  The rows are read with
-  // 16-byte loads from a 16-byte aligned start (v0 rounded down; the V rows themselves are 128-byte aligned), all
-  // loads of a row in flight together -- the tile load is latency-bound, not bandwidth-bound.
-  const int dv = v0 & 3;               // columns added in front by the alignment
-  const int span_a = span + dv;
-  constexpr int kIt = 5;               // 5 x 128 columns >= the largest tile (pitch <= 640 enforced by the launcher)
-  for (unsigned r = warp; r < rows; r += kResWarps)
+  for (unsigned r = warp; r < rows; r += GB)
   {
-    float4 v[NCH][kIt];
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch)
+    const float* b0 = p.bbV + (size_t)(s0 + r) * p.a_stride + v0;
+    const float* b1 = p.rawV + (size_t)(s0 + r) * p.a_stride + v0;
+    float* x0 = X + (size_t)r * pitch;
+    float* x1 = X + (size_t)(32 + r) * pitch;
+    for (int c = lane; c < nq; c += 32)
     {
-      const float* b = src[ch] + (size_t)(s0 + r) * p.a_stride + (v0 - dv);
-#pragma unroll
-      for (int it = 0; it < kIt; ++it)
-      {
-        const int c = 4 * ((int)lane + 32 * it);
-        v[ch][it] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c + 3 < span_a)
-          v[ch][it] = *reinterpret_cast<const float4*>(b + c);
-        else if (c < span_a)
-        {
-          v[ch][it].x = b[c];
-          if (c + 1 < span_a) v[ch][it].y = b[c + 1];
-          if (c + 2 < span_a) v[ch][it].z = b[c + 2];
-        }
-      }
+      cp_async_16(x0 + 4 * c, b0 + 4 * c);
+      cp_async_16(x1 + 4 * c, b1 + 4 * c);
     }
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch)
-#pragma unroll
-      for (int it = 0; it < kIt; ++it)
-      {
-        const int c = 4 * ((int)lane + 32 * it);
-        float* xr = X + (ch * 32 + r) * pitch + c;
-        if (c < span_a)
-        {
-          xr[0] = v[ch][it].x;
-          if (c + 1 < span_a) xr[1] = v[ch][it].y;
-          if (c + 2 < span_a) xr[2] = v[ch][it].z;
-          if (c + 3 < span_a) xr[3] = v[ch][it].w;
-        }
-      }
   }
+  cp_async_commit();
+  cp_async_wait<0>();
   __syncthreads();
-  if (lane >= rows)
+  if (lane >= rows || warp >= gn)
     return;
-  const float* x0 = X + lane * pitch;
-  const float* x1 = X + (32 + lane) * pitch;
-  for (unsigned gi = warp; gi < gn; gi += kResWarps)
+  const int off = s_meta[2 * warp] - v0;
+  const int Lq = s_meta[2 * warp + 1] >> 2;
+  const float4* kk = KK + (size_t)warp * p.lp;
+  const float4* x0 = reinterpret_cast<const float4*>(X + (size_t)lane * pitch + off);
+  const float4* x1 = reinterpret_cast<const float4*>(X + (size_t)(32 + lane) * pitch + off);
+  float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+#define RS_STEP(k, m, sv)                                                                     \
+  a[0] = addf(a[0], mulf((k).x, m)); a[1] = addf(a[1], mulf((k).y, m));                       \
+  a[2] = addf(a[2], mulf((k).z, m)); a[3] = addf(a[3], mulf((k).w, m));                       \
+  b[0] = addf(b[0], mulf((k).x, sv)); b[1] = addf(b[1], mulf((k).y, sv));                     \
+  b[2] = addf(b[2], mulf((k).z, sv)); b[3] = addf(b[3], mulf((k).w, sv));
+  // software pipeline: the six vectors of step q - 1 are in flight while step q is multiplied out (with three warps
+  // per scheduler the shared-memory latency was this loop's main stall: 1.4 short-scoreboard cycles per issue)
+  float4 m = x0[Lq - 1], sv = x1[Lq - 1];
+  float4 k3 = kk[4 * Lq - 1], k2 = kk[4 * Lq - 2], k1 = kk[4 * Lq - 3], k0 = kk[4 * Lq - 4];
+#pragma unroll 2
+  for (int q = Lq - 1; q > 0; --q)
   {
-    const int off = s_meta[2 * gi] - v0 + dv;
-    const int L = s_meta[2 * gi + 1];
-    const float4* kk = KK + (size_t)gi * p.lp;
-    float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-    for (int tt = L - 1; tt >= 0; --tt)
-    {
-      const float4 k = kk[tt];
-      const float m = x0[off + tt];
-      a[0] = addf(a[0], mulf(k.x, m));
-      a[1] = addf(a[1], mulf(k.y, m));
-      a[2] = addf(a[2], mulf(k.z, m));
-      a[3] = addf(a[3], mulf(k.w, m));
-      if (NCH == 2)
-      {
-        const float sv = x1[off + tt];
-        b[0] = addf(b[0], mulf(k.x, sv));
-        b[1] = addf(b[1], mulf(k.y, sv));
-        b[2] = addf(b[2], mulf(k.z, sv));
-        b[3] = addf(b[3], mulf(k.w, sv));
-      }
-    }
-    const unsigned i = 4 * (g0 + gi);
-    const bool vec = i + 4 <= p.na && ((p.lp_hist | p.lp_stride) & 3u) == 0;
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch)
-    {
-      float* o = dst[ch] + (size_t)(s0 + lane) * p.lp_stride + p.lp_hist + i;
-      const float* acc = ch ? b : a;
-      if (vec)
-        *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-      else
-        for (unsigned r = 0; r < 4 && i + r < p.na; ++r)
-          o[r] = acc[r];
-    }
+    const float4 mn = x0[q - 1], svn = x1[q - 1];
+    const float4 n3 = kk[4 * q - 1], n2 = kk[4 * q - 2], n1 = kk[4 * q - 3], n0 = kk[4 * q - 4];
+    RS_STEP(k3, m.w, sv.w)
+    RS_STEP(k2, m.z, sv.z)
+    RS_STEP(k1, m.y, sv.y)
+    RS_STEP(k0, m.x, sv.x)
+    m = mn; sv = svn; k3 = n3; k2 = n2; k1 = n1; k0 = n0;
   }
+  RS_STEP(k3, m.w, sv.w)
+  RS_STEP(k2, m.z, sv.z)
+  RS_STEP(k1, m.y, sv.y)
+  RS_STEP(k0, m.x, sv.x)
+#undef RS_STEP
+  const unsigned i = 4 * (g0 + warp);
+  const bool vec = i + 4 <= p.na && ((p.lp_hist | p.lp_stride) & 3u) == 0;
+  float* oM = p.lpM + (size_t)(s0 + lane) * p.lp_stride + p.lp_hist + i;
+  float* oS = p.lpS + (size_t)(s0 + lane) * p.lp_stride + p.lp_hist + i;
+  if (vec)
+  {
+    *reinterpret_cast<float4*>(oM) = make_float4(a[0], a[1], a[2], a[3]);
+    *reinterpret_cast<float4*>(oS) = make_float4(b[0], b[1], b[2], b[3]);
+  }
+  else
+    for (unsigned r = 0; r < 4 && i + r < p.na; ++r)
+    {
+      oM[r] = a[r];
+      oS[r] = b[r];
+    }
 }
 
-template <int GB, int NCH>
+template <int GB>
 static void launch_resample_tiled_gb(const ResampleParams& p, unsigned pitch, size_t smem, cudaStream_t st)
 {
-  EnsureDynSmem(k_resample_tiled<GB, NCH>, smem);
-  dim3 grid(cdiv((p.na + 3) / 4, GB), cdiv(p.S, 32), NCH == 2 ? 1 : 2);
-  k_resample_tiled<GB, NCH><<<grid, kResThreads, smem, st>>>(p, pitch);
+  EnsureDynSmem(k_resample_tiled<GB>, smem);
+  dim3 grid(cdiv((p.na + 3) / 4, GB), cdiv(p.S, 32));
+  k_resample_tiled<GB><<<grid, 32 * GB, smem, st>>>(p, pitch);
 }
 
 void launch_resample_tiled(const ResampleParams& p, cudaStream_t st)
 {
   if (p.na == 0 || p.S == 0)
     return;
-  auto need = [&](unsigned gb, unsigned nch, unsigned* pitch) {
-    const unsigned span_max = (unsigned)(4.0f * gb * p.pstep) + p.order + 16; // + alignment slack of the 16-byte loads
-    *pitch = span_max | 1u;
-    if (*pitch > 640)
-      return (size_t)1 << 30; // the staging loop covers 5 x 128 columns
-    return (size_t)gb * p.lp * sizeof(float4) + (size_t)nch * 32 * *pitch * sizeof(float);
+  // rows must allow 16-byte copies from any multiple of 4 samples
+  const bool aligned = ((reinterpret_cast<uintptr_t>(p.bbV) | reinterpret_cast<uintptr_t>(p.rawV)) & 15u) == 0 &&
+                       (p.a_stride & 3u) == 0 && (p.lp & 3u) == 0;
+  auto need = [&](unsigned gb, unsigned* pitch) {
+    // V range of gb groups: 4 gb outputs apart + one window + the alignment slack at both ends
+    const unsigned span_max = ((unsigned)(4.0f * gb * p.pstep) + p.order + 1 + 8 + 3) & ~3u;
+    *pitch = span_max | 4u; // multiple of 4 with pitch / 4 odd: conflict-free LDS.128 across a quarter warp
+    return (size_t)gb * p.lp * sizeof(float4) + (size_t)2 * 32 * *pitch * sizeof(float);
   };
   unsigned pitch = 0;
-  size_t smem;
-#ifdef RFM_EXPERIMENTS
-  static const int variant = KnobInt(RFM_KNOB("RFM_RES_VARIANT"), 0);
-  if (variant == 1 && (smem = need(8, 2, &pitch)) <= 200 * 1024)
-    return launch_resample_tiled_gb<8, 2>(p, pitch, smem, st);
-  if (variant == 2 && (smem = need(8, 1, &pitch)) <= 200 * 1024)
-    return launch_resample_tiled_gb<8, 1>(p, pitch, smem, st);
-  if (variant == 3 && (smem = need(16, 1, &pitch)) <= 200 * 1024)
-    return launch_resample_tiled_gb<16, 1>(p, pitch, smem, st);
-#endif
-  if ((smem = need(16, 2, &pitch)) <= 200 * 1024)
-    return launch_resample_tiled_gb<16, 2>(p, pitch, smem, st);
-  if ((smem = need(8, 2, &pitch)) <= 200 * 1024)
-    return launch_resample_tiled_gb<8, 2>(p, pitch, smem, st);
-  if ((smem = need(4, 2, &pitch)) <= 200 * 1024)
-    return launch_resample_tiled_gb<4, 2>(p, pitch, smem, st);
+  size_t smem = 0;
+  // the largest tile of which two CTAs fit on an SM (one stages while the other computes); else the largest that fits
+  constexpr size_t kTwo = 113 * 1024, kOne = 220 * 1024;
+#define RFM_RS(GBV, LIM)                                              \
+  if (aligned && (smem = need(GBV, &pitch)) <= (LIM))                 \
+    return launch_resample_tiled_gb<GBV>(p, pitch, smem, st);
+  RFM_RS(8, kTwo) RFM_RS(6, kTwo) RFM_RS(4, kTwo) RFM_RS(3, kTwo) RFM_RS(2, kTwo)
+  RFM_RS(8, kOne) RFM_RS(4, kOne) RFM_RS(2, kOne) RFM_RS(1, kOne)
+#undef RFM_RS
   launch_resample(p, st); // very long filters: untiled form
 }
 
@@ -1992,10 +2200,168 @@ __global__ void __launch_bounds__(kRfThreads) k_rds_front(RdsFrontParams p)
 }
 #undef RFM_B
 
+// --------------------------------------------------------------------------------------------------
+// Register-tiled RDS front for the plans the reference's caller produces at 1.0 / 1.2 / 2.4 MS/s: three generic
+// half-band stages (HB15, HB19 | HB23, HB35 | HB43), the LP on its own kernel (lp_v).  Same fusion as k_rds_front --
+// one CTA per stream walks the block in tiles, nothing intermediate in HBM -- but the stage buffers are kept
+// DE-INTERLEAVED (rfm_dsp.cuh: hb_deint): a thread makes R consecutive outputs from registers and the taps are
+// constant-bank operands, so an output costs (L+1)/2R + 1 shared-memory loads instead of one sample load AND one tap
+// load per tap (k_rds_front ran at 85 % of the shared-memory pipe, 6.9 short-scoreboard stall cycles per issue).
+// Arithmetic and summation order are those of hb_generic / DownConvert.cpp:528-540: bit-identical results.
+// --------------------------------------------------------------------------------------------------
+constexpr unsigned kRf3Tile = 1024;   // baseband samples per tile
+constexpr unsigned kRf3Threads = 128;
+
+template <int L, int R>
+__device__ __forceinline__ void rf3_stage(const DcTaps<L>& taps, const float2* E, const float2* O, float2* dstE, float2* dstO,
+                                          unsigned nout, unsigned tid)
+{
+  // dstO == nullptr: last stage, dstE is the output row (natural order); else output o goes to the next stage's
+  // E / O by parity (both pre-offset by that stage's history)
+  for (unsigned g = tid; g * R < nout; g += kRf3Threads)
+  {
+    const unsigned o0 = g * R;
+    float2 acc[R];
+    hb_deint<L, R>(taps, E + o0, O + o0, acc);
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (o0 + r < nout)
+      {
+        const unsigned o = o0 + r;
+        if (!dstO)
+          dstE[o] = acc[r];
+        else
+          ((o & 1u) ? dstO : dstE)[o >> 1] = acc[r];
+      }
+  }
+}
+
+template <int L0, int L1, int L2>
+__global__ void __launch_bounds__(kRf3Threads) k_rds_front3(RdsFrontParams p, DcTaps<L0> t0, DcTaps<L1> t1, DcTaps<L2> t2)
+{
+  constexpr unsigned T = kRf3Tile, SL = 6; // SL: slack behind each buffer (a group of R outputs may read past the tile)
+  constexpr unsigned H0 = (L0 - 1) / 2, H1 = (L1 - 1) / 2, H2 = (L2 - 1) / 2; // history entries in each of E and O
+  constexpr unsigned Z0 = (H0 + T / 2 + SL + 1) & ~1u, Z1 = (H1 + T / 4 + SL + 1) & ~1u, Z2 = (H2 + T / 8 + SL + 1) & ~1u;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* E0 = reinterpret_cast<float2*>(smem_raw);
+  float2* O0 = E0 + Z0;
+  float2* E1 = O0 + Z0;
+  float2* O1 = E1 + Z1;
+  float2* E2 = O1 + Z1;
+  float2* O2 = E2 + Z2;
+  float2* s_osc = O2 + Z2;                              // [T], 16-byte aligned (every Z is even)
+  float* s_bb = reinterpret_cast<float*>(s_osc + T);    // [T]
+  const unsigned tid = threadIdx.x;
+  const unsigned s = blockIdx.x;
+  float2* tails = reinterpret_cast<float2*>(p.tails) + (size_t)s * p.tail_stride;
+  // histories from the previous block: V index i of stage k's [history | tile] row -> (i odd ? O : E)[i / 2]
+  auto load_hist = [&](float2* E, float2* O, unsigned H, unsigned off) {
+    for (unsigned i = tid; i < 2 * H; i += kRf3Threads)
+      ((i & 1u) ? O : E)[i >> 1] = tails[off + i];
+  };
+  load_hist(E0, O0, H0, p.tail_off[0]);
+  load_hist(E1, O1, H1, p.tail_off[1]);
+  load_hist(E2, O2, H2, p.tail_off[2]);
+
+  const float* bb = p.bbV + (size_t)s * p.a_stride + p.a_hist;
+  const float2* osc = reinterpret_cast<const float2*>(p.osc);
+  float2* lpv = reinterpret_cast<float2*>(p.lp_v) + (size_t)s * p.lp_v_stride + (p.lp_n - 1);
+  auto stage_tile = [&](unsigned t0n) {
+    const unsigned tnn = min(T, p.nb - t0n); // multiple of 8
+    for (unsigned i = tid; 2 * i < tnn; i += kRf3Threads)
+    {
+      cp_async_8(&s_bb[2 * i], &bb[t0n + 2 * i]);
+      cp_async_16(&s_osc[2 * i], &osc[t0n + 2 * i]);
+    }
+    cp_async_commit();
+  };
+  stage_tile(0);
+  unsigned out_base = 0;
+  for (unsigned tb = 0; tb < p.nb; tb += T)
+  {
+    const unsigned tn = min(T, p.nb - tb);
+    cp_async_wait<0>();
+    __syncthreads();
+    // mix: real baseband x NCO phasor, imaginary input exactly +0 (RDSProcess.cpp:122-123); sample pairs -> E0 / O0
+    for (unsigned i = tid; 2 * i < tn; i += kRf3Threads)
+    {
+      const float2 b = *reinterpret_cast<const float2*>(&s_bb[2 * i]);
+      const float4 o = *reinterpret_cast<const float4*>(&s_osc[2 * i]);
+      float2 e, d;
+      e.x = subf(mulf(b.x, o.x), mulf(0.0f, o.y));
+      e.y = addf(mulf(b.x, o.y), mulf(0.0f, o.x));
+      d.x = subf(mulf(b.y, o.z), mulf(0.0f, o.w));
+      d.y = addf(mulf(b.y, o.w), mulf(0.0f, o.z));
+      E0[H0 + i] = e;
+      O0[H0 + i] = d;
+    }
+    __syncthreads();
+    if (tb + T < p.nb)
+      stage_tile(tb + T);
+    rf3_stage<L0, 5>(t0, E0, O0, E1 + H1, O1 + H1, tn >> 1, tid);
+    __syncthreads();
+    rf3_stage<L1, 3>(t1, E1, O1, E2 + H2, O2 + H2, tn >> 2, tid);
+    __syncthreads();
+    rf3_stage<L2, 1>(t2, E2, O2, lpv + out_base, nullptr, tn >> 3, tid);
+    out_base += tn >> 3;
+    // carry the histories: the last H entries of [H | n / 2] to the front, in each of E and O (memmove semantics: a
+    // ragged last tile may be shorter than the history)
+    {
+      const float2 a0 = tid < H0 ? E0[(tn >> 1) + tid] : make_float2(0.f, 0.f);
+      const float2 b0 = tid < H0 ? O0[(tn >> 1) + tid] : make_float2(0.f, 0.f);
+      const float2 a1 = tid < H1 ? E1[(tn >> 2) + tid] : make_float2(0.f, 0.f);
+      const float2 b1 = tid < H1 ? O1[(tn >> 2) + tid] : make_float2(0.f, 0.f);
+      const float2 a2 = tid < H2 ? E2[(tn >> 3) + tid] : make_float2(0.f, 0.f);
+      const float2 b2 = tid < H2 ? O2[(tn >> 3) + tid] : make_float2(0.f, 0.f);
+      __syncthreads();
+      if (tid < H0) { E0[tid] = a0; O0[tid] = b0; }
+      if (tid < H1) { E1[tid] = a1; O1[tid] = b1; }
+      if (tid < H2) { E2[tid] = a2; O2[tid] = b2; }
+    }
+    // (the next iteration's first barrier orders these writes before any reader)
+  }
+  __syncthreads();
+  auto store_hist = [&](const float2* E, const float2* O, unsigned H, unsigned off) {
+    for (unsigned i = tid; i < 2 * H; i += kRf3Threads)
+      tails[off + i] = ((i & 1u) ? O : E)[i >> 1];
+  };
+  store_hist(E0, O0, H0, p.tail_off[0]);
+  store_hist(E1, O1, H1, p.tail_off[1]);
+  store_hist(E2, O2, H2, p.tail_off[2]);
+}
+
+template <int L0, int L1, int L2>
+static void launch_rds_front3(const RdsFrontParams& p, cudaStream_t st)
+{
+  DcTaps<L0> t0;
+  DcTaps<L1> t1;
+  DcTaps<L2> t2;
+  memcpy(t0.h, p.st[0].h_host, sizeof(t0.h));
+  memcpy(t1.h, p.st[1].h_host, sizeof(t1.h));
+  memcpy(t2.h, p.st[2].h_host, sizeof(t2.h));
+  constexpr unsigned T = kRf3Tile, SL = 6;
+  constexpr unsigned Z0 = ((L0 - 1) / 2 + T / 2 + SL + 1) & ~1u, Z1 = ((L1 - 1) / 2 + T / 4 + SL + 1) & ~1u,
+                     Z2 = ((L2 - 1) / 2 + T / 8 + SL + 1) & ~1u;
+  const size_t smem = (size_t)(2 * (Z0 + Z1 + Z2) + T) * sizeof(float2) + T * sizeof(float);
+  EnsureDynSmem(k_rds_front3<L0, L1, L2>, smem);
+  k_rds_front3<L0, L1, L2><<<p.S, kRf3Threads, smem, st>>>(p, t0, t1, t2);
+}
+
 void launch_rds_front(const RdsFrontParams& p, cudaStream_t st)
 {
   if (p.S == 0 || p.nb == 0)
     return;
+  // the three-stage plans of the reference's caller, LP on its own kernel
+  if (p.nst == 3 && p.lp_v && !p.dec_out && p.nb % 8 == 0 && p.st[0].kind == 0 && p.st[1].kind == 0 && p.st[2].kind == 0 &&
+      p.st[0].h_host && p.st[1].h_host && p.st[2].h_host && (p.a_hist & 1u) == 0 && (p.a_stride & 1u) == 0 &&
+      (reinterpret_cast<uintptr_t>(p.osc) & 15u) == 0 && (reinterpret_cast<uintptr_t>(p.bbV) & 7u) == 0)
+  {
+    const unsigned l0 = p.st[0].len, l1 = p.st[1].len, l2 = p.st[2].len;
+    if (l0 == 15 && l1 == 23 && l2 == 43)
+      return launch_rds_front3<15, 23, 43>(p, st);
+    if (l0 == 15 && l1 == 19 && l2 == 35)
+      return launch_rds_front3<15, 19, 35>(p, st);
+  }
   size_t floats = 0;
   for (unsigned k = 0; k < p.nst; ++k)
     floats += (p.st[k].len + 1u) & ~1u;

@@ -100,6 +100,7 @@ struct FrontParams
   cf32* tail;              // [S][order] tuned history (m_stateComplex)
   cf32* z;                 // [S][z_stride] FIR output
   size_t z_stride;
+  unsigned sm_count = 0;   // SMs of the launching stream's partition (0: the whole device); sizes persistent grids
 };
 void launch_front(const FrontParams& p, bool u8, cudaStream_t st);
 void launch_front_tail(const FrontParams& p, bool u8, cudaStream_t st);
@@ -227,6 +228,7 @@ struct RdsFrontStage
   int kind;                // 0 generic half-band, 1 fixed 11-tap, 2 CIC3
   unsigned len, hist;
   const float* h;          // device taps (nullptr for CIC3)
+  const float* h_host;     // the same taps on the host (constant-bank form of the register-tiled kernel), may be nullptr
 };
 struct RdsFrontParams
 {
