@@ -62,9 +62,10 @@ typedef struct rfm_config
   uint32_t n_groups;       /* internal stream groups pipelined on separate CUDA streams, 0 = auto */
   uint32_t lanes_sms;      /* SM partition: the one-lane-per-stream recurrences (pilot PLL / DC tracker) run in a
                             * green context of this many SMs (multiple of 8, >= 8), every FIR kernel in the rest, so
-                            * neither waits for the other's issue slots.  0 = no partition.  Placement only: results
-                            * are identical.  Ignored (with rfm_last_error set, creation still succeeds) when the
-                            * driver has no green contexts. */
+                            * neither waits for the other's issue slots.  0 = automatic (24 SMs when n_streams >= 2048
+                            * on a device of >= 100 SMs, none otherwise), 1 = never.  Placement only: results are
+                            * identical.  Ignored (rfm_last_error says why, creation still succeeds) when the driver
+                            * has no green contexts. */
 } rfm_config;
 
 RFM_API void rfm_config_default(rfm_config* cfg);

@@ -60,6 +60,7 @@ int Fail(int code, const std::string& msg)
   } while (0)
 
 constexpr size_t kMaxKeptBits = 1u << 16; // raw RDS bits retained per stream between rfm_decoder_rds_take_bits calls
+constexpr size_t kMaxKeptGroups = 4096;   // decoded groups retained per stream between rfm_decoder_rds_take_groups calls (6 min)
 
 unsigned AlignUp(unsigned v, unsigned a) { return (v + a - 1) / a * a; }
 
@@ -176,6 +177,7 @@ struct rfm_decoder
   unsigned pending_bits_bound = 0; // worst-case undrained bits per stream
   // geometry of the last block (for taps)
   unsigned last_n = 0, last_nb = 0, last_na = 0, last_nr = 0;
+  unsigned last_nb_rds = 0; // baseband samples the RDS branch took from the last block (0 when it was skipped)
   unsigned last_hb_n[kMaxDecStages + 1] = {0};
   // host RDS state
   std::vector<RdsBlockSync> sync;
@@ -502,6 +504,11 @@ int DrainBits(rfm_decoder* d)
       auto& ud = d->uecp[s];
       for (size_t w = had; w + 4 <= sy.Groups().size(); w += 4)
         ud.Decode(sy.Groups().data() + w);
+      // groups are kept for rfm_decoder_rds_take_groups, bounded like the raw bits (a caller that only reads the UECP
+      // stream never takes them): the oldest go first
+      auto& kept = sy.Groups();
+      if (kept.size() > 4 * kMaxKeptGroups)
+        kept.erase(kept.begin(), kept.begin() + (kept.size() - 4 * kMaxKeptGroups));
     }
   };
   const unsigned nthreads = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), std::max(1u, d->S / 64));
@@ -524,10 +531,20 @@ struct BlockGeom
 {
   unsigned n, nb, na, nr;
   unsigned hb_n[kMaxDecStages + 1]; // samples entering stage k; hb_n[nstages] == nr
+  unsigned short_mask;              // stage k received fewer samples than its FIR is long (DownConvert.cpp:519-520)
+  bool rds_skip;                    // the RDS branch does not run for this block (see PlanBlock)
   float a_pos_next;
   unsigned in_pos_next;
 };
 
+// Sample counts of one block.  The audio path takes ANY n (>= the input FIR order).  The RDS decimate-by-2 chain
+// follows the reference for counts it was not written for (DownConvert.cpp:498-550, pinned against the compiled
+// reference in tests/test_gpu_parity.py::test_default_rtlsdr_block_at_1200k): a generic half-band stage fed an ODD
+// count m makes (m + 1) / 2 outputs (its loop runs i = 0, 2, .. < m; the last output ends on the newest sample) and
+// restarts its decimation phase at the next block's first sample; fed FEWER samples than it has taps it returns the
+// first m / 2 inputs unfiltered and keeps its delay line.  Only the fixed 11-tap and CIC3 stages (rates below
+// ~480 kS/s) read outside their input for odd / short counts in the reference -- undefined there, so such a block
+// skips the RDS branch here (no bits, RDS state untouched) while its audio is produced as usual.
 int PlanBlock(const rfm_decoder* d, unsigned n, BlockGeom* g)
 {
   const DecoderPlan& p = d->plan;
@@ -538,20 +555,35 @@ int PlanBlock(const rfm_decoder* d, unsigned n, BlockGeom* g)
   g->nb = (pos < n) ? (n - pos + ds - 1) / ds : 0;
   g->in_pos_next = pos + g->nb * ds - n;
   g->na = FractionalOutputs(d->a_pos, p.a_pstep, g->nb, &g->a_pos_next);
+  g->short_mask = 0;
+  g->rds_skip = false;
   unsigned m = g->nb;
   for (size_t k = 0; k < p.rds_stages.size(); ++k)
   {
     g->hb_n[k] = m;
-    const unsigned L = (unsigned)p.rds_stages[k].len;
-    if (m % 2 != 0 || m < std::max(L, 2u))
-      return Fail(RFM_ERR_UNSUPPORTED,
-                  "block length leaves an odd or too short (< FIR length) sample count in the RDS half-band "
-                  "chain; the reference mis-handles this case too (DownConvert.cpp:519-524): choose n so that "
-                  "n/downsample is a multiple of 2^stages");
-    m /= 2;
+    const HalfBandStage& hs = p.rds_stages[k];
+    const bool generic = hs.len != 3 && !hs.fixed11;
+    if (generic)
+    {
+      if (m < (unsigned)hs.len)
+      {
+        g->short_mask |= 1u << k;
+        m /= 2;
+      }
+      else
+        m = (m + 1) / 2;
+    }
+    else
+    {
+      if (m % 2 != 0 || m < 18)
+        g->rds_skip = true;
+      m /= 2;
+    }
   }
   g->hb_n[p.rds_stages.size()] = m;
   g->nr = m;
+  if (g->rds_skip)
+    g->nr = 0;
   return RFM_OK;
 }
 
@@ -672,6 +704,8 @@ void EnqueueStageB(rfm_decoder* d, Group& g, const BlockGeom& bg, unsigned par, 
 
   // ---- sR: RDS front (mix, decimate-by-2 chain, LP)
   st = g.sR;
+  if (!bg.rds_skip)
+  {
   RdsFrontParams rf;
   memset(&rf, 0, sizeof(rf));
   rf.bbV = g.bbV[par3].p; rf.a_stride = d->a_stride; rf.a_hist = a_hist;
@@ -691,6 +725,7 @@ void EnqueueStageB(rfm_decoder* d, Group& g, const BlockGeom& bg, unsigned par, 
   rf.tails = g.rds_tails.p; rf.tail_stride = d->rds_tail_stride;
   rf.out = nullptr; rf.dec_out = nullptr; rf.out_stride = d->nr_stride;
   rf.lp_v = g.rlpV.p; rf.lp_v_stride = d->rlp_stride; // decimator output -> [LP history | block] rows
+  rf.short_mask = bg.short_mask;
   RFM_PROF(g.prof, "k_rds_front", st, launch_rds_front(rf, st));
   {
     // the 2.4 kHz LP (RDSProcess.cpp:128), lane = stream form, then its history carry
@@ -705,12 +740,15 @@ void EnqueueStageB(rfm_decoder* d, Group& g, const BlockGeom& bg, unsigned par, 
     tpl.d[0] = {g.rlpV.p, g.rlpV.p, d->rlp_stride * sizeof(cf32), rlp_taps - 1, bg.nr, 8, S};
     RFM_PROF(g.prof, "k_tails", st, launch_tails(tpl, S, st));
   }
+  }
   cudaEventRecord(g.ev_rds[par3], st);
   g_launches += 3;
 
   // ---- sP: Costas loop, matched filter, bit clock + slicer
   st = g.sP;
   cudaStreamWaitEvent(st, g.ev_rds[par3], 0);
+  if (bg.rds_skip)
+    return;
   RdsPllParams pp;
   pp.in = g.rlp_out[par].p; pp.in_stride = d->nr_stride; pp.nr = bg.nr; pp.S = S; pp.state = g.state.p;
   pp.lo = p.rpll_lo; pp.hi = p.rpll_hi; pp.alpha = p.rpll_alpha; pp.beta = p.rpll_beta;
@@ -787,10 +825,10 @@ int ProcessDevice(rfm_decoder* d, const void* d_in, size_t in_stride, bool u8, u
   {
     TailParams tp;
     tp.count = 1;
-    tp.d[0] = {d->oscV[prev3].p, d->oscV[par3].p, 0, d->osc_hist, d->last_nb, 8, 1};
+    tp.d[0] = {d->oscV[prev3].p, d->oscV[par3].p, 0, d->osc_hist, d->last_nb_rds, 8, 1};
     RFM_PROF(d->main_prof, "k_tails", d->s_osc, launch_tails(tp, 1, d->s_osc));
     OscParams op;
-    op.oscV = d->oscV[par3].p; op.osc_hist = d->osc_hist; op.nb = bg.nb; op.osc1 = d->osc1.p;
+    op.oscV = d->oscV[par3].p; op.osc_hist = d->osc_hist; op.nb = bg.rds_skip ? 0u : bg.nb; op.osc1 = d->osc1.p;
     op.cosv = d->plan.rds_osc.cosv; op.sinv = d->plan.rds_osc.sinv;
     RFM_PROF(d->main_prof, "k_osc", d->s_osc, launch_osc(op, d->s_osc));
     ResTapsParams tp2;
@@ -881,6 +919,7 @@ int ProcessDevice(rfm_decoder* d, const void* d_in, size_t in_stride, bool u8, u
   d->mf_g = (d->mf_g + bg.nr) % (unsigned)d->plan.mf_coef.size();
   d->pending_bits_bound += worst_bits;
   d->last_n = n; d->last_nb = bg.nb; d->last_na = bg.na; d->last_nr = bg.nr;
+  d->last_nb_rds = bg.rds_skip ? 0u : bg.nb;
   memcpy(d->last_hb_n, bg.hb_n, sizeof(bg.hb_n));
   d->block_index += 1;
   if (n_audio_floats)
@@ -1055,6 +1094,8 @@ int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out)
   {
     // SM partition (rfm_config::lanes_sms; RFM_LANES_SMS overrides it in the experiments build)
     unsigned n = cfg->lanes_sms;
+    if (n == 0) // automatic: a batch wide enough that the FIR kernels fill the device (measured: DESIGN.md section 4)
+      n = (cfg->n_streams >= 2048 && prop.multiProcessorCount >= 100) ? 24u : 0u;
     if (const char* e = RFM_KNOB("RFM_LANES_SMS"))
       n = (unsigned)KnobInt(e, 0);
     if (n >= 8)

@@ -60,18 +60,31 @@ struct rfm_demux
   uint64_t blocks_done = 0;
   uint32_t source_block = 0;   // cRtlSdrSource::m_BlockLength for rfm_demux_source_cb
   uint64_t short_reads = 0;
+  int pending_error = RFM_OK;  // a read-ahead submit failed after a packet had been completed: reported by the next read
+  // what GetSignalStatus reports (RadioReceiver.cpp:544-556), cached under `mu` when a block is collected: the status
+  // call comes from another thread and must neither touch the decoder nor wait for the block in flight
+  float st_interface_level = 0.0f, st_audio_level = 0.0f;
+  int st_stereo = 0;
+  bool st_valid = false;
 };
 
 namespace
 {
 
+void Recycle(rfm_demux* m, const PinnedBlock& b);
+
+// The block goes into the OTHER audio buffer; `cur` only flips once the decoder has accepted it, and a refused block's
+// pinned memory goes back to the pool.
 int Submit(rfm_demux* m, const PinnedBlock& b)
 {
-  m->cur ^= 1;
   uint32_t nfl = 0;
-  const int rc = rfm_decoder_submit_u8(m->dec, b.p, b.n, m->audio[m->cur], m->audio_cap, &nfl);
+  const int rc = rfm_decoder_submit_u8(m->dec, b.p, b.n, m->audio[m->cur ^ 1], m->audio_cap, &nfl);
   if (rc != RFM_OK)
+  {
+    Recycle(m, b);
     return rc;
+  }
+  m->cur ^= 1;
   m->flying = b;
   m->flying_floats = nfl;
   m->in_flight = true;
@@ -214,6 +227,12 @@ int rfm_demux_read(rfm_demux* m, rfm_demux_packet* pkt)
   if (!m || !pkt)
     return RFM_ERR_INVALID;
   memset(pkt, 0, sizeof(*pkt));
+  if (m->pending_error != RFM_OK)
+  {
+    const int rc = m->pending_error;
+    m->pending_error = RFM_OK;
+    return rc;
+  }
   if (m->stream_change)
   {
     pkt->stream_id = RFM_DEMUX_STREAMCHANGE;
@@ -271,6 +290,27 @@ int rfm_demux_read(rfm_demux* m, rfm_demux_packet* pkt)
     (void)vsum;
     m->audio_level = (float)(0.95 * m->audio_level + 0.05 * rms);
   }
+  {
+    rfm_stream_status st;
+    rc = rfm_decoder_get_status(m->dec, 0, &st); // the decoder is idle here: the next block is submitted further down
+    if (rc != RFM_OK)
+      return rc;
+    std::lock_guard<std::mutex> lock(m->mu);
+    m->st_interface_level = st.interface_level;
+    m->st_audio_level = m->audio_level;
+    m->st_stereo = st.stereo_detected;
+    m->st_valid = true;
+  }
+  {
+    // this loop only consumes the UECP stream: the decoded groups themselves would pile up in the block synchroniser
+    uint32_t k = 0;
+    do
+    {
+      rc = rfm_decoder_rds_take_groups(m->dec, 0, nullptr, 1024, &k);
+    } while (rc == RFM_OK && k == 1024);
+    if (rc != RFM_OK)
+      return rc;
+  }
   const double duration = (double)nfl * kStreamTimeBase / 2 / m->cfg.sample_rate_pcm;
   pkt->stream_id = 1;
   pkt->data = a;
@@ -282,12 +322,8 @@ int rfm_demux_read(rfm_demux* m, rfm_demux_packet* pkt)
   // read-ahead: the next block, if it is already queued, decodes while the caller consumes this packet
   PinnedBlock nb;
   if (PopBlock(m, &nb, false))
-  {
-    rc = Submit(m, nb);
-    if (rc != RFM_OK)
-      return rc;
-    // (this packet's audio buffer is the OTHER one: it stays valid until the next audio packet is read)
-  }
+    m->pending_error = Submit(m, nb); // this packet is complete and is handed out; a failure surfaces on the next read
+  // (this packet's audio buffer is the OTHER one: it stays valid until the next audio packet is read)
   return RFM_OK;
 }
 
@@ -341,18 +377,15 @@ int rfm_demux_signal_status(rfm_demux* m, float* interface_level, float* audio_l
 {
   if (!m)
     return RFM_ERR_INVALID;
-  if (m->stream_change)
+  std::lock_guard<std::mutex> lock(m->mu);
+  if (!m->st_valid)
     return RFM_ERR_INVALID; // the reference returns false until the first DemuxRead
-  rfm_stream_status st;
-  const int rc = rfm_decoder_get_status(m->dec, 0, &st);
-  if (rc != RFM_OK)
-    return rc;
   if (interface_level)
-    *interface_level = (float)(20 * log10((double)st.interface_level));
+    *interface_level = (float)(20 * log10((double)m->st_interface_level));
   if (audio_level_db)
-    *audio_level_db = (float)(20 * log10((double)m->audio_level) + 3.01);
+    *audio_level_db = (float)(20 * log10((double)m->st_audio_level) + 3.01);
   if (stereo)
-    *stereo = st.stereo_detected;
+    *stereo = m->st_stereo;
   return RFM_OK;
 }
 

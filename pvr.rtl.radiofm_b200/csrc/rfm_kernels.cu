@@ -363,7 +363,8 @@ struct FrontGeom3
   static constexpr int R = 3, T = 128, ORDER = 8 * DS, OB = T * R, SEG = R * DS;
   static constexpr int W = (OB - 1) * DS + ORDER;          // window samples
   static constexpr int WIN = ORDER + DS * (R - 1);         // samples one thread touches
-  static constexpr int RAW_ELEMS = (W + 3 + 3) / 4 + 1;    // 8-byte elements that cover any alignment of the window
+  static constexpr int RAW_ELEMS = (W + 7 + 3) / 4 + 1;    // 8-byte elements that cover any alignment of the window (a box
+                                                           // must start on a 16-byte boundary of global memory: 8 IQ pairs)
   static constexpr int BOXES = (RAW_ELEMS + 255) / 256;    // 2 KB boxes
   static constexpr int NPAIR = (BOXES * 512 + T - 1) / T;  // IQ pairs of pairs (32-bit words) per thread
   static constexpr int XBYTES = (W + 1) * 8;               // + 1: the window is shifted by one slot when vlo is odd
@@ -391,7 +392,9 @@ __global__ void __launch_bounds__(128) k_front_tma(FrontParams p, FrontCoef cf, 
   // flight while this tile is converted and filtered
   auto issue = [&](unsigned tile) {
     const unsigned s = tile / tiles_per_row, bx = tile - s * tiles_per_row;
-    const int c0 = ((int)(p.p0 + bx * G::OB * DS) - G::ORDER) >> 2; // first 8-byte element (floor; negative at a row's start)
+    // first 8-byte element: the window start rounded down to 8 IQ pairs (16 bytes -- the TMA unit faults on a box whose
+    // first byte is not 16-byte aligned); negative at a row's start
+    const int c0 = (((int)(p.p0 + bx * G::OB * DS) - G::ORDER) >> 3) * 2;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(G::BOXES * 2048) : "memory");
 #pragma unroll
     for (int b = 0; b < G::BOXES; ++b)
@@ -419,7 +422,7 @@ __global__ void __launch_bounds__(128) k_front_tma(FrontParams p, FrontCoef cf, 
     const int count = (int)(nt - 1) * DS + G::ORDER;
     const int i_lo = max(0, vlo - G::ORDER);                       // block samples [i_lo, i_hi) -> w = i + order - vlo
     const int i_hi = min((int)p.n, vlo + count - G::ORDER);
-    const int c0 = (vlo - G::ORDER) >> 2;
+    const int c0 = ((vlo - G::ORDER) >> 3) * 2;
     // A thread converts the IQ pairs 2 m, 2 m + 1 (counted from the raw window's first pair), m = tid + 128 j: one
     // 32-bit load, one 16-byte store per pair -- consecutive lanes touch consecutive words / quads of shared memory, so
     // neither side has bank conflicts (8 consecutive pairs per lane made the window stores collide 8-way: 120 M
@@ -2131,7 +2134,10 @@ __global__ void __launch_bounds__(kRfThreads) k_rds_front(RdsFrontParams p)
     unsigned n = tn;
     for (unsigned k = 0; k < p.nst; ++k)
     {
-      const unsigned nout = n >> 1;
+      // an odd count (generic half-band only: the host plans it) makes (n + 1) / 2 outputs, the last one ending on the
+      // newest sample; a stage that is SHORT this block passes the first n / 2 inputs through (DownConvert.cpp:498-550)
+      const bool shortk = (p.short_mask >> k) & 1u;
+      const unsigned nout = shortk ? (n >> 1) : ((n + 1) >> 1);
       const unsigned ohist = s_hist[k + 1];
       const unsigned kind = s_kind[k], len = s_len[k];
       const float* hk = s_h + s_hoff[k];
@@ -2141,7 +2147,7 @@ __global__ void __launch_bounds__(kRfThreads) k_rds_front(RdsFrontParams p)
       const bool to_lpv = (k + 1 == p.nst) && ext_lp;
       for (unsigned o = tid; o < nout; o += kRfThreads)
       {
-        const float2 v = hb_out((int)kind, len, hk, bin, o);
+        const float2 v = shortk ? bin[s_hist[k] + o] : hb_out((int)kind, len, hk, bin, o);
         if (to_lpv)
           lpv[out_base + o] = v;
         else
@@ -2178,7 +2184,8 @@ __global__ void __launch_bounds__(kRfThreads) k_rds_front(RdsFrontParams p)
       unsigned nk = tn;
       for (unsigned k = 0; k < nbuf; ++k)
       {
-        const unsigned hist = s_hist[k];
+        const bool shortk = k < p.nst && ((p.short_mask >> k) & 1u); // a short stage keeps its delay line
+        const unsigned hist = shortk ? 0u : s_hist[k];
         float2* bk = RFM_B(k);
         float2 v0 = make_float2(0.f, 0.f);
         if (tid < hist)
@@ -2186,7 +2193,7 @@ __global__ void __launch_bounds__(kRfThreads) k_rds_front(RdsFrontParams p)
         __syncthreads();
         if (tid < hist)
           bk[tid] = v0;
-        nk >>= 1;
+        nk = shortk ? (nk >> 1) : ((nk + 1) >> 1);
       }
     }
     __syncthreads();
@@ -2352,7 +2359,7 @@ void launch_rds_front(const RdsFrontParams& p, cudaStream_t st)
   if (p.S == 0 || p.nb == 0)
     return;
   // the three-stage plans of the reference's caller, LP on its own kernel
-  if (p.nst == 3 && p.lp_v && !p.dec_out && p.nb % 8 == 0 && p.st[0].kind == 0 && p.st[1].kind == 0 && p.st[2].kind == 0 &&
+  if (p.nst == 3 && p.lp_v && !p.dec_out && p.nb % 8 == 0 && p.short_mask == 0 && p.st[0].kind == 0 && p.st[1].kind == 0 && p.st[2].kind == 0 &&
       p.st[0].h_host && p.st[1].h_host && p.st[2].h_host && (p.a_hist & 1u) == 0 && (p.a_stride & 1u) == 0 &&
       (reinterpret_cast<uintptr_t>(p.osc) & 15u) == 0 && (reinterpret_cast<uintptr_t>(p.bbV) & 7u) == 0)
   {

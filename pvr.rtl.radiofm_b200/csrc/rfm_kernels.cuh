@@ -246,6 +246,7 @@ struct RdsFrontParams
   cf32* out;               // [S][out_stride] LP output
   cf32* dec_out;           // [S][out_stride] decimator output (optional, for the stage taps)
   size_t out_stride;
+  unsigned short_mask;     // bit k: stage k gets fewer samples than its FIR is long this block -> passes the first half through
   cf32* lp_v;              // when set: the last stage's outputs go to this V buffer ([lp_n - 1 history | n] rows) and the LP
   size_t lp_v_stride;      // is NOT applied here (the caller runs launch_rotfir on it); `out` / the LP tail are unused
 };

@@ -524,6 +524,9 @@ struct rfm_rdsproc
 
 namespace
 {
+constexpr size_t kMaxKeptBitsProc = 1u << 16;   // raw bits / groups retained per row between the take calls
+constexpr size_t kMaxKeptGroupsProc = 4096;
+
 int RdsDrain(rfm_rdsproc* r)
 {
   if (r->pending == 0)
@@ -547,8 +550,13 @@ int RdsDrain(rfm_rdsproc* r)
     {
       const uint8_t* b = r->h_bits.data() + (size_t)s * mx;
       r->bits[s].insert(r->bits[s].end(), b, b + r->h_counts[s]);
+      if (r->bits[s].size() > kMaxKeptBitsProc) // bounded: a caller without a bit sink never takes them
+        r->bits[s].erase(r->bits[s].begin(), r->bits[s].begin() + (r->bits[s].size() - kMaxKeptBitsProc));
       for (unsigned i = 0; i < r->h_counts[s]; ++i)
         r->sync[s].PushBit(b[i]); // ProcessNewRdsBit, RDSProcess.cpp:272-375
+      auto& kept = r->sync[s].Groups();
+      if (kept.size() > 4 * kMaxKeptGroupsProc)
+        kept.erase(kept.begin(), kept.begin() + (kept.size() - 4 * kMaxKeptGroupsProc));
     }
     if (cudaMemset(r->d_count, 0, r->rows * sizeof(unsigned)) != cudaSuccess)
       return PFail(RFM_ERR_CUDA, "rfm_rdsproc: bit count reset failed");

@@ -15,13 +15,18 @@ CUOBJDUMP = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
 
 # kernel-name fragment -> (max registers per thread, note)
 HOT = {
-    "k_front_tiledILb1ELi11E": (64, "128 threads, 4 outputs per thread: >= 8 CTAs per SM"),
+    "k_front_tmaILi11E": (64, "persistent, 128 threads, 3 outputs per thread, five CTAs per SM (TMA-staged window)"),
+    "k_front_tmaILi5E": (64, ""),
+    "k_front_tiledILb1ELi11E": (64, "128 threads, 4 outputs per thread: >= 8 CTAs per SM (rows a tensor map cannot describe)"),
     "k_front_tiledILb1ELi4E": (64, ""),
     "k_front_tiledILb1ELi5E": (64, ""),
     "k_bb_lanesILb0ELb0ELb0E": (128, "64 threads; pilot state + 13 double constants in registers"),
     "k_bb_lanesILb0ELb1ELb0E": (128, "immediate-barrier form (SM partition: up to 12 CTAs per SM)"),
     "k_demod_spec": (96, "32-thread CTAs, ~17 per SM"),
-    "k_resample_tiledILi16ELi2E": (96, ""),
+    "k_resample_tiledILi6E": (64, "192 threads, two CTAs per SM"),
+    "k_resample_tiledILi4E": (64, ""),
+    "k_rds_front3ILi15ELi23ELi43E": (64, "128 threads, eight CTAs per SM"),
+    "k_rds_front3ILi15ELi19ELi35E": (64, ""),
     "k_rotfir_lanesILi0E": (64, ""),
     "k_rotfir_lanesILi1E": (64, ""),
     "k_rotfir_lanesILi2E": (64, ""),
@@ -85,3 +90,26 @@ def test_product_library_reads_no_environment_knobs():
     for frag in (b"RFM_DEBUG_", b"RFM_LANES_", b"RFM_RES_", b"RFM_ROTFIR_", b"FAKE_SINCOS"):
         assert frag not in blob, frag
     assert b"k_bb_lanesILb1E" not in blob  # the fake-sincos timing kernel is not even instantiated
+
+
+def test_tma_is_really_used():
+    """north_star: the front end's window is staged by the TMA unit -- the SASS of its kernel holds UTMALDG
+    (cp.async.bulk.tensor) and the mbarrier wait (SYNCS), and none of the LDG-based staging of the fallback kernel."""
+    lib = os.path.join(ROOT, "pvr.rtl.radiofm_b200", "libradiofm_b200.so")
+    if not os.path.exists(lib) or not os.path.exists(CUOBJDUMP):
+        pytest.skip("library / cuobjdump not available")
+    r = subprocess.run([CUOBJDUMP, "-sass", lib], capture_output=True, text=True)
+    assert r.returncode == 0
+    cur, ops = None, {}
+    for line in r.stdout.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            continue
+        if cur and "k_front_tma" in cur:
+            for op in ("UTMALDG", "SYNCS", "LDG.E.128"):
+                if op in line:
+                    ops.setdefault(cur, set()).add(op)
+    assert len(ops) == 3, sorted(ops)   # ds = 1, 5, 11
+    for k, v in ops.items():
+        assert "UTMALDG" in v and "SYNCS" in v and "LDG.E.128" not in v, (k, v)

@@ -43,12 +43,16 @@ def tolerances(a_gpu, a_ref):
     assert float(np.max(np.abs((g[:, 0] - g[:, 1]) - (r[:, 0] - r[:, 1])))) <= 2e-4
 
 
-@pytest.mark.parametrize("rate,nblk", [("1.0M", 10), ("1.2M", 11), ("2.4M", 18), ("390k", 12)])
-def test_chain_every_stage_bit_exact(rfm, port, rate, nblk):
+# lanes_sms: 1 = no SM partition (what a single stream gets by default), 24 = the partition wide batches run in
+# (rfm_config::lanes_sms: placement only -- the immediate-barrier lanes kernel and the persistent front end sized to the
+# partition must produce the same bits)
+@pytest.mark.parametrize("rate,nblk,lanes_sms", [("1.0M", 10, 1), ("1.2M", 11, 1), ("2.4M", 18, 1), ("390k", 12, 1),
+                                                 ("2.4M", 18, 24), ("1.0M", 10, 16)])
+def test_chain_every_stage_bit_exact(rfm, port, rate, nblk, lanes_sms):
     fs, ds, blk = RATES[rate]
     iq, sent = station(rate, nblk)
     o = port.OracleFmDecoder(fs, -0.15 * fs, downsample=ds)
-    d = rfm.FmDecoderBatch(fs, -0.15 * fs, downsample=ds, n_streams=1, max_block_len=blk)
+    d = rfm.FmDecoderBatch(fs, -0.15 * fs, downsample=ds, n_streams=1, max_block_len=blk, lanes_sms=lanes_sms)
     assert np.array_equal(o.constants()[:51], d.constants()[:51])
     saw_stereo = False
     for b in range(nblk):
@@ -286,14 +290,63 @@ def test_ragged_block_lengths_and_edges(rfm, port):
     # errors are reported, not swallowed
     with pytest.raises(rfm.RadioFmError, match="max_block_len"):
         d.process_u8(np.zeros((1, blk + 32, 2), dtype=np.uint8))
-    with pytest.raises(rfm.RadioFmError, match="odd or too short"):
-        d.process_u8(np.zeros((1, 1000, 2), dtype=np.uint8))   # 250 -> 125: the reference mis-handles it too
+    with pytest.raises(rfm.RadioFmError, match="shorter than the input FIR order"):
+        d.process_u8(np.zeros((1, 20, 2), dtype=np.uint8))
     import ctypes as C
     k = C.c_uint32(0)
     small = np.zeros(8, dtype=np.float32)
     rc = rfm.lib().rfm_decoder_process_u8(d._h, x.ctypes.data_as(C.POINTER(C.c_uint8)), 4096,
                                           small.ctypes.data_as(C.POINTER(C.c_float)), 8, C.byref(k))
     assert rc == -5  # RFM_ERR_OVERFLOW
+
+
+def test_default_rtlsdr_block_at_1200k_and_odd_short_blocks(rfm, port, ref):
+    """Any block length yields audio, and the RDS branch follows the reference through the counts its half-band
+    stages were not written for (DownConvert.cpp:498-550).  cRtlSdrSource's default block of 65536 samples at
+    1.2 MS/s / 5 leaves 13107 or 13108 baseband samples: odd counts make (m + 1) / 2 outputs per stage and restart the
+    decimation phase every block; blocks so short that a stage gets fewer samples than taps pass through unfiltered.
+    Checked against the UNMODIFIED reference where oracle/_ref travelled (and always against the oracle port)."""
+    fs, ds = 1.2e6, 5
+    blk = 65536
+    iq, _ = station("1.2M", 12)
+    d = rfm.FmDecoderBatch(fs, -0.15 * fs, downsample=ds, n_streams=2, max_block_len=blk)
+    o = port.OracleFmDecoder(fs, -0.15 * fs, downsample=ds)
+    r = ref.RefFmDecoder(fs, -0.15 * fs, downsample=ds)
+    pos = 0
+    sizes = [blk] * 9 + [100, 333, 1000, 47, 4096, 65521, 777, 20000, 41, 65535, 4097]
+    for n in sizes:
+        x = iq[pos:pos + n]
+        pos += n
+        a = d.process_u8(np.stack([x, x]))
+        a_o = o.process_u8(x)
+        a_r, _ = r.process_staged(ref.u8_to_cf32(x), want=())
+        assert bits_equal(a_o, a_r), n
+        assert bits_equal(a[0], a_o) and bits_equal(a[1], a_o), n
+        assert bits_equal(d.tap("rds_dec"), o.tap("rds_dec")) and bits_equal(d.tap("rds_mf"), o.tap("rds_mf")), n
+    bo = o.take_bits()
+    assert bo.size > 700 and np.array_equal(bo, r.take_bits())
+    assert np.array_equal(d.take_bits(0), bo) and np.array_equal(d.take_bits(1), bo)
+    go = o.take_groups()
+    assert len(go) >= 5 and np.array_equal(go, r.take_groups()) and np.array_equal(d.take_groups(1), go)
+
+
+@pytest.mark.parametrize("rate,n", [("2.4M", 65536), ("2.4M", 20000), ("1.2M", 4096), ("390k", 16004)])
+def test_decimator_phase_walks_through_every_window_alignment(rfm, port, rate, n):
+    """Block lengths that are not a multiple of the decimation make the decimator phase p0 -- and with it the first
+    sample of every front-end window -- walk through all residues: the TMA boxes must start on 16-byte boundaries of
+    global memory whatever p0 is (an odd 8-byte coordinate is an illegal instruction), the window is shifted by one
+    slot for odd starts, rows whose pitch a tensor map cannot describe take the LDG kernel."""
+    fs, ds, _ = RATES[rate]
+    iq, _ = station(rate, 4)
+    o = port.OracleFmDecoder(fs, -0.15 * fs, downsample=ds)
+    d = rfm.FmDecoderBatch(fs, -0.15 * fs, downsample=ds, n_streams=3, max_block_len=n)
+    for b in range(min(12, iq.shape[0] // n)):
+        x = iq[b * n:(b + 1) * n]
+        a = d.process_u8(np.stack([x, x, x]))
+        a_o = o.process_u8(x)
+        assert bits_equal(a[0], a_o) and bits_equal(a[2], a_o), (rate, n, b)
+        assert bits_equal(d.tap("demod_in", 1), o.tap("demod_in")), (rate, n, b)
+    assert np.array_equal(d.take_bits(2), o.take_bits())
 
 
 def test_device_pointer_entry_point(rfm, port):
