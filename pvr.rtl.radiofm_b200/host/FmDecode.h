@@ -5,20 +5,27 @@
 // throws std::runtime_error when no sm_100 device / library is usable.
 //
 // RDS: the reference hands decoded groups to its cRDSGroupDecoder from inside ProcessStream
-// (RDSProcess.cpp:312,355).  Here the groups decoded during a ProcessStream call are delivered, in order and on the
-// calling thread, to the sink set with SetRdsGroupSink() before ProcessStream returns -- e.g.
-//     dec.SetRdsGroupSink([&](uint16_t* blk) { m_Decoder.DecodeRDS(blk); });   // RDSGroupDecoder.h:29
+// (cFmDecoder -> cRDSRxSignalProcessor m_RDSProcess -> cRDSGroupDecoder m_Decoder(proc): RDSProcess.cpp:312,355,
+// RDSGroupDecoder.cpp:979-991 -> cRadioReceiver::AddUECPDataFrame, RadioReceiver.cpp:387).  So does this class: built
+// with a receiver (proc != nullptr) it owns a cRDSGroupDecoder (host/RDSGroupDecoder.h) bound to it, and every group
+// decoded during a ProcessStream call goes through DecodeRDS -- in order, on the calling thread, before ProcessStream
+// returns -- which calls proc->AddUECPDataFrame / SetChannelName / IsSettingActive exactly as the reference does.
+// RadioReceiver.cpp needs NO change beyond the include.  (cRadioReceiver must be a complete type by the end of the
+// translation unit, as in RadioReceiver.cpp.)  SetRdsGroupSink() replaces that route by a callback of your own:
+//     dec.SetRdsGroupSink([&](uint16_t* blk) { ... });
 #pragma once
 
 #include <stdint.h>
 
 #include <functional>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
 
 #include "../../include/radiofm_b200.h"
 #include "Definitions.h"
+#include "RDSGroupDecoder.h"
 
 #define DEFAULT_BANDWIDTH_PCM 15000 // FmDecode.h:22
 
@@ -43,12 +50,19 @@ public:
     cfg.device = cuda_device;
     if (rfm_decoder_create(&cfg, &m_dec) != RFM_OK)
       throw std::runtime_error(std::string("cFmDecoder (B200): ") + rfm_last_error());
+    if (proc) // m_RDSProcess(proc, ...) -> m_Decoder(proc), FmDecode.cpp:247, RDSProcess.cpp:43
+      m_groups.reset(new cRDSGroupDecoder(proc));
   }
   virtual ~cFmDecoder() { rfm_decoder_destroy(m_dec); }
   cFmDecoder(const cFmDecoder&) = delete;
   cFmDecoder& operator=(const cFmDecoder&) = delete;
 
-  void Reset() { rfm_decoder_reset(m_dec); } // FmDecode.cpp:326-338
+  void Reset() // FmDecode.cpp:326-338 -> cRDSRxSignalProcessor::Reset -> m_Decoder.Reset(), RDSProcess.cpp:92
+  {
+    rfm_decoder_reset(m_dec);
+    if (m_groups)
+      m_groups->Reset();
+  }
 
   // FmDecode.h:135 -- returns the number of floats written (2 x frames, interleaved L,R)
   unsigned int ProcessStream(const ComplexType* samples_in, unsigned int samples, float* audio)
@@ -95,12 +109,18 @@ private:
     {
       if (rfm_decoder_rds_take_groups(m_dec, 0, &blk[0][0], 64, &n) != RFM_OK)
         return;
-      for (uint32_t i = 0; i < n && m_sink; ++i)
-        m_sink(blk[i]);
+      for (uint32_t i = 0; i < n; ++i)
+      {
+        if (m_sink)
+          m_sink(blk[i]);
+        else if (m_groups)
+          m_groups->DecodeRDS(blk[i]);
+      }
     } while (n == 64);
   }
 
   cRadioReceiver* m_proc;
   rfm_decoder* m_dec = nullptr;
   std::function<void(uint16_t*)> m_sink;
+  std::unique_ptr<cRDSGroupDecoder> m_groups; // the reference's m_RDSProcess.m_Decoder
 };

@@ -3,13 +3,34 @@
 // as in RTL_SDR_Source.cpp:207-211, one ProcessStream call per block, audio appended to a file, RDS groups
 // collected through the sink.  tests/test_gpu_host_api.py compares the files with the oracle.
 //   usage: host_api_driver <iq_u8.bin> <fs> <tuning_offset> <downsample> <block> <audio_out.bin> <groups_out.bin> <shift_hz>
+//                          [<uecp_out.bin> [<reset_after_block>]]
+// With a 9th argument the decoder is built WITH a receiver and NO sink -- the unchanged-caller case: the class's own
+// cRDSGroupDecoder delivers the UECP frames to cRadioReceiver::AddUECPDataFrame from inside ProcessStream; the raw
+// frames (u16 length + bytes) go to <uecp_out.bin>.
 #include <stdio.h>
 #include <stdlib.h>
 
 #include <vector>
 
+#include <string>
+
 #include "FmDecode.h"
 #include "FreqShift.h"
+
+class cRadioReceiver // stand-in for the PVR client: the three members cRDSGroupDecoder calls (RadioReceiver.h:77,80,115)
+{
+public:
+  bool AddUECPDataFrame(uint8_t* frame, unsigned len)
+  {
+    const uint16_t l = (uint16_t)len;
+    frames.insert(frames.end(), reinterpret_cast<const uint8_t*>(&l), reinterpret_cast<const uint8_t*>(&l) + 2);
+    frames.insert(frames.end(), frame, frame + len);
+    return true;
+  }
+  bool SetChannelName(std::string) { return true; }
+  bool IsSettingActive() { return false; }
+  std::vector<uint8_t> frames;
+};
 
 int main(int argc, char** argv)
 {
@@ -27,9 +48,13 @@ int main(int argc, char** argv)
   std::vector<uint16_t> groups;
   try
   {
-    cFmDecoder dec(nullptr, fs, off, 48000.0, DEFAULT_BANDWIDTH_PCM, ds);
+    cRadioReceiver radio;
+    const bool unchanged_caller = argc > 9;
+    const int reset_after = argc > 10 ? atoi(argv[10]) : -1;
+    cFmDecoder dec(unchanged_caller ? &radio : nullptr, fs, off, 48000.0, DEFAULT_BANDWIDTH_PCM, ds);
     cFreqShift fsh(shift, (RealType)fs, blk);
-    dec.SetRdsGroupSink([&](uint16_t* b) { groups.insert(groups.end(), b, b + 4); });
+    if (!unchanged_caller)
+      dec.SetRdsGroupSink([&](uint16_t* b) { groups.insert(groups.end(), b, b + 4); });
     FILE* fa = fopen(argv[6], "wb");
     unsigned stereo_blocks = 0, blocks = 0;
     while (fread(raw.data(), 2, blk, f) == blk)
@@ -44,6 +69,14 @@ int main(int argc, char** argv)
       fwrite(audio.data(), sizeof(float), n, fa);
       stereo_blocks += dec.StereoDetected();
       ++blocks;
+      if ((int)blocks == reset_after)
+        dec.Reset();
+    }
+    if (unchanged_caller)
+    {
+      FILE* fu = fopen(argv[9], "wb");
+      fwrite(radio.frames.data(), 1, radio.frames.size(), fu);
+      fclose(fu);
     }
     fclose(fa);
     FILE* fg = fopen(argv[7], "wb");

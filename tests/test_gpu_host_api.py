@@ -45,6 +45,40 @@ def test_cfmdecoder_class_matches_oracle(driver, port):
     assert np.float32(words[11]) == st["pilot_level"] and np.float32(words[13]) == st["tuning_offset"]
 
 
+def test_unchanged_caller_gets_uecp_frames_through_the_receiver(driver, port):
+    """cFmDecoder built with a receiver and no sink (what RadioReceiver.cpp:296-300 does): the frames reach
+    cRadioReceiver::AddUECPDataFrame from inside ProcessStream, as in the reference (RDSProcess.cpp:312,355,
+    RDSGroupDecoder.cpp:979-991) -- including the re-announcement after a Reset() (RDSProcess.cpp:92)."""
+    from oracle import uecp_port
+    exe, d = driver
+    fs, ds, blk = RATES["1.0M"]
+    nblk, cut = 14, 7
+    iq, _ = station("1.0M", 7)
+    iq2 = np.concatenate([iq, iq])                      # the same station again after the reset
+    (d / "iq3.bin").write_bytes(iq2.tobytes())
+    out = subprocess.run([exe, str(d / "iq3.bin"), str(fs), str(-0.15 * fs), str(ds), str(blk), str(d / "audio3.bin"),
+                          str(d / "groups3.bin"), "0", str(d / "uecp3.bin"), str(cut)], capture_output=True, text=True,
+                         timeout=300)
+    assert out.returncode == 0, out.stderr
+    o = port.OracleFmDecoder(fs, -0.15 * fs, downsample=ds)
+    u = uecp_port.OracleGroupDecoder()
+    want, audio = [], []
+    for b in range(nblk):
+        audio.append(o.process_cf32(port.u8_to_cf32(iq2[b * blk:(b + 1) * blk])))
+        want += u.decode(o.take_groups())
+        if b + 1 == cut:
+            o.reset()
+            u.reset()
+    assert bits_equal(np.fromfile(d / "audio3.bin", dtype=np.float32), np.concatenate(audio))
+    raw = (d / "uecp3.bin").read_bytes()
+    got, i = [], 0
+    while i < len(raw):
+        ln = raw[i] | (raw[i + 1] << 8)
+        got.append(raw[i + 2:i + 2 + ln])
+        i += 2 + ln
+    assert len(want) >= 8 and got == want
+
+
 def test_cfreqshift_then_decoder(driver, port):
     """cFreqShift::Process in front of the decoder (the wideband composition): shift the capture by +50 kHz with the
     GPU mixer, decode with tuning offset -100 kHz; must equal the oracle's cFreqShift + chain."""
