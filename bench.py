@@ -35,19 +35,32 @@ STREAMS_PER_GPU = 4096
 BYTES_PER_SAMPLE = 2.0 + 8.0 * 48000.0 / FS   # u8 I,Q in + f32 L,R out = 2.160 B / complex sample
 METRIC = "demodulated complex MS/s per GPU (stereo+RDS) at 1/2/4/8 B200; % of HBM roofline"
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch at the C4 workload (4096 streams, one 65472-sample block),
-# from one `ncu --set full` capture per kernel: profiles/r01_ncu_top_kernels.txt
-NCU_TRAFFIC_BYTES = {
-    "k_bb_lanes": 98.327808e6 + 137.724672e6,
-    "k_front": 539.337728e6 + 174.3936e6,
-    "k_demod_spec": 242.277632e6 + 67.041792e6,
-    "k_resample": 204.107264e6 + 32.296448e6,
-    "k_rds_front": 101.139968e6 + 12.347392e6,
-}
+# ncu-derived constants (dram bytes per launch of each kernel, warp instructions per step) live in
+# profiles/ncu_constants.json, written by tools/ncu_constants.py from an `ncu --set full` capture and STAMPED with the
+# SHA-256 of the kernel sources it was captured from.  They are printed only when the stamp matches the sources this
+# run was built from; otherwise roofline.traffic / roofline.issue are null (a stale constant is not a measurement).
+def kernel_sources_sha():
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "pvr.rtl.radiofm_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh", ".cpp", ".h", ".inc")):
+            h.update(name.encode())
+            h.update(open(os.path.join(d, name), "rb").read())
+    return h.hexdigest()[:16]
 
-# warp instructions of one step (one block of 4096 streams through every kernel of the chain), ncu
-# smsp__inst_executed.sum summed over the step's launches (profiles/r01_ncu_top_kernels.txt)
-NCU_WARP_INSTR_PER_STEP = 1.35e9
+
+def load_ncu_constants():
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_constants.json")) as f:
+            c = json.load(f)
+        if c.get("kernel_sources_sha") != kernel_sources_sha():
+            return None, f"stale (captured at sources {c.get('kernel_sources_sha')}, commit {c.get('commit')})"
+        return c, f"profiles/ncu_constants.json (commit {c.get('commit')}, {c.get('capture')})"
+    except Exception as e:
+        return None, f"absent ({type(e).__name__})"
+
+
 SCHEDULERS = 148 * 4
 
 
@@ -184,6 +197,99 @@ def cpu_baseline_leg():
 
 
 # --------------------------------------------------------------------------------------------------------------
+# Extra legs of the same JSON line: the add-on's own call, strong scaling, the wideband config.
+# --------------------------------------------------------------------------------------------------------------
+def single_stream_leg(rfm, local):
+    """The call the add-on actually makes (RadioReceiver.cpp:515-525): ONE stream, 65536 complex samples at 1.0 MS/s,
+    blocking cFmDecoder::ProcessStream == rfm_decoder_process_cf32 with host buffers; next to the reference's own
+    ProcessStream on one host core (oracle/_ref, cpu_baseline leg)."""
+    import importlib
+    synth = importlib.import_module("radiofm_b200.synth")
+    from oracle import ref, port
+    fs, ds, blk, nblk = 1.0e6, 4, 65536, 12
+    iq, _ = synth.make_station_u8(fs, nblk * blk, stream_id=0)
+    x = port.u8_to_cf32(iq).reshape(nblk, blk, 2)
+    d = rfm.FmDecoderBatch(fs, -0.15 * fs, downsample=ds, n_streams=1, max_block_len=blk, device=local)
+    ts = []
+    for r in range(3):
+        for b in range(nblk):
+            t0 = time.perf_counter()
+            d.process_cf32(x[b][None])
+            ts.append((time.perf_counter() - t0) * 1e3)
+    d.close()
+    gpu_ms = statistics.median(ts[nblk:])
+    kind, ref_ms = "port", None
+    dec = ref.RefFmDecoder(fs, -0.15 * fs, downsample=ds) if ref.available() else port.OracleFmDecoder(fs, -0.15 * fs, downsample=ds)
+    kind = "reference" if ref.available() else "port"
+    tr = []
+    for r in range(2):
+        for b in range(nblk):
+            t0 = time.perf_counter()
+            dec.process_cf32(x[b])
+            tr.append((time.perf_counter() - t0) * 1e3)
+    ref_ms = statistics.median(tr[nblk:])
+    return {"workload": "1 stream, 65536 complex samples per call at 1.0 MS/s (65.5 ms of signal), host cf32 in, host audio out",
+            "api": "rfm_decoder_process_cf32 (blocking; == cFmDecoder::ProcessStream, RadioReceiver.cpp:515-525)",
+            "b200_ms_per_call": gpu_ms, "reference_ms_per_call": ref_ms, "reference_kind": kind, "reference_cores": 1,
+            "realtime_factor_b200": 65.536 / gpu_ms, "realtime_factor_reference": 65.536 / ref_ms,
+            "note": "one stream cannot fill a GPU: every per-stream recurrence runs one lane, so a call costs its dependent "
+                    "chain (block latency, ~20 kernel launches); the batch is where the GPU pays"}
+
+
+def c5_leg(torch, rfm, rank, world, local, barrier, max_over_ranks, steps=4, warmup=2):
+    """BASELINE.json configs[4]: one shared 50 MS/s capture, 100 stations on a 200 kHz raster sharded over the ranks
+    (no collective; every rank reads the same capture), both mixers.  One step = one demodulator call = 64 front-end
+    blocks of 32000 capture samples (41 ms of signal)."""
+    import importlib
+    synth_device = importlib.import_module("radiofm_b200.synth_device")
+    wideband = importlib.import_module("radiofm_b200.wideband")
+    shard = importlib.import_module("radiofm_b200.shard")
+    FS5, BLK5, BPC5 = 50.0e6, 32000, 64
+    n_call, n_st = BLK5 * BPC5, 100
+    freqs = [(k - n_st // 2) * 200000.0 for k in range(n_st)]
+    lo, hi = shard.shard_range(n_st, rank, world)
+    dev = torch.device("cuda", local)
+    ncalls = 3
+    capture = synth_device.make_wideband_u8(torch, FS5, ncalls * n_call, freqs, dev)
+    peak, _ = load_peaks()
+    out = {"workload": f"C5: one shared 50 MS/s u8 capture, {n_st} FM stations on a 200 kHz raster sharded by station over "
+                       f"{world} GPU(s), mixer + CRDSDownConvert (7 x HB51) + cFmDecoder per station; one step = {BPC5} "
+                       f"front-end blocks of {BLK5} samples (41 ms of signal)", "stations": n_st,
+           "stations_this_rank": hi - lo, "scaling": "strong"}
+    for mixer in ("freqshift", "osc"):
+        wb = wideband.WidebandReceiver(torch, freqs[lo:hi], FS5, BLK5, BPC5, mixer=mixer, device=local)
+        for i in range(warmup):
+            wb.process_device(capture.data_ptr() + 2 * (i % ncalls) * n_call)
+        wb.wait()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            nfl = wb.process_device(capture.data_ptr() + 2 * ((warmup + i) % ncalls) * n_call)
+        wb.wait()
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+        # front end alone (mixer + decimation chain): CUDA events around one more call of it
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        wb.dc.process_device(1, capture.data_ptr(), n_call, wb.bb.data_ptr(), wb.n_bb, n_call)
+        f1.record()
+        torch.cuda.synchronize()
+        front_ms = f0.elapsed_time(f1)
+        algo = 2.0 * n_call + (hi - lo) * nfl * 4.0      # per rank per step: one read of the capture + the audio
+        out[mixer] = {"value": n_st * n_call / (ms * 1e-3) / 1e6, "unit": "MS/s (station-samples, whole job)",
+                      "ms_per_step": ms, "realtime_factor": (n_call / FS5) / (ms * 1e-3), "front_end_ms": front_ms,
+                      "roofline": {"bound": "hbm", "kernel": "k_dc_chain_uniform" + (" + k_dc_osc" if mixer == "osc" else ""),
+                                   "achieved": algo / (front_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                   "frac": algo / (front_ms * 1e-3) / 1e9 / peak, "traffic": None,
+                                   "note": "FP32-issue-bound (129 un-fused flop per station-sample), the capture is read once "
+                                           "from L2 by all stations: DESIGN.md 8.1"}}
+        wb.close()
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------------
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -219,7 +325,7 @@ def run_b200(args):
     iq = synth_device.make_batch_u8(torch, S, FS, nres * BLK, dev, first_stream=rank * S)
     torch.cuda.synchronize()
     dec = rfm.FmDecoderBatch(FS, -0.15 * FS, downsample=DS, n_streams=S, max_block_len=BLK, device=local,
-                             n_groups=args.groups)
+                             n_groups=args.groups, lanes_sms=args.lanes_sms)
     stride = dec.max_audio_floats(BLK)
     audio = torch.zeros((S, stride), dtype=torch.float32, device=dev)
     stream = torch.cuda.Stream()
@@ -280,9 +386,14 @@ def run_b200(args):
     units_per_launch = S * BLK / n_groups
     avg_ms = top_ms / max(top_n, 1)
     achieved = BYTES_PER_SAMPLE * units_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
-    traffic = NCU_TRAFFIC_BYTES.get(top_name) if (S == STREAMS_PER_GPU and n_groups == 1) else None
+    ncu_c, ncu_src = load_ncu_constants()
+    traffic = None
+    if ncu_c and S == STREAMS_PER_GPU and n_groups == 1:
+        traffic = ncu_c.get("dram_bytes_per_launch", {}).get(top_name)
+    step_traffic = ncu_c.get("dram_bytes_per_step") if (ncu_c and S == STREAMS_PER_GPU) else None
     roofline = {"bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": how,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": how, "ncu_constants": ncu_src,
+                "step_dram_bytes": step_traffic,
                 "note": "the chain is latency-bound (one-lane-per-stream pilot PLL recurrence, k_bb_lanes) and FP32-issue-"
                         "bound (bit-exact un-fused FIRs), not HBM-bound: see DESIGN.md sections 3, 3.2",
                 "avg_launch_ms": avg_ms, "launches": top_n, "units_per_launch": units_per_launch,
@@ -292,15 +403,16 @@ def run_b200(args):
                 "timed_pass": "second pass of the same K steps with per-kernel CUDA events (the metric pass carries none)",
                 "ms_per_step_with_events": (ms_prof / K) if ms_prof else None,
                 "kernel_ms_per_step": {k: round(v[0] / K, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
-    if S == STREAMS_PER_GPU and clk.get("sm_mhz"):
+    if ncu_c and S == STREAMS_PER_GPU and clk.get("sm_mhz"):
         # the bound that actually binds beside the pilot recurrence: warp-instruction issue slots (SURVEY.md 8d asks for
         # the FP32 figure alongside the HBM one); every FP32 operation of the bit-exact chain is its own instruction
+        wi = float(ncu_c["warp_instructions_per_step"])
         issue_peak = SCHEDULERS * float(clk["sm_mhz"]) * 1e6
-        roofline["issue"] = {"warp_instructions_per_step": NCU_WARP_INSTR_PER_STEP, "schedulers": SCHEDULERS,
-                             "achieved_per_s": NCU_WARP_INSTR_PER_STEP / (ms / K * 1e-3), "peak_per_s": issue_peak,
-                             "frac": NCU_WARP_INSTR_PER_STEP / (ms / K * 1e-3) / issue_peak,
-                             "source": "ncu smsp__inst_executed.sum over the step's kernels (profiles/), one issue slot "
-                                       "per scheduler per cycle at the sampled SM clock"}
+        roofline["issue"] = {"warp_instructions_per_step": wi, "schedulers": SCHEDULERS,
+                             "achieved_per_s": wi / (ms / K * 1e-3), "peak_per_s": issue_peak,
+                             "frac": wi / (ms / K * 1e-3) / issue_peak,
+                             "source": "ncu smsp__inst_executed.sum over the step's kernels (" + ncu_src + "), one issue "
+                                       "slot per scheduler per cycle at the sampled SM clock"}
 
     # ---- e2e: host buffers through the public host-pointer entry point (its own decoder: stream groups overlap
     # the H2D copy of one group with the kernels / D2H of the others)
@@ -312,7 +424,7 @@ def run_b200(args):
         return
     dec.close()
     dec = rfm.FmDecoderBatch(FS, -0.15 * FS, downsample=DS, n_streams=S, max_block_len=BLK, device=local,
-                             n_groups=args.host_groups)
+                             n_groups=args.host_groups, lanes_sms=args.lanes_sms)
     nh = min(nres, 2)
     h_iq = torch.empty((nh, S, BLK, 2), dtype=torch.uint8).pin_memory()
     h_iq.copy_(iq.view(S, nres, BLK, 2)[:, :nh].permute(1, 0, 2, 3))
@@ -375,6 +487,59 @@ def run_b200(args):
                   "in, host audio out)",
            "blocking": e2e_sync}
 
+    # bare pinned-host -> device copies of the same bytes on every rank at once: the ceiling of any e2e figure on this host
+    probe_stream = torch.cuda.Stream()
+    d_probe = torch.empty((S, BLK, 2), dtype=torch.uint8, device=dev)
+    barrier()
+    t0 = time.perf_counter()
+    with torch.cuda.stream(probe_stream):
+        for i in range(K):
+            d_probe.copy_(h_iq[i % nh], non_blocking=True)
+    probe_stream.synchronize()
+    dt_probe = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    del d_probe
+    h2d_gbs = world * S * BLK * 2 * K / dt_probe / 1e9
+    e2e["h2d_ceiling_gbs"] = h2d_gbs
+    e2e["h2d_ceiling_value"] = world * S * BLK * K / dt_probe / 1e6
+    e2e["h2d_achieved_gbs"] = e2e["value"] * 1e6 * 2 / 1e9
+    e2e["note"] = ("PCIe-bound: h2d_ceiling_* is a bare cudaMemcpyAsync of the same pinned input blocks on all ranks at "
+                   "once, nothing else running")
+    dec.close()
+
+    # ---- strong scaling: 4096 streams in TOTAL over the ranks (the same figure as `value` at N = 1)
+    strong = None
+    if world > 1:
+        Ss = STREAMS_PER_GPU // world
+        dec_s = rfm.FmDecoderBatch(FS, -0.15 * FS, downsample=DS, n_streams=Ss, max_block_len=BLK, device=local)
+        def step_strong(i):
+            return dec_s.process_u8_device(iq.data_ptr() + (i % nres) * BLK * esz, nres * BLK, BLK, audio.data_ptr(), stride,
+                                           stream.cuda_stream)
+        with torch.cuda.stream(stream):
+            for i in range(W):
+                step_strong(i)
+            dec_s.wait(stream.cuda_stream)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for i in range(K):
+                step_strong(W + i)
+            dec_s.wait(stream.cuda_stream)
+            e1.record(stream)
+        barrier()
+        ms_s = max_over_ranks(e0.elapsed_time(e1))
+        strong = {"value": world * Ss * BLK * K / (ms_s * 1e-3) / 1e6, "unit": "MS/s", "ms_per_step": ms_s / K,
+                  "streams_total": world * Ss, "streams_per_gpu": Ss, "scaling": "strong",
+                  "note": "fewer streams per GPU starve the lane-per-stream kernels (their time does not depend on the "
+                          "stream count): DESIGN.md section 5"}
+        dec_s.close()
+    elif not args.no_extras:
+        strong = {"value": value, "unit": "MS/s", "ms_per_step": ms / K, "streams_total": S, "streams_per_gpu": S,
+                  "scaling": "strong", "note": "N = 1: identical to the weak-scaling figure"}
+
+    c5 = c5_leg(torch, rfm, rank, world, local, barrier, max_over_ranks) if not args.no_extras else None
+    single = single_stream_leg(rfm, local) if (rank == 0 and not args.no_extras) else None
     cpu = cpu_baseline_leg() if (rank == 0 and world == 1 and not args.no_cpu) else None
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "MS/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -382,7 +547,8 @@ def run_b200(args):
                 "dtype": "f32", "data": "synthetic", "config": workload_config(world), "roofline": roofline,
                 "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
                 "audio_floats_per_stream_per_step": nfl,
-                "demod_chunks_repaired": repairs, "host_enqueue_ms_per_step": host_enqueue_ms}
+                "demod_chunks_repaired": repairs, "host_enqueue_ms_per_step": host_enqueue_ms,
+                "strong": strong, "c5": c5, "single_stream": single}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -401,6 +567,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-prof", action="store_true", help="do not bracket kernels with CUDA events (roofline leg off)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the strong-scaling / C5 / single-stream legs")
+    ap.add_argument("--lanes-sms", type=int, default=0, help="rfm_config::lanes_sms (0 = automatic, 1 = no SM partition)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

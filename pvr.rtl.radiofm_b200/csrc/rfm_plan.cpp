@@ -1,6 +1,25 @@
-// rfm_plan.cpp -- see rfm_plan.h.  Build with plain g++ -O2 -ffp-contract=off (no -march/-ffast-math):
-// the tables must come out bit-identical to what the reference's constructors compute with the same
-// libm (tests/test_plan.py checks that against the compiled reference).
+// rfm_plan.cpp -- the reference's CONSTRUCTORS restated on the host: filter designs, PLL constants, the decimation-chain
+// planner (interface: rfm_plan.h).  Host only, run once per decoder.
+//
+// Attribution.  The kernels of this library consume coefficient tables and constants that must be bit-identical to
+// what the reference computes (one different ulp in a tap moves every output), so this file -- unlike the rest of the
+// library -- follows the reference's initialisation code expression by expression, in its precision and operation
+// order.  It is a derived work of pvr.rtl.radiofm (GPL-2.0-or-later):
+//     Izero / PlanKaiserLP / PlanKaiserHP   <- src/FirFilter.cpp:39-58,78-148,195-264
+//                                              Copyright (C) 2010-2013 Moe Wheatley, (C) 2015-2020 Alwin Esch (Team KODI)
+//     PlanBiquad                            <- src/IirFilter.cpp:11-51          (same authors)
+//     PlanLanczos, PlanDecimationChain      <- src/DownConvert.cpp:18-56,327-371,378-399
+//                                              Copyright (C) 2010-2013 Moe Wheatley, (C) 2013 Joris van Rantwijk,
+//                                              (C) 2015-2020 Alwin Esch (Team KODI)
+//     PlanPilot, PlanDecoder                <- src/FmDecode.cpp:45-64,88-139,237-324
+//                                              Copyright (C) 2013 Joris van Rantwijk, (C) 2015-2020 Alwin Esch (Team KODI)
+//     RDS process constants                 <- src/RDSProcess.cpp:43-118         (Moe Wheatley / Alwin Esch)
+//     halfband_taps.inc                     <- src/filtercoef.h (tap DATA; Moe Wheatley, Simplified-BSD in CuteSDR)
+// and is distributed under the same licence terms (SPDX-License-Identifier: GPL-2.0-or-later).
+//
+// Build with plain g++ -O2 -ffp-contract=off (no -march / -ffast-math): the tables must come out bit-identical to what
+// the reference's constructors compute with the same libm -- tests/test_abi_host.py and tests/test_oracle_port.py
+// check every constant and table against the compiled reference and the golden fixtures.
 #include "rfm_plan.h"
 
 #include <math.h>
