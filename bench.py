@@ -325,7 +325,7 @@ def run_b200(args):
     iq = synth_device.make_batch_u8(torch, S, FS, nres * BLK, dev, first_stream=rank * S)
     torch.cuda.synchronize()
     dec = rfm.FmDecoderBatch(FS, -0.15 * FS, downsample=DS, n_streams=S, max_block_len=BLK, device=local,
-                             n_groups=args.groups, lanes_sms=args.lanes_sms)
+                             n_groups=args.groups, lanes_sms=args.lanes_sms, fir_fused=args.fir_fused)
     stride = dec.max_audio_floats(BLK)
     audio = torch.zeros((S, stride), dtype=torch.float32, device=dev)
     stream = torch.cuda.Stream()
@@ -538,6 +538,49 @@ def run_b200(args):
         strong = {"value": value, "unit": "MS/s", "ms_per_step": ms / K, "streams_total": S, "streams_per_gpu": S,
                   "scaling": "strong", "note": "N = 1: identical to the weak-scaling figure"}
 
+    # ---- tolerance mode (rfm_config::fir_fused = 1, opt-in): the same device-resident steps with
+    # fused multiply-adds in the FIRs, and how far the audio moves from the exact mode's on the same blocks
+    tol = None
+    if not args.no_extras:
+        dec_t = rfm.FmDecoderBatch(FS, -0.15 * FS, downsample=DS, n_streams=S, max_block_len=BLK, device=local,
+                                   lanes_sms=args.lanes_sms, fir_fused=1)
+        dec_x = rfm.FmDecoderBatch(FS, -0.15 * FS, downsample=DS, n_streams=S, max_block_len=BLK, device=local,
+                                   lanes_sms=args.lanes_sms)
+        audio_t = torch.zeros_like(audio)
+        err, err_sum, err_dif = 0.0, 0.0, 0.0
+        nchk = 20
+        with torch.cuda.stream(stream):
+            for i in range(max(W, nchk)):
+                k_t = dec_t.process_u8_device(iq.data_ptr() + (i % nres) * BLK * esz, nres * BLK, BLK, audio_t.data_ptr(), stride,
+                                              stream.cuda_stream)
+                dec_t.wait(stream.cuda_stream)
+                if i < nchk:
+                    dec_x.process_u8_device(iq.data_ptr() + (i % nres) * BLK * esz, nres * BLK, BLK, audio.data_ptr(), stride,
+                                            stream.cuda_stream)
+                    dec_x.wait(stream.cuda_stream)
+                    a_t, a_x = audio_t[:, :k_t].double().view(S, -1, 2), audio[:, :k_t].double().view(S, -1, 2)
+                    err = max(err, float((a_t - a_x).abs().max()))
+                    err_sum = max(err_sum, float((a_t.sum(-1) - a_x.sum(-1)).abs().max()))
+                    err_dif = max(err_dif, float(((a_t[..., 0] - a_t[..., 1]) - (a_x[..., 0] - a_x[..., 1])).abs().max()))
+        dec_x.close()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for i in range(K):
+                dec_t.process_u8_device(iq.data_ptr() + ((W + i) % nres) * BLK * esz, nres * BLK, BLK, audio_t.data_ptr(), stride,
+                                        stream.cuda_stream)
+            dec_t.wait(stream.cuda_stream)
+            e1.record(stream)
+        barrier()
+        ms_t = max_over_ranks(e0.elapsed_time(e1))
+        dec_t.close()
+        tol = {"config": "rfm_config::fir_fused = 1 (FFMA in the front-end FIR, the resamplers and the rotating FIRs; every PLL / "
+                         "IIR / conversion unchanged)", "value": world * S * BLK * K / (ms_t * 1e-3) / 1e6, "unit": "MS/s",
+               "ms_per_step": ms_t / K, "max_abs_audio_diff_vs_exact": err, "max_abs_LplusR_diff": err_sum,
+               "max_abs_LminusR_diff": err_dif, "blocks_compared": nchk, "streams_compared": S,
+               "note": "not the headline: the default (and every parity test) is the bit-exact mode"}
+
     c5 = c5_leg(torch, rfm, rank, world, local, barrier, max_over_ranks) if not args.no_extras else None
     single = single_stream_leg(rfm, local) if (rank == 0 and not args.no_extras) else None
     cpu = cpu_baseline_leg() if (rank == 0 and world == 1 and not args.no_cpu) else None
@@ -548,7 +591,7 @@ def run_b200(args):
                 "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
                 "audio_floats_per_stream_per_step": nfl,
                 "demod_chunks_repaired": repairs, "host_enqueue_ms_per_step": host_enqueue_ms,
-                "strong": strong, "c5": c5, "single_stream": single}
+                "strong": strong, "c5": c5, "single_stream": single, "tolerance_mode": tol}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -569,6 +612,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the strong-scaling / C5 / single-stream legs")
     ap.add_argument("--lanes-sms", type=int, default=0, help="rfm_config::lanes_sms (0 = automatic, 1 = no SM partition)")
+    ap.add_argument("--fir-fused", type=int, default=0, help="rfm_config::fir_fused for the main legs (1 = tolerance mode; the "
+                                                             "headline is the default 0)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -31,7 +31,7 @@ class RfmConfig(C.Structure):
     _fields_ = [("sample_rate_if", C.c_double), ("tuning_offset", C.c_double), ("sample_rate_pcm", C.c_double),
                 ("bandwidth_pcm", C.c_double), ("downsample", C.c_uint32), ("us_deemphasis", C.c_int32),
                 ("n_streams", C.c_uint32), ("max_block_len", C.c_uint32), ("device", C.c_int32),
-                ("n_groups", C.c_uint32), ("lanes_sms", C.c_uint32)]
+                ("n_groups", C.c_uint32), ("lanes_sms", C.c_uint32), ("fir_fused", C.c_uint32)]
 
 
 class RfmStreamStatus(C.Structure):
@@ -262,13 +262,14 @@ _COMPLEX_TAPS = {"demod_in", "rds_dec", "rds_lp"}
 
 
 def _config(fs_if, tuning_offset, fs_pcm=48000.0, bw_pcm=15000.0, downsample=1, usver=False, n_streams=1,
-            max_block_len=65536, device=-1, n_groups=0, lanes_sms=0) -> RfmConfig:
+            max_block_len=65536, device=-1, n_groups=0, lanes_sms=0, fir_fused=0) -> RfmConfig:
     cfg = RfmConfig()
     lib().rfm_config_default(C.byref(cfg))
     cfg.sample_rate_if, cfg.tuning_offset, cfg.sample_rate_pcm, cfg.bandwidth_pcm = fs_if, tuning_offset, fs_pcm, bw_pcm
     cfg.downsample, cfg.us_deemphasis, cfg.n_streams = downsample, int(usver), n_streams
     cfg.max_block_len, cfg.device, cfg.n_groups = max_block_len, device, n_groups
     cfg.lanes_sms = lanes_sms
+    cfg.fir_fused = fir_fused
     return cfg
 
 
@@ -295,9 +296,9 @@ class FmDecoderBatch:
 
     def __init__(self, fs_if: float, tuning_offset: float, fs_pcm: float = 48000.0, bw_pcm: float = 15000.0,
                  downsample: int = 1, usver: bool = False, n_streams: int = 1, max_block_len: int = 65536,
-                 device: int = -1, n_groups: int = 0, lanes_sms: int = 0):
+                 device: int = -1, n_groups: int = 0, lanes_sms: int = 0, fir_fused: int = 0):
         cfg = _config(fs_if, tuning_offset, fs_pcm, bw_pcm, downsample, usver, n_streams, max_block_len, device,
-                      n_groups, lanes_sms)
+                      n_groups, lanes_sms, fir_fused)
         self.n_streams = n_streams
         self._h = C.c_void_p()
         _check(lib().rfm_decoder_create(C.byref(cfg), C.byref(self._h)))

@@ -607,6 +607,7 @@ void EnqueueStageF(rfm_decoder* d, Group& g, const void* d_in, size_t in_stride,
   fp.p0 = d->in_pos; fp.nout = bg.nb; fp.idx0 = d->tuner_idx; fp.lut = d->d_lut.p; fp.tuner = d->d_tuner.p;
   fp.coeff = d->d_in_coeff.p; fp.coeff_host = p.in_coeff.data(); fp.tail = g.tail.p; fp.z = g.z[par].p; fp.z_stride = d->z_stride;
   fp.sm_count = d->part.rest ? d->part.rest_sms : 0;
+  fp.fused = d->cfg.fir_fused != 0;
   RFM_PROF(g.prof, "k_if_level", st, launch_if_level(fp, g.state.p, u8, st));
   RFM_PROF(g.prof, "k_front", st, launch_front(fp, u8, st));
   RFM_PROF(g.prof, "k_front_tail", st, launch_front_tail(fp, u8, st));
@@ -674,6 +675,7 @@ void EnqueueStageB(rfm_decoder* d, Group& g, const BlockGeom& bg, unsigned par, 
   rp.S = S; rp.na = bg.na; rp.pos_frac = d->a_pos; rp.pstep = p.a_pstep; rp.coeff = d->d_a_coeff.p;
   rp.lpS = g.lpS[par].p; rp.lpM = g.lpM[par].p; rp.lp_stride = d->lp_stride; rp.lp_hist = lp_taps - 1;
   rp.kk = d->res_kk[par3].p; rp.meta = d->res_meta[par3].p; rp.lp = d->res_lp;
+  rp.fused = d->cfg.fir_fused != 0;
   RFM_PROF(g.prof, "k_resample", st, launch_resample_tiled(rp, st));
   cudaEventRecord(g.ev_res[par], st);
   ++g_launches;
@@ -692,7 +694,7 @@ void EnqueueStageB(rfm_decoder* d, Group& g, const BlockGeom& bg, unsigned par, 
   RotFirParams f29;
   f29.inA = g.lpS[par].p; f29.inB = g.lpM[par].p; f29.in_stride = d->lp_stride; f29.outA = g.fS.p; f29.outB = g.fM.p;
   f29.out_stride = d->na_max; f29.out_off = 0; f29.n = bg.na; f29.S = S; f29.taps = lp_taps; f29.g0 = d->lp_g;
-  f29.coef = d->d_lp_coef.p; f29.cplx = 0;
+  f29.coef = d->d_lp_coef.p; f29.cplx = 0; f29.fused = d->cfg.fir_fused != 0;
   RFM_PROF(g.prof, "k_rotfir_lp29", st, launch_rotfir(f29, st));
 
   AudioTailParams at;
@@ -733,7 +735,7 @@ void EnqueueStageB(rfm_decoder* d, Group& g, const BlockGeom& bg, unsigned par, 
     flp.inA = reinterpret_cast<const float*>(g.rlpV.p); flp.inB = nullptr; flp.in_stride = d->rlp_stride;
     flp.outA = reinterpret_cast<float*>(g.rlp_out[par].p); flp.outB = nullptr; flp.out_stride = d->nr_stride;
     flp.out_off = 0; flp.n = bg.nr; flp.S = S; flp.taps = rlp_taps; flp.g0 = d->rlp_g; flp.coef = d->d_rlp_coef.p;
-    flp.cplx = 1;
+    flp.cplx = 1; flp.fused = d->cfg.fir_fused != 0;
     RFM_PROF(g.prof, "k_rotfir_rdslp", st, launch_rotfir(flp, st));
     TailParams tpl;
     tpl.count = 1;
@@ -758,7 +760,7 @@ void EnqueueStageB(rfm_decoder* d, Group& g, const BlockGeom& bg, unsigned par, 
   RotFirParams fmf;
   fmf.inA = g.mfV.p; fmf.inB = nullptr; fmf.in_stride = d->mf_stride; fmf.outA = g.mf_out.p; fmf.outB = nullptr;
   fmf.out_stride = d->nr_stride; fmf.out_off = 0; fmf.n = bg.nr; fmf.S = S; fmf.taps = mf_taps; fmf.g0 = d->mf_g;
-  fmf.coef = d->d_mf_coef.p; fmf.cplx = 0;
+  fmf.coef = d->d_mf_coef.p; fmf.cplx = 0; fmf.fused = d->cfg.fir_fused != 0;
   RFM_PROF(g.prof, "k_rotfir_rdsmf", st, launch_rotfir(fmf, st));
 
   RdsSliceParams sp;
@@ -980,6 +982,7 @@ void rfm_config_default(rfm_config* c)
   c->device = -1;
   c->n_groups = 0;
   c->lanes_sms = 0;
+  c->fir_fused = 0;
 }
 
 int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out)

@@ -376,7 +376,7 @@ struct FrontGeom3
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-template <int DS>
+template <int DS, bool FUSED>
 __global__ void __launch_bounds__(128) k_front_tma(FrontParams p, FrontCoef cf, const __grid_constant__ CUtensorMap tmap,
                                                    unsigned tiles_per_row, unsigned total_tiles)
 {
@@ -507,8 +507,8 @@ __global__ void __launch_bounds__(128) k_front_tma(FrontParams p, FrontCoef cf, 
           const int j = u + 1 - DS * (G::R - 1 - i); // tap of output i that meets this sample
           if (j >= 1 && j <= G::ORDER)
           {
-            acc[i].x = addf(acc[i].x, mulf(v.x, cf.c[j]));
-            acc[i].y = addf(acc[i].y, mulf(v.y, cf.c[j]));
+            acc[i].x = macf<FUSED>(acc[i].x, v.x, cf.c[j]);
+            acc[i].y = macf<FUSED>(acc[i].y, v.y, cf.c[j]);
           }
         }
       }
@@ -549,14 +549,14 @@ static bool EncodeFrontMap(const FrontParams& p, CUtensorMap* map)
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int DS>
+template <int DS, bool FUSED>
 static bool launch_front_tma(const FrontParams& p, const FrontCoef& cf, cudaStream_t st)
 {
   using G = FrontGeom3<DS>;
   CUtensorMap map;
   if (!EncodeFrontMap(p, &map))
     return false;
-  EnsureDynSmem(k_front_tma<DS>, G::SMEM);
+  EnsureDynSmem(k_front_tma<DS, FUSED>, G::SMEM);
   const unsigned tpr = cdiv(p.nout, G::OB), total = tpr * p.S;
   // persistent: one wave of resident CTAs (as many as fit on the device), each walks total / grid tiles
   int dev = 0, sms = 0, occ = 0;
@@ -564,10 +564,10 @@ static bool launch_front_tma(const FrontParams& p, const FrontCoef& cf, cudaStre
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (p.sm_count) // the launching stream lives in an SM partition
     sms = (int)p.sm_count;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_front_tma<DS>, G::T, G::SMEM) != cudaSuccess)
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_front_tma<DS, FUSED>, G::T, G::SMEM) != cudaSuccess)
     occ = 1;
   const unsigned grid = std::min<unsigned>(total, (unsigned)(std::max(sms, 1) * std::max(occ, 1)));
-  k_front_tma<DS><<<grid, G::T, G::SMEM, st>>>(p, cf, map, tpr, total);
+  k_front_tma<DS, FUSED><<<grid, G::T, G::SMEM, st>>>(p, cf, map, tpr, total);
   return true;
 }
 
@@ -596,7 +596,11 @@ void launch_front(const FrontParams& p, bool u8, cudaStream_t st)
     if (u8 && p.tuner && (p.ds == 1 || p.ds == 5 || p.ds == 11) && p.n % 4 == 0 && p.n >= 4 &&
         (reinterpret_cast<uintptr_t>(p.in) & 15u) == 0 && (p.in_stride * 2) % 16 == 0)
     {
-      const bool ok = p.ds == 11 ? launch_front_tma<11>(p, cf, st) : p.ds == 5 ? launch_front_tma<5>(p, cf, st) : launch_front_tma<1>(p, cf, st);
+      bool ok;
+      if (p.fused)
+        ok = p.ds == 11 ? launch_front_tma<11, true>(p, cf, st) : p.ds == 5 ? launch_front_tma<5, true>(p, cf, st) : launch_front_tma<1, true>(p, cf, st);
+      else
+        ok = p.ds == 11 ? launch_front_tma<11, false>(p, cf, st) : p.ds == 5 ? launch_front_tma<5, false>(p, cf, st) : launch_front_tma<1, false>(p, cf, st);
       if (ok)
         return;
     }
@@ -1435,7 +1439,7 @@ __device__ __forceinline__ void cp_async_16(void* smem, const void* gmem)
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
 
-template <int GB> // groups of 4 outputs per CTA == warps per CTA
+template <int GB, bool FUSED> // groups of 4 outputs per CTA == warps per CTA
 __global__ void __launch_bounds__(32 * GB) k_resample_tiled(ResampleParams p, unsigned pitch)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1483,10 +1487,10 @@ __global__ void __launch_bounds__(32 * GB) k_resample_tiled(ResampleParams p, un
   const float4* x1 = reinterpret_cast<const float4*>(X + (size_t)(32 + lane) * pitch + off);
   float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
 #define RS_STEP(k, m, sv)                                                                     \
-  a[0] = addf(a[0], mulf((k).x, m)); a[1] = addf(a[1], mulf((k).y, m));                       \
-  a[2] = addf(a[2], mulf((k).z, m)); a[3] = addf(a[3], mulf((k).w, m));                       \
-  b[0] = addf(b[0], mulf((k).x, sv)); b[1] = addf(b[1], mulf((k).y, sv));                     \
-  b[2] = addf(b[2], mulf((k).z, sv)); b[3] = addf(b[3], mulf((k).w, sv));
+  a[0] = macf<FUSED>(a[0], (k).x, m); a[1] = macf<FUSED>(a[1], (k).y, m);                     \
+  a[2] = macf<FUSED>(a[2], (k).z, m); a[3] = macf<FUSED>(a[3], (k).w, m);                     \
+  b[0] = macf<FUSED>(b[0], (k).x, sv); b[1] = macf<FUSED>(b[1], (k).y, sv);                   \
+  b[2] = macf<FUSED>(b[2], (k).z, sv); b[3] = macf<FUSED>(b[3], (k).w, sv);
   // software pipeline: the six vectors of step q - 1 are in flight while step q is multiplied out (with three warps
   // per scheduler the shared-memory latency was this loop's main stall: 1.4 short-scoreboard cycles per issue)
   float4 m = x0[Lq - 1], sv = x1[Lq - 1];
@@ -1527,9 +1531,17 @@ __global__ void __launch_bounds__(32 * GB) k_resample_tiled(ResampleParams p, un
 template <int GB>
 static void launch_resample_tiled_gb(const ResampleParams& p, unsigned pitch, size_t smem, cudaStream_t st)
 {
-  EnsureDynSmem(k_resample_tiled<GB>, smem);
   dim3 grid(cdiv((p.na + 3) / 4, GB), cdiv(p.S, 32));
-  k_resample_tiled<GB><<<grid, 32 * GB, smem, st>>>(p, pitch);
+  if (p.fused)
+  {
+    EnsureDynSmem(k_resample_tiled<GB, true>, smem);
+    k_resample_tiled<GB, true><<<grid, 32 * GB, smem, st>>>(p, pitch);
+  }
+  else
+  {
+    EnsureDynSmem(k_resample_tiled<GB, false>, smem);
+    k_resample_tiled<GB, false><<<grid, 32 * GB, smem, st>>>(p, pitch);
+  }
 }
 
 void launch_resample_tiled(const ResampleParams& p, cudaStream_t st)
@@ -1659,7 +1671,7 @@ __global__ void __launch_bounds__(kFirTile) k_rotfir(RotFirParams p)
 // --------------------------------------------------------------------------------------------------
 constexpr unsigned kRlWarps = 4;
 
-template <int MODE> // 0 real, 1 real pair, 2 complex
+template <int MODE, bool FUSED> // 0 real, 1 real pair, 2 complex
 __global__ void __launch_bounds__(32 * kRlWarps) k_rotfir_lanes(RotFirParams p, unsigned cyc, unsigned pitch)
 {
   extern __shared__ __align__(16) float rl_smem[];
@@ -1765,10 +1777,10 @@ __global__ void __launch_bounds__(32 * kRlWarps) k_rotfir_lanes(RotFirParams p, 
         if (TWO) { a0.y = mulf(w0, x.y); a1.y = mulf(w1, x.y); a2.y = mulf(w2, x.y); a3.y = mulf(w3, x.y); }
       }
 #define RL_STEP4(x)                                                                                           \
-  a0.x = addf(a0.x, mulf(w0, (x).x)); a1.x = addf(a1.x, mulf(w1, (x).x));                                     \
-  a2.x = addf(a2.x, mulf(w2, (x).x)); a3.x = addf(a3.x, mulf(w3, (x).x));                                     \
-  if (TWO) { a0.y = addf(a0.y, mulf(w0, (x).y)); a1.y = addf(a1.y, mulf(w1, (x).y));                          \
-             a2.y = addf(a2.y, mulf(w2, (x).y)); a3.y = addf(a3.y, mulf(w3, (x).y)); }
+  a0.x = macf<FUSED>(a0.x, w0, (x).x); a1.x = macf<FUSED>(a1.x, w1, (x).x);                                     \
+  a2.x = macf<FUSED>(a2.x, w2, (x).x); a3.x = macf<FUSED>(a3.x, w3, (x).x);                                     \
+  if (TWO) { a0.y = macf<FUSED>(a0.y, w0, (x).y); a1.y = macf<FUSED>(a1.y, w1, (x).y);                          \
+             a2.y = macf<FUSED>(a2.y, w2, (x).y); a3.y = macf<FUSED>(a3.y, w3, (x).y); }
 #pragma unroll 4
       for (int m = 1; m < M1; ++m)
       {
@@ -1779,26 +1791,26 @@ __global__ void __launch_bounds__(32 * kRlWarps) k_rotfir_lanes(RotFirParams p, 
       col -= M1;
       { // phase-1 triangle: taps (N-3, N-2, N-1), (N-2, N-1), (N-1) = (w1, w2, w3), (w2, w3), (w3)
         float2 x = ld(col);
-        a0.x = addf(a0.x, mulf(w1, x.x)); a1.x = addf(a1.x, mulf(w2, x.x)); a2.x = addf(a2.x, mulf(w3, x.x));
-        if (TWO) { a0.y = addf(a0.y, mulf(w1, x.y)); a1.y = addf(a1.y, mulf(w2, x.y)); a2.y = addf(a2.y, mulf(w3, x.y)); }
+        a0.x = macf<FUSED>(a0.x, w1, (x).x); a1.x = macf<FUSED>(a1.x, w2, (x).x); a2.x = macf<FUSED>(a2.x, w3, (x).x);
+        if (TWO) { a0.y = macf<FUSED>(a0.y, w1, (x).y); a1.y = macf<FUSED>(a1.y, w2, (x).y); a2.y = macf<FUSED>(a2.y, w3, (x).y); }
         x = ld(col - 1);
-        a0.x = addf(a0.x, mulf(w2, x.x)); a1.x = addf(a1.x, mulf(w3, x.x));
-        if (TWO) { a0.y = addf(a0.y, mulf(w2, x.y)); a1.y = addf(a1.y, mulf(w3, x.y)); }
+        a0.x = macf<FUSED>(a0.x, w2, (x).x); a1.x = macf<FUSED>(a1.x, w3, (x).x);
+        if (TWO) { a0.y = macf<FUSED>(a0.y, w2, (x).y); a1.y = macf<FUSED>(a1.y, w3, (x).y); }
         x = ld(col - 2);
-        a0.x = addf(a0.x, mulf(w3, x.x));
-        if (TWO) { a0.y = addf(a0.y, mulf(w3, x.y)); }
+        a0.x = macf<FUSED>(a0.x, w3, (x).x);
+        if (TWO) { a0.y = macf<FUSED>(a0.y, w3, (x).y); }
       }
       w0 = s_h[0]; w1 = s_h[1]; w2 = s_h[2]; w3 = s_h[3];
       { // phase-2 triangle: samples V[N-1 + i0 + 3], + 2, + 1
         float2 x = ld(col0 + 3);
-        a3.x = addf(a3.x, mulf(w0, x.x));
-        if (TWO) { a3.y = addf(a3.y, mulf(w0, x.y)); }
+        a3.x = macf<FUSED>(a3.x, w0, (x).x);
+        if (TWO) { a3.y = macf<FUSED>(a3.y, w0, (x).y); }
         x = ld(col0 + 2);
-        a2.x = addf(a2.x, mulf(w0, x.x)); a3.x = addf(a3.x, mulf(w1, x.x));
-        if (TWO) { a2.y = addf(a2.y, mulf(w0, x.y)); a3.y = addf(a3.y, mulf(w1, x.y)); }
+        a2.x = macf<FUSED>(a2.x, w0, (x).x); a3.x = macf<FUSED>(a3.x, w1, (x).x);
+        if (TWO) { a2.y = macf<FUSED>(a2.y, w0, (x).y); a3.y = macf<FUSED>(a3.y, w1, (x).y); }
         x = ld(col0 + 1);
-        a1.x = addf(a1.x, mulf(w0, x.x)); a2.x = addf(a2.x, mulf(w1, x.x)); a3.x = addf(a3.x, mulf(w2, x.x));
-        if (TWO) { a1.y = addf(a1.y, mulf(w0, x.y)); a2.y = addf(a2.y, mulf(w1, x.y)); a3.y = addf(a3.y, mulf(w2, x.y)); }
+        a1.x = macf<FUSED>(a1.x, w0, (x).x); a2.x = macf<FUSED>(a2.x, w1, (x).x); a3.x = macf<FUSED>(a3.x, w2, (x).x);
+        if (TWO) { a1.y = macf<FUSED>(a1.y, w0, (x).y); a2.y = macf<FUSED>(a2.y, w1, (x).y); a3.y = macf<FUSED>(a3.y, w2, (x).y); }
       }
 #pragma unroll 4
       for (int u = 0; u < k0; ++u)
@@ -1867,10 +1879,18 @@ static void launch_rotfir_lanes(const RotFirParams& p, cudaStream_t st)
   const unsigned cyc = std::max(1u, (target + N / 2) / N); // ~128 outputs per CTA
   const unsigned pitch = (cyc * N + N - 1) | 1u;        // odd: lanes (rows) hit distinct banks
   const size_t smem = (((N + 4 + 3) & ~3u) + (size_t)(MODE == 0 ? 1 : 2) * 32 * pitch) * sizeof(float);
-  EnsureDynSmem(k_rotfir_lanes<MODE>, smem);
   const unsigned cycles = (p.g0 % N + p.n + N - 1) / N;
   dim3 grid(cdiv(cycles, cyc), cdiv(p.S, 32));
-  k_rotfir_lanes<MODE><<<grid, 32 * kRlWarps, smem, st>>>(p, cyc, pitch);
+  if (p.fused)
+  {
+    EnsureDynSmem(k_rotfir_lanes<MODE, true>, smem);
+    k_rotfir_lanes<MODE, true><<<grid, 32 * kRlWarps, smem, st>>>(p, cyc, pitch);
+  }
+  else
+  {
+    EnsureDynSmem(k_rotfir_lanes<MODE, false>, smem);
+    k_rotfir_lanes<MODE, false><<<grid, 32 * kRlWarps, smem, st>>>(p, cyc, pitch);
+  }
 }
 
 void launch_rotfir(const RotFirParams& p, cudaStream_t st)

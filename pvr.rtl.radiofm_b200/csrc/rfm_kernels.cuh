@@ -101,6 +101,7 @@ struct FrontParams
   cf32* z;                 // [S][z_stride] FIR output
   size_t z_stride;
   unsigned sm_count = 0;   // SMs of the launching stream's partition (0: the whole device); sizes persistent grids
+  bool fused = false;      // tolerance mode (rfm_config::fir_fused): FFMA in the FIR, not bit-exact
 };
 void launch_front(const FrontParams& p, bool u8, cudaStream_t st);
 void launch_front_tail(const FrontParams& p, bool u8, cudaStream_t st);
@@ -164,6 +165,7 @@ struct ResampleParams
   const float* kk;         // [groups][lp][4]
   const int* meta;         // [groups][2]: first V index, length
   unsigned lp;             // time steps reserved per group (>= order + 1 + 3 * ceil(ratio) + 1)
+  bool fused = false;      // tolerance mode
 };
 void launch_resample(const ResampleParams& p, cudaStream_t st);
 void launch_resample_tiled(const ResampleParams& p, cudaStream_t st);
@@ -192,6 +194,7 @@ struct RotFirParams
   unsigned g0;             // samples filtered since the last (re)initialisation, mod taps
   const float* coef;       // [taps]
   int cplx;                // 1: rows are cf32, same taps for re and im
+  bool fused = false;      // tolerance mode
 };
 void launch_rotfir(const RotFirParams& p, cudaStream_t st);
 

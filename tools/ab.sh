@@ -6,7 +6,7 @@ EXP=$PWD/pvr.rtl.radiofm_b200/libradiofm_b200_exp.so
 for spec in "$@"; do
   label=${spec%%|*}; envs=${spec#*|}
   envs=${envs//@EXP/RFM_LIB_PATH=$EXP}
-  env $envs python bench.py --no-e2e --no-cpu --steps ${STEPS:-16} --warmup 4 2>/dev/null | python -c "
+  env $envs python bench.py --no-e2e --no-cpu --no-extras ${BENCH_ARGS:-} --steps ${STEPS:-16} --warmup 4 2>/dev/null | python -c "
 import json,sys
 try:
     d=json.loads(sys.stdin.readlines()[-1]); k=d['kernel_ms_per_step']
