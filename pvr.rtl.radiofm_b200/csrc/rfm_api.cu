@@ -965,7 +965,7 @@ extern "C"
 {
 
 const char* rfm_last_error(void) { return g_err.c_str(); }
-const char* rfm_version(void) { return "radiofm_b200 0.1 (sm_100a)"; }
+const char* rfm_version(void) { return "radiofm_b200 0.2 (sm_100a)"; }
 uint64_t rfm_launch_count(void) { return g_launches.load(); }
 
 void rfm_config_default(rfm_config* c)
