@@ -430,6 +430,27 @@ RFM_API uint32_t rfm_source_block_length(uint32_t requested);
 RFM_API int rfm_demux_set_source_block_length(rfm_demux* m, uint32_t requested);
 RFM_API void rfm_demux_source_cb(unsigned char* buf, uint32_t len, void* ctx);
 RFM_API uint64_t rfm_demux_short_reads(rfm_demux* m);
+
+/* cRtlSdrSource itself (RTL_SDR_Source.h:21-86, RTL_SDR_Source.cpp:27-256): librtlsdr bound at run time with dlopen
+ * (`library` = path or soname, NULL = librtlsdr.so.0 / librtlsdr.so; RFM_ERR_UNSUPPORTED when it cannot be loaded,
+ * RFM_ERR_NO_DEVICE when rtlsdr_open fails).  open = cRtlSdrSource::Open; configure = Configure (sample rate, centre
+ * frequency, manual gain in 0.1 dB or INT_MIN for automatic, RTL AGC, block length by the rule above,
+ * rtlsdr_reset_buffer) and starts the reader thread (Process: rtlsdr_read_async with 15 buffers of 2 * block bytes,
+ * up to five re-configure attempts after a failed read, EndDataBuffer at the end); every full block is queued raw into
+ * `demux` by rfm_demux_source_cb; close = Close (rtlsdr_cancel_async, join) + rtlsdr_close. */
+typedef struct rfm_rtlsdr rfm_rtlsdr;
+RFM_API int rfm_rtlsdr_device_count(const char* library);
+RFM_API int rfm_rtlsdr_open(rfm_demux* demux, const char* library, int dev_index, rfm_rtlsdr** out);
+RFM_API int rfm_rtlsdr_configure(rfm_rtlsdr* s, uint32_t sample_rate, uint32_t frequency, int tuner_gain,
+                                 int block_length, int agcmode);
+RFM_API void rfm_rtlsdr_close(rfm_rtlsdr* s);
+RFM_API uint32_t rfm_rtlsdr_get_sample_rate(rfm_rtlsdr* s);   /* GetSampleRate */
+RFM_API uint32_t rfm_rtlsdr_get_frequency(rfm_rtlsdr* s);     /* GetFrequency */
+RFM_API void rfm_rtlsdr_set_frequency(rfm_rtlsdr* s, uint32_t freq);
+RFM_API int rfm_rtlsdr_get_tuner_gain(rfm_rtlsdr* s);         /* GetTunerGain */
+RFM_API uint32_t rfm_rtlsdr_block_length(const rfm_rtlsdr* s); /* m_BlockLength */
+RFM_API uint32_t rfm_rtlsdr_restarts(const rfm_rtlsdr* s);
+RFM_API const char* rfm_rtlsdr_error(const rfm_rtlsdr* s);    /* error() */
 /* GetSignalStatus(float&, float&, bool&), RadioReceiver.cpp:544-556: levels in dB */
 RFM_API int rfm_demux_signal_status(rfm_demux* m, float* interface_level_db, float* audio_level_db, int* stereo);
 

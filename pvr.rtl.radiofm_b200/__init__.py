@@ -51,6 +51,9 @@ EXPORTED_SYMBOLS = (
     "rfm_demux_queued_samples", "rfm_demux_set_stream_change", "rfm_demux_read", "rfm_demux_audio_level",
     "rfm_demux_signal_status", "rfm_source_block_length", "rfm_demux_set_source_block_length", "rfm_demux_source_cb",
     "rfm_demux_short_reads",
+    "rfm_rtlsdr_device_count", "rfm_rtlsdr_open", "rfm_rtlsdr_configure", "rfm_rtlsdr_close", "rfm_rtlsdr_get_sample_rate",
+    "rfm_rtlsdr_get_frequency", "rfm_rtlsdr_set_frequency", "rfm_rtlsdr_get_tuner_gain", "rfm_rtlsdr_block_length",
+    "rfm_rtlsdr_restarts", "rfm_rtlsdr_error",
     "rfm_decoder_constants", "rfm_decoder_table", "rfm_plan_constants", "rfm_plan_table", "rfm_decoder_set_profiling",
     "rfm_decoder_profile_read", "rfm_decoder_tap", "rfm_rdssync_create",
     "rfm_rdssync_destroy", "rfm_rdssync_reset", "rfm_rdssync_push_bits", "rfm_rdssync_take_groups",
@@ -502,6 +505,50 @@ class RdsGroupDecoder:
         buf = C.create_string_buffer(9)
         _check(lib().rfm_rdsgroup_channel_name(self._h, buf))
         return buf.raw[:8]
+
+
+class RtlSdrSource:
+    """cRtlSdrSource (RTL_SDR_Source.h:21-86) in front of a Demux: librtlsdr bound at run time (rfm_rtlsdr_*)."""
+    AUTO_GAIN = -(1 << 31)   # INT_MIN
+
+    def __init__(self, demux: "Demux", library: str | None = None, dev_index: int = 0):
+        L = lib()
+        L.rfm_rtlsdr_open.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.rfm_rtlsdr_configure.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int]
+        L.rfm_rtlsdr_close.argtypes = [C.c_void_p]
+        L.rfm_rtlsdr_set_frequency.argtypes = [C.c_void_p, C.c_uint32]
+        for n in ("get_sample_rate", "get_frequency", "block_length", "restarts"):
+            f = getattr(L, "rfm_rtlsdr_" + n)
+            f.argtypes, f.restype = [C.c_void_p], C.c_uint32
+        L.rfm_rtlsdr_get_tuner_gain.argtypes = [C.c_void_p]
+        L.rfm_rtlsdr_error.argtypes, L.rfm_rtlsdr_error.restype = [C.c_void_p], C.c_char_p
+        self._h = C.c_void_p()
+        self._demux = demux
+        rc = L.rfm_rtlsdr_open(demux._h, library.encode() if library else None, dev_index, C.byref(self._h))
+        if rc != RFM_OK:
+            raise RadioFmError(f"rfm_rtlsdr_open: error {rc}")
+
+    def configure(self, sample_rate: int, frequency: int, tuner_gain: int = AUTO_GAIN, block_length: int = 65536,
+                  agcmode: bool = False):
+        rc = lib().rfm_rtlsdr_configure(self._h, sample_rate, frequency, tuner_gain, block_length, int(agcmode))
+        if rc != RFM_OK:
+            raise RadioFmError(f"rfm_rtlsdr_configure: error {rc}: {lib().rfm_rtlsdr_error(self._h).decode()}")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().rfm_rtlsdr_close(self._h)
+            self._h = None
+
+    __del__ = close
+
+    sample_rate = property(lambda self: int(lib().rfm_rtlsdr_get_sample_rate(self._h)))
+    frequency = property(lambda self: int(lib().rfm_rtlsdr_get_frequency(self._h)))
+    tuner_gain = property(lambda self: int(lib().rfm_rtlsdr_get_tuner_gain(self._h)))
+    block_length = property(lambda self: int(lib().rfm_rtlsdr_block_length(self._h)))
+    restarts = property(lambda self: int(lib().rfm_rtlsdr_restarts(self._h)))
+
+    def set_frequency(self, f: int):
+        lib().rfm_rtlsdr_set_frequency(self._h, f)
 
 
 class Demux:

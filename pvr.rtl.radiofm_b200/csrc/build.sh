@@ -23,7 +23,7 @@ for f in rfm_kernels rfm_api rfm_probe rfm_freqshift rfm_downconvert rfm_primiti
   $NVCC $NVFLAGS -c $f.cu -o $B/$f.o &
   pids="$pids $!"
 done
-for f in rfm_plan rfm_rdssync rfm_rdsgroup; do
+for f in rfm_plan rfm_rdssync rfm_rdsgroup rfm_source; do
   g++ $CXXFLAGS -c $f.cpp -o $B/$f.o &
   pids="$pids $!"
 done
@@ -32,5 +32,5 @@ pids="$pids $!"
 for p in $pids; do
   wait $p
 done
-$NVCC $ARCH -shared -o $OUT $B/rfm_kernels.o $B/rfm_api.o $B/rfm_probe.o $B/rfm_freqshift.o $B/rfm_downconvert.o $B/rfm_primitives.o $B/rfm_plan.o $B/rfm_rdssync.o $B/rfm_rdsgroup.o $B/rfm_demux.o -lcudart_static -lpthread -ldl -lrt
+$NVCC $ARCH -shared -o $OUT $B/rfm_kernels.o $B/rfm_api.o $B/rfm_probe.o $B/rfm_freqshift.o $B/rfm_downconvert.o $B/rfm_primitives.o $B/rfm_plan.o $B/rfm_rdssync.o $B/rfm_rdsgroup.o $B/rfm_source.o $B/rfm_demux.o -lcudart_static -lpthread -ldl -lrt
 echo "built $(readlink -f $OUT)"

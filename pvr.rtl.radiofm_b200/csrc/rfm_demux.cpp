@@ -17,6 +17,7 @@
 
 #include <chrono>
 #include <condition_variable>
+#include <atomic>
 #include <deque>
 #include <mutex>
 #include <vector>
@@ -46,7 +47,7 @@ struct rfm_demux
   size_t queued_samples = 0;
   bool end_marked = false;
   // ---- demux side (one thread)
-  bool stream_change = true;          // OpenLiveStream sets it, RadioReceiver.cpp:345
+  std::atomic<bool> stream_change{true}; // OpenLiveStream sets it, RadioReceiver.cpp:345 (any thread: SetStreamChange)
   double pts_next = kStreamTimeBase;  // :347
   float audio_level = 0.0f;           // :188
   std::vector<uint8_t> uecp;          // m_UECPOutputBuffer
@@ -370,7 +371,14 @@ uint64_t rfm_demux_short_reads(rfm_demux* m)
   return m->short_reads;
 }
 
-float rfm_demux_audio_level(const rfm_demux* m) { return m ? m->audio_level : 0.0f; }
+float rfm_demux_audio_level(const rfm_demux* m)
+{
+  if (!m)
+    return 0.0f;
+  rfm_demux* mm = const_cast<rfm_demux*>(m);
+  std::lock_guard<std::mutex> lock(mm->mu);
+  return mm->st_valid ? mm->st_audio_level : 0.0f; // the value cached when the last block was collected (any thread)
+}
 
 /* GetSignalStatus, RadioReceiver.cpp:544-556: interface level and audio level in dB, stereo flag */
 int rfm_demux_signal_status(rfm_demux* m, float* interface_level, float* audio_level_db, int* stereo)

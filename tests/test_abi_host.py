@@ -163,3 +163,16 @@ def test_source_block_length_rule(rfm):
                       (65536, 65536), (65537, 65536), (100000, 98304), (1 << 20, 1 << 20), ((1 << 20) + 1, 1 << 20),
                       (0xFFFFFFFF, 1 << 20)):
         assert L.rfm_source_block_length(req) == want, (req, want)
+
+
+def test_rtlsdr_adapter_binds_librtlsdr_at_run_time(rfm, tmp_path):
+    """SURVEY.md 8f N4 (host logic, no GPU): librtlsdr is dlopen-ed -- absent, the calls answer RFM_ERR_UNSUPPORTED and
+    nothing else breaks; present (here: the stand-in tests/cpp/fake_rtlsdr.c) every entry point the adapter needs resolves."""
+    import ctypes as C
+    import subprocess
+    L = rfm.lib()
+    L.rfm_rtlsdr_device_count.argtypes = [C.c_char_p]
+    assert L.rfm_rtlsdr_device_count(str(tmp_path / "absent.so").encode()) == -3
+    so = tmp_path / "libfake_rtlsdr.so"
+    subprocess.check_call(["gcc", "-O1", "-shared", "-fPIC", os.path.join(ROOT, "tests", "cpp", "fake_rtlsdr.c"), "-o", str(so)])
+    assert L.rfm_rtlsdr_device_count(str(so).encode()) == 1

@@ -110,6 +110,6 @@ def test_tma_is_really_used():
             for op in ("UTMALDG", "SYNCS", "LDG.E.128"):
                 if op in line:
                     ops.setdefault(cur, set()).add(op)
-    assert len(ops) == 3, sorted(ops)   # ds = 1, 5, 11
+    assert len(ops) == 6, sorted(ops)   # ds = 1, 5, 11, exact and fused
     for k, v in ops.items():
         assert "UTMALDG" in v and "SYNCS" in v and "LDG.E.128" not in v, (k, v)

@@ -3,12 +3,13 @@
 same packet order, ids, sizes, pts / duration (exact doubles), bit-identical audio, identical UECP bytes."""
 from __future__ import annotations
 
+import os
 import threading
 
 import numpy as np
 import pytest
 
-from conftest import station
+from conftest import ROOT, station
 
 pytestmark = pytest.mark.gpu
 
@@ -133,3 +134,58 @@ def test_source_callback_block_rule_and_short_reads(rfm):
             break
         want.append(p)
     same_packets(read_all(dm), want)
+
+
+def test_rtlsdr_source_adapter_against_a_stand_in_library(rfm, tmp_path):
+    """cRtlSdrSource end to end: librtlsdr is bound with dlopen, so a stand-in library
+    (tests/cpp/fake_rtlsdr.c, a file player) exercises the adapter -- Open, Configure's call sequence and block-length
+    rule, the reader thread around rtlsdr_read_async, the short read it must drop, the restart after a failed read,
+    Close -- and the packets that come out of the demux are the oracle's."""
+    import subprocess
+    from oracle import demux_port
+    so = tmp_path / "libfake_rtlsdr.so"
+    subprocess.check_call(["gcc", "-O1", "-shared", "-fPIC", os.path.join(ROOT, "tests", "cpp", "fake_rtlsdr.c"), "-o", str(so)])
+    fs, ds, blk, nblk = 1.0e6, 4, 65536, 4
+    iq, _ = station("1.0M", nblk)
+    (tmp_path / "iq.bin").write_bytes(iq.tobytes())
+    os.environ["FAKE_RTLSDR_FILE"] = str(tmp_path / "iq.bin")
+    os.environ["FAKE_RTLSDR_LOG"] = str(tmp_path / "calls.log")
+    os.environ["FAKE_RTLSDR_FAIL"] = "1"
+    try:
+        dm = rfm.Demux(fs, -0.15 * fs, downsample=ds, max_block_len=blk)
+        src = rfm.RtlSdrSource(dm, str(so), 0)
+        src.configure(1000000, 98500000, tuner_gain=297, block_length=blk + 1000, agcmode=True)   # 66536 -> 65536
+        assert (src.block_length, src.sample_rate, src.frequency, src.tuner_gain) == (blk, 1000000, 98500000, 297)
+        om = demux_port.OracleDemux(fs, -0.15 * fs, downsample=ds)
+        for b in range(nblk):
+            om.write_u8(iq[b * blk:(b + 1) * blk])
+        want = []
+        while True:
+            p = om.read()
+            if p is None:
+                break
+            want.append(p)
+        got = []
+        while sum(1 for q in got if q[0] == 1) < nblk:     # the file player never ends by itself: read what it holds
+            p = dm.read()
+            assert p is not None
+            got.append(p)
+        src.set_frequency(101300000)
+        assert src.frequency == 101300000 and src.restarts == 1 and dm.short_reads() == 1
+        src.close()                                          # cancel_async, join, EndDataBuffer
+        while True:
+            p = dm.read()
+            if p is None:
+                break
+            got.append(p)
+        same_packets(got, want)
+        calls = (tmp_path / "calls.log").read_text().split("\n")
+        first = [c for c in calls if c][:8]
+        assert first == ["open 0", "sample_rate 1000000", "center_freq 98500000", "gain_mode 1", "gain 297", "agc 1",
+                         "reset_buffer", f"read_async 15 {2 * blk}"], first
+        assert "close" in calls
+        with pytest.raises(rfm.RadioFmError):
+            rfm.RtlSdrSource(dm, str(tmp_path / "no_such_library.so"), 0)
+    finally:
+        for k in ("FAKE_RTLSDR_FILE", "FAKE_RTLSDR_LOG", "FAKE_RTLSDR_FAIL"):
+            os.environ.pop(k, None)
