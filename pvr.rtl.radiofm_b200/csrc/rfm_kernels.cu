@@ -1028,7 +1028,7 @@ struct LanesSmem
 // FAKE_SINCOS: RFM_DEBUG_FAKE_SINCOS timing experiment (wrong results, experiments build only).  IMMBAR: barrier ids as
 // immediates (5 named barriers per CTA instead of the 16 ptxas reserves for register ids, so up to 12 CTAs fit on an
 // SM; same hand-off) -- the product form; the register-id form remains as an experiment (RFM_LANES_REGBAR).
-template <bool FAKE_SINCOS, bool IMMBAR = false, bool SPEC = false>
+template <bool FAKE_SINCOS, bool IMMBAR = false, bool SPEC = false, bool XUFREE = false>
 __global__ void __launch_bounds__(64) k_bb_lanes(LanesParams p)
 {
   __shared__ LanesSmem sm;
@@ -1085,7 +1085,37 @@ __global__ void __launch_bounds__(64) k_bb_lanes(LanesParams p)
       __syncwarp();
       if (t >= 2)
         sync_bar(BAR_EMPTY, b);
-      if (valid)
+      if (XUFREE)
+      {
+        // conversions on the integer pipe (rfm_math.cuh); a flagged tile is replayed with the conversion instructions
+        const float dc0 = dc, vs0 = vsum, vq0 = vsumsq;
+        bool bad = false;
+        if (valid)
+        {
+          for (unsigned k = 0; k < tn; ++k)
+          {
+            const float bb = demod_output_bits(sm.win[b][lane][k], dc, p.demod.gain, bad);
+            vsum = addf(vsum, bb);
+            vsumsq = addf(vsumsq, mulf(bb, bb));
+            sm.ring[b][lane][k] = bb;
+          }
+        }
+        if (__any_sync(0xffffffffu, bad))
+        {
+          dc = dc0; vsum = vs0; vsumsq = vq0;
+          if (valid)
+          {
+            for (unsigned k = 0; k < tn; ++k)
+            {
+              const float bb = demod_output(sm.win[b][lane][k], dc, p.demod.gain);
+              vsum = addf(vsum, bb);
+              vsumsq = addf(vsumsq, mulf(bb, bb));
+              sm.ring[b][lane][k] = bb;
+            }
+          }
+        }
+      }
+      else if (valid)
       {
         for (unsigned k = 0; k < tn; ++k)
         {
@@ -1189,7 +1219,7 @@ __global__ void __launch_bounds__(64) k_bb_lanes(LanesParams p)
           for (unsigned k = 0; k < tn; ++k)
           {
             const float bb = sm.ring[b][lane][k];
-            const float p38 = pilot_step_fast<FAKE_SINCOS>(pl, bb, pk, sca, bad);
+            const float p38 = pilot_step_fast<FAKE_SINCOS, XUFREE>(pl, bb, pk, sca, bad);
             sm.rawt[lane][k] = mulf(p38, mulf(2.0f, bb)); // FmDecode.cpp:455-456
           }
         }
@@ -1281,6 +1311,10 @@ void launch_bb_lanes(const LanesParams& p_in, cudaStream_t st)
   static const bool spec = KnobInt(RFM_KNOB("RFM_LANES_SPEC"), 0) != 0;
   if (spec)
     return (void)k_bb_lanes<false, true, true><<<cdiv(p.S, 32), 64, 0, st>>>(p);
+  static const int xufree = KnobInt(RFM_KNOB("RFM_LANES_XUFREE"), 0);
+  if (xufree == 1)
+    return p.packed ? (void)k_bb_lanes<false, true, false, true><<<cdiv(p.S, 32), 64, 0, st>>>(p)
+                    : (void)k_bb_lanes<false, false, false, true><<<cdiv(p.S, 32), 64, 0, st>>>(p);
   static const int immbar = KnobInt(RFM_KNOB("RFM_LANES_IMMBAR"), -1);
   if (immbar == 1)
     return (void)k_bb_lanes<false, true><<<cdiv(p.S, 32), 64, 0, st>>>(p);
@@ -1290,6 +1324,9 @@ void launch_bb_lanes(const LanesParams& p_in, cudaStream_t st)
   // Barrier ids as immediates let up to 12 lanes CTAs share an SM, which is what an SM partition of a few SMs needs;
   // without a partition that packing is harmful (co-resident pilot warps queue for the SM's one conversion / MUFU
   // pipe: 2.28 ms per step against 2.08), and the register-id form's 16 reserved barriers keep it at 4 CTAs per SM.
+  // (The conversions of the pilot / DC-tracker steps on the integer pipe -- rfm_f2d_bits / rfm_d2f_bits, bit-exact --
+  // were measured too, RFM_LANES_XUFREE=1 in the experiments build: 130 + 57 instructions per sample instead of
+  // 94 + 16 trade the XU queue for the half-rate ALU pipe and lose: 1.83 ms on 24 SMs against 1.44.)
   if (p.packed)
     k_bb_lanes<false, true><<<cdiv(p.S, 32), 64, 0, st>>>(p);
   else

@@ -77,6 +77,20 @@ RFM_HD float demod_output(float incr, float& dc, float gain)
   return mulf(subf(pinc, dc), gain);
 }
 
+// The same with the three conversions on the integer pipe (rfm_math.cuh: rfm_f2d_bits / rfm_d2f_bits); `bad` -> replay
+RFM_HD float demod_output_bits(float incr, float& dc, float gain, bool& bad)
+{
+  const float pinc = mulf(2.0f, incr);
+  const double v = addd(muld(1 - 0.0001, rfm_f2d_bits(dc, bad)), muld(0.0001, rfm_f2d_bits(pinc, bad)));
+  // the tracker's value is tiny and may be zero at a stream's start: zero is not "normal" for the narrowing
+  bool nb = false;
+  const float f = rfm_d2f_bits(v, nb);
+  const bool vz = v == 0.0;
+  bad = bad | (nb & !vz);
+  dc = vz ? u2f(rfm_d_hi(v) & 0x80000000u) : f;
+  return mulf(subf(pinc, dc), gain);
+}
+
 // ---- 19 kHz pilot PLL, cPilotPhaseLock::Process loop body (FmDecode.cpp:149-216); returns sin(2 phi) -------------
 struct PilotState
 {
@@ -115,7 +129,7 @@ RFM_HD float pilot_step(PilotState& st, float x, const PilotConstDev& k)
 
 // FAKE_SINCOS: timing experiment only (RFM_DEBUG_FAKE_SINCOS: what would a shorter pilot chain buy?) -- the hardware's
 // approximate sincos, results are NOT the reference's
-template <bool FAKE_SINCOS = false>
+template <bool FAKE_SINCOS = false, bool XUFREE = false>
 RFM_HD float pilot_step_fast(PilotState& st, float x, const PilotConstDev& k, const SinCosRegs& sca, bool& bad)
 {
   float ps, pc;
@@ -125,6 +139,12 @@ RFM_HD float pilot_step_fast(PilotState& st, float x, const PilotConstDev& k, co
     __sincosf(st.phase, &ps, &pc);
   else
 #endif
+  if (XUFREE)
+  {
+    bad = bad | (st.phase == 0.0f);        // sin(+-0): the narrowing has no zero; the replay handles it
+    rfm_sincos_core_b(st.phase, sca, &ps, &pc, bad);
+  }
+  else
     rfm_sincos_core_a(st.phase, sca, &ps, &pc);
   const float out = mulf(mulf(2.0f, ps), pc);
   float pi = mulf(ps, x);

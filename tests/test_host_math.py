@@ -61,6 +61,26 @@ unsigned long long cmp_atan2f_generic(const float* y, const float* x, unsigned n
   }
   return bad;
 }
+// integer-pipe conversions (rfm_f2d_bits / rfm_d2f_bits) and the routines built on them, against the conversion
+// instructions: returns unflagged mismatches; *flagged gets the number of operands the bit forms refused
+unsigned long long cmp_bit_conversions(const unsigned* fbits, const double* d, unsigned n, unsigned long long* flagged) {
+  unsigned long long bad = 0; *flagged = 0;
+  const rfm::SinCosRegs R = rfm::rfm_sincos_regs();
+  for (unsigned i = 0; i < n; ++i) {
+    bool f1 = false; const float x = rfm::u2f(fbits[i]);
+    const double w = rfm::rfm_f2d_bits(x, f1); const double we = (double)x;
+    if (f1) ++*flagged; else bad += memcmp(&w, &we, 8) != 0;
+    bool f2 = false; const float nrw = rfm::rfm_d2f_bits(d[i], f2);
+    if (f2) ++*flagged; else bad += rfm::f2u(nrw) != rfm::f2u((float)d[i]);
+    const float ph = fabsf(x) < 6.9f ? fabsf(x) : (float)fmod(fabs((double)x), 6.9);
+    if (ph == ph && ph != 0.0f) {
+      bool f3 = false; float s, c, es, ec;
+      rfm::rfm_sincos_core_b(ph, R, &s, &c, f3); rfm::rfm_sincos_core_a(ph, R, &es, &ec);
+      if (f3) ++*flagged; else bad += rfm::f2u(s) != rfm::f2u(es) || rfm::f2u(c) != rfm::f2u(ec);
+    }
+  }
+  return bad;
+}
 unsigned long long cmp_fmod(const float* p, unsigned n) {
   unsigned long long bad = 0;
   const float twopif = (float)RFM_K_2PI;
@@ -84,7 +104,8 @@ def shim(tmp_path_factory):
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++",
                            "-I", os.path.join(ROOT, "pvr.rtl.radiofm_b200", "csrc"), str(src), "-o", str(so), "-lm"])
     L = C.CDLL(str(so))
-    for f in (L.cmp_atan2f, L.cmp_sincos, L.cmp_fmod, L.cmp_wraps, L.cmp_sincos_generic, L.cmp_atan2f_generic):
+    for f in (L.cmp_atan2f, L.cmp_sincos, L.cmp_fmod, L.cmp_wraps, L.cmp_sincos_generic, L.cmp_atan2f_generic,
+              L.cmp_bit_conversions):
         f.restype = C.c_ulonglong
     return L
 
@@ -170,3 +191,23 @@ def test_osc_gain_float_form_is_exact():
     r = (s + (e + cl).astype(f)).astype(f)
     assert q.size == 14176749
     assert np.array_equal(r.view(np.uint32), ref.view(np.uint32))
+
+
+def test_integer_pipe_conversions_are_exact_or_flagged(shim):
+    """rfm_f2d_bits / rfm_d2f_bits (float <-> double as bit manipulation, for the XU-free lanes experiment) and
+    rfm_sincos_core_b on top of them: bit-identical to the conversion instructions wherever they do not raise the
+    replay flag -- random bit patterns, doubles across and beyond the float range, exact ties and near-ties."""
+    rng = np.random.default_rng(7)
+    n = 4_000_000
+    fbits = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    f = (rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32) & np.uint32(0xbfffffff)).view(np.float32)
+    ulp = (np.nextafter(f, np.float32(np.inf)).astype(np.float64) - f.astype(np.float64))
+    k = rng.integers(-2, 3, n)
+    d = f.astype(np.float64) + 0.5 * ulp + k * ulp * 2.0 ** -29          # around the rounding boundary, ties included
+    wide = rng.integers(0, 1 << 63, n // 4, dtype=np.uint64).view(np.float64)
+    d[: n // 4] = np.where(np.isfinite(wide), wide, 1.0)
+    d = np.ascontiguousarray(np.nan_to_num(d, nan=1.0, posinf=3e38, neginf=-3e38))
+    flagged = C.c_ulonglong(0)
+    bad = shim.cmp_bit_conversions(fbits.ctypes.data_as(C.POINTER(C.c_uint)), d.ctypes.data_as(C.POINTER(C.c_double)), n,
+                                   C.byref(flagged))
+    assert bad == 0 and 0 < flagged.value < n
