@@ -2,8 +2,9 @@
 (RadioReceiver.cpp:420-542, audio level :528-529 / :584-598), composed from the oracle's own cFmDecoder restatement
 (oracle/port.py) and group decoder restatement (oracle/uecp_port.py).
 
-TEST INFRASTRUCTURE ONLY -- see oracle/README.md.  RadioReceiver.cpp cannot be compiled here (Kodi PVR dev-kit,
-librtlsdr): parity unpinned for these ~80 lines of sequencing; what they sequence (audio, groups, frames) is pinned.
+TEST INFRASTRUCTURE ONLY -- see oracle/README.md.  Parity pinned: tests/test_ref_addon.py runs this restatement
+against the UNMODIFIED RadioReceiver.cpp / RTL_SDR_Source.cpp compiled in place (oracle/ref_addon_harness.cpp) --
+packet order, ids, pts / duration, audio bits, UECP bytes, audio level.
 """
 from __future__ import annotations
 

@@ -12,7 +12,8 @@
 //     reference's return rule, RadioReceiver.cpp:600-612: false while a settings dialog is registered);
 //   * IsSettingActive() is the reference's own inline (m_SettingsDialog != nullptr) reading a zeroed stand-in object
 //     whose m_SettingsDialog this harness sets; no cRadioReceiver is ever constructed.
-// The transport framing of RadioReceiver.cpp:387-414 is therefore NOT covered by this library ("parity unpinned" for
+// The transport framing of RadioReceiver.cpp:387-414 is therefore NOT covered by THIS library (ref_addon_harness.cpp,
+// which compiles RadioReceiver.cpp itself against a fuller stand-in dev-kit, covers it; here: "parity unpinned" for
 // those lines: they are restated in oracle/uecp_port.py and checked against hand-made vectors).
 // The decoder object is placement-constructed in zeroed storage: the members its constructor and Reset() leave
 // uninitialised (m_PTY, m_DI_Finished, m_RadioText_ABFlag, m_PTYN_ABFlag, m_UECPDataFrameSeqCnt) start at zero.

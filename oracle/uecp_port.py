@@ -4,8 +4,8 @@ transport framing of cRadioReceiver::AddUECPDataFrame (RadioReceiver.cpp:387-414
 TEST INFRASTRUCTURE ONLY -- see oracle/README.md.  Pure Python (11 groups/s per stream: small cases only).
 Pin: tests/test_uecp.py checks it frame for frame against the compiled reference (oracle/ref_uecp.py) where that
 library exists, and against tests/golden/uecp_kat.npz (generated from the compiled reference by
-tests/golden/make_golden_uecp.py) everywhere.  The framing (stuff_frame) has no compiled counterpart
-(RadioReceiver.cpp needs the Kodi dev-kit): parity unpinned for those 12 lines, checked on hand-made vectors.
+tests/golden/make_golden_uecp.py) everywhere.  The framing (stuff_frame) is checked on hand-made
+vectors and, through oracle/demux_port.py, against RadioReceiver.cpp compiled in place (tests/test_ref_addon.py).
 Members the reference leaves uninitialised start at zero (the compiled reference is constructed in zeroed storage).
 """
 from __future__ import annotations

@@ -388,10 +388,12 @@ int rfm_demux_signal_status(rfm_demux* m, float* interface_level, float* audio_l
   std::lock_guard<std::mutex> lock(m->mu);
   if (!m->st_valid)
     return RFM_ERR_INVALID; // the reference returns false until the first DemuxRead
+  // the reference's operands are float: log10 resolves to the float overload, the product by 20 is a float product, and
+  // only "+ 3.01" is done in double (pinned against the compiled add-on: tests/test_ref_addon.py, test_gpu_demux.py)
   if (interface_level)
-    *interface_level = (float)(20 * log10((double)m->st_interface_level));
+    *interface_level = 20 * log10f(m->st_interface_level);
   if (audio_level_db)
-    *audio_level_db = (float)(20 * log10((double)m->st_audio_level) + 3.01);
+    *audio_level_db = (float)(20 * log10f(m->st_audio_level) + 3.01);
   if (stereo)
     *stereo = m->st_stereo;
   return RFM_OK;

@@ -189,3 +189,58 @@ def test_rtlsdr_source_adapter_against_a_stand_in_library(rfm, tmp_path):
     finally:
         for k in ("FAKE_RTLSDR_FILE", "FAKE_RTLSDR_LOG", "FAKE_RTLSDR_FAIL"):
             os.environ.pop(k, None)
+
+
+def test_demux_and_source_adapter_against_the_compiled_reference_addon(rfm, tmp_path):
+    """The product against the UNMODIFIED reference add-on itself (oracle/ref_addon_harness.cpp: cRadioReceiver +
+    cRtlSdrSource + cFmDecoder + the RDS chain, every source file compiled in place): the device-configuration calls of
+    OpenLiveStream / Configure, then every DemuxRead packet -- order, ids, pts / duration, audio bits, UECP bytes -- the
+    audio level and the signal status in dB."""
+    import subprocess
+    from oracle import ref_addon
+    if not ref_addon.available():
+        pytest.skip("oracle/_ref/libradiofm_ref_addon.so not built")
+    nblk = 8
+    iq, _ = station("1.0M", nblk)
+    addon = ref_addon.RefAddon(100.0e6)
+    assert addon.open()
+    par = addon.params()
+    fs, off, ds, blk = par["if_rate"], par["tuning_offset"], par["downsample"], par["block_length"]
+    # the source adapter, configured the way OpenLiveStream configures cRtlSdrSource, talks to its device identically
+    so = tmp_path / "libfake_rtlsdr.so"
+    subprocess.check_call(["gcc", "-O1", "-shared", "-fPIC", os.path.join(ROOT, "tests", "cpp", "fake_rtlsdr.c"), "-o", str(so)])
+    (tmp_path / "iq.bin").write_bytes(iq[:nblk * blk].tobytes())
+    os.environ["FAKE_RTLSDR_FILE"] = str(tmp_path / "iq.bin")
+    os.environ["FAKE_RTLSDR_LOG"] = str(tmp_path / "calls.log")
+    try:
+        dm = rfm.Demux(fs, off, downsample=ds, max_block_len=blk)
+        src = rfm.RtlSdrSource(dm, str(so), 0)
+        src.configure(int(fs), int(par["tuner_freq"]), tuner_gain=197, block_length=65536, agcmode=True)
+        assert src.block_length == blk
+        for b in range(nblk):
+            addon.feed(iq[b * blk:(b + 1) * blk], short_read_after_next=(b == 0))   # the file player does the same
+        want = addon.read_all()
+        got = []
+        while sum(1 for q in got if q[0] == 1) < nblk:
+            p = dm.read()
+            assert p is not None
+            got.append(p)
+        src.close()
+        while True:
+            p = dm.read()
+            if p is None:
+                break
+            got.append(p)
+        same_packets(got, want)
+        calls = [c for c in (tmp_path / "calls.log").read_text().split("\n") if c]
+        assert calls[:8] == addon.device_log()[:8]
+        assert np.float32(dm.audio_level()) == addon.audio_level()
+        il, al, stereo = dm.signal_status()
+        sig = addon.signal()
+        assert (np.float32(il), np.float32(al), bool(stereo)) == \
+            (np.float32(sig["if_level_db"]), np.float32(sig["audio_level_db"]), sig["stereo"])
+    finally:
+        for k in ("FAKE_RTLSDR_FILE", "FAKE_RTLSDR_LOG"):
+            os.environ.pop(k, None)
+        addon.close()
+        addon.destroy()
