@@ -236,7 +236,7 @@ def single_stream_leg(rfm, local):
                     "chain (block latency, ~20 kernel launches); the batch is where the GPU pays"}
 
 
-def c5_leg(torch, rfm, rank, world, local, barrier, max_over_ranks, steps=4, warmup=2):
+def c5_leg(torch, rfm, rank, world, local, barrier, max_over_ranks, steps=12, warmup=3):
     """BASELINE.json configs[4]: one shared 50 MS/s capture, 100 stations on a 200 kHz raster sharded over the ranks
     (no collective; every rank reads the same capture), both mixers.  One step = one demodulator call = 64 front-end
     blocks of 32000 capture samples (41 ms of signal)."""

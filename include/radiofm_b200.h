@@ -165,6 +165,12 @@ RFM_API int rfm_plan_table(const rfm_config* cfg, int which, float* out, uint32_
  * (index 0 synchronises and collects).  No reference counterpart (the reference only has commented-out
  * StartPerformance()/StopPerformance() hooks, DownConvert.cpp:418,487). */
 RFM_API int rfm_decoder_set_profiling(rfm_decoder* d, int on);
+/* A CUDA stream (cudaStream_t, owned by the decoder) on the FIR side of the decoder's SM partition -- an ordinary
+ * non-blocking stream when rfm_config::lanes_sms leaves the decoder unpartitioned -- for the caller's own kernels that
+ * produce the decoder's device input (rfm_downconvert / rfm_freqshift in front of rfm_decoder_process_cf32_device: the
+ * composition of CRDSDownConvert::ProcessData and cFmDecoder::ProcessStream).  Work launched there never shares an SM
+ * with the latency-bound lanes kernel (cPilotPhaseLock::Process and the other per-stream recurrences, FmDecode.cpp:149-216). */
+RFM_API int rfm_decoder_companion_stream(rfm_decoder* d, void** stream);
 RFM_API int rfm_decoder_profile_read(rfm_decoder* d, uint32_t index, char* name, uint32_t name_cap,
                                      double* total_ms, uint64_t* launches);
 

@@ -55,6 +55,7 @@ EXPORTED_SYMBOLS = (
     "rfm_rtlsdr_get_frequency", "rfm_rtlsdr_set_frequency", "rfm_rtlsdr_get_tuner_gain", "rfm_rtlsdr_block_length",
     "rfm_rtlsdr_restarts", "rfm_rtlsdr_error",
     "rfm_decoder_constants", "rfm_decoder_table", "rfm_plan_constants", "rfm_plan_table", "rfm_decoder_set_profiling",
+    "rfm_decoder_companion_stream",
     "rfm_decoder_profile_read", "rfm_decoder_tap", "rfm_rdssync_create",
     "rfm_rdssync_destroy", "rfm_rdssync_reset", "rfm_rdssync_push_bits", "rfm_rdssync_take_groups",
     "rfm_rds_check_block", "rfm_math_probe", "rfm_div_selftest", "rfm_freqshift_create",
@@ -174,6 +175,7 @@ def lib():
         L.rfm_plan_constants.argtypes = [C.POINTER(RfmConfig), _f64p, C.c_uint32]
         L.rfm_plan_table.argtypes = [C.POINTER(RfmConfig), C.c_int, _f32p, C.c_uint32, _u32p]
         L.rfm_decoder_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        L.rfm_decoder_companion_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.rfm_decoder_profile_read.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_uint32, _f64p,
                                                C.POINTER(C.c_uint64)]
         L.rfm_decoder_tap.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, _f32p, C.c_uint32, _u32p]
@@ -248,6 +250,16 @@ def lib():
     return _lib
 
 
+def _quiet_del(close):
+    """__del__ form of a close() method: at interpreter shutdown the module globals may already be gone"""
+    def __del__(self):
+        try:
+            close(self)
+        except TypeError:
+            pass
+    return __del__
+
+
 def _check(rc: int):
     if rc != RFM_OK:
         raise RadioFmError(f"radiofm_b200 error {rc}: {lib().rfm_last_error().decode()}")
@@ -311,7 +323,7 @@ class FmDecoderBatch:
             lib().rfm_decoder_destroy(self._h)
             self._h = None
 
-    __del__ = close
+    __del__ = _quiet_del(close)
 
     def reset(self):
         _check(lib().rfm_decoder_reset(self._h))
@@ -395,6 +407,12 @@ class FmDecoderBatch:
                 "bb_level": np.float32(s.baseband_level), "bb_mean": np.float32(s.baseband_mean),
                 "pilot_level": np.float32(s.pilot_level), "tuning_offset": np.float32(s.tuning_offset)}
 
+    def companion_stream(self) -> int:
+        """cudaStream_t (as an int) on the FIR side of the decoder's SM partition, for the kernels that make its input."""
+        st = C.c_void_p()
+        _check(lib().rfm_decoder_companion_stream(self._h, C.byref(st)))
+        return int(st.value or 0)
+
     def set_profiling(self, on: bool):
         _check(lib().rfm_decoder_set_profiling(self._h, int(on)))
 
@@ -446,7 +464,7 @@ class RdsBlockSync:
             lib().rfm_rdssync_destroy(self._h)
             self._h = None
 
-    __del__ = close
+    __del__ = _quiet_del(close)
 
     def reset(self):
         lib().rfm_rdssync_reset(self._h)
@@ -486,7 +504,7 @@ class RdsGroupDecoder:
             lib().rfm_rdsgroup_destroy(self._h)
             self._h = None
 
-    __del__ = close
+    __del__ = _quiet_del(close)
 
     def reset(self):
         lib().rfm_rdsgroup_reset(self._h)
@@ -539,7 +557,7 @@ class RtlSdrSource:
             lib().rfm_rtlsdr_close(self._h)
             self._h = None
 
-    __del__ = close
+    __del__ = _quiet_del(close)
 
     sample_rate = property(lambda self: int(lib().rfm_rtlsdr_get_sample_rate(self._h)))
     frequency = property(lambda self: int(lib().rfm_rtlsdr_get_frequency(self._h)))
@@ -565,7 +583,7 @@ class Demux:
             lib().rfm_demux_destroy(self._h)
             self._h = None
 
-    __del__ = close
+    __del__ = _quiet_del(close)
 
     def write_u8(self, iq_u8: np.ndarray):
         iq_u8 = np.ascontiguousarray(iq_u8, dtype=np.uint8).reshape(-1, 2)
@@ -638,7 +656,7 @@ class FreqShiftBatch:
             lib().rfm_freqshift_destroy(self._h)
             self._h = None
 
-    __del__ = close
+    __del__ = _quiet_del(close)
 
     def reset(self):
         _check(lib().rfm_freqshift_reset(self._h))
@@ -680,7 +698,7 @@ class DownConvertBatch:
             lib().rfm_downconvert_destroy(self._h)
             self._h = None
 
-    __del__ = close
+    __del__ = _quiet_del(close)
 
     def reset(self):
         _check(lib().rfm_downconvert_reset(self._h))
@@ -734,7 +752,7 @@ class _RowFilter:
             getattr(lib(), f"rfm_{self._kind}_destroy")(self._h)
             self._h = None
 
-    __del__ = close
+    __del__ = _quiet_del(close)
 
     def process_real(self, x: np.ndarray) -> np.ndarray:
         x = np.array(x, dtype=np.float32, order="C").reshape(self.rows, -1)
@@ -820,7 +838,7 @@ class DownsampleFilterBatch:
             lib().rfm_downsample_destroy(self._h)
             self._h = None
 
-    __del__ = close
+    __del__ = _quiet_del(close)
 
     def reset(self):
         _check(lib().rfm_downsample_reset(self._h))
@@ -862,7 +880,7 @@ class RdsProcessorBatch:
             lib().rfm_rdsproc_destroy(self._h)
             self._h = None
 
-    __del__ = close
+    __del__ = _quiet_del(close)
 
     def reset(self):
         _check(lib().rfm_rdsproc_reset(self._h))

@@ -161,6 +161,7 @@ struct rfm_decoder
   DevBuf<int> res_meta[3];
   unsigned res_lp = 0;
   cudaStream_t s_osc = nullptr;
+  cudaStream_t s_companion = nullptr; // rfm_decoder_companion_stream: created on first use
   cudaEvent_t ev_osc[3] = {nullptr, nullptr, nullptr};
   uint64_t block_index = 0; // blocks enqueued so far; parity selects the double buffers
   std::vector<Group> groups;
@@ -317,6 +318,8 @@ void FreeDecoder(rfm_decoder* d)
       cudaEventDestroy(e);
   if (d->s_osc)
     cudaStreamDestroy(d->s_osc);
+  if (d->s_companion)
+    cudaStreamDestroy(d->s_companion);
   if (d->h_drain)
     cudaFreeHost(d->h_drain);
   FreeSmPartition(&d->part);
@@ -1147,7 +1150,9 @@ int rfm_decoder_create(const rfm_config* cfg, rfm_decoder** out)
       // sA (demodulator + lanes) is the critical chain, the front end feeds it; the audio / RDS branches have slack
       const char* flow = RFM_KNOB("RFM_DEBUG_FLOW");
       const int mode = KnobInt(flow, 0);
-      int pA = prio_hi, pF = std::min(prio_lo, prio_hi + 1), pB = prio_lo;
+      // (stage B one step above the lowest priority: the lowest is left to the companion stream, whose long-running
+      // front-end CTAs otherwise keep the small stage-B kernels of a narrow batch waiting for an SM slot for milliseconds)
+      int pA = prio_hi, pF = std::min(prio_lo, prio_hi + 1), pB = (prio_lo - 1 > prio_hi + 1) ? prio_lo - 1 : prio_lo;
       int pL = KnobInt(RFM_KNOB("RFM_DEBUG_LANEPRIO"), 0) + prio_hi; // small lane kernels of stage B
       if (mode == 1) { pF = prio_lo; }
       if (mode == 2) { pF = prio_lo; pB = std::min(prio_lo, prio_hi + 1); }
@@ -1522,6 +1527,24 @@ int rfm_decoder_table(const rfm_decoder* d, int which, float* out, uint32_t max_
   if (!d)
     return Fail(RFM_ERR_INVALID, "bad argument");
   return PlanTable(d->plan, which, out, max_floats, n);
+}
+
+/* A stream on the FIR side of the decoder's SM partition (an ordinary non-blocking stream when the decoder has none),
+ * for the caller's own kernels that produce the decoder's input (e.g. rfm_downconvert in front of
+ * rfm_decoder_process_cf32_device): what runs there never shares an SM with the lanes kernel.  Owned by the decoder. */
+int rfm_decoder_companion_stream(rfm_decoder* d, void** stream)
+{
+  if (!d || !stream)
+    return Fail(RFM_ERR_INVALID, "bad argument");
+  if (!d->s_companion)
+  {
+    RFM_CUDA(cudaSetDevice(d->device));
+    int prio_lo = 0, prio_hi = 0;
+    RFM_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    RFM_CUDA(MakeStream(d->part.rest, &d->s_companion, prio_lo));
+  }
+  *stream = d->s_companion;
+  return RFM_OK;
 }
 
 int rfm_decoder_set_profiling(rfm_decoder* d, int on)

@@ -409,8 +409,23 @@ __global__ void __launch_bounds__(kDcThreads) k_dc_chain_uniform(DcParams p, DcT
     const bool store = pos >= c_lo;
     const unsigned tn = min(kDcTileFast, (store ? c_hi : c_lo) - pos);
     // mix; V index 2 * HH + i: even i -> E[HH + i / 2], odd i -> O[HH + i / 2]
-    for (unsigned i = tid; i < tn; i += kDcThreads)
-      ((i & 1u) ? O_(0) : E_(0))[HH + (i >> 1)] = dc_sample<IN>(p, osc, row, pos + i);
+    if (p.pre)
+    {
+      // the pre-mixer's table index walks with the sample: one modulo per tile and thread instead of one per sample
+      const float2* pre = p.pre + (size_t)row * p.pre_stride;
+      const unsigned step = kDcThreads % p.pre_period;
+      unsigned pi = (unsigned)(((unsigned long long)p.pre_pos + pos + tid) % p.pre_period);
+      for (unsigned i = tid; i < tn; i += kDcThreads)
+      {
+        const float2 d = dc_mix(dc_load<IN>(p, row, pos + i), pre[pi]);
+        ((i & 1u) ? O_(0) : E_(0))[HH + (i >> 1)] = dc_mix(d, osc[pos + i]);
+        pi += step;
+        pi = pi >= p.pre_period ? pi - p.pre_period : pi;
+      }
+    }
+    else
+      for (unsigned i = tid; i < tn; i += kDcThreads)
+        ((i & 1u) ? O_(0) : E_(0))[HH + (i >> 1)] = dc_sample<IN>(p, osc, row, pos + i);
     __syncthreads();
     // operands of the next tile on their way into L2 while this one is filtered
     {

@@ -25,7 +25,7 @@ from . import DownConvertBatch, FmDecoderBatch, FreqShiftBatch
 
 class WidebandReceiver:
     def __init__(self, torch, station_freqs, fs: float = 50.0e6, front_block: int = 32000, blocks_per_call: int = 64,
-                 mixer: str = "osc", max_bw: float = 100000.0, device: int = 0):
+                 mixer: str = "osc", max_bw: float = 100000.0, device: int = 0, lanes_sms: int = 8, n_slots: int = 3):
         assert mixer in ("osc", "freqshift", "freqshift_unfused")
         self.torch, self.mixer, self.fs = torch, mixer, fs
         self.freqs = np.ascontiguousarray(station_freqs, dtype=np.float64)
@@ -49,15 +49,25 @@ class WidebandReceiver:
             else:
                 self.mixed = torch.empty((S, self.n_call, 2), dtype=torch.float32, device=dev)
         self.n_bb = self.n_call >> self.dc.n_stages
+        # The demodulator's lanes kernel (one warp per 32 stations, a latency chain) gets an SM partition of its own and
+        # the front end runs on the demodulator's companion stream, i.e. on the OTHER SMs: sharing SMs with the
+        # decimation chain's CTAs stretched the lanes kernel from 2.5 to 3.3 ms per call at 100 stations
         self.dec = FmDecoderBatch(self.dc.output_rate, 0.0, downsample=1, n_streams=S, max_block_len=self.n_bb,
-                                  device=device)
+                                  device=device, lanes_sms=lanes_sms if lanes_sms >= 8 else 1)
         self.audio_stride = max(self.dec.max_audio_floats(self.n_bb), 2)
-        # two slots: the front end of call k+1 runs while the demodulator (latency-bound lanes) still works on call k
-        self.bbs = [torch.empty((S, self.n_bb, 2), dtype=torch.float32, device=dev) for _ in range(2)]
-        self.audios = [torch.empty((S, self.audio_stride), dtype=torch.float32, device=dev) for _ in range(2)]
-        self.s_front = torch.cuda.Stream(device=dev)
+        # three slots: the front end of call k+1 runs while the demodulator (latency-bound lanes) still works on call k.
+        # With two, the front end of k+1 had to wait for the END of call k-1 and the step was (front end + demodulator
+        # entry + lanes + audio tail) / 2 = 3.0 ms at 100 stations; with three it is the lanes kernel's own chain
+        self.n_slots = n_slots
+        self.bbs = [torch.empty((S, self.n_bb, 2), dtype=torch.float32, device=dev) for _ in range(self.n_slots)]
+        self.audios = [torch.empty((S, self.audio_stride), dtype=torch.float32, device=dev) for _ in range(self.n_slots)]
+        # the front end and the demodulator are submitted on different streams: on one stream the front end of call k+1
+        # would queue behind the demodulator's entry kernels of call k and the step would be their SUM (3.1 ms measured at
+        # 100 stations) instead of the longer of the two (the lanes kernel, 2.5 ms)
+        self.s_front = torch.cuda.ExternalStream(self.dec.companion_stream(), device=dev)
+        self.s_dec = torch.cuda.Stream(device=dev)
         self.s_done = torch.cuda.Stream(device=dev)
-        self.ev = [None, None]
+        self.ev = [None] * self.n_slots
         self.calls = 0
         self.bb, self.audio = self.bbs[0], self.audios[0]
 
@@ -71,7 +81,7 @@ class WidebandReceiver:
         current stream).  Only enqueues; returns the audio floats per station that self.audio (this call's slot) will hold
         once wait() has ordered the current stream after the call."""
         torch = self.torch
-        slot = self.calls & 1
+        slot = self.calls % self.n_slots
         sf = self.s_front.cuda_stream
         self.s_front.wait_stream(torch.cuda.current_stream())
         if self.ev[slot] is not None:
@@ -87,7 +97,11 @@ class WidebandReceiver:
             self.s_front.wait_stream(torch.cuda.default_stream())
             m = self.dc.process_device(0, self.mixed.data_ptr(), self.n_call, bb.data_ptr(), self.n_bb, self.n_call, sf)
         assert m == self.n_bb
-        k = self.dec.process_cf32_device(bb.data_ptr(), self.n_bb, self.n_bb, audio.data_ptr(), self.audio_stride, sf)
+        ev_bb = torch.cuda.Event()
+        ev_bb.record(self.s_front)
+        self.s_dec.wait_event(ev_bb)
+        k = self.dec.process_cf32_device(bb.data_ptr(), self.n_bb, self.n_bb, audio.data_ptr(), self.audio_stride,
+                                         self.s_dec.cuda_stream)
         self.dec.wait(self.s_done.cuda_stream)
         self.ev[slot] = torch.cuda.Event()
         self.ev[slot].record(self.s_done)

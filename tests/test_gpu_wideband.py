@@ -77,3 +77,23 @@ def test_wideband_100_stations_on_the_raster(rfm, port, mixer):
         so, sd = o.dec.status(), wb.dec.status(s)
         assert all(np.float32(so[k]) == np.float32(sd[k]) for k in so), (s, so, sd)
     wb.close()
+
+
+def test_companion_stream_is_usable_and_placement_only(rfm, port, capture):
+    """rfm_decoder_companion_stream: with and without an SM partition the receiver produces the same bits (the partition
+    and the stream are placement, not arithmetic), and the handle is a live stream owned by the decoder."""
+    import torch
+    wb_mod = importlib.import_module("radiofm_b200.wideband")
+    n_call = BPC * BLK
+    outs = []
+    for lanes_sms, n_slots in ((8, 3), (1, 2)):
+        wb = wb_mod.WidebandReceiver(torch, FREQS, FS, BLK, BPC, mixer="freqshift", device=0, lanes_sms=lanes_sms, n_slots=n_slots)
+        h = wb.dec.companion_stream()
+        assert h != 0 and h == wb.dec.companion_stream()
+        a = [wb.process_u8(capture[c * n_call:(c + 1) * n_call]).copy() for c in range(2)]
+        outs.append((a, [wb.dec.take_bits(s) for s in range(len(FREQS))]))
+        wb.close()
+    for c in range(2):
+        assert bits_equal(outs[0][0][c], outs[1][0][c])
+    for s in range(len(FREQS)):
+        assert np.array_equal(outs[0][1][s], outs[1][1][s])
