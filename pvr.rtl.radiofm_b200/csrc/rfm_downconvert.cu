@@ -45,8 +45,16 @@ namespace
 {
 constexpr unsigned kDcMaxStages = 9;   // MAX_DECSTAGES - 1, DownConvert.h:63
 constexpr unsigned kDcThreads = 512;
+#ifndef RFM_DC_THREADS
+#define RFM_DC_THREADS 256
+#endif
+constexpr unsigned kDcThreadsFast = RFM_DC_THREADS; // uniform half-band kernel: 256 threads x 2 CTAs per SM, every thread two groups
+                                                    // of 5 outputs in the first stage (1.75 ms against 1.86 with 512: profiles/r02_c5_dc_chain_ab.txt)
 constexpr unsigned kDcTileGeneric = 2048; // input samples per tile, generic kernel
-constexpr unsigned kDcTileFast = 5120;    // uniform half-band kernel (multiple of 2^9 and of 5 * 2 * 512)
+#ifndef RFM_DC_TILE
+#define RFM_DC_TILE 5120
+#endif
+constexpr unsigned kDcTileFast = RFM_DC_TILE; // uniform half-band kernel (multiple of 2^9; 5120 = 5 * 2 * 512: whole groups)
 
 struct DcStage
 {
@@ -337,35 +345,37 @@ __global__ void __launch_bounds__(kDcThreads) k_dc_chain(DcParams p)
 // uniform chain: every stage is the same generic half-band of L taps (SetWfmDataRate: all HB51).  The V buffers are
 // kept de-interleaved -- E[m] = V[2m], O[m] = V[2m+1] -- so that output o = sum_j h[2j] E[o + j] + h[c] O[o + (c-1)/2]
 // reads consecutive entries; a thread makes R = 5 consecutive outputs from 26 + 4 even and 5 odd samples held in
-// registers (7 LDS.64 per output instead of 27; lane stride 5 float2 = 10 banks: conflict-free), taps are constant-bank
-// operands.  Same products, same summation order as hb_generic.
+// registers (7 LDS.64 per output instead of 27; lane stride 5 float2 = 10 banks: conflict-free).  The arithmetic is on
+// packed (re, im) pairs -- hb_deint_pk: every exact product and every exact sum one FFMA2, two issue slots per tap
+// instead of four (the kernel is issue-bound with the fma pipe a third full).  Same products, same summation order as
+// hb_generic.
 // --------------------------------------------------------------------------------------------------
 // one stage over a tile: groups of R consecutive outputs per thread; dstO == nullptr: last stage, dstE is the output row
 // (natural order), else output o goes to the next stage's E / O by parity
 template <int L, int R>
-__device__ __forceinline__ void dc_stage(const DcTaps<L>& taps, const float2* E, const float2* O, float2* dstE, float2* dstO,
+__device__ __forceinline__ void dc_stage(const DcTapsPk<L>& taps, const float2* E, const float2* O, float2* dstE, float2* dstO,
                                          unsigned nout, unsigned tid)
 {
-  for (unsigned g = tid; g * R < nout; g += kDcThreads)
+  for (unsigned g = tid; g * R < nout; g += kDcThreadsFast)
   {
     const unsigned o0 = g * R;
-    float2 acc[R];
-    hb_deint<L, R>(taps, E + o0, O + o0, acc);
+    f32x2 acc[R];
+    hb_deint_pk<L, R>(taps, reinterpret_cast<const f32x2*>(E + o0), reinterpret_cast<const f32x2*>(O + o0), acc);
 #pragma unroll
     for (int r = 0; r < R; ++r)
       if (o0 + r < nout)
       {
         const unsigned o = o0 + r;
         if (!dstO)
-          dstE[o] = acc[r];
+          reinterpret_cast<f32x2*>(dstE)[o] = acc[r];
         else
-          ((o & 1u) ? dstO : dstE)[o >> 1] = acc[r];
+          reinterpret_cast<f32x2*>((o & 1u) ? dstO : dstE)[o >> 1] = acc[r];
       }
   }
 }
 
 template <int IN, int L>
-__global__ void __launch_bounds__(kDcThreads) k_dc_chain_uniform(DcParams p, DcTaps<L> taps)
+__global__ void __launch_bounds__(kDcThreadsFast) k_dc_chain_uniform(DcParams p, DcTapsPk<L> taps)
 {
   constexpr int R = 5;                 // largest group: sizes the slack behind each buffer
   constexpr unsigned HH = (L - 1) / 2; // history entries in each of E and O
@@ -387,13 +397,13 @@ __global__ void __launch_bounds__(kDcThreads) k_dc_chain_uniform(DcParams p, DcT
   const float2* tin = p.tails_in + (size_t)row * p.tail_stride;
   for (unsigned k = 0; k < p.nst; ++k)
   {
-    for (unsigned i = tid; i < 2 * HH; i += kDcThreads)
+    for (unsigned i = tid; i < 2 * HH; i += kDcThreadsFast)
     {
       const float2 v = (c == 0) ? tin[p.tail_off[k] + i] : make_float2(0.f, 0.f);
       ((i & 1u) ? O_(k) : E_(k))[i >> 1] = v;
     }
     // slack entries: defined values (they are read into registers by the last partial group, never accumulated)
-    for (unsigned i = tid; i < (unsigned)R; i += kDcThreads)
+    for (unsigned i = tid; i < (unsigned)R; i += kDcThreadsFast)
     {
       const unsigned e = HH + (kDcTileFast >> (k + 1));
       E_(k)[e + i] = make_float2(0.f, 0.f);
@@ -413,9 +423,9 @@ __global__ void __launch_bounds__(kDcThreads) k_dc_chain_uniform(DcParams p, DcT
     {
       // the pre-mixer's table index walks with the sample: one modulo per tile and thread instead of one per sample
       const float2* pre = p.pre + (size_t)row * p.pre_stride;
-      const unsigned step = kDcThreads % p.pre_period;
+      const unsigned step = kDcThreadsFast % p.pre_period;
       unsigned pi = (unsigned)(((unsigned long long)p.pre_pos + pos + tid) % p.pre_period);
-      for (unsigned i = tid; i < tn; i += kDcThreads)
+      for (unsigned i = tid; i < tn; i += kDcThreadsFast)
       {
         const float2 d = dc_mix(dc_load<IN>(p, row, pos + i), pre[pi]);
         ((i & 1u) ? O_(0) : E_(0))[HH + (i >> 1)] = dc_mix(d, osc[pos + i]);
@@ -424,7 +434,7 @@ __global__ void __launch_bounds__(kDcThreads) k_dc_chain_uniform(DcParams p, DcT
       }
     }
     else
-      for (unsigned i = tid; i < tn; i += kDcThreads)
+      for (unsigned i = tid; i < tn; i += kDcThreadsFast)
         ((i & 1u) ? O_(0) : E_(0))[HH + (i >> 1)] = dc_sample<IN>(p, osc, row, pos + i);
     __syncthreads();
     // operands of the next tile on their way into L2 while this one is filtered
@@ -443,9 +453,9 @@ __global__ void __launch_bounds__(kDcThreads) k_dc_chain_uniform(DcParams p, DcT
         float2* dstE = last ? out + (pos >> p.nst) : E_(k + 1) + HH;
         float2* dstO = last ? nullptr : O_(k + 1) + HH;
         // outputs per thread: 5 while that keeps every warp busy, fewer for the short late stages (latency-bound)
-        if (nout >= 2 * kDcThreads)
+        if (nout >= 2 * kDcThreadsFast)
           dc_stage<L, 5>(taps, E_(k), O_(k), dstE, dstO, nout, tid);
-        else if (nout >= kDcThreads / 2)
+        else if (nout >= kDcThreadsFast / 2)
           dc_stage<L, 3>(taps, E_(k), O_(k), dstE, dstO, nout, tid);
         else
           dc_stage<L, 1>(taps, E_(k), O_(k), dstE, dstO, nout, tid);
@@ -453,24 +463,34 @@ __global__ void __launch_bounds__(kDcThreads) k_dc_chain_uniform(DcParams p, DcT
       __syncthreads();
       n = nout;
     }
-    // carry: E[i] = E[n_k / 2 + i], O likewise, i < HH
+    // carry: E[i] = E[n_k / 2 + i], O likewise, i < HH.  Warp w takes stages w, w + warps, ..: all stages are read into
+    // registers at once, one barrier, all are written (the stage loop above ended with a barrier; the one below closes
+    // the tile) -- two barriers per tile instead of two per stage
     {
-      unsigned nk = tn;
-      for (unsigned k = 0; k < p.nst; ++k)
+      constexpr unsigned NW = kDcThreadsFast / 32, PER = (kDcMaxStages + NW - 1) / NW;
+      static_assert(HH <= 32, "one lane per history entry");
+      const unsigned w = tid >> 5, l = tid & 31u;
+      float2 ve[PER], vo[PER];
+#pragma unroll
+      for (unsigned q = 0; q < PER; ++q)
       {
-        float2 ve = make_float2(0.f, 0.f), vo = ve;
-        if (tid < HH)
+        const unsigned k = w + q * NW;
+        if (k < p.nst && l < HH)
         {
-          ve = E_(k)[nk / 2 + tid];
-          vo = O_(k)[nk / 2 + tid];
+          ve[q] = E_(k)[(tn >> (k + 1)) + l];
+          vo[q] = O_(k)[(tn >> (k + 1)) + l];
         }
-        __syncthreads();
-        if (tid < HH)
+      }
+      __syncthreads();
+#pragma unroll
+      for (unsigned q = 0; q < PER; ++q)
+      {
+        const unsigned k = w + q * NW;
+        if (k < p.nst && l < HH)
         {
-          E_(k)[tid] = ve;
-          O_(k)[tid] = vo;
+          E_(k)[l] = ve[q];
+          O_(k)[l] = vo[q];
         }
-        nk >>= 1;
       }
     }
     __syncthreads();
@@ -480,7 +500,7 @@ __global__ void __launch_bounds__(kDcThreads) k_dc_chain_uniform(DcParams p, DcT
   {
     float2* tout = p.tails_out + (size_t)row * p.tail_stride;
     for (unsigned k = 0; k < p.nst; ++k)
-      for (unsigned i = tid; i < 2 * HH; i += kDcThreads)
+      for (unsigned i = tid; i < 2 * HH; i += kDcThreadsFast)
         tout[p.tail_off[k] + i] = ((i & 1u) ? O_(k) : E_(k))[i >> 1];
   }
 }
@@ -497,7 +517,7 @@ cudaError_t DevAlloc(T** p, size_t n)
 struct rfm_downconvert
 {
   unsigned rows = 0, cap = 0, nst = 0;
-  int device = 0;
+  int device = 0, sm_count = 148;
   float in_rate = 0.f, max_bw = 0.f, out_rate = 0.f;
   bool wfm = false, uniform51 = false, osc_shared = false;
   std::vector<HalfBandStage> stages;
@@ -570,7 +590,7 @@ void LaunchChain(rfm_downconvert* d, const DcParams& p, cudaStream_t st)
       n >>= 1;
     }
     EnsureDynSmem(k_dc_chain_uniform<IN, 51>, smem);
-    k_dc_chain_uniform<IN, 51><<<grid, kDcThreads, smem, st>>>(p, d->taps51);
+    k_dc_chain_uniform<IN, 51><<<grid, kDcThreadsFast, smem, st>>>(p, MakeDcTapsPk(d->taps51));
   }
   else
   {
@@ -623,18 +643,24 @@ int Run(rfm_downconvert* d, int mode, const void* d_in, size_t in_stride, float2
   p.tails_out = d->d_tails[d->tails_cur ^ 1];
   p.tail_stride = d->tail_stride;
   p.out = d_out; p.out_stride = out_stride;
-  // chunking: the chunk count that minimises (waves of CTAs) x (chunk + warm-up) -- full waves on the 148 SMs with two
-  // resident CTAs each, warm-up overhead kept small
+  // chunking: the chunk count that minimises (waves of CTAs) x (chunk + warm-up) -- full waves on the device's SMs with
+  // two resident CTAs each, warm-up overhead kept small (the time is flat within 3 % from 10 to 25 chunks)
   const unsigned gran = 1u << d->nst;
   unsigned nchunks = 1, chunk = n;
   {
-    const unsigned slots = 2 * 148;
+    static const int kslots = KnobInt(RFM_KNOB("RFM_DC_SLOTS"), 0);
+    const unsigned slots = kslots > 0 ? (unsigned)kslots : 2u * (unsigned)d->sm_count;
     double best = 1e300;
     const unsigned max_chunks = d->warm ? std::max(1u, n / (4 * d->warm)) : 1u;
+    static const int kforce = KnobInt(RFM_KNOB("RFM_DC_CHUNKS"), 0);
     for (unsigned c = 1; c <= std::min(max_chunks, 64u); ++c)
     {
+      if (kforce > 0 && c != (unsigned)kforce)
+        continue;
       unsigned len = (n + c - 1) / c;
       len = (len + gran - 1) / gran * gran;
+      if (d->uniform51 && len >= kDcTileFast) // whole tiles: a partial last tile costs nearly a full one (its barriers)
+        len = (len + kDcTileFast - 1) / kDcTileFast * kDcTileFast;
       const unsigned cnt = (n + len - 1) / len;
       const unsigned waves = (cnt * d->rows + slots - 1) / slots;
       const double cost = (double)waves * (len + (cnt > 1 ? d->warm : 0));
@@ -682,6 +708,8 @@ int rfm_downconvert_create(uint32_t rows, const float* nco_freq, float in_rate, 
     return DcFail(RFM_ERR_CUDA, "cudaSetDevice failed");
   rfm_downconvert* d = new rfm_downconvert;
   d->rows = rows; d->cap = max_len; d->device = device;
+  if (cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || d->sm_count <= 0)
+    d->sm_count = 148;
   d->in_rate = in_rate; d->max_bw = max_bw; d->wfm = wfm != 0;
   d->freq.assign(nco_freq, nco_freq + rows);
   d->out_rate = PlanDecimationChain(in_rate, max_bw, d->wfm, &d->stages);

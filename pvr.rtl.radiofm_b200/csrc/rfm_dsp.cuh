@@ -170,4 +170,51 @@ __device__ __forceinline__ void hb_deint(const DcTaps<L>& t, const float2* E, co
   }
 }
 
+// the same taps as pairs (h, h) for the packed form below: even taps e[j] = h[2 j], centre tap c
+template <int L>
+struct DcTapsPk
+{
+  unsigned long long e[(L + 1) / 2], c;
+  PairConst pk;
+};
+
+template <int L>
+inline DcTapsPk<L> MakeDcTapsPk(const DcTaps<L>& t)
+{
+  DcTapsPk<L> o;
+  for (int j = 0; j < (L + 1) / 2; ++j)
+    o.e[j] = rfm_pair_bits(t.h[2 * j], t.h[2 * j]);
+  o.c = rfm_pair_bits(t.h[(L - 1) / 2], t.h[(L - 1) / 2]);
+  o.pk = kPairConst;
+  return o;
+}
+
+#ifdef __CUDACC__
+// hb_deint on packed pairs: (re, im) of a sample is one 64-bit operand, every product and every sum one FFMA2 (exact:
+// rfm_math.cuh) -- 2 issue slots per tap instead of 4, same products, same order
+template <int L, int R>
+__device__ __forceinline__ void hb_deint_pk(const DcTapsPk<L>& t, const f32x2* E, const f32x2* O, f32x2 (&acc)[R])
+{
+  constexpr int NE = (L + 1) / 2;
+  constexpr int C = (L - 1) / 2;
+#pragma unroll
+  for (int m = 0; m < NE + R - 1; ++m)
+  {
+    const f32x2 v = E[m];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+    {
+      const int j = m - r;
+      if (j == 0)
+        acc[r] = pk_mul(v, t.e[0], t.pk);                          // DownConvert.cpp:528-529
+      if (j >= 0 && j < NE)
+        acc[r] = pk_add(pk_mul(v, t.e[j], t.pk), acc[r], t.pk);    // :533-534 (j = 0 again: tap 0 is counted twice)
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+    acc[r] = pk_add(pk_mul(O[r + (C - 1) / 2], t.c, t.pk), acc[r], t.pk); // :537-540
+}
+#endif
+
 } // namespace rfm
