@@ -605,7 +605,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU)
     ap.add_argument("--groups", type=int, default=0)
-    ap.add_argument("--host-groups", type=int, default=8)
+    ap.add_argument("--host-groups", type=int, default=4,
+                    help="stream groups of the host-buffer (e2e) decoder: 4 measured best for 4096 streams -- blocking call 12.0 ms "
+                         "(8 groups: 14.3, 1 group: 13.9), streaming 10.2 ms (profiles/r02_e2e_host_groups.txt)")
     ap.add_argument("--resident-blocks", type=int, default=12)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-prof", action="store_true", help="do not bracket kernels with CUDA events (roofline leg off)")

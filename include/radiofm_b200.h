@@ -59,7 +59,10 @@ typedef struct rfm_config
   uint32_t n_streams;      /* >= 1 */
   uint32_t max_block_len;  /* largest n per call; the reference's limit is 65536 (FmDecode.cpp:277) */
   int32_t device;          /* CUDA device ordinal, -1 = current */
-  uint32_t n_groups;       /* internal stream groups pipelined on separate CUDA streams, 0 = auto */
+  uint32_t n_groups;       /* internal stream groups pipelined on separate CUDA streams, 0 = one group.  Device-pointer
+                            * callers want 1 (every group pays the lanes kernel's ~1 ms latency chain); host-buffer
+                            * callers of a wide batch want ~4, so that the H2D copy of one group overlaps the kernels of
+                            * the others (4096 streams: blocking call 12.0 ms with 4, 13.9 with 1, 14.3 with 8) */
   uint32_t lanes_sms;      /* SM partition: the one-lane-per-stream recurrences (pilot PLL / DC tracker) run in a
                             * green context of this many SMs (multiple of 8, >= 8), every FIR kernel in the rest, so
                             * neither waits for the other's issue slots.  0 = automatic (24 SMs when n_streams >= 2048
