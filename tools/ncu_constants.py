@@ -22,8 +22,8 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 PROF_NAME = [("k_bb_lanes", "k_bb_lanes"), ("k_front", "k_front"), ("k_demod_spec", "k_demod_spec"),
-             ("k_resample", "k_resample"), ("k_rds_front", "k_rds_front"), ("k_rotfir_lanes<1>", "k_rotfir_lp29"),
-             ("k_rotfir_lanes<2>", "k_rotfir_rdslp"), ("k_rotfir_lanes<0>", "k_rotfir_rdsmf"), ("k_rds_pll", "k_rds_pll"),
+             ("k_resample", "k_resample"), ("k_rds_front", "k_rds_front"), ("k_rotfir_lanes<1,", "k_rotfir_lp29"),
+             ("k_rotfir_lanes<2,", "k_rotfir_rdslp"), ("k_rotfir_lanes<0,", "k_rotfir_rdsmf"), ("k_rds_pll", "k_rds_pll"),
              ("k_audio_tail", "k_audio_tail"), ("k_rds_slice", "k_rds_slice"), ("k_demod_repair", "k_demod_fix"),
              ("k_demod_fix", "k_demod_fix"), ("k_if_level", "k_if_level"), ("k_osc", "k_osc"), ("k_res_taps", "k_res_taps"),
              ("k_tails", "k_tails")]
