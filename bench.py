@@ -147,7 +147,8 @@ def run_reference(args):
     cores = len(os.sched_getaffinity(0))
     iq = cpu_input(8)
     decoders = [make() for _ in range(cores)]
-    bpt = 8   # blocks per thread per step: ~0.2 s of CPU work per thread per step
+    bpt = 64  # blocks per thread per step: ~0.2 s of CPU work per thread per step (with 8 the 24 ms steps measured the
+              # thread pool's hand-over as much as the chain: 344 MS/s against the 440 of the 10 s cpu_baseline leg)
     with cf.ThreadPoolExecutor(cores) as pool:
         for w in range(args.warmup):
             cpu_step(decoders, iq, pool, bpt, w * bpt)
