@@ -189,8 +189,8 @@ def cpu_baseline_leg():
         t0 = time.perf_counter()
         samples, b = 0, 0
         while time.perf_counter() - t0 < 10.0:
-            samples += cpu_step(decoders, iq, pool, 8, b)
-            b += 8
+            samples += cpu_step(decoders, iq, pool, 64, b)
+            b += 64
         dt = time.perf_counter() - t0
     return {"value": samples / dt / 1e6, "unit": "MS/s", "cores": cores, "kind": kind,
             "sample": f"{cores} threads, one decoder each, same 2.4 MS/s stereo+RDS blocks of {BLK} samples, "
