@@ -126,9 +126,9 @@ __device__ __forceinline__ float2 hb_out(int kind, unsigned L, const float* h, c
 // --------------------------------------------------------------------------------------------------
 // The generic half-band over DE-INTERLEAVED V buffers -- E[m] = V[2m], O[m] = V[2m+1] -- so that output
 // o = sum_j h[2j] E[o + j] + h[c] O[o + (c-1)/2] reads consecutive entries: a thread makes R consecutive outputs from
-// (L+1)/2 + R - 1 even and R odd samples held in registers, the taps are constant-bank operands (kernel parameters).
-// Same products, same summation order as hb_generic (DownConvert.cpp:528-540).  Used by the wideband chain
-// (rfm_downconvert.cu) and by the RDS front (rfm_kernels.cu).
+// (L+1)/2 + R - 1 even and R odd samples held in registers, the taps are kernel parameters.  Same products, same
+// summation order as hb_generic (DownConvert.cpp:528-540).  Used by the wideband chain (rfm_downconvert.cu) and by the
+// RDS front (rfm_kernels.cu), both through the packed form hb_deint_pk below.
 // --------------------------------------------------------------------------------------------------
 template <int L>
 struct DcTaps
@@ -136,41 +136,7 @@ struct DcTaps
   float h[L];
 };
 
-template <int L, int R>
-__device__ __forceinline__ void hb_deint(const DcTaps<L>& t, const float2* E, const float2* O, float2 (&acc)[R])
-{
-  constexpr int NE = (L + 1) / 2; // even taps 0, 2, .., L - 1
-  constexpr int C = (L - 1) / 2;  // centre tap (odd index)
-#pragma unroll
-  for (int m = 0; m < NE + R - 1; ++m)
-  {
-    const float2 v = E[m];
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-    {
-      const int j = m - r;
-      if (j == 0)
-      {
-        acc[r].x = mulf(v.x, t.h[0]);                 // DownConvert.cpp:528-529
-        acc[r].y = mulf(v.y, t.h[0]);
-      }
-      if (j >= 0 && j < NE)
-      {
-        acc[r].x = addf(acc[r].x, mulf(v.x, t.h[2 * j])); // :533-534 (j = 0 again: tap 0 is counted twice)
-        acc[r].y = addf(acc[r].y, mulf(v.y, t.h[2 * j]));
-      }
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < R; ++r)
-  {
-    const float2 v = O[r + (C - 1) / 2];
-    acc[r].x = addf(acc[r].x, mulf(v.x, t.h[C]));       // :537-540
-    acc[r].y = addf(acc[r].y, mulf(v.y, t.h[C]));
-  }
-}
-
-// the same taps as pairs (h, h) for the packed form below: even taps e[j] = h[2 j], centre tap c
+// the taps as pairs (h, h): even taps e[j] = h[2 j], centre tap c, and the two constants of the packed arithmetic
 template <int L>
 struct DcTapsPk
 {
@@ -190,8 +156,8 @@ inline DcTapsPk<L> MakeDcTapsPk(const DcTaps<L>& t)
 }
 
 #ifdef __CUDACC__
-// hb_deint on packed pairs: (re, im) of a sample is one 64-bit operand, every product and every sum one FFMA2 (exact:
-// rfm_math.cuh) -- 2 issue slots per tap instead of 4, same products, same order
+// (re, im) of a sample is one 64-bit operand, every product and every sum one FFMA2 (exact: rfm_math.cuh) -- 2 issue
+// slots per tap instead of 4 (FMUL, FMUL, FADD, FADD), same products, same order
 template <int L, int R>
 __device__ __forceinline__ void hb_deint_pk(const DcTapsPk<L>& t, const f32x2* E, const f32x2* O, f32x2 (&acc)[R])
 {

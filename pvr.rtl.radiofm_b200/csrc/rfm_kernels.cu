@@ -2282,31 +2282,31 @@ constexpr unsigned kRf3Tile = 1024;   // baseband samples per tile
 constexpr unsigned kRf3Threads = 128;
 
 template <int L, int R>
-__device__ __forceinline__ void rf3_stage(const DcTaps<L>& taps, const float2* E, const float2* O, float2* dstE, float2* dstO,
+__device__ __forceinline__ void rf3_stage(const DcTapsPk<L>& taps, const float2* E, const float2* O, float2* dstE, float2* dstO,
                                           unsigned nout, unsigned tid)
 {
   // dstO == nullptr: last stage, dstE is the output row (natural order); else output o goes to the next stage's
-  // E / O by parity (both pre-offset by that stage's history)
+  // E / O by parity (both pre-offset by that stage's history).  Arithmetic on packed (re, im) pairs: hb_deint_pk
   for (unsigned g = tid; g * R < nout; g += kRf3Threads)
   {
     const unsigned o0 = g * R;
-    float2 acc[R];
-    hb_deint<L, R>(taps, E + o0, O + o0, acc);
+    f32x2 acc[R];
+    hb_deint_pk<L, R>(taps, reinterpret_cast<const f32x2*>(E + o0), reinterpret_cast<const f32x2*>(O + o0), acc);
 #pragma unroll
     for (int r = 0; r < R; ++r)
       if (o0 + r < nout)
       {
         const unsigned o = o0 + r;
         if (!dstO)
-          dstE[o] = acc[r];
+          reinterpret_cast<f32x2*>(dstE)[o] = acc[r];
         else
-          ((o & 1u) ? dstO : dstE)[o >> 1] = acc[r];
+          reinterpret_cast<f32x2*>((o & 1u) ? dstO : dstE)[o >> 1] = acc[r];
       }
   }
 }
 
 template <int L0, int L1, int L2>
-__global__ void __launch_bounds__(kRf3Threads) k_rds_front3(RdsFrontParams p, DcTaps<L0> t0, DcTaps<L1> t1, DcTaps<L2> t2)
+__global__ void __launch_bounds__(kRf3Threads) k_rds_front3(RdsFrontParams p, DcTapsPk<L0> t0, DcTapsPk<L1> t1, DcTapsPk<L2> t2)
 {
   constexpr unsigned T = kRf3Tile, SL = 6; // SL: slack behind each buffer (a group of R outputs may read past the tile)
   constexpr unsigned H0 = (L0 - 1) / 2, H1 = (L1 - 1) / 2, H2 = (L2 - 1) / 2; // history entries in each of E and O
@@ -2413,7 +2413,7 @@ static void launch_rds_front3(const RdsFrontParams& p, cudaStream_t st)
                      Z2 = ((L2 - 1) / 2 + T / 8 + SL + 1) & ~1u;
   const size_t smem = (size_t)(2 * (Z0 + Z1 + Z2) + T) * sizeof(float2) + T * sizeof(float);
   EnsureDynSmem(k_rds_front3<L0, L1, L2>, smem);
-  k_rds_front3<L0, L1, L2><<<p.S, kRf3Threads, smem, st>>>(p, t0, t1, t2);
+  k_rds_front3<L0, L1, L2><<<p.S, kRf3Threads, smem, st>>>(p, MakeDcTapsPk(t0), MakeDcTapsPk(t1), MakeDcTapsPk(t2));
 }
 
 void launch_rds_front(const RdsFrontParams& p, cudaStream_t st)

@@ -34,7 +34,7 @@ HOT = {
     "k_rds_pll": (96, ""),
     "k_rds_slice": (96, ""),
     "k_audio_tail": (128, ""),
-    "k_dc_chain_uniform": (64, "512 threads, two CTAs per SM"),
+    "k_dc_chain_uniform": (64, "256 threads, two CTAs per SM (shared memory)"),
     "k_dc_oscE": (64, ""),
 }
 
@@ -113,3 +113,33 @@ def test_tma_is_really_used():
     assert len(ops) == 6, sorted(ops)   # ds = 1, 5, 11, exact and fused
     for k, v in ops.items():
         assert "UTMALDG" in v and "SYNCS" in v and "LDG.E.128" not in v, (k, v)
+
+
+def test_packed_pairs_are_really_used_and_never_contracted():
+    """The half-band chains (wideband front end, RDS front) do their taps on packed (re, im) pairs: their SASS holds
+    FFMA2 and no scalar FMUL/FADD tap loop.  The exact product / exact sum are fma(a, b, -0) and fma(p, 1, c) with the
+    two constants passed as kernel arguments -- ptxas contracts the literal forms into ONE FFMA2 per tap (not the
+    reference's arithmetic): every such kernel must therefore hold an EVEN number of FFMA2, two per tap."""
+    lib = os.path.join(ROOT, "pvr.rtl.radiofm_b200", "libradiofm_b200.so")
+    if not os.path.exists(lib) or not os.path.exists(CUOBJDUMP):
+        pytest.skip("library / cuobjdump not available")
+    r = subprocess.run([CUOBJDUMP, "-sass", lib], capture_output=True, text=True)
+    assert r.returncode == 0
+    cur, n2, nscalar = None, {}, {}
+    for line in r.stdout.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            continue
+        if cur and ("k_dc_chain_uniform" in cur or "k_rds_front3" in cur):
+            if re.search(r"\bFFMA2\b", line):
+                n2[cur] = n2.get(cur, 0) + 1
+            elif re.search(r"\b(FMUL|FADD)\b", line):
+                nscalar[cur] = nscalar.get(cur, 0) + 1
+    assert len(n2) >= 5, sorted(n2)     # k_dc_chain_uniform<0..2, 51> and both k_rds_front3 plans
+    for k, v in n2.items():
+        taps = {"k_dc_chain_uniform": (5 + 3 + 1) * 28, "k_rds_front3ILi15ELi23ELi43": 5 * 9 + 3 * 13 + 23,
+                "k_rds_front3ILi15ELi19ELi35": 5 * 9 + 3 * 11 + 19}
+        want = next(t for name, t in taps.items() if name in k)
+        assert v == 2 * want, (k, v, want)            # two FFMA2 per tap: nothing was contracted
+        assert nscalar.get(k, 0) < v, (k, nscalar.get(k), v)   # what is left is the mixer in front of the taps
