@@ -138,8 +138,11 @@ def test_packed_pairs_are_really_used_and_never_contracted():
                 nscalar[cur] = nscalar.get(cur, 0) + 1
     assert len(n2) >= 5, sorted(n2)     # k_dc_chain_uniform<0..2, 51> and both k_rds_front3 plans
     for k, v in n2.items():
-        taps = {"k_dc_chain_uniform": (5 + 3 + 1) * 28, "k_rds_front3ILi15ELi23ELi43": 5 * 9 + 3 * 13 + 23,
-                "k_rds_front3ILi15ELi19ELi35": 5 * 9 + 3 * 11 + 19}
-        want = next(t for name, t in taps.items() if name in k)
-        assert v == 2 * want, (k, v, want)            # two FFMA2 per tap: nothing was contracted
+        # taps per output = (L + 1) / 2 even taps + the centre tap; outputs per thread 5 / 3 / 1 by stage
+        if "k_dc_chain_uniform" in k:
+            per_out = 2 * 27                          # HB51; the compiler may clone a stage body: whole outputs only
+            assert v >= 9 * per_out and v % per_out == 0, (k, v)
+        else:
+            want = 5 * 9 + 3 * 13 + 23 if "ILi15ELi23ELi43" in k else 5 * 9 + 3 * 11 + 19
+            assert v == 2 * want, (k, v, want)        # two FFMA2 per tap: nothing was contracted
         assert nscalar.get(k, 0) < v, (k, nscalar.get(k), v)   # what is left is the mixer in front of the taps
